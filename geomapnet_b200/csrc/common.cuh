@@ -1,0 +1,98 @@
+// Shared device/host helpers for the MapNet B200 hot path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace mapnet {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing: no exception crosses the C boundary -------------------
+void set_last_error(const char* fmt, ...);
+const char* get_last_error();
+
+#define MN_CUDA(expr)                                                           \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      mapnet::set_last_error("%s:%d CUDA error %d (%s) in %s", __FILE__,        \
+                             __LINE__, (int)_e, cudaGetErrorString(_e), #expr); \
+      return 1;                                                                 \
+    }                                                                           \
+  } while (0)
+
+#define MN_CHECK(cond, ...)                         \
+  do {                                              \
+    if (!(cond)) {                                  \
+      mapnet::set_last_error(__VA_ARGS__);          \
+      return 2;                                     \
+    }                                               \
+  } while (0)
+
+#define MN_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+#define MN_LAUNCH_CHECK() MN_CUDA(cudaGetLastError())
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- activation element access ---------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 8-wide channel vectors: 16 B for bf16, 2x16 B for fp32.  All activation
+// tensors are NHWC with C % 8 == 0 (C in {8(padded stem),64,128,256,512}).
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  float v[8];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<bf16> {
+  float v[8];
+  __device__ __forceinline__ void load(const bf16* p) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ __forceinline__ void store(bf16* p) const {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace mapnet

@@ -1,0 +1,187 @@
+// Pose-regression head: global average pool -> fc(512->feat_dim) -> ReLU ->
+// dropout -> fc_xyz / fc_wpqr (feat_dim->3 each), forward and backward.
+// Replaces AdaptiveAvgPool2d(1), three cuBLAS sgemm calls, F.relu, F.dropout and
+// torch.cat of /root/reference/models/posenet.py:44-49,65-73 and the NaN filter
+// hook :28-34.  ~1 MFLOP/image: latency-bound, so a small strided fp32 GEMM with
+// fused epilogues is used for every product (no tensor cores here by design).
+#include "kernels.h"
+
+namespace mapnet {
+
+// ---- global average pool ------------------------------------------------------
+template <typename T>
+__global__ void k_gap(const T* __restrict__ z, float* __restrict__ feat, int B, int HW, int C) {
+  const int cv = C >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * cv) return;
+  const int b = i / cv, c0 = (i % cv) * 8;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int p = 0; p < HW; ++p) {
+    Vec8<T> v; v.load(z + ((long long)b * HW + p) * C + c0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+  }
+  const float inv = 1.0f / (float)HW;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) feat[(long long)b * C + c0 + k] = acc[k] * inv;
+}
+template <typename T>
+int launch_gap(const T* z, float* feat, int B, int HW, int C, cudaStream_t st) {
+  const int n = B * (C >> 3);
+  k_gap<T><<<cdiv(n, 128), 128, 0, st>>>(z, feat, B, HW, C);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+template int launch_gap<float>(const float*, float*, int, int, int, cudaStream_t);
+template int launch_gap<bf16>(const bf16*, float*, int, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void k_gap_bwd(const float* __restrict__ dfeat, T* __restrict__ dz, int B, int HW, int C) {
+  const int cv = C >> 3;
+  const long long nvec = (long long)B * HW * cv;
+  const float inv = 1.0f / (float)HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    const int b = (int)(i / ((long long)cv * HW));
+    Vec8<T> o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = dfeat[(long long)b * C + c0 + k] * inv;
+    o.store(dz + i * 8);
+  }
+}
+template <typename T>
+int launch_gap_bwd(const float* dfeat, T* dz, int B, int HW, int C, cudaStream_t st) {
+  const long long nvec = (long long)B * HW * (C >> 3);
+  long long grid = (nvec + 255) / 256; if (grid > 148 * 8) grid = 148 * 8;
+  k_gap_bwd<T><<<(int)grid, 256, 0, st>>>(dfeat, dz, B, HW, C);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+template int launch_gap_bwd<float>(const float*, float*, int, int, int, cudaStream_t);
+template int launch_gap_bwd<bf16>(const float*, bf16*, int, int, int, cudaStream_t);
+
+// ---- small strided fp32 GEMM:  C[m*ldc+n] = epi( sum_k A[m*sam+k*sak] * B[n*sbn+k*sbk] ) ----
+// EPI 0: + bias[n] (bias may be null)
+// EPI 1: pre = acc + bias[n]; aux[m*ldc+n] = pre; out = relu(pre) * (mask ? mask[m*ldc+n] : 1)
+// EPI 2: out = acc * (mask ? mask : 1) * [aux > 0]          (ReLU/dropout gate in backward)
+template <int EPI>
+__global__ void __launch_bounds__(256)
+k_small_gemm(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm,
+             long long sbn, long long sbk, float* __restrict__ C, int ldc, int M, int N, int K,
+             const float* __restrict__ bias, float* __restrict__ aux, const float* __restrict__ mask) {
+  __shared__ float As[32][33];
+  __shared__ float Bs[32][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int e = threadIdx.x; e < 1024; e += 256) {
+      // make the fastest-varying loader index follow the unit-stride dimension
+      int r, kk;
+      if (sak == 1) { r = e >> 5; kk = e & 31; } else { kk = e >> 5; r = e & 31; }
+      const int m = m0 + r, k = k0 + kk;
+      As[kk][r] = (m < M && k < K) ? A[(long long)m * sam + (long long)k * sak] : 0.f;
+      int rb, kb;
+      if (sbk == 1) { rb = e >> 5; kb = e & 31; } else { kb = e >> 5; rb = e & 31; }
+      const int n = n0 + rb, k2 = k0 + kb;
+      Bs[kb][rb] = (n < N && k2 < K) ? Bm[(long long)n * sbn + (long long)k2 * sbk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
+      const float b0 = Bs[kk][tx * 2], b1 = Bs[kk][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
+      if (m >= M || n >= N) continue;
+      const long long o = (long long)m * ldc + n;
+      float v = acc[i][j];
+      if (EPI == 0) {
+        if (bias != nullptr) v += bias[n];
+      } else if (EPI == 1) {
+        v += bias[n];
+        aux[o] = v;
+        v = fmaxf(v, 0.f);
+        if (mask != nullptr) v *= mask[o];
+      } else {
+        if (mask != nullptr) v *= mask[o];
+        v = (aux[o] > 0.f) ? v : 0.f;
+      }
+      C[o] = v;
+    }
+}
+
+int launch_small_gemm(int epi, const float* A, long long sam, long long sak, const float* Bm, long long sbn,
+                      long long sbk, float* C, int ldc, int M, int N, int K, const float* bias, float* aux,
+                      const float* mask, cudaStream_t st) {
+  dim3 grid(cdiv(N, 32), cdiv(M, 32));
+  if (epi == 0) k_small_gemm<0><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask);
+  else if (epi == 1) k_small_gemm<1><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask);
+  else k_small_gemm<2><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
+// column sums: out[n] = sum_m A[m*lda + n]
+__global__ void k_colsum(const float* __restrict__ A, int lda, int M, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) s += A[(long long)m * lda + n];
+  out[n] = s;
+}
+int launch_colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st) {
+  k_colsum<<<cdiv(N, 128), 128, 0, st>>>(A, lda, M, N, out);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
+// dpred copy with the NaN filter of models/posenet.py:28-34 applied to the
+// rotation half (the gradient entering fc_wpqr).
+__global__ void k_dpred_filter(const float* __restrict__ in, float* __restrict__ out, int n, int filter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = in[i];
+  if (filter && (i % 6) >= 3 && v != v) v = 0.f;
+  out[i] = v;
+}
+int launch_dpred_filter(const float* in, float* out, int n, int filter, cudaStream_t st) {
+  k_dpred_filter<<<cdiv(n, 128), 128, 0, st>>>(in, out, n, filter);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
+// counter-based dropout mask: mask = (u >= p) / (1-p), u from splitmix64(seed, offset+i)
+__global__ void k_dropout_mask(float* __restrict__ mask, long long n, float p, unsigned long long seed,
+                               unsigned long long offset) {
+  const float keep_scale = 1.0f / (1.0f - p);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (offset + (unsigned long long)i + 1ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+    mask[i] = (u >= p) ? keep_scale : 0.f;
+  }
+}
+int launch_dropout_mask(float* mask, long long n, float p, unsigned long long seed, unsigned long long offset,
+                        cudaStream_t st) {
+  long long grid = (n + 255) / 256; if (grid > 592) grid = 592;
+  k_dropout_mask<<<(int)grid, 256, 0, st>>>(mask, n, p, seed, offset);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mapnet

@@ -1,0 +1,206 @@
+"""Regenerate tests/golden/*.npz by RUNNING THE REFERENCE (build container only).
+
+TEST INFRASTRUCTURE.  Usage:  python -m oracle.make_goldens [--full]
+
+Every golden holds the outputs of the reference's own modules
+(models/posenet.py, common/criterion.py, common/pose_utils.py, executed from
+/root/reference through oracle.ref_loader) on seed-generated inputs and
+seed-generated weights (oracle.weights).  Inputs/weights are NOT stored for the
+large configs -- they are regenerated from the seed on the test side; a
+checksum of each guards against generator drift.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import ref_loader, weights
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+SVALS = dict(sax=0.0, saq=-3.0, srx=0.0, srq=-3.0)   # scripts/train.py:59-66 + mapnet.ini beta/gamma
+
+# name -> cfg.  T is the frame count the MODEL sees per tuple.
+STEP_CONFIGS = {
+    "posenet_tiny":     dict(kind="posenet", N=4, H=64, W=64),
+    "posenet_ragged":   dict(kind="posenet", N=3, H=72, W=88),
+    "mapnet_tiny":      dict(kind="mapnet", N=2, T=3, H=64, W=64),
+    "online_tiny":      dict(kind="online", N=2, T=6, H=64, W=64, lr=1e-5, wd=0.0, clip=5.0),
+    "online_gps_tiny":  dict(kind="online_gps", N=2, T=6, H=64, W=64, lr=1e-5, wd=0.0, clip=5.0),
+    "posenet_b8_256":   dict(kind="posenet", N=8, H=256, W=256),
+}
+FULL_CONFIGS = {
+    "posenet_b64_256":  dict(kind="posenet", N=64, H=256, W=256),            # BASELINE configs[1]
+    "mapnet_n32t3_256": dict(kind="mapnet", N=32, T=3, H=256, W=256),        # BASELINE configs[2]
+}
+
+
+def _crit(ns, kind):
+    if kind == "posenet":
+        return ns.PoseNetCriterion(sax=SVALS["sax"], saq=SVALS["saq"], learn_beta=True)
+    kw = dict(sax=SVALS["sax"], saq=SVALS["saq"], srx=SVALS["srx"], srq=SVALS["srq"],
+              learn_beta=True, learn_gamma=True)
+    if kind == "mapnet":
+        return ns.MapNetCriterion(**kw)
+    return ns.MapNetOnlineCriterion(gps_mode=(kind == "online_gps"), **kw)
+
+
+def tensor_stats(t):
+    t = t.detach().double().flatten()
+    head = torch.zeros(8, dtype=torch.float64)
+    n = min(8, t.numel())
+    head[:n] = t[:n]
+    return float(t.sum()), float(t.norm()), head.numpy()
+
+
+def run_step_config(name, cfg, seed=7):
+    ns = ref_loader.load()
+    st = weights.make_state(seed)
+    x, targ = weights.make_inputs(cfg, seed)
+    kind = cfg["kind"]
+    model = ref_loader.build_reference_model(st, "posenet" if kind == "posenet" else "mapnet",
+                                             droprate=0.0, filter_nans=kind.startswith("online"))
+    model.train()
+    crit = _crit(ns, kind)
+    t0 = time.time()
+    loss, pred, grads, cgrads = ref_loader.reference_step(
+        model, crit, x, targ, lr=cfg.get("lr", 1e-4), weight_decay=cfg.get("wd", 5e-4),
+        max_grad_norm=cfg.get("clip", 0.0))
+    dt = time.time() - t0
+    names = [k.replace("mapnet.", "", 1) for k in grads.keys()]
+    gsum, gnorm, ghead = [], [], []
+    for k in grads:
+        s, n, h = tensor_stats(grads[k])
+        gsum.append(s), gnorm.append(n), ghead.append(h)
+    post = model.state_dict()
+    pnames, psum, pnorm, phead = [], [], [], []
+    for k, v in post.items():
+        if k.endswith("num_batches_tracked"):
+            continue
+        s, n, h = tensor_stats(v)
+        pnames.append(k.replace("mapnet.", "", 1)), psum.append(s), pnorm.append(n), phead.append(h)
+    out = dict(
+        name=name, seed=seed, cfg=repr(cfg), ref_seconds=dt,
+        x_checksum=float(x.double().sum()), targ=targ.numpy(),
+        pred=pred.numpy(), loss=np.float64(loss),
+        grad_names=np.array(names), grad_sum=np.array(gsum), grad_norm=np.array(gnorm),
+        grad_head=np.stack(ghead),
+        post_names=np.array(pnames), post_sum=np.array(psum), post_norm=np.array(pnorm),
+        post_head=np.stack(phead),
+        sgrad_names=np.array(list(cgrads.keys())),
+        sgrads=np.array([float(v) if v is not None else np.nan for v in cgrads.values()]),
+        post_svals=np.array([float(p.detach()) for _, p in crit.named_parameters()]),
+    )
+    if x.numel() <= 4 * 6 * 3 * 64 * 64:
+        out["x"] = x.numpy()
+    np.savez_compressed(os.path.join(GOLD, "step_%s.npz" % name), **out)
+    print("golden step_%s: loss=%.6f  ref time %.2fs" % (name, loss, dt), flush=True)
+
+
+def run_pose_math(seed=7):
+    """Known-answer vectors for the torch pose math and criteria alone
+    (common/pose_utils.py:21-260, common/criterion.py), incl. edge cases."""
+    ns = ref_loader.load()
+    pu = ns.pose_utils
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    v = torch.randn(64, 3, generator=g)
+    v[0] = 0.0                      # zero rotation: clamp(1e-8) path (pose_utils.py:80)
+    v[1] = torch.tensor([1e-9, 0, 0])
+    v[2] = torch.tensor([3.0, 0.5, -0.2])   # |v| > pi/2
+    out["qexp_in"] = v.numpy()
+    out["qexp_out"] = pu.qexp_t(v).numpy()
+    q = pu.qexp_t(v)
+    out["qlog_out"] = pu.qlog_t(q).numpy()
+    for N, T in ((5, 3), (16, 5), (3, 2), (4, 7)):
+        poses = torch.cat([torch.randn(N, T, 3, generator=g), 0.8 * torch.randn(N, T, 3, generator=g)], 2)
+        poses.requires_grad_(True)
+        vs = pu.calc_vos_simple(poses)
+        vv = pu.calc_vos(poses)
+        w = torch.randn(vv.shape, generator=g)
+        (vv * w).sum().backward()
+        key = "n%dt%d" % (N, T)
+        out["vos_in_" + key] = poses.detach().numpy()
+        out["vos_simple_" + key] = vs.detach().numpy()
+        out["vos_" + key] = vv.detach().numpy()
+        out["vos_w_" + key] = w.numpy()
+        out["vos_grad_" + key] = poses.grad.numpy()
+    # criteria with gradients
+    for kind, N, T in (("posenet", 64, 1), ("posenet", 7, 1), ("mapnet", 32, 3), ("mapnet", 5, 2),
+                       ("online", 16, 10), ("online", 3, 4), ("online_gps", 16, 10), ("online_gps", 2, 6)):
+        cfg = dict(kind=kind, N=N, T=T, H=1, W=1)
+        _, targ = weights.make_inputs(cfg, seed + N)
+        if kind == "posenet":
+            pred = targ.clone()
+        else:   # the model predicts T absolute poses per tuple
+            _, pred = weights.make_inputs(dict(kind="mapnet", N=N, T=T, H=1, W=1), seed + N)
+        pred = pred + 0.3 * torch.randn(pred.shape, generator=g)
+        pred.requires_grad_(True)
+        crit = _crit(ns, kind)
+        loss = crit(pred, targ)
+        loss.backward()
+        key = "%s_n%dt%d" % (kind, N, T)
+        out["crit_pred_" + key] = pred.detach().numpy()
+        out["crit_targ_" + key] = targ.numpy()
+        out["crit_loss_" + key] = loss.detach().numpy()
+        out["crit_dpred_" + key] = pred.grad.numpy()
+        out["crit_ds_" + key] = np.array([float(p.grad) if p.grad is not None else np.nan
+                                          for _, p in crit.named_parameters()])
+    # degenerate: identical consecutive predicted rotations -> NaN gradient in the
+    # reference (acos'(1) * 0), the case filter_hook exists for (posenet.py:28-34)
+    poses = torch.zeros(2, 3, 6)
+    poses[:, :, :3] = torch.randn(2, 3, 3, generator=g)
+    poses[:, :, 3:] = torch.tensor([0.1, 0.2, -0.1])
+    poses.requires_grad_(True)
+    vv = pu.calc_vos(poses)
+    vv.sum().backward()
+    out["vos_degen_in"] = poses.detach().numpy()
+    out["vos_degen_out"] = vv.detach().numpy()
+    out["vos_degen_grad"] = poses.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "pose_math.npz"), **out)
+    print("golden pose_math: %d arrays" % len(out), flush=True)
+
+
+def run_keys():
+    """The reference module's state_dict / named_parameters key order (drop-in
+    contract for common/train.py:22-53,198-204)."""
+    import torchvision
+    ns = ref_loader.load()
+    net = ns.PoseNet(torchvision.models.resnet34(weights=None), droprate=0.0, pretrained=False)
+    mp = ns.MapNet(mapnet=net)
+    np.savez_compressed(
+        os.path.join(GOLD, "keys.npz"),
+        posenet_state_keys=np.array(list(net.state_dict().keys())),
+        posenet_param_names=np.array([n for n, _ in net.named_parameters()]),
+        posenet_param_shapes=np.array([repr(tuple(p.shape)) for _, p in net.named_parameters()]),
+        mapnet_state_keys=np.array(list(mp.state_dict().keys())),
+        n_params=np.int64(sum(p.numel() for p in net.parameters())))
+    print("golden keys: %d state entries" % len(net.state_dict()), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also the BASELINE full-size configs (minutes)")
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    if not ref_loader.available():
+        sys.exit("reference tree not available; goldens can only be regenerated in the build container")
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    if a.only is None:
+        run_keys()
+        run_pose_math()
+    cfgs = dict(STEP_CONFIGS)
+    if a.full:
+        cfgs.update(FULL_CONFIGS)
+    for name, cfg in cfgs.items():
+        if a.only and a.only != name:
+            continue
+        run_step_config(name, cfg)
+
+
+if __name__ == "__main__":
+    main()
