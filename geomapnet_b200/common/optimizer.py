@@ -1,0 +1,158 @@
+"""Optimizer wrapper with the reference's surface + a flat-buffer fused Adam.
+
+Mirror of /root/reference/common/optimizer.py:8-47 (``Optimizer(params, method,
+base_lr, weight_decay, **kwargs)``, ``.learner``, ``.adjust_lr``, ``.mult_lr``).
+``method='adam'`` builds ``FusedAdam``: one CUDA launch per contiguous run of
+parameters (the whole PoseNet is one run -- its parameters are views of one flat
+buffer) instead of ~10 pointwise launches x 114 tensors.
+``FusedAdam`` is a torch.optim.Optimizer: param_groups / state_dict() have
+torch.optim.Adam's structure (step, exp_avg, exp_avg_sq per parameter) so
+common/train.py:167-176,202 (checkpoint resume) keeps working.
+"""
+import ctypes
+
+import torch
+import torch.optim as optim
+
+from .. import _lib
+
+__all__ = ["Optimizer", "FusedAdam"]
+
+_PAD = 64  # alignment padding (floats) between parameters in the flat buffer
+
+
+class FusedAdam(optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameter")
+        super(FusedAdam, self).__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._runs = {}
+        self._scratch = None
+
+    # -- contiguous runs --------------------------------------------------------
+    def _plan(self, gi, params):
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
+        cached = self._runs.get(gi)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        order = sorted(params, key=lambda p: p.data_ptr())
+        runs, cur = [], None
+        for p in order:
+            if cur is not None:
+                last = cur["params"][-1]
+                gap = (p.data_ptr() - (last.data_ptr() + last.numel() * 4)) // 4
+                same = (p.device == last.device and 0 <= gap < _PAD and
+                        (p.data_ptr() - last.data_ptr()) == (p.grad.data_ptr() - last.grad.data_ptr()))
+                if same:
+                    cur["params"].append(p)
+                    continue
+            cur = {"params": [p]}
+            runs.append(cur)
+        for r in runs:
+            first, last = r["params"][0], r["params"][-1]
+            r["n"] = (last.data_ptr() + last.numel() * 4 - first.data_ptr()) // 4
+            old = cached[1] if cached is not None else []
+            m = torch.zeros(r["n"], dtype=torch.float32, device=first.device)
+            v = torch.zeros(r["n"], dtype=torch.float32, device=first.device)
+            for p in r["params"]:
+                off = (p.data_ptr() - first.data_ptr()) // 4
+                st = self.state[p]
+                mv, vv = m[off:off + p.numel()].view(p.shape), v[off:off + p.numel()].view(p.shape)
+                if "exp_avg" in st:          # resumed / re-planned: keep the moments
+                    mv.copy_(st["exp_avg"].to(p.device)); vv.copy_(st["exp_avg_sq"].to(p.device))
+                st["exp_avg"], st["exp_avg_sq"] = mv, vv
+                if "step" not in st:
+                    st["step"] = torch.tensor(0.0)
+            r["m"], r["v"] = m, v
+            del old
+        self._runs[gi] = (key, runs)
+        return runs
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=1.0, max_grad_norm=0.0):
+        """grad_scale multiplies every gradient first (1/world_size after a sum-allreduce);
+        max_grad_norm > 0 applies clip_grad_norm_ over ALL groups' gradients (fused)."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        L = _lib.lib()
+        groups = []
+        for gi, group in enumerate(self.param_groups):
+            params = [p for p in group["params"] if p.grad is not None]
+            if not params:
+                continue
+            for p in params:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients (no CPU path)")
+            groups.append((group, self._plan(gi, params)))
+        if not groups:
+            return loss
+        dev = groups[0][1][0]["params"][0].device
+        sq_ptr = None
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr()
+            if max_grad_norm and max_grad_norm > 0.0:
+                if self._scratch is None or self._scratch.device != dev:
+                    self._scratch = torch.zeros(2048, dtype=torch.float32, device=dev)
+                total = self._scratch[1024:1025]
+                total.zero_()
+                part = self._scratch[1025:1026]
+                for group, runs in groups:
+                    for r in runs:
+                        g0 = r["params"][0].grad
+                        _lib.check(L.mapnet_sqnorm(g0.data_ptr(), r["n"], self._scratch.data_ptr(),
+                                                   part.data_ptr(), st), "mapnet_sqnorm")
+                        total += part
+                sq_ptr = total.data_ptr()
+            for group, runs in groups:
+                b1, b2 = group["betas"]
+                for r in runs:
+                    p0 = r["params"][0]
+                    stp = self.state[p0]["step"]
+                    step = int(float(stp)) + 1
+                    stp_new = torch.tensor(float(step))
+                    for p in r["params"]:
+                        self.state[p]["step"] = stp_new
+                    _lib.check(L.mapnet_adam_step(
+                        p0.data_ptr(), p0.grad.data_ptr(), r["m"].data_ptr(), r["v"].data_ptr(), r["n"],
+                        float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                        float(group["weight_decay"]), step, float(grad_scale),
+                        ctypes.c_void_p(sq_ptr) if sq_ptr else None, float(max_grad_norm or 0.0), st),
+                        "mapnet_adam_step")
+        return loss
+
+
+class Optimizer:
+    """Wrapper around the learner + learning-rate schedule (common/optimizer.py:8-47)."""
+
+    def __init__(self, params, method, base_lr, weight_decay, **kwargs):
+        self.method = method
+        self.base_lr = base_lr
+        if self.method == 'sgd':
+            self.lr_decay = kwargs.pop('lr_decay')
+            self.lr_stepvalues = sorted(kwargs.pop('lr_stepvalues'))
+            self.learner = optim.SGD(params, lr=self.base_lr, weight_decay=weight_decay, **kwargs)
+        elif self.method == 'adam':
+            self.learner = FusedAdam(params, lr=self.base_lr, weight_decay=weight_decay, **kwargs)
+        elif self.method == 'rmsprop':
+            self.learner = optim.RMSprop(params, lr=self.base_lr, weight_decay=weight_decay, **kwargs)
+        else:
+            raise NotImplementedError(method)
+
+    def adjust_lr(self, epoch):
+        if self.method != 'sgd':
+            return self.base_lr
+        decay_factor = 1
+        for s in self.lr_stepvalues:
+            if epoch < s:
+                break
+            decay_factor *= self.lr_decay
+        lr = self.base_lr * decay_factor
+        for param_group in self.learner.param_groups:
+            param_group['lr'] = lr
+        return lr
+
+    def mult_lr(self, f):
+        for param_group in self.learner.param_groups:
+            param_group['lr'] *= f

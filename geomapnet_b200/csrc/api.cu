@@ -1,0 +1,123 @@
+// extern "C" entry points declared in include/mapnet_b200.h.
+#include <math.h>
+
+#include "../../include/mapnet_b200.h"
+#include "net.h"
+
+using namespace mapnet;
+
+struct mapnet_trunk { Net net; };
+
+extern "C" {
+
+const char* mapnet_last_error(void) { return get_last_error(); }
+int mapnet_abi_version(void) { return 1; }
+
+static int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_last_error("no CUDA device available (%s): this library has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return 10;
+  }
+  return 0;
+}
+
+int mapnet_trunk_create(mapnet_trunk_t** out, int max_B, int H, int W, int feat_dim, int precision) {
+  MN_CHECK(out != nullptr, "trunk_create: null out pointer");
+  *out = nullptr;
+  if (max_B > 0) MN_TRY(require_device());
+  mapnet_trunk* h = new mapnet_trunk();
+  int r = h->net.init(max_B, H, W, feat_dim, precision);
+  if (r != 0) { h->net.destroy(); delete h; return r; }
+  *out = h;
+  return 0;
+}
+
+int mapnet_trunk_destroy(mapnet_trunk_t* h) {
+  if (h == nullptr) return 0;
+  h->net.destroy();
+  delete h;
+  return 0;
+}
+
+int mapnet_param_count(mapnet_trunk_t* h) { return h ? (int)h->net.table.size() : -1; }
+
+int mapnet_param_info(mapnet_trunk_t* h, int i, char* host_name, int name_cap, int* host_kind, int* host_ndim,
+                      int64_t* host_shape4, int64_t* host_offset) {
+  MN_CHECK(h != nullptr, "param_info: null handle");
+  MN_CHECK(i >= 0 && i < (int)h->net.table.size(), "param_info: index %d out of range", i);
+  const ParamEntry& e = h->net.table[i];
+  if (host_name && name_cap > 0) { strncpy(host_name, e.name.c_str(), name_cap - 1); host_name[name_cap - 1] = 0; }
+  if (host_kind) *host_kind = e.kind;
+  if (host_ndim) *host_ndim = e.ndim;
+  if (host_shape4) for (int k = 0; k < 4; ++k) host_shape4[k] = e.shape[k];
+  if (host_offset) *host_offset = e.offset;
+  return 0;
+}
+
+int64_t mapnet_params_numel(mapnet_trunk_t* h) { return h ? h->net.n_params : -1; }
+int64_t mapnet_bufs_numel(mapnet_trunk_t* h) { return h ? h->net.n_bufs : -1; }
+
+int mapnet_forward(mapnet_trunk_t* h, const float* x, const float* params_flat, float* bufs_flat, int B,
+                   int training, float droprate, uint64_t seed, uint64_t step, float* pred, void* stream) {
+  MN_CHECK(h != nullptr, "forward: null handle");
+  return h->net.forward(x, params_flat, bufs_flat, B, training, droprate, seed, step, pred, (cudaStream_t)stream);
+}
+
+int mapnet_backward(mapnet_trunk_t* h, const float* dpred, const float* params_flat, float* grads_flat,
+                    int filter_nans, void* stream) {
+  MN_CHECK(h != nullptr, "backward: null handle");
+  return h->net.backward(dpred, params_flat, grads_flat, filter_nans, (cudaStream_t)stream);
+}
+
+int mapnet_loss_fwd_bwd(int mode, const float* pred, const float* targ, int N, int T_pred, int T_targ,
+                        const float* s4, float* loss, float* dpred, float* ds4, void* stream) {
+  MN_CHECK(pred && targ && s4 && loss && dpred && ds4, "loss_fwd_bwd: null pointer argument");
+  return launch_loss(mode, pred, targ, N, T_pred, T_targ, s4, loss, dpred, ds4, (cudaStream_t)stream);
+}
+
+int mapnet_sqnorm(const float* g, int64_t n, float* scratch1024, float* out_sq, void* stream) {
+  MN_CHECK(g && scratch1024 && out_sq && n > 0, "sqnorm: bad argument");
+  return launch_sqnorm(g, n, scratch1024, out_sq, (cudaStream_t)stream);
+}
+
+int mapnet_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                     const float* sqnorm, float max_norm, void* stream) {
+  MN_CHECK(p && g && exp_avg && exp_avg_sq && n > 0, "adam_step: bad argument");
+  MN_CHECK(step >= 1, "adam_step: step counts from 1 (got %lld)", (long long)step);
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+  return launch_adam(p, g, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
+                     sqnorm, max_norm, (cudaStream_t)stream);
+}
+
+int mapnet_test_conv(int precision, int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride,
+                     const void* in0, const void* in1, const void* wmat, void* out, void* stream) {
+  MN_TRY(require_device());
+  ConvGeom g;
+  g.B = B; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Co = Co; g.KH = g.KW = k; g.stride = stride; g.pad = (k - 1) / 2;
+  g.Ho = (Hi + 2 * g.pad - k) / stride + 1; g.Wo = (Wi + 2 * g.pad - k) / stride + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == PREC_FP32) {
+    if (kind == 0) return launch_conv_simt_fprop<float>(g, (const float*)in0, (const float*)wmat, nullptr, (float*)out, st);
+    if (kind == 1) return launch_conv_simt_dgrad<float>(g, (const float*)in0, (const float*)wmat, nullptr, (float*)out, st);
+    return launch_conv_simt_wgrad<float>(g, (const float*)in0, (const float*)in1, (float*)out, st);
+  }
+  if (precision == PREC_BF16_SIMT) {
+    if (kind == 0) return launch_conv_simt_fprop<bf16>(g, (const bf16*)in0, (const float*)wmat, nullptr, (bf16*)out, st);
+    if (kind == 1) return launch_conv_simt_dgrad<bf16>(g, (const bf16*)in0, (const float*)wmat, nullptr, (bf16*)out, st);
+    return launch_conv_simt_wgrad<bf16>(g, (const bf16*)in0, (const bf16*)in1, (float*)out, st);
+  }
+  MN_CHECK(precision == PREC_BF16_TC, "test_conv: bad precision");
+  TcConvPlan* plan = nullptr;
+  MN_TRY(tc_plan_create(&plan, g, kind, (const bf16*)wmat));
+  int r = tc_conv_run(plan, (const bf16*)in0, (const bf16*)in1, nullptr, out, st);
+  if (r == 0) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) { set_last_error("test_conv: %s", cudaGetErrorString(e)); r = 1; } }
+  tc_plan_destroy(plan);
+  return r;
+}
+
+}  // extern "C"

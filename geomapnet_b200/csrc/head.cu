@@ -185,3 +185,28 @@ int launch_dropout_mask(float* mask, long long n, float p, unsigned long long se
 }
 
 }  // namespace mapnet
+
+namespace mapnet {
+// dh[b][j] = (sum_c dpred[b][c]*Wxyz[c][j] + dpred[b][3+c]*Wq[c][j]) * mask[b][j] * [fcpre[b][j] > 0]
+__global__ void k_head_dh(const float* __restrict__ dpred, const float* __restrict__ wx,
+                          const float* __restrict__ wq, const float* __restrict__ mask,
+                          const float* __restrict__ fcpre, float* __restrict__ dh, int B, int F) {
+  const long long n = (long long)B * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / F), j = (int)(i % F);
+    const float* d = dpred + b * 6;
+    float v = d[0] * wx[j] + d[1] * wx[F + j] + d[2] * wx[2 * F + j] +
+              d[3] * wq[j] + d[4] * wq[F + j] + d[5] * wq[2 * F + j];
+    if (mask != nullptr) v *= mask[i];
+    dh[i] = (fcpre[i] > 0.f) ? v : 0.f;
+  }
+}
+int launch_head_dh(const float* dpred, const float* wx, const float* wq, const float* mask, const float* fcpre,
+                   float* dh, int B, int F, cudaStream_t st) {
+  long long grid = ((long long)B * F + 255) / 256; if (grid > 592) grid = 592;
+  k_head_dh<<<(int)grid, 256, 0, st>>>(dpred, wx, wq, mask, fcpre, dh, B, F);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace mapnet

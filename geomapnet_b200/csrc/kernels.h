@@ -7,9 +7,9 @@ namespace mapnet {
 // Geometry of one convolution (NHWC activations, weights [Co][KH][KW][Ci] "KRSC").
 struct ConvGeom {
   int B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad;
-  long long M_out() const { return (long long)B * Ho * Wo; }
-  long long M_in() const { return (long long)B * Hi * Wi; }
-  int Kdim() const { return KH * KW * Ci; }
+  __host__ __device__ long long M_out() const { return (long long)B * Ho * Wo; }
+  __host__ __device__ long long M_in() const { return (long long)B * Hi * Wi; }
+  __host__ __device__ int Kdim() const { return KH * KW * Ci; }
 };
 
 // ---- bn.cu -------------------------------------------------------------------
@@ -44,12 +44,12 @@ template <typename T>
 int launch_conv_simt_wgrad(const ConvGeom& g, const T* x, const T* dy, float* dw_krsc /*zeroed, accumulated*/, cudaStream_t st);
 
 // ---- conv_tc.cu: tcgen05 / TMA implicit GEMM (bf16 tensor-core path) ------------
-struct TcConvPlan;   // opaque: tensor maps + tap tables for one conv at one batch size
-int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind /*0 fprop,1 dgrad,2 wgrad*/, const bf16* act_in,
-                   const bf16* wmat, const bf16* act_in2, void* out_ptr);
+struct TcConvPlan;   // opaque: tile shapes, tap tables and cached TMA tensor maps of one conv
+// kind 0 fprop (wmat = [Co][KH][KW][Ci]), 1 dgrad (wmat = [Ci][KH][KW][Co]), 2 wgrad (wmat unused)
+int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wmat);
 void tc_plan_destroy(TcConvPlan* p);
-int tc_conv_run(TcConvPlan* p, const bf16* residual, cudaStream_t st);
-int tc_selftest(int which, float* max_err_out, cudaStream_t st);
+// fprop: in0 = x, out = y (bf16);  dgrad: in0 = dy, out = dx (bf16);  wgrad: in0 = x, in1 = dy, out = fp32 dW (accumulated)
+int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st);
 
 // ---- layout.cu -----------------------------------------------------------------
 struct WeightDesc {   // one conv's weight in the flat parameter buffer and in the packed matrices
@@ -60,7 +60,7 @@ struct WeightDesc {   // one conv's weight in the flat parameter buffer and in t
 };
 template <typename TW>
 int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* params, TW* w_krsc, TW* w_dg,
-                        int max_elems, cudaStream_t st);
+                        int max_elems, int round_bf16, cudaStream_t st);
 int launch_unpack_wgrads(const WeightDesc* d_descs, int nconv, const float* dw_krsc, float* grads,
                          int max_elems, cudaStream_t st);
 template <typename T>
@@ -69,15 +69,17 @@ int launch_stem_im2col(const float* x_nchw, T* A, int B, int H, int W, int Ho, i
 // ---- head.cu -------------------------------------------------------------------
 template <typename T>
 int launch_gap(const T* z, float* feat, int B, int HW, int C, cudaStream_t st);
-int launch_fc_fwd(const float* in, const float* w, const float* bias, float* out, int B, int In, int Out,
-                  int relu, const float* mask_or_null, cudaStream_t st);
-int launch_dropout_mask(float* mask, long long n, float p, unsigned long long seed, unsigned long long offset,
-                        cudaStream_t st);
-int launch_head_bwd(const float* dpred, const float* feat, const float* fcpre /*pre-relu [B,F]*/, const float* mask,
-                    const float* w_fc, const float* w6, float* dh, float* dfeat, float* g_wfc, float* g_bfc,
-                    float* g_w6, float* g_b6, int B, int C, int F, int filter_nans, cudaStream_t st);
 template <typename T>
 int launch_gap_bwd(const float* dfeat, T* dz, int B, int HW, int C, cudaStream_t st);
+int launch_small_gemm(int epi, const float* A, long long sam, long long sak, const float* Bm, long long sbn,
+                      long long sbk, float* C, int ldc, int M, int N, int K, const float* bias, float* aux,
+                      const float* mask, cudaStream_t st);
+int launch_colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
+int launch_dpred_filter(const float* in, float* out, int n, int filter, cudaStream_t st);
+int launch_dropout_mask(float* mask, long long n, float p, unsigned long long seed, unsigned long long offset,
+                        cudaStream_t st);
+int launch_head_dh(const float* dpred, const float* wx, const float* wq, const float* mask, const float* fcpre,
+                   float* dh, int B, int F, cudaStream_t st);
 
 // ---- loss.cu -------------------------------------------------------------------
 int launch_loss(int mode, const float* pred, const float* targ, int N, int Tp, int Tt, const float* s4,

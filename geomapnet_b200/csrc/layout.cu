@@ -17,7 +17,7 @@ template <> __device__ __forceinline__ bf16 cvt_w<bf16>(float v) { return __floa
 
 template <typename TW>
 __global__ void k_pack_weights(const WeightDesc* __restrict__ descs, const float* __restrict__ params,
-                               TW* __restrict__ w_krsc, TW* __restrict__ w_dg) {
+                               TW* __restrict__ w_krsc, TW* __restrict__ w_dg, int round_bf16) {
   const WeightDesc d = descs[blockIdx.y];
   const int KK = d.KH * d.KW;
   const long long total = (long long)d.Co * KK * d.Ci;
@@ -34,10 +34,12 @@ __global__ void k_pack_weights(const WeightDesc* __restrict__ descs, const float
         const int c = ci % d.Ci_real, t = ci / d.Ci_real;   // t = kh*7+kw
         v = params[d.p_off + ((long long)co * d.Ci_real + c) * 49 + t];
       }
+      if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
       w_krsc[d.k_off + e] = cvt_w<TW>(v);
     } else {
       const int kh = tap / d.KW, kw = tap - kh * d.KW;
       v = params[d.p_off + (((long long)co * d.Ci_real + ci) * d.KH + kh) * d.KW + kw];
+      if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
       w_krsc[d.k_off + e] = cvt_w<TW>(v);
       if (w_dg != nullptr) w_dg[d.k_off + ((long long)ci * KK + tap) * d.Co + co] = cvt_w<TW>(v);
     }
@@ -46,14 +48,14 @@ __global__ void k_pack_weights(const WeightDesc* __restrict__ descs, const float
 
 template <typename TW>
 int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* params, TW* w_krsc, TW* w_dg,
-                        int max_elems, cudaStream_t st) {
+                        int max_elems, int round_bf16, cudaStream_t st) {
   dim3 grid(cdiv(max_elems, 256) < 512 ? cdiv(max_elems, 256) : 512, nconv);
-  k_pack_weights<TW><<<grid, 256, 0, st>>>(d_descs, params, w_krsc, w_dg);
+  k_pack_weights<TW><<<grid, 256, 0, st>>>(d_descs, params, w_krsc, w_dg, round_bf16);
   MN_LAUNCH_CHECK();
   return 0;
 }
-template int launch_pack_weights<float>(const WeightDesc*, int, const float*, float*, float*, int, cudaStream_t);
-template int launch_pack_weights<bf16>(const WeightDesc*, int, const float*, bf16*, bf16*, int, cudaStream_t);
+template int launch_pack_weights<float>(const WeightDesc*, int, const float*, float*, float*, int, int, cudaStream_t);
+template int launch_pack_weights<bf16>(const WeightDesc*, int, const float*, bf16*, bf16*, int, int, cudaStream_t);
 
 __global__ void k_unpack_wgrads(const WeightDesc* __restrict__ descs, const float* __restrict__ dw,
                                 float* __restrict__ grads) {

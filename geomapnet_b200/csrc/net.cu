@@ -1,0 +1,394 @@
+// PoseNet(ResNet-34) training step plan: explicit forward and backward schedules
+// over a static activation arena -- no autograd graph inside the trunk.
+//
+// Mirrors the graph that /root/reference/models/posenet.py:65-73 runs through
+// torchvision resnet34 (BasicBlock [3,4,6,3]; conv-BN-ReLU-conv-BN-(+id|1x1s2
+// conv+BN)-ReLU) with training-mode BatchNorm.
+#include "net.h"
+
+#include <stdarg.h>
+
+namespace mapnet {
+
+// ---- error string ------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_err; }
+
+static const int kStages[4][3] = {{64, 3, 1}, {128, 4, 2}, {256, 6, 2}, {512, 3, 2}};
+static const int kStemK = 192;   // 7*7*3 = 147 padded to a multiple of 64 (tensor-core K block)
+
+static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+static int conv_out(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
+
+int Net::alloc(void** p, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  MN_CUDA(cudaMalloc(p, bytes));
+  allocs.push_back(*p);
+  return 0;
+}
+
+void Net::build_table() {
+  table.clear();
+  n_params = n_bufs = n_nbt = 0;
+  auto add = [&](const std::string& name, int kind, std::initializer_list<long long> shp) {
+    ParamEntry e;
+    e.name = name; e.kind = kind; e.ndim = (int)shp.size(); e.numel = 1;
+    int i = 0;
+    for (long long s : shp) { e.shape[i++] = s; e.numel *= s; }
+    for (; i < 4; ++i) e.shape[i] = 1;
+    if (kind == 0) { e.offset = n_params; n_params = align_up(n_params + e.numel, 64); }
+    else if (kind == 1) { e.offset = n_bufs; n_bufs = align_up(n_bufs + e.numel, 64); }
+    else { e.offset = n_nbt; n_nbt += 1; }
+    table.push_back(e);
+    return (int)table.size() - 1;
+  };
+  auto add_bn = [&](const std::string& p, int C) {
+    BNL b; b.C = C;
+    b.g_off = table[add(p + ".weight", 0, {C})].offset;
+    b.b_off = table[add(p + ".bias", 0, {C})].offset;
+    b.rm_off = table[add(p + ".running_mean", 1, {C})].offset;
+    b.rv_off = table[add(p + ".running_var", 1, {C})].offset;
+    add(p + ".num_batches_tracked", 2, {});
+    b.mean = b.invstd = b.scale = b.shift = b.coef = nullptr;
+    bns.push_back(b);
+    return (int)bns.size() - 1;
+  };
+  wk_total = 0; max_w_elems = 0;
+  auto add_conv = [&](const std::string& name, int Ci, int Co, int k, int stride, int Hi, int Wi, bool stem) {
+    ConvL c;
+    const int pidx = add(name + ".weight", 0, {Co, stem ? 3 : Ci, k, k});
+    c.wd.p_off = table[pidx].offset;
+    c.wd.k_off = wk_total;
+    c.wd.Co = Co; c.wd.Ci_real = stem ? 3 : Ci;
+    if (stem) {
+      c.wd.Ci = kStemK; c.wd.KH = c.wd.KW = 1; c.wd.im2col_k = kStemK;
+      c.g.Hi = conv_out(Hi, 7, 2, 3); c.g.Wi = conv_out(Wi, 7, 2, 3);   // GEMM view: 1x1 conv over the patch matrix
+      c.g.Ho = c.g.Hi; c.g.Wo = c.g.Wi; c.g.Ci = kStemK; c.g.Co = Co; c.g.KH = c.g.KW = 1; c.g.stride = 1; c.g.pad = 0;
+    } else {
+      c.wd.Ci = Ci; c.wd.KH = c.wd.KW = k; c.wd.im2col_k = 0;
+      c.g.Hi = Hi; c.g.Wi = Wi; c.g.Ci = Ci; c.g.Co = Co; c.g.KH = c.g.KW = k; c.g.stride = stride; c.g.pad = (k - 1) / 2;
+      c.g.Ho = conv_out(Hi, k, stride, c.g.pad); c.g.Wo = conv_out(Wi, k, stride, c.g.pad);
+    }
+    c.g.B = 0;
+    const long long ne = (long long)Co * c.wd.KH * c.wd.KW * c.wd.Ci;
+    wk_total += align_up(ne, 512);        // 1 KB-aligned (bf16) matrices: TMA base alignment
+    if (ne > max_w_elems) max_w_elems = (int)ne;
+    c.bn = -1;
+    convs.push_back(c);
+    return (int)convs.size() - 1;
+  };
+
+  const std::string fe = "feature_extractor.";
+  Hc = conv_out(H, 7, 2, 3); Wc = conv_out(W, 7, 2, 3);
+  Hp = conv_out(Hc, 3, 2, 1); Wp = conv_out(Wc, 3, 2, 1);
+  int c0 = add_conv(fe + "conv1", 3, 64, 7, 2, H, W, true);
+  convs[c0].bn = add_bn(fe + "bn1", 64);
+  int inpl = 64, h = Hp, w = Wp;
+  for (int li = 0; li < 4; ++li) {
+    const int planes = kStages[li][0], nblk = kStages[li][1];
+    for (int b = 0; b < nblk; ++b) {
+      const int s = (b == 0) ? kStages[li][2] : 1;
+      char pre[64];
+      snprintf(pre, sizeof(pre), "%slayer%d.%d.", fe.c_str(), li + 1, b);
+      BlockL bl;
+      bl.Hi = h; bl.Wi = w; bl.Cin = inpl; bl.Cout = planes; bl.stride = s;
+      bl.conv1 = add_conv(std::string(pre) + "conv1", inpl, planes, 3, s, h, w, false);
+      convs[bl.conv1].bn = add_bn(std::string(pre) + "bn1", planes);
+      bl.Ho = convs[bl.conv1].g.Ho; bl.Wo = convs[bl.conv1].g.Wo;
+      bl.conv2 = add_conv(std::string(pre) + "conv2", planes, planes, 3, 1, bl.Ho, bl.Wo, false);
+      convs[bl.conv2].bn = add_bn(std::string(pre) + "bn2", planes);
+      bl.convd = -1;
+      if (s != 1 || inpl != planes) {
+        bl.convd = add_conv(std::string(pre) + "downsample.0", inpl, planes, 1, s, h, w, false);
+        convs[bl.convd].bn = add_bn(std::string(pre) + "downsample.1", planes);
+      }
+      bl.y1 = bl.h = bl.y2 = bl.yd = bl.out = nullptr;
+      blocks.push_back(bl);
+      inpl = planes; h = bl.Ho; w = bl.Wo;
+    }
+  }
+  Hf = h; Wf = w;
+  fc_w = table[add(fe + "fc.weight", 0, {feat_dim, 512})].offset;
+  fc_b = table[add(fe + "fc.bias", 0, {feat_dim})].offset;
+  xyz_w = table[add("fc_xyz.weight", 0, {3, feat_dim})].offset;
+  xyz_b = table[add("fc_xyz.bias", 0, {3})].offset;
+  wpqr_w = table[add("fc_wpqr.weight", 0, {3, feat_dim})].offset;
+  wpqr_b = table[add("fc_wpqr.bias", 0, {3})].offset;
+}
+
+int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
+  max_B = max_B_; H = H_; W = W_; feat_dim = feat_dim_; precision = precision_;
+  MN_CHECK(max_B >= 0 && H >= 32 && W >= 32, "create: need max_B>=0 and H,W>=32 (got %d,%d,%d)", max_B, H, W);
+  MN_CHECK(precision >= 0 && precision <= 2, "create: bad precision %d", precision);
+  MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
+  last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0;
+  build_table();
+  if (max_B == 0) return 0;      // spec-only handle: parameter table, no device memory
+  const size_t es = elt();
+  const long long Bm = max_B;
+  MN_TRY(alloc(&A0, (size_t)(Bm * Hc * Wc * kStemK) * es));
+  MN_TRY(alloc(&y0, (size_t)(Bm * Hc * Wc * 64) * es));
+  MN_TRY(alloc(&z0, (size_t)(Bm * Hp * Wp * 64) * es));
+  MN_TRY(alloc((void**)&amax0, (size_t)(Bm * Hp * Wp * 64)));
+  scratch_elems = Bm * Hc * Wc * 64;
+  for (int i = 0; i < 5; ++i) MN_TRY(alloc(&scratch[i], (size_t)scratch_elems * es));
+  for (auto& bl : blocks) {
+    const size_t n = (size_t)(Bm * bl.Ho * bl.Wo * bl.Cout) * es;
+    MN_TRY(alloc(&bl.y1, n)); MN_TRY(alloc(&bl.h, n)); MN_TRY(alloc(&bl.y2, n)); MN_TRY(alloc(&bl.out, n));
+    if (bl.convd >= 0) MN_TRY(alloc(&bl.yd, n));
+  }
+  const size_t wes = (precision == PREC_BF16_TC) ? 2 : 4;
+  MN_TRY(alloc(&w_krsc, (size_t)wk_total * wes));
+  MN_TRY(alloc(&w_dg, (size_t)wk_total * wes));
+  MN_TRY(alloc((void**)&dw_krsc, (size_t)wk_total * 4));
+  std::vector<WeightDesc> wd;
+  for (auto& c : convs) wd.push_back(c.wd);
+  MN_TRY(alloc((void**)&d_wdescs, wd.size() * sizeof(WeightDesc)));
+  MN_CUDA(cudaMemcpy(d_wdescs, wd.data(), wd.size() * sizeof(WeightDesc), cudaMemcpyHostToDevice));
+  MN_TRY(alloc((void**)&partials, (size_t)(148 * 8) * 3 * 512 * sizeof(float)));
+  long long small = 0;
+  for (auto& b : bns) small += 7LL * b.C;
+  MN_TRY(alloc((void**)&bn_small, (size_t)small * sizeof(float)));
+  float* p = bn_small;
+  for (auto& b : bns) {
+    b.mean = p; p += b.C; b.invstd = p; p += b.C; b.scale = p; p += b.C; b.shift = p; p += b.C;
+    b.coef = p; p += 3 * b.C;
+  }
+  MN_TRY(alloc((void**)&feat, (size_t)Bm * 512 * 4));
+  MN_TRY(alloc((void**)&fcpre, (size_t)Bm * feat_dim * 4));
+  MN_TRY(alloc((void**)&hdrop, (size_t)Bm * feat_dim * 4));
+  MN_TRY(alloc((void**)&mask, (size_t)Bm * feat_dim * 4));
+  MN_TRY(alloc((void**)&dh, (size_t)Bm * feat_dim * 4));
+  MN_TRY(alloc((void**)&dfeat, (size_t)Bm * 512 * 4));
+  MN_TRY(alloc((void**)&dpredf, (size_t)Bm * 6 * 4));
+  MN_TRY(alloc((void**)&sq_partials, 1024 * 4));
+  MN_TRY(alloc((void**)&sq_out, 16));
+  return 0;
+}
+
+void Net::destroy() {
+  for (auto* p : tc_fprop) tc_plan_destroy(p);
+  for (auto* p : tc_dgrad) tc_plan_destroy(p);
+  for (auto* p : tc_wgrad) tc_plan_destroy(p);
+  tc_fprop.clear(); tc_dgrad.clear(); tc_wgrad.clear();
+  for (void* p : allocs) cudaFree(p);
+  allocs.clear();
+}
+
+// ---- conv dispatch -------------------------------------------------------------
+template <typename T>
+int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st) {
+  ConvGeom g = convs[ci].g; g.B = B;
+  return launch_conv_simt_fprop<T>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
+}
+template <typename T>
+int Net::conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st) {
+  ConvGeom g = convs[ci].g; g.B = B;
+  return launch_conv_simt_dgrad<T>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
+}
+template <typename T>
+int Net::conv_wgrad(int ci, const T* x, const T* dy, int B, cudaStream_t st) {
+  ConvGeom g = convs[ci].g; g.B = B;
+  return launch_conv_simt_wgrad<T>(g, x, dy, dw_krsc + convs[ci].wd.k_off, st);
+}
+// bf16 tensor-core specialisations (conv_tc.cu)
+template <>
+int Net::conv_fprop<bf16>(int ci, const bf16* x, const bf16* residual, bf16* y, int B, cudaStream_t st) {
+  if (precision == PREC_BF16_TC) return tc_conv_run(tc_fprop[ci], x, nullptr, residual, y, st);
+  ConvGeom g = convs[ci].g; g.B = B;
+  return launch_conv_simt_fprop<bf16>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
+}
+template <>
+int Net::conv_dgrad<bf16>(int ci, const bf16* dy, const bf16* residual, bf16* dx, int B, cudaStream_t st) {
+  if (precision == PREC_BF16_TC) return tc_conv_run(tc_dgrad[ci], dy, nullptr, residual, dx, st);
+  ConvGeom g = convs[ci].g; g.B = B;
+  return launch_conv_simt_dgrad<bf16>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
+}
+template <>
+int Net::conv_wgrad<bf16>(int ci, const bf16* x, const bf16* dy, int B, cudaStream_t st) {
+  if (precision == PREC_BF16_TC) return tc_conv_run(tc_wgrad[ci], x, dy, nullptr, dw_krsc + convs[ci].wd.k_off, st);
+  ConvGeom g = convs[ci].g; g.B = B;
+  return launch_conv_simt_wgrad<bf16>(g, x, dy, dw_krsc + convs[ci].wd.k_off, st);
+}
+
+int Net::ensure_tc_plans(int B) {
+  if (precision != PREC_BF16_TC || tc_B == B) return 0;
+  for (auto* p : tc_fprop) tc_plan_destroy(p);
+  for (auto* p : tc_dgrad) tc_plan_destroy(p);
+  for (auto* p : tc_wgrad) tc_plan_destroy(p);
+  tc_fprop.assign(convs.size(), nullptr);
+  tc_dgrad.assign(convs.size(), nullptr);
+  tc_wgrad.assign(convs.size(), nullptr);
+  for (size_t i = 0; i < convs.size(); ++i) {
+    ConvGeom g = convs[i].g; g.B = B;
+    const bf16* wk = (const bf16*)w_krsc + convs[i].wd.k_off;
+    const bf16* wd = (const bf16*)w_dg + convs[i].wd.k_off;
+    MN_TRY(tc_plan_create(&tc_fprop[i], g, 0, wk));
+    if (i > 0) MN_TRY(tc_plan_create(&tc_dgrad[i], g, 1, wd));
+    MN_TRY(tc_plan_create(&tc_wgrad[i], g, 2, nullptr));
+  }
+  tc_B = B;
+  return 0;
+}
+
+template <typename T>
+int Net::bn_forward(int bi, const T* y, long long M, const float* params, float* bufs, int training,
+                    cudaStream_t st) {
+  BNL& b = bns[bi];
+  int nblk = 0;
+  if (training) MN_TRY(launch_channel_sums<T>(0, y, nullptr, nullptr, nullptr, M, b.C, partials, &nblk, st));
+  return launch_bn_fwd_finalize(partials, nblk, b.C, M, params + b.g_off, params + b.b_off, bufs + b.rm_off,
+                                bufs + b.rv_off, b.mean, b.invstd, b.scale, b.shift, training, st);
+}
+
+// ---- forward -------------------------------------------------------------------
+template <typename T>
+int Net::forward_t(const float* x, const float* params, float* bufs, int B, int training, float droprate,
+                   unsigned long long seed, unsigned long long step, float* pred, cudaStream_t st) {
+  MN_TRY(ensure_tc_plans(B));
+  // operand copies of the master weights (they change every optimizer step)
+  if (precision == PREC_BF16_TC)
+    MN_TRY(launch_pack_weights<bf16>(d_wdescs, (int)convs.size(), params, (bf16*)w_krsc, (bf16*)w_dg, max_w_elems, 0, st));
+  else
+    MN_TRY(launch_pack_weights<float>(d_wdescs, (int)convs.size(), params, (float*)w_krsc, (float*)w_dg, max_w_elems,
+                                      precision == PREC_BF16_SIMT, st));
+  // stem: im2col -> GEMM -> BN -> ReLU -> maxpool
+  MN_TRY(launch_stem_im2col<T>(x, (T*)A0, B, H, W, Hc, Wc, kStemK, st));
+  MN_TRY(conv_fprop<T>(0, (const T*)A0, nullptr, (T*)y0, B, st));
+  MN_TRY(bn_forward<T>(convs[0].bn, (const T*)y0, (long long)B * Hc * Wc, params, bufs, training, st));
+  {
+    BNL& b = bns[convs[0].bn];
+    MN_TRY(launch_stem_pool<T>((const T*)y0, b.scale, b.shift, (T*)z0, amax0, B, Hc, Wc, Hp, Wp, 64, st));
+  }
+  const T* zin = (const T*)z0;
+  for (auto& bl : blocks) {
+    const long long Mo = (long long)B * bl.Ho * bl.Wo;
+    BNL& b1 = bns[convs[bl.conv1].bn];
+    BNL& b2 = bns[convs[bl.conv2].bn];
+    MN_TRY(conv_fprop<T>(bl.conv1, zin, nullptr, (T*)bl.y1, B, st));
+    MN_TRY(bn_forward<T>(convs[bl.conv1].bn, (const T*)bl.y1, Mo, params, bufs, training, st));
+    MN_TRY(launch_bn_apply<T>((const T*)bl.y1, b1.scale, b1.shift, 0, nullptr, nullptr, nullptr, (T*)bl.h, Mo, bl.Cout, 1, st));
+    MN_TRY(conv_fprop<T>(bl.conv2, (const T*)bl.h, nullptr, (T*)bl.y2, B, st));
+    MN_TRY(bn_forward<T>(convs[bl.conv2].bn, (const T*)bl.y2, Mo, params, bufs, training, st));
+    if (bl.convd >= 0) {
+      BNL& bd = bns[convs[bl.convd].bn];
+      MN_TRY(conv_fprop<T>(bl.convd, zin, nullptr, (T*)bl.yd, B, st));
+      MN_TRY(bn_forward<T>(convs[bl.convd].bn, (const T*)bl.yd, Mo, params, bufs, training, st));
+      MN_TRY(launch_bn_apply<T>((const T*)bl.y2, b2.scale, b2.shift, 2, (const T*)bl.yd, bd.scale, bd.shift, (T*)bl.out, Mo, bl.Cout, 1, st));
+    } else {
+      MN_TRY(launch_bn_apply<T>((const T*)bl.y2, b2.scale, b2.shift, 1, zin, nullptr, nullptr, (T*)bl.out, Mo, bl.Cout, 1, st));
+    }
+    zin = (const T*)bl.out;
+  }
+  // head
+  MN_TRY(launch_gap<T>(zin, feat, B, Hf * Wf, 512, st));
+  const float* mk = nullptr;
+  if (droprate > 0.f) {
+    MN_TRY(launch_dropout_mask(mask, (long long)B * feat_dim, droprate, seed, step * (unsigned long long)max_B * feat_dim, st));
+    mk = mask;
+  }
+  // hdrop = relu(feat @ Wfc^T + b) * mask ; fcpre kept for the ReLU gate
+  MN_TRY(launch_small_gemm(1, feat, 512, 1, params + fc_w, 512, 1, hdrop, feat_dim, B, feat_dim, 512, params + fc_b, fcpre, mk, st));
+  MN_TRY(launch_small_gemm(0, hdrop, feat_dim, 1, params + xyz_w, feat_dim, 1, pred, 6, B, 3, feat_dim, params + xyz_b, nullptr, nullptr, st));
+  MN_TRY(launch_small_gemm(0, hdrop, feat_dim, 1, params + wpqr_w, feat_dim, 1, pred + 3, 6, B, 3, feat_dim, params + wpqr_b, nullptr, nullptr, st));
+  last_B = B; last_training = training; last_has_mask = (mk != nullptr);
+  return 0;
+}
+
+// ---- backward ------------------------------------------------------------------
+template <typename T>
+int Net::backward_t(const float* dpred, const float* params, float* grads, int filter_nans, cudaStream_t st) {
+  MN_CHECK(last_B > 0 && last_training, "backward: no training-mode forward precedes this call");
+  const int B = last_B;
+  const int F = feat_dim;
+  MN_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)wk_total * 4, st));
+  T* S0 = (T*)scratch[0]; T* S1 = (T*)scratch[1]; T* S2 = (T*)scratch[2]; T* S3 = (T*)scratch[3]; T* S4 = (T*)scratch[4];
+
+  // ---- head (models/posenet.py:67-73 backward, NaN filter :28-34) ----
+  MN_TRY(launch_dpred_filter(dpred, dpredf, B * 6, filter_nans, st));
+  // dW_xyz[c][j] = sum_b dpred[b][c] * hdrop[b][j]
+  MN_TRY(launch_small_gemm(0, dpredf, 1, 6, hdrop, 1, F, grads + xyz_w, F, 3, F, B, nullptr, nullptr, nullptr, st));
+  MN_TRY(launch_small_gemm(0, dpredf + 3, 1, 6, hdrop, 1, F, grads + wpqr_w, F, 3, F, B, nullptr, nullptr, nullptr, st));
+  MN_TRY(launch_colsum(dpredf, 6, B, 3, grads + xyz_b, st));
+  MN_TRY(launch_colsum(dpredf + 3, 6, B, 3, grads + wpqr_b, st));
+  MN_TRY(launch_head_dh(dpredf, params + xyz_w, params + wpqr_w, last_has_mask ? mask : nullptr, fcpre, dh, B, F, st));
+  // dW_fc[o][i] = sum_b dh[b][o] * feat[b][i];  db_fc = colsum(dh);  dfeat = dh @ W_fc
+  MN_TRY(launch_small_gemm(0, dh, 1, F, feat, 1, 512, grads + fc_w, 512, F, 512, B, nullptr, nullptr, nullptr, st));
+  MN_TRY(launch_colsum(dh, F, B, F, grads + fc_b, st));
+  MN_TRY(launch_small_gemm(0, dh, F, 1, params + fc_w, 1, 512, dfeat, 512, B, 512, F, nullptr, nullptr, nullptr, st));
+  MN_TRY(launch_gap_bwd<T>(dfeat, S0, B, Hf * Wf, 512, st));
+
+  // ---- residual blocks, last to first ----
+  for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
+    BlockL& bl = blocks[bi];
+    const T* zin = (bi == 0) ? (const T*)z0 : (const T*)blocks[bi - 1].out;
+    const long long Mo = (long long)B * bl.Ho * bl.Wo;
+    const int C = bl.Cout;
+    BNL& b1 = bns[convs[bl.conv1].bn];
+    BNL& b2 = bns[convs[bl.conv2].bn];
+    const bool ds = bl.convd >= 0;
+    int nblk = 0;
+    // out = relu(bn2(y2) + idt): g = dout*[out>0]; BN2 (and downsample BN) backward
+    MN_TRY(launch_channel_sums<T>(ds ? 2 : 1, S0, (const T*)bl.out, (const T*)bl.y2, ds ? (const T*)bl.yd : nullptr, Mo, C, partials, &nblk, st));
+    MN_TRY(launch_bn_bwd_finalize(partials, nblk, ds ? 3 : 2, 1, C, Mo, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef, st));
+    if (ds) {
+      BNL& bd = bns[convs[bl.convd].bn];
+      MN_TRY(launch_bn_bwd_finalize(partials, nblk, 3, 2, C, Mo, params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef, st));
+      MN_TRY(launch_bn_bwd_apply<T>(S0, (const T*)bl.out, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st));
+    } else {
+      MN_TRY(launch_bn_bwd_apply<T>(S0, (const T*)bl.out, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, S3, Mo, C, st));
+    }
+    // conv2
+    MN_TRY(conv_wgrad<T>(bl.conv2, (const T*)bl.h, S1, B, st));
+    MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st));
+    // h = relu(bn1(y1))
+    MN_TRY(launch_channel_sums<T>(1, S4, (const T*)bl.h, (const T*)bl.y1, nullptr, Mo, C, partials, &nblk, st));
+    MN_TRY(launch_bn_bwd_finalize(partials, nblk, 2, 1, C, Mo, params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef, st));
+    MN_TRY(launch_bn_bwd_apply<T>(S4, (const T*)bl.h, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st));
+    // conv1 (+ downsample conv): d zin
+    MN_TRY(conv_wgrad<T>(bl.conv1, zin, S1, B, st));
+    if (ds) {
+      MN_TRY(conv_wgrad<T>(bl.convd, zin, S2, B, st));
+      MN_TRY(conv_dgrad<T>(bl.convd, S2, nullptr, S0, B, st));
+      MN_TRY(conv_dgrad<T>(bl.conv1, S1, S0, S0, B, st));
+    } else {
+      MN_TRY(conv_dgrad<T>(bl.conv1, S1, S3, S0, B, st));
+    }
+  }
+  // ---- stem: maxpool -> ReLU -> BN -> conv (no input gradient: nothing consumes it) ----
+  {
+    BNL& b0 = bns[convs[0].bn];
+    const long long M0 = (long long)B * Hc * Wc;
+    int nblk = 0;
+    MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S1, B, Hc, Wc, Hp, Wp, 64, st));
+    MN_TRY(launch_channel_sums<T>(1, S1, nullptr, (const T*)y0, nullptr, M0, 64, partials, &nblk, st));
+    MN_TRY(launch_bn_bwd_finalize(partials, nblk, 2, 1, 64, M0, params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef, st));
+    MN_TRY(launch_bn_bwd_apply<T>(S1, nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st));
+    MN_TRY(conv_wgrad<T>(0, (const T*)A0, S2, B, st));
+  }
+  MN_TRY(launch_unpack_wgrads(d_wdescs, (int)convs.size(), dw_krsc, grads, max_w_elems, st));
+  return 0;
+}
+
+int Net::forward(const float* x, const float* params, float* bufs, int B, int training, float droprate,
+                 unsigned long long seed, unsigned long long step, float* pred, cudaStream_t st) {
+  MN_CHECK(B >= 1 && B <= max_B, "forward: batch %d outside [1, max_B=%d]", B, max_B);
+  MN_CHECK(x && params && bufs && pred, "forward: null pointer argument");
+  MN_CHECK(droprate >= 0.f && droprate < 1.f, "forward: droprate %f outside [0,1)", droprate);
+  if (precision == PREC_FP32) return forward_t<float>(x, params, bufs, B, training, droprate, seed, step, pred, st);
+  return forward_t<bf16>(x, params, bufs, B, training, droprate, seed, step, pred, st);
+}
+
+int Net::backward(const float* dpred, const float* params, float* grads, int filter_nans, cudaStream_t st) {
+  MN_CHECK(dpred && params && grads, "backward: null pointer argument");
+  if (precision == PREC_FP32) return backward_t<float>(dpred, params, grads, filter_nans, st);
+  return backward_t<bf16>(dpred, params, grads, filter_nans, st);
+}
+
+}  // namespace mapnet

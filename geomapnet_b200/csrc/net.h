@@ -1,0 +1,95 @@
+// Host-side plan of the PoseNet(ResNet-34) training step: parameter table,
+// layer geometry, activation arena, forward / backward schedules.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace mapnet {
+
+enum Precision { PREC_FP32 = 0, PREC_BF16_TC = 1, PREC_BF16_SIMT = 2 };
+
+struct ParamEntry {
+  std::string name;
+  int kind;               // 0 trainable fp32 (params_flat), 1 fp32 buffer (bufs_flat), 2 int64 num_batches_tracked
+  int ndim;
+  long long shape[4];
+  long long numel;
+  long long offset;       // element offset in its flat buffer (kind 2: index into the nbt vector)
+};
+
+struct ConvL {
+  ConvGeom g;             // B filled per call; for the stem this is the 1x1 "GEMM" view over the im2col matrix
+  WeightDesc wd;
+  int bn;
+};
+
+struct BNL {
+  int C;
+  long long g_off, b_off, rm_off, rv_off;
+  float *mean, *invstd, *scale, *shift, *coef;   // device, [C] each (coef [3C])
+};
+
+struct BlockL {
+  int conv1, conv2, convd;       // indices into convs (convd = -1: identity)
+  int Hi, Wi, Ho, Wo, Cin, Cout, stride;
+  void *y1, *h, *y2, *yd, *out;  // activation buffers (T)
+};
+
+struct Net {
+  int max_B, H, W, feat_dim, precision;
+  int Hc, Wc, Hp, Wp;            // stem conv / pooled sizes
+  int Hf, Wf;                    // final feature map size
+  std::vector<ParamEntry> table;
+  long long n_params, n_bufs, n_nbt;
+  std::vector<ConvL> convs;
+  std::vector<BNL> bns;
+  std::vector<BlockL> blocks;
+  long long wk_total;            // packed weight elements
+  int max_w_elems;
+  // parameter offsets of the head
+  long long fc_w, fc_b, xyz_w, xyz_b, wpqr_w, wpqr_b;
+
+  // device memory owned by the handle
+  std::vector<void*> allocs;
+  void *A0, *y0, *z0; uint8_t* amax0;
+  void* scratch[5]; long long scratch_elems;
+  void *w_krsc, *w_dg; float* dw_krsc; WeightDesc* d_wdescs;
+  float* partials;
+  float *feat, *fcpre, *hdrop, *mask, *dh, *dfeat, *dpredf;
+  float* bn_small;               // backing store of the BN small arrays
+  float *sq_partials, *sq_out;
+
+  // tensor-core plans (precision == PREC_BF16_TC), rebuilt when B changes
+  std::vector<TcConvPlan*> tc_fprop, tc_dgrad, tc_wgrad;
+  int tc_B;
+
+  // state of the last forward
+  int last_B, last_training, last_has_mask;
+
+  size_t elt() const { return precision == PREC_FP32 ? 4 : 2; }
+
+  int init(int max_B, int H, int W, int feat_dim, int precision);
+  void destroy();
+  int forward(const float* x, const float* params, float* bufs, int B, int training, float droprate,
+              unsigned long long seed, unsigned long long step, float* pred, cudaStream_t st);
+  int backward(const float* dpred, const float* params, float* grads, int filter_nans, cudaStream_t st);
+
+ private:
+  int alloc(void** p, size_t bytes);
+  void build_table();
+  template <typename T> int forward_t(const float* x, const float* params, float* bufs, int B, int training,
+                                      float droprate, unsigned long long seed, unsigned long long step,
+                                      float* pred, cudaStream_t st);
+  template <typename T> int backward_t(const float* dpred, const float* params, float* grads, int filter_nans,
+                                       cudaStream_t st);
+  template <typename T> int conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st);
+  template <typename T> int conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st);
+  template <typename T> int conv_wgrad(int ci, const T* x, const T* dy, int B, cudaStream_t st);
+  template <typename T> int bn_forward(int bi, const T* y, long long M, const float* params, float* bufs,
+                                       int training, cudaStream_t st);
+  int ensure_tc_plans(int B);
+};
+
+}  // namespace mapnet

@@ -1,0 +1,99 @@
+/* mapnet_b200.h -- C ABI of the B200-native MapNet/PoseNet training hot path.
+ *
+ * Drop-in boundary.  The reference (NVlabs/geomapnet) is pure
+ * Python on PyTorch: it has NO native FFI for this path, so these entry points
+ * are the contract a maintainer binds (ctypes stub in INTEGRATION.md) behind the
+ * reference's own Python surface:
+ *
+ *   reference call site                               entry point that replaces it
+ *   -----------------------------------------------   ------------------------------
+ *   models/posenet.py:65-73  PoseNet.forward          mapnet_forward
+ *   models/posenet.py:93-97  MapNet.forward           mapnet_forward (T folded into B)
+ *   common/train.py:356      loss.backward() (trunk)  mapnet_backward
+ *   common/criterion.py:42-52,76-109,137-184          mapnet_loss_fwd_bwd
+ *   common/pose_utils.py:234-260 calc_vos*            mapnet_loss_fwd_bwd (folded in)
+ *   common/optimizer.py:21-23 + train.py:357-359      mapnet_adam_step (+ mapnet_sqnorm)
+ *   models/posenet.py:37-63  parameter layout         mapnet_param_count / mapnet_param_info
+ *
+ * Conventions: every pointer is a DEVICE pointer unless named host_*; all
+ * tensors are contiguous fp32 in the reference's layouts (images NCHW
+ * [B,3,H,W]; poses [..,6] = xyz + log-quaternion).  Functions enqueue work on
+ * `stream` (a cudaStream_t passed as void*) and return 0 on success; non-zero
+ * means failure and mapnet_last_error() (thread-local) describes it.  No
+ * exception crosses this boundary; the library never frees caller memory.
+ * Handles are not thread-safe (one Python thread drives one GPU, like nn.Module).
+ * There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef MAPNET_B200_H_
+#define MAPNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mapnet_trunk mapnet_trunk_t;
+
+/* precision of the conv engines / stored activations */
+#define MAPNET_PREC_FP32 0      /* fp32 CUDA-core implicit GEMM: strict 1e-4 parity mode            */
+#define MAPNET_PREC_BF16 1      /* tcgen05 tensor-core implicit GEMM, bf16 operands, fp32 accumulate */
+#define MAPNET_PREC_BF16_SIMT 2 /* bf16 storage + CUDA-core fp32 math: cross-check of mode 1         */
+
+/* criterion modes (common/criterion.py) */
+#define MAPNET_LOSS_POSENET 0    /* PoseNetCriterion      pred [N,6],    targ [N,6]        */
+#define MAPNET_LOSS_MAPNET 1     /* MapNetCriterion       pred [N,T,6],  targ [N,T,6]      */
+#define MAPNET_LOSS_ONLINE 2     /* MapNetOnlineCriterion pred [N,2T,6], targ [N,2T-1,6]   */
+#define MAPNET_LOSS_ONLINE_GPS 3 /* ... gps_mode=True     pred [N,2T,6], targ [N,2T,6]     */
+
+const char* mapnet_last_error(void);
+int mapnet_abi_version(void);
+
+/* ---- trunk handle: owns only scratch (activation arena, packed weights, BN partials).
+ * max_B == 0 creates a spec-only handle (parameter table queries, no device needed). */
+int mapnet_trunk_create(mapnet_trunk_t** out, int max_B, int H, int W, int feat_dim, int precision);
+int mapnet_trunk_destroy(mapnet_trunk_t* h);
+
+/* ---- parameter table (state_dict order of the reference PoseNet, 222 entries) */
+/* kind: 0 = trainable fp32 in params_flat, 1 = fp32 buffer (BN running stats) in
+ * bufs_flat, 2 = int64 num_batches_tracked (offset = index in a separate int64 vector) */
+int mapnet_param_count(mapnet_trunk_t* h);
+int mapnet_param_info(mapnet_trunk_t* h, int i, char* host_name, int name_cap, int* host_kind, int* host_ndim,
+                      int64_t* host_shape4, int64_t* host_offset);
+int64_t mapnet_params_numel(mapnet_trunk_t* h); /* floats in params_flat / grads_flat (padded) */
+int64_t mapnet_bufs_numel(mapnet_trunk_t* h);   /* floats in bufs_flat                          */
+
+/* ---- forward: x [B,3,H,W] -> pred [B,6].  training!=0: BN batch statistics + running-
+ * stat update in bufs_flat; activations are kept for mapnet_backward.  droprate>0
+ * applies dropout with a counter-based mask from (seed, step). */
+int mapnet_forward(mapnet_trunk_t* h, const float* x, const float* params_flat, float* bufs_flat, int B,
+                   int training, float droprate, uint64_t seed, uint64_t step, float* pred, void* stream);
+
+/* ---- backward of the last training forward: dpred [B,6] -> every parameter gradient,
+ * written (not accumulated) into grads_flat at the offsets of params_flat.
+ * filter_nans: zero NaNs in dpred[:,3:] first (models/posenet.py:28-34 hook). */
+int mapnet_backward(mapnet_trunk_t* h, const float* dpred, const float* params_flat, float* grads_flat,
+                    int filter_nans, void* stream);
+
+/* ---- fused criterion forward+backward.  s4 = device (sax,saq,srx,srq).
+ * Outputs: loss[1], dpred (same shape as pred), ds4[4] = d loss / d s4. */
+int mapnet_loss_fwd_bwd(int mode, const float* pred, const float* targ, int N, int T_pred, int T_targ,
+                        const float* s4, float* loss, float* dpred, float* ds4, void* stream);
+
+/* ---- optimizer step on flat buffers (torch.optim.Adam semantics, L2 weight decay).
+ * grad_scale multiplies the gradient first (1/world_size after a sum-allreduce).
+ * sqnorm: device scalar holding the squared global grad norm (mapnet_sqnorm) to
+ * apply clip_grad_norm_(max_norm), or NULL for no clipping. */
+int mapnet_sqnorm(const float* g, int64_t n, float* scratch1024, float* out_sq, void* stream);
+int mapnet_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                     const float* sqnorm, float max_norm, void* stream);
+
+/* ---- unit entry points used by the parity tests (tests/test_gpu_kernels.py) */
+int mapnet_test_conv(int precision, int kind /*0 fprop 1 dgrad 2 wgrad*/, int B, int Hi, int Wi, int Ci, int Co,
+                     int k, int stride, const void* in0, const void* in1, const void* wmat, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPNET_B200_H_ */

