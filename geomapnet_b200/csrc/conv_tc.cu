@@ -1,8 +1,614 @@
-// placeholder: replaced by the tcgen05 kernels
+// tcgen05 / TMA implicit-GEMM convolution engines for sm_100a (bf16 operands,
+// fp32 accumulation in TMEM): fprop, dgrad, wgrad of every ResNet-34 conv.
+//
+// Replaces cuDNN conv fwd / bwd-data / bwd-filter behind torchvision resnet34
+// (/root/reference/models/posenet.py:66) with hand-written kernels:
+//
+//  k_tc_conv  (fprop, dgrad)  D[pixel][cout] = sum_{tap,c} A_tap[pixel][c] * W[cout][tap][c]
+//     * im2col is done ON THE FLY by TMA: the A tile of one (tap, 64-channel block)
+//       is a 4-D box {64 ch, TW, TH, TN} of the NHWC activation tensor at the tap's
+//       spatial offset; out-of-bounds pixels (padding, ragged edges) are zero-filled
+//       by the TMA unit.  Stride-2 convs read parity views of the tensor (4 maps).
+//     * warp-specialised, persistent CTAs: warp0 = TMA producer, warp1 = MMA issuer
+//       (single elected thread, tcgen05.mma cta_group::1, M=128, N=64/128, K=16),
+//       warps2-5 = epilogue (tcgen05.ld -> +residual -> bf16 -> global), with a
+//       double-buffered TMEM accumulator so the epilogue of tile i overlaps the
+//       mainloop of tile i+1.
+//  k_tc_wgrad  dW[cout][tap][c] += sum_pixels dY[pixel][cout] * X_tap[pixel][c]
+//     * both operands are MN-major (pixels = K): two 64-channel X chunks form the
+//       128 rows of A, dY supplies up to 256 columns of B; split-K over pixel tiles
+//       with fp32 red.global.add into the flat wgrad buffer.
+#include <cudaTypedefs.h>
+
+#include <vector>
+
 #include "kernels.h"
+#include "tc_ptx.cuh"
+
 namespace mapnet {
-struct TcConvPlan { int dummy; };
-int tc_plan_create(TcConvPlan** out, const ConvGeom&, int, const bf16*) { *out = nullptr; set_last_error("tcgen05 conv path not built yet"); return 7; }
-void tc_plan_destroy(TcConvPlan* p) { delete p; }
-int tc_conv_run(TcConvPlan*, const bf16*, const bf16*, const bf16*, void*, cudaStream_t) { set_last_error("tcgen05 conv path not built yet"); return 7; }
+
+using namespace ptx;
+
+// ---------------------------------------------------------------------------------
+// host: tensor-map encoding through the driver entry point (no libcuda link dependency)
+// ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
 }
+
+// 4-D NHWC view: dims {C, W, H, N} with byte strides; box {64, bw, bh, bn}; 128B swizzle; OOB -> 0
+static int encode_act_map(CUtensorMap* m, const void* base, int C, int Wd, int Hd, int Nd, long long sw_bytes,
+                          long long sh_bytes, long long sn_bytes, int bw, int bh, int bn) {
+  auto fn = get_encode_fn();
+  MN_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)Nd};
+  cuuint64_t strides[3] = {(cuuint64_t)sw_bytes, (cuuint64_t)sh_bytes, (cuuint64_t)sn_bytes};
+  cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act %dx%dx%dx%d box %d,%d,%d) failed: %d", C, Wd, Hd, Nd, bw, bh, bn, (int)r);
+  return 0;
+}
+// 2-D weight matrix [rows][K] (K contiguous): box {64, brows}
+static int encode_w_map(CUtensorMap* m, const void* base, int K, int rows, int brows) {
+  auto fn = get_encode_fn();
+  MN_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)brows};
+  cuuint32_t es[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights K=%d rows=%d) failed: %d", K, rows, (int)r);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// device parameter blocks
+// ---------------------------------------------------------------------------------
+struct TapDesc { int dh, dw, map, kidx; };
+
+struct ConvParams {
+  // M space: (n, jh, jw) over [Nimg, Hs, Ws]; tile box TN x TH x TW = 128 pixels
+  int Nimg, Hs, Ws, TW, TH, TN, tiles_w, tiles_h, tiles_n, n_tiles_m, n_tiles_n;
+  // K space
+  int num_taps, cblocks, Cs;
+  TapDesc taps[9];
+  // output tensor [Nimg, Hout, Wout, Cout]; pixel (n, jh*os+oa, jw*os+ob)
+  int Hout, Wout, Cout, os, oa, ob;
+};
+
+struct WgradChunk { int dh, dw, map, c0, tap; };   // one 64-channel slice of X at one filter tap
+
+struct WgradParams {
+  int Nimg, Ho, Wo, TW, TH, TN, tiles_w, tiles_h, tiles_n, n_pix_tiles;
+  int n_chunks;            // total X chunks = taps * Ci/64
+  int n_mtiles;            // ceil(n_chunks / 2)
+  int n_ntiles, BN;        // Co tiles of BN columns
+  int splits, tiles_per_split;
+  int Ci, Co, KK;          // dW layout [Co][KK][Ci]
+  WgradChunk chunks[72];
+};
+
+static const int kStagesConv = 5;
+
+// ---------------------------------------------------------------------------------
+// fprop / dgrad kernel
+// ---------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+          const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+          const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
+          bf16* __restrict__ out) {
+  constexpr int STAGES = kStagesConv;
+  constexpr uint32_t A_BYTES = 128 * 128;        // 128 pixels x 64 ch bf16
+  constexpr uint32_t B_BYTES = BN * 128;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int total_tiles = P.n_tiles_m * P.n_tiles_n;
+  const int kblocks = P.num_taps * P.cblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tn = tile % P.n_tiles_n;
+        int tm = tile / P.n_tiles_n;
+        const int tw = tm % P.tiles_w; tm /= P.tiles_w;
+        const int th = tm % P.tiles_h;
+        const int tb = tm / P.tiles_h;
+        const int jw0 = tw * P.TW, jh0 = th * P.TH, n0 = tb * P.TN;
+        for (int t = 0; t < P.num_taps; ++t) {
+          const TapDesc tap = P.taps[t];
+          const CUtensorMap* mA = (tap.map == 0) ? &mapA0 : (tap.map == 1) ? &mapA1 : (tap.map == 2) ? &mapA2 : &mapA3;
+          for (int cb = 0; cb < P.cblocks; ++cb) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+            tma_load_4d(sa, mA, full0 + 8 * stage, cb * 64, jw0 + tap.dw, jh0 + tap.dh, n0);
+            tma_load_2d(sa + A_BYTES, &mapB, full0 + 8 * stage, tap.kidx * P.Cs + cb * 64, tn * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint64_t DESC_BASE = make_smem_desc_base(16, 1024);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_bf16(d_tmem, smem_desc(DESC_BASE, sa + k * 32), smem_desc(DESC_BASE, sb + k * 32), IDESC,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(empty0 + 8 * stage);
+          if (kb == kblocks - 1) mma_commit(tfull0 + 8 * as);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (kblocks == 0 && lane == 0) mbar_arrive(tfull0 + 8 * as);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                 // row of the tile = TMEM lane
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tn = tile % P.n_tiles_n;
+      int tm = tile / P.n_tiles_n;
+      const int tw = tm % P.tiles_w; tm /= P.tiles_w;
+      const int th = tm % P.tiles_h;
+      const int tb = tm / P.tiles_h;
+      // pixel of this thread inside the TN x TH x TW box (w fastest)
+      const int lw = m % P.TW;
+      const int lh = (m / P.TW) % P.TH;
+      const int ln = m / (P.TW * P.TH);
+      const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
+      const bool valid = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
+      const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
+      const long long obase = pix * P.Cout + tn * BN;
+      mbar_wait(tfull0 + 8 * as, aphase);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t v[32];
+        if (kblocks > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (cc == BN / 32 - 1) {
+          // all TMEM reads of this accumulator stage are complete: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+        }
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(residual + obase + cc * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 r = rp[j];
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 t = __bfloat1622float2(h[i]);
+                f[j * 8 + 2 * i] += t.x; f[j * 8 + 2 * i + 1] += t.y;
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(out + obase + cc * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[j * 8 + 2 * i], f[j * 8 + 2 * i + 1]);
+            op[j] = o;
+          }
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------
+// wgrad kernel: one CTA per (M-tile of 2 X chunks, N-tile of BN couts, K split)
+// ---------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
+           const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapX3,
+           const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ WgradParams P,
+           float* __restrict__ dw) {
+  constexpr int STAGES = (BN <= 128) ? 5 : 4;
+  constexpr uint32_t CHUNK_BYTES = 64 * 128;     // 64 pixels x 64 ch bf16
+  constexpr uint32_t A_BYTES = 2 * CHUNK_BYTES;
+  constexpr uint32_t B_BYTES = (BN / 64) * CHUNK_BYTES;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull = smem_u32(&bars[2 * STAGES]);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // unit decode
+  int u = blockIdx.x;
+  const int split = u % P.splits; u /= P.splits;
+  const int nt = u % P.n_ntiles;
+  const int mt = u / P.n_ntiles;
+  const int c_lo = mt * 2;
+  const int n_valid_chunks = (c_lo + 1 < P.n_chunks) ? 2 : 1;
+  const int t_beg = split * P.tiles_per_split;
+  int t_end = t_beg + P.tiles_per_split; if (t_end > P.n_pix_tiles) t_end = P.n_pix_tiles;
+  const int ksteps = (t_end > t_beg) ? (t_end - t_beg) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapX0); prefetch_tmap(&mapDY);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const WgradChunk ch0 = P.chunks[c_lo];
+      const WgradChunk ch1 = P.chunks[(n_valid_chunks == 2) ? c_lo + 1 : c_lo];
+      const CUtensorMap* m0 = (ch0.map == 0) ? &mapX0 : (ch0.map == 1) ? &mapX1 : (ch0.map == 2) ? &mapX2 : &mapX3;
+      const CUtensorMap* m1 = (ch1.map == 0) ? &mapX0 : (ch1.map == 1) ? &mapX1 : (ch1.map == 2) ? &mapX2 : &mapX3;
+      for (int t = t_beg; t < t_end; ++t) {
+        int tt = t;
+        const int tw = tt % P.tiles_w; tt /= P.tiles_w;
+        const int th = tt % P.tiles_h;
+        const int tb = tt / P.tiles_h;
+        const int ow0 = tw * P.TW, oh0 = th * P.TH, n0 = tb * P.TN;
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+        tma_load_4d(sa, m0, full0 + 8 * stage, ch0.c0, ow0 + ch0.dw, oh0 + ch0.dh, n0);
+        tma_load_4d(sa + CHUNK_BYTES, m1, full0 + 8 * stage, ch1.c0, ow0 + ch1.dw, oh0 + ch1.dh, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(sa + A_BYTES + j * CHUNK_BYTES, &mapDY, full0 + 8 * stage, nt * BN + j * 64, ow0, oh0, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 1, 1);
+    // MN-major, 128B swizzle: LBO = stride between 64-element MN chunks, SBO = 8-pixel group stride
+    constexpr uint64_t DESC_BASE = make_smem_desc_base(CHUNK_BYTES, 1024);
+    int stage = 0; uint32_t phase = 0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      mbar_wait(full0 + 8 * stage, phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {     // 64 pixels per stage = 4 x K16; 16 pixel rows = 2048 B
+          mma_bf16(tmem_base, smem_desc(DESC_BASE, sa + k * 2048), smem_desc(DESC_BASE, sb + k * 2048), IDESC,
+                   (ks > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(empty0 + 8 * stage);
+        if (ks == ksteps - 1) mma_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (ksteps > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int j = m >> 6, ci_l = m & 63;
+    const bool valid = j < n_valid_chunks;
+    const WgradChunk ch = P.chunks[valid ? c_lo + j : c_lo];
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int co = nt * BN + cc * 32 + i;
+          if (co < P.Co)
+            atomicAdd(dw + ((long long)co * P.KK + ch.tap) * P.Ci + ch.c0 + ci_l, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------
+// host plans
+// ---------------------------------------------------------------------------------
+struct ConvLaunch {
+  ConvParams P;
+  CUtensorMap mapA[4], mapB;
+  int n_maps;
+  // parity views: (a,b) of map i
+  int pa[4], pb[4];
+};
+
+struct TcConvPlan {
+  ConvGeom g;
+  int kind;
+  const bf16* wmat;
+  int BN;
+  std::vector<ConvLaunch> launches;     // fprop: 1; dgrad: 1 (stride 1) or 4 (stride 2)
+  // wgrad
+  WgradParams WP;
+  CUtensorMap mapX[4], mapDY;
+  int wpa[4], wpb[4], w_nmaps;
+  // cached pointers the maps were encoded for
+  const void *c_in0, *c_in1;
+  bool smem_attr_set;
+};
+
+static void pick_box(int Wd, int Hd, int pixels, int* TW, int* TH, int* TN) {
+  int tw = 8;
+  while (tw < Wd && tw < pixels) tw *= 2;
+  int th = 1;
+  while (tw * th < pixels && th < Hd) th *= 2;
+  int tn = pixels / (tw * th);
+  if (tn < 1) tn = 1;
+  *TW = tw; *TH = th; *TN = tn;
+}
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static int posmod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
+
+int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wmat) {
+  *out = nullptr;
+  MN_CHECK(g.stride == 1 || g.stride == 2, "tc conv: stride %d unsupported", g.stride);
+  MN_CHECK(g.Ci % 64 == 0 && g.Co % 64 == 0, "tc conv: channels must be multiples of 64 (Ci=%d Co=%d)", g.Ci, g.Co);
+  MN_CHECK(g.KH == g.KW && (g.KH == 1 || g.KH == 3), "tc conv: kernel %dx%d unsupported", g.KH, g.KW);
+  TcConvPlan* p = new TcConvPlan();
+  p->g = g; p->kind = kind; p->wmat = wmat; p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false;
+  const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
+  if (kind == 0) {
+    // ---------------- fprop ----------------
+    p->BN = (g.Co >= 128) ? 128 : 64;
+    ConvLaunch L; memset(&L, 0, sizeof(L));
+    ConvParams& P = L.P;
+    P.Nimg = g.B; P.Hs = g.Ho; P.Ws = g.Wo;
+    pick_box(g.Wo, g.Ho, 128, &P.TW, &P.TH, &P.TN);
+    P.tiles_w = cdiv(g.Wo, P.TW); P.tiles_h = cdiv(g.Ho, P.TH); P.tiles_n = cdiv(g.B, P.TN);
+    P.n_tiles_m = P.tiles_w * P.tiles_h * P.tiles_n; P.n_tiles_n = g.Co / p->BN;
+    P.num_taps = KK; P.cblocks = g.Ci / 64; P.Cs = g.Ci;
+    P.Hout = g.Ho; P.Wout = g.Wo; P.Cout = g.Co; P.os = 1; P.oa = 0; P.ob = 0;
+    L.n_maps = 0;
+    for (int kh = 0; kh < g.KH; ++kh)
+      for (int kw = 0; kw < g.KW; ++kw) {
+        TapDesc& t = P.taps[kh * g.KW + kw];
+        t.kidx = kh * g.KW + kw;
+        if (s == 1) { t.dh = kh - pad; t.dw = kw - pad; t.map = 0; L.pa[0] = L.pb[0] = 0; if (L.n_maps < 1) L.n_maps = 1; }
+        else {
+          const int a = posmod(kh - pad, 2), b = posmod(kw - pad, 2);
+          t.dh = floordiv(kh - pad, 2); t.dw = floordiv(kw - pad, 2);
+          int mi = -1;
+          for (int i = 0; i < L.n_maps; ++i) if (L.pa[i] == a && L.pb[i] == b) mi = i;
+          if (mi < 0) { mi = L.n_maps++; L.pa[mi] = a; L.pb[mi] = b; }
+          t.map = mi;
+        }
+      }
+    p->launches.push_back(L);
+  } else if (kind == 1) {
+    // ---------------- dgrad: gather over dY [B,Ho,Wo,Co], output dX [B,Hi,Wi,Ci] ----------------
+    p->BN = (g.Ci >= 128) ? 128 : 64;
+    for (int a = 0; a < s; ++a)
+      for (int b = 0; b < s; ++b) {
+        ConvLaunch L; memset(&L, 0, sizeof(L));
+        ConvParams& P = L.P;
+        P.Nimg = g.B; P.Hs = cdiv(g.Hi - a, s); P.Ws = cdiv(g.Wi - b, s);
+        if (P.Hs <= 0 || P.Ws <= 0) continue;
+        pick_box(P.Ws, P.Hs, 128, &P.TW, &P.TH, &P.TN);
+        P.tiles_w = cdiv(P.Ws, P.TW); P.tiles_h = cdiv(P.Hs, P.TH); P.tiles_n = cdiv(g.B, P.TN);
+        P.n_tiles_m = P.tiles_w * P.tiles_h * P.tiles_n; P.n_tiles_n = g.Ci / p->BN;
+        P.cblocks = g.Co / 64; P.Cs = g.Co;
+        P.Hout = g.Hi; P.Wout = g.Wi; P.Cout = g.Ci; P.os = s; P.oa = a; P.ob = b;
+        P.num_taps = 0;
+        for (int kh = 0; kh < g.KH; ++kh)
+          for (int kw = 0; kw < g.KW; ++kw) {
+            const int eh = a + pad - kh, ew = b + pad - kw;
+            if (posmod(eh, s) != 0 || posmod(ew, s) != 0) continue;
+            TapDesc& t = P.taps[P.num_taps++];
+            t.dh = floordiv(eh, s); t.dw = floordiv(ew, s); t.map = 0; t.kidx = kh * g.KW + kw;
+          }
+        L.n_maps = 1; L.pa[0] = L.pb[0] = 0;
+        p->launches.push_back(L);
+      }
+  } else {
+    // ---------------- wgrad ----------------
+    WgradParams& P = p->WP; memset(&P, 0, sizeof(P));
+    p->BN = (g.Co >= 256) ? 256 : g.Co;
+    MN_CHECK(p->BN == 64 || p->BN == 128 || p->BN == 256, "tc wgrad: Co=%d unsupported", g.Co);
+    P.BN = p->BN; P.Nimg = g.B; P.Ho = g.Ho; P.Wo = g.Wo; P.Ci = g.Ci; P.Co = g.Co; P.KK = KK;
+    pick_box(g.Wo, g.Ho, 64, &P.TW, &P.TH, &P.TN);
+    P.tiles_w = cdiv(g.Wo, P.TW); P.tiles_h = cdiv(g.Ho, P.TH); P.tiles_n = cdiv(g.B, P.TN);
+    P.n_pix_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
+    P.n_chunks = KK * (g.Ci / 64);
+    MN_CHECK(P.n_chunks <= 72, "tc wgrad: too many chunks");
+    P.n_mtiles = cdiv(P.n_chunks, 2); P.n_ntiles = g.Co / p->BN;
+    p->w_nmaps = 0;
+    int ci = 0;
+    for (int kh = 0; kh < g.KH; ++kh)
+      for (int kw = 0; kw < g.KW; ++kw)
+        for (int cb = 0; cb < g.Ci / 64; ++cb) {
+          WgradChunk& c = P.chunks[ci++];
+          c.tap = kh * g.KW + kw; c.c0 = cb * 64;
+          if (s == 1) { c.dh = kh - pad; c.dw = kw - pad; c.map = 0; p->wpa[0] = p->wpb[0] = 0; if (p->w_nmaps < 1) p->w_nmaps = 1; }
+          else {
+            const int a = posmod(kh - pad, 2), b = posmod(kw - pad, 2);
+            c.dh = floordiv(kh - pad, 2); c.dw = floordiv(kw - pad, 2);
+            int mi = -1;
+            for (int i = 0; i < p->w_nmaps; ++i) if (p->wpa[i] == a && p->wpb[i] == b) mi = i;
+            if (mi < 0) { mi = p->w_nmaps++; p->wpa[mi] = a; p->wpb[mi] = b; }
+            c.map = mi;
+          }
+        }
+    const int units = P.n_mtiles * P.n_ntiles;
+    int splits = (148 * 2) / units; if (splits < 1) splits = 1;
+    if (splits > P.n_pix_tiles) splits = P.n_pix_tiles;
+    P.tiles_per_split = cdiv(P.n_pix_tiles, splits);
+    P.splits = cdiv(P.n_pix_tiles, P.tiles_per_split);
+  }
+  *out = p;
+  return 0;
+}
+
+void tc_plan_destroy(TcConvPlan* p) { delete p; }
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  MN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+// activation map (optionally a stride-2 parity view) over [N, Hd, Wd, C]
+static int encode_view(CUtensorMap* m, const bf16* base, int N, int Hd, int Wd, int C, int s, int a, int b, int bw,
+                       int bh, int bn) {
+  const long long rowb = (long long)Wd * C * 2, imgb = (long long)Hd * rowb;
+  if (s == 1) return encode_act_map(m, base, C, Wd, Hd, N, (long long)C * 2, rowb, imgb, bw, bh, bn);
+  const int Hq = cdiv(Hd - a, 2), Wq = cdiv(Wd - b, 2);
+  const bf16* vb = base + ((long long)a * Wd + b) * C;
+  return encode_act_map(m, vb, C, Wq > 0 ? Wq : 1, Hq > 0 ? Hq : 1, N, (long long)C * 4, rowb * 2, imgb, bw, bh, bn);
+}
+
+int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st) {
+  MN_CHECK(p != nullptr, "tc_conv_run: null plan");
+  const ConvGeom& g = p->g;
+  int nsm = 148;
+  if (p->kind == 0 || p->kind == 1) {
+    if (p->c_in0 != in0) {
+      for (auto& L : p->launches) {
+        if (p->kind == 0) {
+          for (int i = 0; i < L.n_maps; ++i)
+            MN_TRY(encode_view(&L.mapA[i], in0, g.B, g.Hi, g.Wi, g.Ci, g.stride, L.pa[i], L.pb[i], L.P.TW, L.P.TH, L.P.TN));
+          MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Ci, g.Co, p->BN));
+        } else {
+          MN_TRY(encode_view(&L.mapA[0], in0, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, L.P.TW, L.P.TH, L.P.TN));
+          MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Co, g.Ci, p->BN));
+        }
+        for (int i = L.n_maps; i < 4; ++i) L.mapA[i] = L.mapA[0];
+      }
+      p->c_in0 = in0;
+    }
+    const size_t smem = (size_t)kStagesConv * (128 * 128 + p->BN * 128) + 1024;
+    if (!p->smem_attr_set) {
+      if (p->BN == 64) MN_TRY(set_smem(k_tc_conv<64>, smem)); else MN_TRY(set_smem(k_tc_conv<128>, smem));
+      p->smem_attr_set = true;
+    }
+    for (auto& L : p->launches) {
+      const int total = L.P.n_tiles_m * L.P.n_tiles_n;
+      const int grid = total < nsm ? total : nsm;
+      if (p->BN == 64)
+        k_tc_conv<64><<<grid, 192, smem, st>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out);
+      else
+        k_tc_conv<128><<<grid, 192, smem, st>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out);
+      MN_LAUNCH_CHECK();
+    }
+    return 0;
+  }
+  // wgrad: in0 = x [B,Hi,Wi,Ci], in1 = dy [B,Ho,Wo,Co]
+  WgradParams& P = p->WP;
+  if (p->c_in0 != in0 || p->c_in1 != in1) {
+    for (int i = 0; i < p->w_nmaps; ++i)
+      MN_TRY(encode_view(&p->mapX[i], in0, g.B, g.Hi, g.Wi, g.Ci, g.stride, p->wpa[i], p->wpb[i], P.TW, P.TH, P.TN));
+    for (int i = p->w_nmaps; i < 4; ++i) p->mapX[i] = p->mapX[0];
+    MN_TRY(encode_view(&p->mapDY, in1, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, P.TW, P.TH, P.TN));
+    p->c_in0 = in0; p->c_in1 = in1;
+  }
+  const int stages = (p->BN <= 128) ? 5 : 4;
+  const size_t smem = (size_t)stages * (2 * 8192 + (p->BN / 64) * 8192) + 1024;
+  if (!p->smem_attr_set) {
+    if (p->BN == 64) MN_TRY(set_smem(k_tc_wgrad<64>, smem));
+    else if (p->BN == 128) MN_TRY(set_smem(k_tc_wgrad<128>, smem));
+    else MN_TRY(set_smem(k_tc_wgrad<256>, smem));
+    p->smem_attr_set = true;
+  }
+  const int grid = P.n_mtiles * P.n_ntiles * P.splits;
+  if (p->BN == 64) k_tc_wgrad<64><<<grid, 192, smem, st>>>(p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out);
+  else if (p->BN == 128) k_tc_wgrad<128><<<grid, 192, smem, st>>>(p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out);
+  else k_tc_wgrad<256><<<grid, 192, smem, st>>>(p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mapnet
