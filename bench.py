@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the MapNet/PoseNet ResNet-34 training step on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload posenet_bs64|mapnet_n32t3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+A "step" is common/train.py:339-361: forward, criterion, backward, [one NCCL
+allreduce of the flat gradient buffer], Adam.  `value` = whole-job images/sec
+with inputs resident in HBM; `e2e` = the same step through the reference-facing
+nn.Module surface with HOST (pinned) inputs, H2D copies and loss.item() inside
+the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: PoseNet ResNet-34 bs64 256x256, PoseNetCriterion
+    "posenet_bs64": dict(kind="posenet", N=64, T=1, H=256, W=256, lr=1e-4, wd=5e-4, clip=0.0),
+    # BASELINE.json configs[2]/[3]: MapNet steps=3 bs32 (96 frames), MapNetCriterion
+    "mapnet_n32t3": dict(kind="mapnet", N=32, T=3, H=256, W=256, lr=1e-4, wd=5e-4, clip=0.0),
+    # BASELINE.json configs[4]: MapNet++ steps=5 bs16 through MFOnline (160 frames), MapNetOnlineCriterion
+    "mapnetpp_n16t10": dict(kind="online", N=16, T=10, H=256, W=256, lr=1e-5, wd=0.0, clip=5.0),
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tc_burst=float(d["bf16_tflops"]),
+                    tc_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self._stop.is_set():
+                    break
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        if self.proc is not None:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, c in self.rows:
+            if ts < t0 or ts > t1 + 0.2 or len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx = max(mx, float(c[1]))
+            except ValueError:
+                continue
+            for i, nm in enumerate(names):
+                if c[3 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            for ts, c in self.rows[-3:]:
+                try:
+                    sm.append(float(c[0])); mx = max(mx, float(c[1]))
+                except Exception:
+                    pass
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(mx or None),
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def make_batches(cfg, n, seed, device=None, pinned=False):
+    """Synthetic inputs of the workload's shape; distinct per step."""
+    import torch
+    from oracle import weights
+    out = []
+    for i in range(n):
+        x, targ = weights.make_inputs(dict(kind=cfg["kind"], N=cfg["N"], T=cfg["T"], H=cfg["H"], W=cfg["W"]), seed + i)
+        if device is not None:
+            x, targ = x.to(device), targ.to(device)
+        elif pinned:
+            x, targ = x.pin_memory(), targ.pin_memory()
+        out.append((x, targ))
+    return out
+
+
+def frames(cfg):
+    return cfg["N"] * cfg["T"]
+
+
+# --------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation (oracle port) on the host cores
+# --------------------------------------------------------------------------------
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    import torch
+    from oracle import weights, mapnet_oracle as O
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    st = weights.make_state(7)
+    sv = dict(sax=0.0, saq=-3.0, srx=0.0, srq=-3.0)
+    # bounded sample: each timed step is one full step of the workload at a reduced
+    # tuple count so that K+W steps end within minutes on any host
+    n_tuples = min(cfg["N"], max(1, args.ref_frames // cfg["T"]))
+    scfg = dict(cfg, N=n_tuples)
+    batches = make_batches(scfg, args.steps + args.warmup, 100)
+    times = []
+    for i, (x, targ) in enumerate(batches):
+        t0 = time.time()
+        O.train_step(cfg["kind"], st, x, targ, sv, lr=cfg["lr"], weight_decay=cfg["wd"], max_grad_norm=cfg["clip"])
+        dt = time.time() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    val = frames(scfg) / (ms / 1000.0)
+    line = {
+        "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "frames_per_step": frames(scfg),
+                   "note": "oracle port of the reference CPU path (torch CPU ops, all host threads)"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "%d-frame steps of %s (bounded sample of the %d-frame workload)"
+                                   % (frames(scfg), args.workload, frames(cfg))},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------
+def run_b200(args, cfg, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import torchvision
+    from geomapnet_b200 import _lib
+    from geomapnet_b200.models.posenet import PoseNet, MapNet
+    from geomapnet_b200.common.criterion import PoseNetCriterion, MapNetCriterion, MapNetOnlineCriterion
+    from geomapnet_b200.common.optimizer import Optimizer
+    from geomapnet_b200.ddp import FlatDataParallel
+    from oracle import mapnet_oracle as O      # FLOP model only (roofline denominator)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(7)
+    fe = torchvision.models.resnet34(weights=None)
+    net = PoseNet(fe, droprate=args.droprate, pretrained=False, filter_nans=(cfg["kind"] == "online"),
+                  precision=args.precision, seed=7 + rank)
+    model = net if cfg["kind"] == "posenet" else MapNet(net)
+    kw = dict(sax=0.0, saq=-3.0)
+    if cfg["kind"] == "posenet":
+        crit = PoseNetCriterion(learn_beta=True, **kw)
+    elif cfg["kind"] == "mapnet":
+        crit = MapNetCriterion(srx=0.0, srq=-3.0, learn_beta=True, learn_gamma=True, **kw)
+    else:
+        crit = MapNetOnlineCriterion(srx=0.0, srq=-3.0, learn_beta=True, learn_gamma=True, **kw)
+    params = [{"params": model.parameters()}, {"params": list(crit.parameters())}]
+    opt = Optimizer(params=params, method="adam", base_lr=cfg["lr"], weight_decay=cfg["wd"])
+    model.cuda(); crit.cuda(); model.train()
+    dp = None
+
+    def step(x, targ):
+        out = model(x)
+        loss = crit(out, targ)
+        opt.learner.zero_grad()
+        loss.backward()
+        scale = 1.0
+        if dp is not None:
+            scale = dp.allreduce_grads()
+        opt.learner.step(grad_scale=scale, max_grad_norm=cfg["clip"])
+        return loss
+
+    nb = max(2, min(4, args.steps))
+    dev_batches = make_batches(cfg, nb, 1000 * (rank + 1), device=dev)
+    # first step: builds the arena / flattens parameters
+    step(*dev_batches[0])
+    if world > 1:
+        dp = FlatDataParallel(model, crit)
+        dp.broadcast_parameters()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    L = _lib.lib()
+    # ---------------- value: inputs resident in HBM ----------------
+    for i in range(args.warmup):
+        step(*dev_batches[i % nb])
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    lc0 = L.mapnet_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(*dev_batches[i % nb])
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = (L.mapnet_launch_count() - lc0) // max(1, args.steps)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = world * frames(cfg) / (ms_step / 1000.0)
+    clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
+
+    # ---------------- e2e: host (pinned) inputs, H2D + loss.item() inside the timed region ----------
+    host_batches = make_batches(cfg, nb, 2000 * (rank + 1), pinned=True)
+    xd = torch.empty_like(dev_batches[0][0]); td = torch.empty_like(dev_batches[0][1])
+
+    def e2e_step(i):
+        xh, th = host_batches[i % nb]
+        xd.copy_(xh, non_blocking=True)        # common/train.py:341,347  (.cuda(async=True))
+        td.copy_(th, non_blocking=True)
+        loss = step(xd, td)
+        return loss.item()                      # common/train.py:361  D2H + sync every step
+
+    for i in range(min(2, args.warmup)):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    e2e_ms = max_over_ranks(f0.elapsed_time(f1)) / args.steps
+    e2e_val = world * frames(cfg) / (e2e_ms / 1000.0)
+    h2d = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 4
+    if sampler:
+        sampler.stop()
+
+    # ---------------- roofline of the dominant kernel class (conv engines), rank 0 ----------------
+    roof = None
+    peaks = _peaks()
+    if rank == 0:
+        B = frames(cfg)
+        trunk = net._trunks[(dev.index, cfg["H"], cfg["W"])]
+        import ctypes
+        _lib.check(L.mapnet_profile(trunk.h, 1), "mapnet_profile")
+        psteps = 3
+        for i in range(psteps):
+            step(*dev_batches[i % nb])
+        ms3 = (ctypes.c_double * 3)(); fl3 = (ctypes.c_double * 3)(); n3 = (ctypes.c_int * 3)()
+        _lib.check(L.mapnet_profile_read(trunk.h, ms3, fl3, n3), "mapnet_profile_read")
+        _lib.check(L.mapnet_profile(trunk.h, 0), "mapnet_profile")
+        tot_ms = sum(ms3); tot_fl = sum(fl3); tot_n = sum(n3)
+        achieved = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        peak = peaks["tc_sustained"]
+        per_class = {}
+        for k, nm in enumerate(("fprop", "dgrad", "wgrad")):
+            if ms3[k] > 0:
+                per_class[nm] = {"tflops": fl3[k] / (ms3[k] * 1e-3) / 1e12, "ms_per_step": ms3[k] / psteps,
+                                 "launches_per_step": n3[k] // psteps}
+        roof = {"bound": "tensor", "kernel": "k_tc_conv/k_tc_wgrad (all conv launches of a step)"
+                if args.precision == "bf16" else "k_conv_simt (fp32 CUDA-core strict path)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": "%s (MEASURED_PEAKS.json bf16_tflops_sustained)" % peaks["src"],
+                "traffic": None, "conv_ms_per_step": tot_ms / psteps, "conv_launches_per_step": tot_n // psteps,
+                "conv_share_of_step": (tot_ms / psteps) / ms_step, "per_class": per_class,
+                "step_frac_of_conv_flop_roofline": (value / world) * O.train_flops_per_image(cfg["H"], cfg["W"]) / (peak * 1e12)}
+
+    # ---------------- cpu baseline: oracle port on the host cores (rank 0, N=1 only) -------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import weights
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        st = weights.make_state(7)
+        sv = dict(sax=0.0, saq=-3.0, srx=0.0, srq=-3.0)
+        n_tuples = min(cfg["N"], max(1, args.ref_frames // cfg["T"]))
+        scfg = dict(cfg, N=n_tuples)
+        cb = make_batches(scfg, 3, 300)
+        ts = []
+        for i, (x, targ) in enumerate(cb):
+            t0 = time.time()
+            O.train_step(cfg["kind"], st, x, targ, sv, lr=cfg["lr"], weight_decay=cfg["wd"], max_grad_norm=cfg["clip"])
+            if i >= 1:
+                ts.append(time.time() - t0)
+        cpu = {"value": frames(scfg) / (sum(ts) / len(ts)), "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "2 timed %d-frame steps of %s after 1 warm-up (oracle port, torch CPU ops)"
+                         % (frames(scfg), args.workload)}
+
+    if rank == 0:
+        line = {
+            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision.startswith("bf16") else "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "model": "PoseNet/MapNet ResNet-34", "frames_per_gpu": frames(cfg),
+                       "global_frames": world * frames(cfg), "image": "%dx%d" % (cfg["H"], cfg["W"]),
+                       "criterion": cfg["kind"], "optimizer": "adam (fused, flat)", "droprate": args.droprate,
+                       "parallelism": "dp%d" % world, "precision": args.precision,
+                       "l2": "per-step working set (activations + gradients, >3 GB) exceeds the 126 MB L2; "
+                             "%d distinct input batches rotate" % nb},
+            "e2e": {"value": e2e_val, "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="posenet_bs64", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt"])
+    ap.add_argument("--droprate", type=float, default=0.5)       # every reference .ini uses 0.5
+    ap.add_argument("--ref-frames", type=int, default=32, help="frames per CPU step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        print("warning: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+    if args.gpus > 1 and world == 1 and args.impl == "b200":
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 3
+        args.warmup = args.warmup if args.warmup is not None else 1
+        run_reference(args, cfg, rank, world)
+        return
+    args.steps = args.steps if args.steps is not None else 20
+    args.warmup = args.warmup if args.warmup is not None else 5
+    if args.warmup < 3:
+        args.warmup = 3
+    run_b200(args, cfg, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

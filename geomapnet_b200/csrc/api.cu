@@ -94,6 +94,19 @@ int mapnet_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq
                      sqnorm, max_norm, (cudaStream_t)stream);
 }
 
+unsigned long long mapnet_launch_count(void) { return g_launch_count; }
+
+int mapnet_profile(mapnet_trunk_t* h, int enable) {
+  MN_CHECK(h != nullptr, "profile: null handle");
+  h->net.profile_on = enable ? 1 : 0;
+  return 0;
+}
+
+int mapnet_profile_read(mapnet_trunk_t* h, double* host_ms3, double* host_flops3, int* host_launches3) {
+  MN_CHECK(h != nullptr && host_ms3 && host_flops3 && host_launches3, "profile_read: bad argument");
+  return h->net.prof_read(host_ms3, host_flops3, host_launches3);
+}
+
 int mapnet_test_conv(int precision, int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride,
                      const void* in0, const void* in1, const void* wmat, void* out, void* stream) {
   MN_TRY(require_device());

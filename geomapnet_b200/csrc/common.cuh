@@ -38,7 +38,12 @@ const char* get_last_error();
     if (_r != 0) return _r;   \
   } while (0)
 
-#define MN_LAUNCH_CHECK() MN_CUDA(cudaGetLastError())
+extern unsigned long long g_launch_count;   // kernels launched by this library (host-side counter)
+#define MN_LAUNCH_CHECK()              \
+  do {                                 \
+    ++mapnet::g_launch_count;          \
+    MN_CUDA(cudaGetLastError());       \
+  } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -444,7 +444,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
   if (kind == 0) {
     // ---------------- fprop ----------------
-    p->BN = (g.Co >= 128) ? 128 : 64;
+    p->BN = (g.Co % 128 == 0) ? 128 : 64;
     ConvLaunch L; memset(&L, 0, sizeof(L));
     ConvParams& P = L.P;
     P.Nimg = g.B; P.Hs = g.Ho; P.Ws = g.Wo;
@@ -471,7 +471,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     p->launches.push_back(L);
   } else if (kind == 1) {
     // ---------------- dgrad: gather over dY [B,Ho,Wo,Co], output dX [B,Hi,Wi,Ci] ----------------
-    p->BN = (g.Ci >= 128) ? 128 : 64;
+    p->BN = (g.Ci % 128 == 0) ? 128 : 64;
     for (int a = 0; a < s; ++a)
       for (int b = 0; b < s; ++b) {
         ConvLaunch L; memset(&L, 0, sizeof(L));
@@ -497,7 +497,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   } else {
     // ---------------- wgrad ----------------
     WgradParams& P = p->WP; memset(&P, 0, sizeof(P));
-    p->BN = (g.Co >= 256) ? 256 : g.Co;
+    p->BN = (g.Co % 256 == 0) ? 256 : ((g.Co % 128 == 0) ? 128 : 64);
     MN_CHECK(p->BN == 64 || p->BN == 128 || p->BN == 256, "tc wgrad: Co=%d unsupported", g.Co);
     P.BN = p->BN; P.Nimg = g.B; P.Ho = g.Ho; P.Wo = g.Wo; P.Ci = g.Ci; P.Co = g.Co; P.KK = KK;
     pick_box(g.Wo, g.Ho, 64, &P.TW, &P.TH, &P.TN);

@@ -11,6 +11,7 @@
 namespace mapnet {
 
 // ---- error string ------------------------------------------------------------
+unsigned long long g_launch_count = 0;
 static thread_local char g_err[1024] = "";
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -127,7 +128,7 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_CHECK(max_B >= 0 && H >= 32 && W >= 32, "create: need max_B>=0 and H,W>=32 (got %d,%d,%d)", max_B, H, W);
   MN_CHECK(precision >= 0 && precision <= 2, "create: bad precision %d", precision);
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
-  last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0;
+  last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0;
   build_table();
   if (max_B == 0) return 0;      // spec-only handle: parameter table, no device memory
   const size_t es = elt();
@@ -182,39 +183,70 @@ void Net::destroy() {
 }
 
 // ---- conv dispatch -------------------------------------------------------------
+int Net::prof_begin(cudaStream_t st, cudaEvent_t* e0) {
+  if (!profile_on) return 0;
+  MN_CUDA(cudaEventCreate(e0));
+  MN_CUDA(cudaEventRecord(*e0, st));
+  return 0;
+}
+void Net::prof_end(cudaStream_t st, cudaEvent_t e0, int cls, double flops) {
+  if (!profile_on) return;
+  ProfRec r; r.e0 = e0; r.cls = cls; r.flops = flops;
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e1, st);
+  prof.push_back(r);
+}
+int Net::prof_read(double* ms3, double* flops3, int* launches3) {
+  for (int i = 0; i < 3; ++i) { ms3[i] = 0; flops3[i] = 0; launches3[i] = 0; }
+  MN_CUDA(cudaDeviceSynchronize());
+  for (auto& r : prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    ms3[r.cls] += ms; flops3[r.cls] += r.flops; launches3[r.cls] += 1;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  prof.clear();
+  return 0;
+}
+
+static double conv_flops(const ConvGeom& g, int B, bool stem) {
+  // algorithmic MACs of the convolution (the stem's zero padding of K to 192 is not counted)
+  const double k = stem ? 147.0 : (double)g.KH * g.KW * g.Ci;
+  return 2.0 * (double)B * g.Ho * g.Wo * g.Co * k;
+}
+
 template <typename T>
 int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st) {
   ConvGeom g = convs[ci].g; g.B = B;
-  return launch_conv_simt_fprop<T>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
+  cudaEvent_t e0 = nullptr;
+  MN_TRY(prof_begin(st, &e0));
+  int r;
+  if (precision == PREC_BF16_TC) r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st);
+  else r = launch_conv_simt_fprop<T>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
+  prof_end(st, e0, 0, conv_flops(g, B, ci == 0));
+  return r;
 }
 template <typename T>
 int Net::conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st) {
   ConvGeom g = convs[ci].g; g.B = B;
-  return launch_conv_simt_dgrad<T>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
+  cudaEvent_t e0 = nullptr;
+  MN_TRY(prof_begin(st, &e0));
+  int r;
+  if (precision == PREC_BF16_TC) r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, nullptr, (const bf16*)residual, dx, st);
+  else r = launch_conv_simt_dgrad<T>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
+  prof_end(st, e0, 1, conv_flops(g, B, false));
+  return r;
 }
 template <typename T>
 int Net::conv_wgrad(int ci, const T* x, const T* dy, int B, cudaStream_t st) {
   ConvGeom g = convs[ci].g; g.B = B;
-  return launch_conv_simt_wgrad<T>(g, x, dy, dw_krsc + convs[ci].wd.k_off, st);
-}
-// bf16 tensor-core specialisations (conv_tc.cu)
-template <>
-int Net::conv_fprop<bf16>(int ci, const bf16* x, const bf16* residual, bf16* y, int B, cudaStream_t st) {
-  if (precision == PREC_BF16_TC) return tc_conv_run(tc_fprop[ci], x, nullptr, residual, y, st);
-  ConvGeom g = convs[ci].g; g.B = B;
-  return launch_conv_simt_fprop<bf16>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
-}
-template <>
-int Net::conv_dgrad<bf16>(int ci, const bf16* dy, const bf16* residual, bf16* dx, int B, cudaStream_t st) {
-  if (precision == PREC_BF16_TC) return tc_conv_run(tc_dgrad[ci], dy, nullptr, residual, dx, st);
-  ConvGeom g = convs[ci].g; g.B = B;
-  return launch_conv_simt_dgrad<bf16>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
-}
-template <>
-int Net::conv_wgrad<bf16>(int ci, const bf16* x, const bf16* dy, int B, cudaStream_t st) {
-  if (precision == PREC_BF16_TC) return tc_conv_run(tc_wgrad[ci], x, dy, nullptr, dw_krsc + convs[ci].wd.k_off, st);
-  ConvGeom g = convs[ci].g; g.B = B;
-  return launch_conv_simt_wgrad<bf16>(g, x, dy, dw_krsc + convs[ci].wd.k_off, st);
+  cudaEvent_t e0 = nullptr;
+  MN_TRY(prof_begin(st, &e0));
+  int r;
+  if (precision == PREC_BF16_TC) r = tc_conv_run(tc_wgrad[ci], (const bf16*)x, (const bf16*)dy, nullptr, dw_krsc + convs[ci].wd.k_off, st);
+  else r = launch_conv_simt_wgrad<T>(g, x, dy, dw_krsc + convs[ci].wd.k_off, st);
+  prof_end(st, e0, 2, conv_flops(g, B, ci == 0));
+  return r;
 }
 
 int Net::ensure_tc_plans(int B) {

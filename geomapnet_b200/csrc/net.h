@@ -68,6 +68,14 @@ struct Net {
   // state of the last forward
   int last_B, last_training, last_has_mask;
 
+  // optional per-conv-launch timing (bench.py roofline): CUDA events around every conv call
+  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
+  int profile_on;
+  std::vector<ProfRec> prof;
+  int prof_begin(cudaStream_t st, cudaEvent_t* e0);
+  void prof_end(cudaStream_t st, cudaEvent_t e0, int cls, double flops);
+  int prof_read(double* ms3, double* flops3, int* launches3);   // classes: 0 fprop, 1 dgrad, 2 wgrad
+
   size_t elt() const { return precision == PREC_FP32 ? 4 : 2; }
 
   int init(int max_B, int H, int W, int feat_dim, int precision);

@@ -89,6 +89,13 @@ int mapnet_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq
                      float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                      const float* sqnorm, float max_norm, void* stream);
 
+/* ---- measurement support (bench.py): number of kernels this library has launched so
+ * far in this process, and per-class conv timing with CUDA events on the launching
+ * stream (class 0 fprop, 1 dgrad, 2 wgrad; algorithmic FLOPs of each launch summed). */
+unsigned long long mapnet_launch_count(void);
+int mapnet_profile(mapnet_trunk_t* h, int enable);
+int mapnet_profile_read(mapnet_trunk_t* h, double* host_ms3, double* host_flops3, int* host_launches3);
+
 /* ---- unit entry points used by the parity tests (tests/test_gpu_kernels.py) */
 int mapnet_test_conv(int precision, int kind /*0 fprop 1 dgrad 2 wgrad*/, int B, int Hi, int Wi, int Ci, int Co,
                      int k, int stride, const void* in0, const void* in1, const void* wmat, void* out, void* stream);
