@@ -1,7 +1,7 @@
 // BatchNorm (training statistics) + ReLU + residual add + stem max-pool, forward
 // and backward, on NHWC activations.  HBM-bound: 128-bit vectorised accesses,
-// fp32 math, per-thread channel-vector accumulators, deterministic two-stage
-// reductions (per-block partials -> fp64 finalize), no atomics.
+// fp32 math, per-thread channel-vector accumulators; block partials are combined with
+// fp64 atomics and the LAST block to arrive finalizes (no separate finalize launch).
 //
 // Replaces the library calls behind torchvision BasicBlock / ResNet.forward
 // (cuDNN BN fwd-training/bwd, THCUNN threshold, TH add, SpatialDilatedMaxPooling;
@@ -13,15 +13,30 @@ namespace mapnet {
 static const int kEwThreads = 256;
 
 // ---------------------------------------------------------------------------
-// per-channel sums over pixels:  out partials [nblk][NACC][C]
-//   NACC=2: (sum y, sum y^2)                        -- forward statistics
-//   bwd   : (sum g, sum g*y [, sum g*yd])           -- g = dout * [z > 0]
+// per-channel sums over pixels, finalize fused into the LAST block to arrive:
+//   MODE 0: (sum y, sum y^2)            -> batch mean / invstd / scale / shift, running stats
+//   MODE 1: (sum g, sum g*y)            -> d gamma, d beta, dy = A*g + B*y + C coefficients
+//   MODE 2: (sum g, sum g*y, sum g*yd)  -> the same for the main AND the downsample BN
+//   g = dout * [z > 0]
+// Block partials are combined with fp64 atomics into a [3][C] accumulator (reset by
+// the finalizing block), so no separate finalize launch and no long serial loop.
 // ---------------------------------------------------------------------------
-template <typename T, int MODE>  // MODE 0: stats(y); 1: bwd(dout,zmask,y); 2: bwd with yd
+struct BnFin {
+  // forward (MODE 0)
+  const float *gamma, *beta;
+  float *run_mean, *run_var, *mean, *invstd, *scale, *shift;
+  int training;
+  // backward (MODE 1/2): main BN then downsample BN
+  const float *gamma2, *mean2, *invstd2;
+  float *dgamma, *dbeta, *coef, *dgamma2, *dbeta2, *coef2;
+};
+
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kEwThreads)
 k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __restrict__ y,
-               const T* __restrict__ yd, long long M, int C, float* __restrict__ partials) {
-  constexpr int NACC = (MODE == 0) ? 2 : (MODE == 1 ? 2 : 3);
+               const T* __restrict__ yd, long long M, int C, double* __restrict__ accum,
+               unsigned int* __restrict__ counter, BnFin f) {
+  constexpr int NACC = (MODE == 2) ? 3 : 2;
   const int cv = C >> 3;                      // channel vectors per pixel
   const int rows_par = kEwThreads / cv;       // pixels processed in parallel by the block
   const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
@@ -30,118 +45,163 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
   for (int j = 0; j < NACC; ++j)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
-  if (ty < rows_par) {
-    for (long long r = (long long)blockIdx.x * rows_par + ty; r < M; r += (long long)gridDim.x * rows_par) {
-      const long long off = r * C + tx * 8;
-      if (MODE == 0) {
-        Vec8<T> v; v.load(a + off);
+  const long long rstep = (long long)gridDim.x * rows_par;
+  for (long long r = (long long)blockIdx.x * rows_par + ty; r < M; r += rstep) {
+    const long long off = r * C + tx * 8;
+    if (MODE == 0) {
+      Vec8<T> v; v.load(a + off);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[0][i] += v.v[i]; acc[1][i] += v.v[i] * v.v[i]; }
-      } else {
-        Vec8<T> g, yy; g.load(a + off); yy.load(y + off);
-        if (zmask != nullptr) {
-          Vec8<T> z; z.load(zmask + off);
+      for (int i = 0; i < 8; ++i) { acc[0][i] += v.v[i]; acc[1][i] += v.v[i] * v.v[i]; }
+    } else {
+      Vec8<T> g, yy; g.load(a + off); yy.load(y + off);
+      if (zmask != nullptr) {
+        Vec8<T> z; z.load(zmask + off);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g.v[i] = (z.v[i] > 0.f) ? g.v[i] : 0.f;
-        }
+        for (int i = 0; i < 8; ++i) g.v[i] = (z.v[i] > 0.f) ? g.v[i] : 0.f;
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[0][i] += g.v[i]; acc[1][i] += g.v[i] * yy.v[i]; }
-        if (MODE == 2) {
-          Vec8<T> y2; y2.load(yd + off);
+      for (int i = 0; i < 8; ++i) { acc[0][i] += g.v[i]; acc[1][i] += g.v[i] * yy.v[i]; }
+      if (MODE == 2) {
+        Vec8<T> y2; y2.load(yd + off);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[2][i] += g.v[i] * y2.v[i];
-        }
+        for (int i = 0; i < 8; ++i) acc[2][i] += g.v[i] * y2.v[i];
       }
     }
   }
   // reduce across ty through shared memory (rows_par <= 32)
   extern __shared__ float sm[];               // [rows_par][NACC][C]
-  if (ty < rows_par) {
 #pragma unroll
-    for (int j = 0; j < NACC; ++j)
+  for (int j = 0; j < NACC; ++j)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sm[((size_t)ty * NACC + j) * C + tx * 8 + i] = acc[j][i];
-  }
+    for (int i = 0; i < 8; ++i) sm[((size_t)ty * NACC + j) * C + tx * 8 + i] = acc[j][i];
   __syncthreads();
   for (int idx = threadIdx.x; idx < NACC * C; idx += kEwThreads) {
     float s = 0.f;
     for (int t = 0; t < rows_par; ++t) s += sm[(size_t)t * NACC * C + idx];
-    partials[(size_t)blockIdx.x * NACC * C + idx] = s;
+    atomicAdd(accum + idx, (double)s);
   }
+  // ---- last block finalizes ----
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double invM = 1.0 / (double)M;
+  for (int c = threadIdx.x; c < C; c += kEwThreads) {
+    const double s0 = __ldcg(accum + c), s1 = __ldcg(accum + C + c);
+    if (MODE == 0) {
+      const double m = s0 * invM;
+      double var = s1 * invM - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)m;
+      const float invstd = (float)(1.0 / sqrt(var + 1e-5));
+      const double unbiased = (M > 1) ? var * (double)M / (double)(M - 1) : var;
+      f.run_mean[c] = 0.9f * f.run_mean[c] + 0.1f * mean;
+      f.run_var[c] = 0.9f * f.run_var[c] + 0.1f * (float)unbiased;
+      f.mean[c] = mean;
+      f.invstd[c] = invstd;
+      const float sc = f.gamma[c] * invstd;
+      f.scale[c] = sc;
+      f.shift[c] = f.beta[c] - mean * sc;
+    } else {
+      {
+        const double mu = (double)f.mean[c], is = (double)f.invstd[c];
+        const double s2 = is * (s1 - mu * s0);          // sum g * xhat
+        f.dgamma[c] = (float)s2;
+        f.dbeta[c] = (float)s0;
+        const double A = (double)f.gamma[c] * is;
+        const double Bc = -A * is * s2 * invM;
+        const double Cc = -A * s0 * invM - Bc * mu;
+        f.coef[c] = (float)A; f.coef[C + c] = (float)Bc; f.coef[2 * C + c] = (float)Cc;
+      }
+      if (MODE == 2) {
+        const double s1d = __ldcg(accum + 2 * C + c);
+        const double mu = (double)f.mean2[c], is = (double)f.invstd2[c];
+        const double s2 = is * (s1d - mu * s0);
+        f.dgamma2[c] = (float)s2;
+        f.dbeta2[c] = (float)s0;
+        const double A = (double)f.gamma2[c] * is;
+        const double Bc = -A * is * s2 * invM;
+        const double Cc = -A * s0 * invM - Bc * mu;
+        f.coef2[c] = (float)A; f.coef2[C + c] = (float)Bc; f.coef2[2 * C + c] = (float)Cc;
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NACC * C; idx += kEwThreads) accum[idx] = 0.0;
+  if (threadIdx.x == 0) *counter = 0u;
 }
 
 static int sums_grid(long long M, int C) {
   const int rows_par = kEwThreads / (C >> 3);
-  long long want = (M + (long long)rows_par * 16 - 1) / ((long long)rows_par * 16);   // >=16 rows per thread
-  long long cap = 148LL * 8;
+  long long want = (M + (long long)rows_par * 8 - 1) / ((long long)rows_par * 8);   // >= 8 rows per thread
+  const long long cap = 148LL * 4;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
 }
 
 template <typename T>
-int launch_channel_sums(int mode, const T* a, const T* zmask, const T* y, const T* yd, long long M, int C,
-                        float* partials, int* nblk_out, cudaStream_t st) {
-  MN_CHECK(C % 8 == 0 && C >= 8 && (kEwThreads % (C >> 3)) == 0 && C <= 2048, "channel_sums: unsupported C=%d", C);
+static int launch_sums(int mode, const T* a, const T* zmask, const T* y, const T* yd, long long M, int C,
+                       double* accum, unsigned int* counter, const BnFin& f, cudaStream_t st) {
+  MN_CHECK(C % 8 == 0 && C >= 8 && (kEwThreads % (C >> 3)) == 0 && C <= 512, "channel_sums: unsupported C=%d", C);
   const int grid = sums_grid(M, C);
   const int rows_par = kEwThreads / (C >> 3);
   const int nacc = (mode == 2) ? 3 : 2;
   const size_t smem = (size_t)rows_par * nacc * C * sizeof(float);
-  if (mode == 0) k_channel_sums<T, 0><<<grid, kEwThreads, smem, st>>>(a, nullptr, nullptr, nullptr, M, C, partials);
-  else if (mode == 1) k_channel_sums<T, 1><<<grid, kEwThreads, smem, st>>>(a, zmask, y, nullptr, M, C, partials);
-  else k_channel_sums<T, 2><<<grid, kEwThreads, smem, st>>>(a, zmask, y, yd, M, C, partials);
+  if (mode == 0) k_channel_sums<T, 0><<<grid, kEwThreads, smem, st>>>(a, nullptr, nullptr, nullptr, M, C, accum, counter, f);
+  else if (mode == 1) k_channel_sums<T, 1><<<grid, kEwThreads, smem, st>>>(a, zmask, y, nullptr, M, C, accum, counter, f);
+  else k_channel_sums<T, 2><<<grid, kEwThreads, smem, st>>>(a, zmask, y, yd, M, C, accum, counter, f);
   MN_LAUNCH_CHECK();
-  *nblk_out = grid;
   return 0;
 }
-template int launch_channel_sums<float>(int, const float*, const float*, const float*, const float*, long long, int, float*, int*, cudaStream_t);
-template int launch_channel_sums<bf16>(int, const bf16*, const bf16*, const bf16*, const bf16*, long long, int, float*, int*, cudaStream_t);
 
-// ---------------------------------------------------------------------------
-// forward finalize: batch mean / biased var -> scale, shift; running-stat update
-// (momentum 0.1, unbiased running var, eps 1e-5: torch.nn.BatchNorm2d defaults)
-// ---------------------------------------------------------------------------
-__global__ void k_bn_fwd_finalize(const float* __restrict__ partials, int nblk, int C, long long M,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  float* __restrict__ run_mean, float* __restrict__ run_var,
-                                  float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                  float* __restrict__ scale, float* __restrict__ shift,
-                                  int training, float eps, float momentum) {
+// eval-mode scale/shift from the running statistics (no batch statistics)
+__global__ void k_bn_eval_scale(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ run_mean, const float* __restrict__ run_var,
+                                float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                float* __restrict__ scale, float* __restrict__ shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  float mean, invstd;
-  if (training) {
-    double s = 0.0, ss = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-      s += (double)partials[(size_t)b * 2 * C + c];
-      ss += (double)partials[(size_t)b * 2 * C + C + c];
-    }
-    const double m = s / (double)M;
-    double var = ss / (double)M - m * m;
-    if (var < 0.0) var = 0.0;
-    mean = (float)m;
-    invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const double unbiased = (M > 1) ? var * (double)M / (double)(M - 1) : var;
-    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
-    run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unbiased;
-  } else {
-    mean = run_mean[c];
-    invstd = 1.0f / sqrtf(run_var[c] + eps);
-  }
-  mean_out[c] = mean;
-  invstd_out[c] = invstd;
+  const float mean = run_mean[c];
+  const float invstd = 1.0f / sqrtf(run_var[c] + 1e-5f);
+  mean_out[c] = mean; invstd_out[c] = invstd;
   const float sc = gamma[c] * invstd;
-  scale[c] = sc;
-  shift[c] = beta[c] - mean * sc;
+  scale[c] = sc; shift[c] = beta[c] - mean * sc;
 }
 
-int launch_bn_fwd_finalize(const float* partials, int nblk, int C, long long M, const float* gamma,
-                           const float* beta, float* run_mean, float* run_var, float* mean_out,
-                           float* invstd_out, float* scale, float* shift, int training, cudaStream_t st) {
-  k_bn_fwd_finalize<<<cdiv(C, 128), 128, 0, st>>>(partials, nblk, C, M, gamma, beta, run_mean, run_var,
-                                                  mean_out, invstd_out, scale, shift, training, 1e-5f, 0.1f);
-  MN_LAUNCH_CHECK();
-  return 0;
+template <typename T>
+int launch_bn_stats(const T* y, long long M, int C, const float* gamma, const float* beta, float* run_mean,
+                    float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift, int training,
+                    double* accum, unsigned int* counter, cudaStream_t st) {
+  if (!training) {
+    k_bn_eval_scale<<<cdiv(C, 128), 128, 0, st>>>(C, gamma, beta, run_mean, run_var, mean_out, invstd_out, scale, shift);
+    MN_LAUNCH_CHECK();
+    return 0;
+  }
+  BnFin f; memset(&f, 0, sizeof(f));
+  f.gamma = gamma; f.beta = beta; f.run_mean = run_mean; f.run_var = run_var; f.mean = mean_out;
+  f.invstd = invstd_out; f.scale = scale; f.shift = shift; f.training = 1;
+  return launch_sums<T>(0, y, nullptr, nullptr, nullptr, M, C, accum, counter, f, st);
 }
+template int launch_bn_stats<float>(const float*, long long, int, const float*, const float*, float*, float*, float*, float*, float*, float*, int, double*, unsigned int*, cudaStream_t);
+template int launch_bn_stats<bf16>(const bf16*, long long, int, const float*, const float*, float*, float*, float*, float*, float*, float*, int, double*, unsigned int*, cudaStream_t);
+
+template <typename T>
+int launch_bn_bwd_reduce(const T* dout, const T* zmask, const T* y, const T* yd, long long M, int C,
+                         const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                         float* coef, const float* gamma2, const float* mean2, const float* invstd2,
+                         float* dgamma2, float* dbeta2, float* coef2, double* accum, unsigned int* counter,
+                         cudaStream_t st) {
+  BnFin f; memset(&f, 0, sizeof(f));
+  f.gamma = gamma; f.mean = const_cast<float*>(mean); f.invstd = const_cast<float*>(invstd);
+  f.dgamma = dgamma; f.dbeta = dbeta; f.coef = coef;
+  f.gamma2 = gamma2; f.mean2 = mean2; f.invstd2 = invstd2; f.dgamma2 = dgamma2; f.dbeta2 = dbeta2; f.coef2 = coef2;
+  return launch_sums<T>(yd != nullptr ? 2 : 1, dout, zmask, y, yd, M, C, accum, counter, f, st);
+}
+template int launch_bn_bwd_reduce<float>(const float*, const float*, const float*, const float*, long long, int, const float*, const float*, const float*, float*, float*, float*, const float*, const float*, const float*, float*, float*, float*, double*, unsigned int*, cudaStream_t);
+template int launch_bn_bwd_reduce<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, long long, int, const float*, const float*, const float*, float*, float*, float*, const float*, const float*, const float*, float*, float*, float*, double*, unsigned int*, cudaStream_t);
 
 // ---------------------------------------------------------------------------
 // forward apply:  z = relu?( scale*y + shift  [+ zres | + scale2*y2 + shift2] )
@@ -319,42 +379,6 @@ int launch_stem_pool_bwd(const T* dz, const uint8_t* amax, const T* y, const flo
 }
 template int launch_stem_pool_bwd<float>(const float*, const uint8_t*, const float*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 template int launch_stem_pool_bwd<bf16>(const bf16*, const uint8_t*, const bf16*, const float*, const float*, bf16*, int, int, int, int, int, int, cudaStream_t);
-
-// ---------------------------------------------------------------------------
-// backward finalize: d gamma, d beta and the per-channel affine coefficients of
-//   dy = A*g + Bc*y + Cc     (g = dout*[z>0];  xhat = (y-mean)*invstd)
-// ---------------------------------------------------------------------------
-__global__ void k_bn_bwd_finalize(const float* __restrict__ partials, int nblk, int nacc, int which, int C,
-                                  long long M, const float* __restrict__ gamma, const float* __restrict__ mean,
-                                  const float* __restrict__ invstd, float* __restrict__ dgamma,
-                                  float* __restrict__ dbeta, float* __restrict__ coef /*[3][C]*/) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, sy = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s1 += (double)partials[(size_t)b * nacc * C + c];
-    sy += (double)partials[(size_t)b * nacc * C + (size_t)which * C + c];
-  }
-  const double mu = (double)mean[c], is = (double)invstd[c];
-  const double s2 = is * (sy - mu * s1);          // sum g * xhat
-  dgamma[c] = (float)s2;
-  dbeta[c] = (float)s1;
-  const double A = (double)gamma[c] * is;
-  const double Bc = -A * is * s2 / (double)M;
-  const double Cc = -A * s1 / (double)M - Bc * mu;
-  coef[c] = (float)A;
-  coef[C + c] = (float)Bc;
-  coef[2 * C + c] = (float)Cc;
-}
-
-int launch_bn_bwd_finalize(const float* partials, int nblk, int nacc, int which, int C, long long M,
-                           const float* gamma, const float* mean, const float* invstd, float* dgamma,
-                           float* dbeta, float* coef, cudaStream_t st) {
-  k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, st>>>(partials, nblk, nacc, which, C, M, gamma, mean, invstd,
-                                                  dgamma, dbeta, coef);
-  MN_LAUNCH_CHECK();
-  return 0;
-}
 
 // backward apply: dy = A*g + B*y + C  [, dyd = Ad*g + Bd*yd + Cd] [, gout = g]
 template <typename T, int DS, int GOUT>

@@ -71,23 +71,28 @@ template <int EPI>
 __global__ void __launch_bounds__(256)
 k_small_gemm(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm,
              long long sbn, long long sbk, float* __restrict__ C, int ldc, int M, int N, int K,
-             const float* __restrict__ bias, float* __restrict__ aux, const float* __restrict__ mask) {
+             const float* __restrict__ bias, float* __restrict__ aux, const float* __restrict__ mask,
+             int kchunk) {
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < K; k0 += 32) {
+  // split-K (EPI 0 only): blockIdx.z owns [kbeg, kend) and adds atomically into a zeroed C
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
+  const bool split = gridDim.z > 1;
+  for (int k0 = kbeg; k0 < kend; k0 += 32) {
     for (int e = threadIdx.x; e < 1024; e += 256) {
       // make the fastest-varying loader index follow the unit-stride dimension
       int r, kk;
       if (sak == 1) { r = e >> 5; kk = e & 31; } else { kk = e >> 5; r = e & 31; }
       const int m = m0 + r, k = k0 + kk;
-      As[kk][r] = (m < M && k < K) ? A[(long long)m * sam + (long long)k * sak] : 0.f;
+      As[kk][r] = (m < M && k < kend) ? A[(long long)m * sam + (long long)k * sak] : 0.f;
       int rb, kb;
       if (sbk == 1) { rb = e >> 5; kb = e & 31; } else { kb = e >> 5; rb = e & 31; }
       const int n = n0 + rb, k2 = k0 + kb;
-      Bs[kb][rb] = (n < N && k2 < K) ? Bm[(long long)n * sbn + (long long)k2 * sbk] : 0.f;
+      Bs[kb][rb] = (n < N && k2 < kend) ? Bm[(long long)n * sbn + (long long)k2 * sbk] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -108,7 +113,8 @@ k_small_gemm(const float* __restrict__ A, long long sam, long long sak, const fl
       const long long o = (long long)m * ldc + n;
       float v = acc[i][j];
       if (EPI == 0) {
-        if (bias != nullptr) v += bias[n];
+        if (bias != nullptr && blockIdx.z == 0) v += bias[n];
+        if (split) { atomicAdd(C + o, v); continue; }
       } else if (EPI == 1) {
         v += bias[n];
         aux[o] = v;
@@ -125,10 +131,20 @@ k_small_gemm(const float* __restrict__ A, long long sam, long long sak, const fl
 int launch_small_gemm(int epi, const float* A, long long sam, long long sak, const float* Bm, long long sbn,
                       long long sbk, float* C, int ldc, int M, int N, int K, const float* bias, float* aux,
                       const float* mask, cudaStream_t st) {
-  dim3 grid(cdiv(N, 32), cdiv(M, 32));
-  if (epi == 0) k_small_gemm<0><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask);
-  else if (epi == 1) k_small_gemm<1><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask);
-  else k_small_gemm<2><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask);
+  dim3 grid(cdiv(N, 32), cdiv(M, 32), 1);
+  int kchunk = K;
+  if (epi == 0 && (int)(grid.x * grid.y) < 74 && K >= 256) {
+    int splits = 148 / (int)(grid.x * grid.y);
+    if (splits > K / 64) splits = K / 64;
+    if (splits > 1) {
+      kchunk = ((K + splits - 1) / splits + 31) / 32 * 32;
+      grid.z = cdiv(K, kchunk);
+      MN_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+    }
+  }
+  if (epi == 0) k_small_gemm<0><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask, kchunk);
+  else if (epi == 1) k_small_gemm<1><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask, kchunk);
+  else k_small_gemm<2><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask, kchunk);
   MN_LAUNCH_CHECK();
   return 0;
 }

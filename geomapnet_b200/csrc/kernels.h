@@ -14,11 +14,15 @@ struct ConvGeom {
 
 // ---- bn.cu -------------------------------------------------------------------
 template <typename T>
-int launch_channel_sums(int mode, const T* a, const T* zmask, const T* y, const T* yd, long long M, int C,
-                        float* partials, int* nblk_out, cudaStream_t st);
-int launch_bn_fwd_finalize(const float* partials, int nblk, int C, long long M, const float* gamma,
-                           const float* beta, float* run_mean, float* run_var, float* mean_out,
-                           float* invstd_out, float* scale, float* shift, int training, cudaStream_t st);
+int launch_bn_stats(const T* y, long long M, int C, const float* gamma, const float* beta, float* run_mean,
+                    float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift, int training,
+                    double* accum, unsigned int* counter, cudaStream_t st);
+template <typename T>
+int launch_bn_bwd_reduce(const T* dout, const T* zmask, const T* y, const T* yd, long long M, int C,
+                         const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                         float* coef, const float* gamma2, const float* mean2, const float* invstd2,
+                         float* dgamma2, float* dbeta2, float* coef2, double* accum, unsigned int* counter,
+                         cudaStream_t st);
 template <typename T>
 int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_mode, const T* res,
                     const float* scale2, const float* shift2, T* z, long long M, int C, int relu, cudaStream_t st);
@@ -28,9 +32,6 @@ int launch_stem_pool(const T* y, const float* scale, const float* shift, T* z, u
 template <typename T>
 int launch_stem_pool_bwd(const T* dz, const uint8_t* amax, const T* y, const float* scale, const float* shift,
                          T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st);
-int launch_bn_bwd_finalize(const float* partials, int nblk, int nacc, int which, int C, long long M,
-                           const float* gamma, const float* mean, const float* invstd, float* dgamma,
-                           float* dbeta, float* coef, cudaStream_t st);
 template <typename T>
 int launch_bn_bwd_apply(const T* dout, const T* zmask, const T* y, const float* coef, T* dy, const T* yd,
                         const float* coefd, T* dyd, T* gout, long long M, int C, cudaStream_t st);

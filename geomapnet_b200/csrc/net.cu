@@ -152,7 +152,9 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   for (auto& c : convs) wd.push_back(c.wd);
   MN_TRY(alloc((void**)&d_wdescs, wd.size() * sizeof(WeightDesc)));
   MN_CUDA(cudaMemcpy(d_wdescs, wd.data(), wd.size() * sizeof(WeightDesc), cudaMemcpyHostToDevice));
-  MN_TRY(alloc((void**)&partials, (size_t)(148 * 8) * 3 * 512 * sizeof(float)));
+  MN_TRY(alloc((void**)&bn_accum, 3 * 512 * sizeof(double) + 64));
+  MN_CUDA(cudaMemset(bn_accum, 0, 3 * 512 * sizeof(double) + 64));
+  bn_counter = (unsigned int*)(bn_accum + 3 * 512);
   long long small = 0;
   for (auto& b : bns) small += 7LL * b.C;
   MN_TRY(alloc((void**)&bn_small, (size_t)small * sizeof(float)));
@@ -273,10 +275,8 @@ template <typename T>
 int Net::bn_forward(int bi, const T* y, long long M, const float* params, float* bufs, int training,
                     cudaStream_t st) {
   BNL& b = bns[bi];
-  int nblk = 0;
-  if (training) MN_TRY(launch_channel_sums<T>(0, y, nullptr, nullptr, nullptr, M, b.C, partials, &nblk, st));
-  return launch_bn_fwd_finalize(partials, nblk, b.C, M, params + b.g_off, params + b.b_off, bufs + b.rm_off,
-                                bufs + b.rv_off, b.mean, b.invstd, b.scale, b.shift, training, st);
+  return launch_bn_stats<T>(y, M, b.C, params + b.g_off, params + b.b_off, bufs + b.rm_off, bufs + b.rv_off,
+                            b.mean, b.invstd, b.scale, b.shift, training, bn_accum, bn_counter, st);
 }
 
 // ---- forward -------------------------------------------------------------------
@@ -365,23 +365,27 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     BNL& b1 = bns[convs[bl.conv1].bn];
     BNL& b2 = bns[convs[bl.conv2].bn];
     const bool ds = bl.convd >= 0;
-    int nblk = 0;
     // out = relu(bn2(y2) + idt): g = dout*[out>0]; BN2 (and downsample BN) backward
-    MN_TRY(launch_channel_sums<T>(ds ? 2 : 1, S0, (const T*)bl.out, (const T*)bl.y2, ds ? (const T*)bl.yd : nullptr, Mo, C, partials, &nblk, st));
-    MN_TRY(launch_bn_bwd_finalize(partials, nblk, ds ? 3 : 2, 1, C, Mo, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef, st));
     if (ds) {
       BNL& bd = bns[convs[bl.convd].bn];
-      MN_TRY(launch_bn_bwd_finalize(partials, nblk, 3, 2, C, Mo, params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef, st));
+      MN_TRY(launch_bn_bwd_reduce<T>(S0, (const T*)bl.out, (const T*)bl.y2, (const T*)bl.yd, Mo, C,
+                                     params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
+                                     params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef,
+                                     bn_accum, bn_counter, st));
       MN_TRY(launch_bn_bwd_apply<T>(S0, (const T*)bl.out, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st));
     } else {
+      MN_TRY(launch_bn_bwd_reduce<T>(S0, (const T*)bl.out, (const T*)bl.y2, nullptr, Mo, C,
+                                     params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
+                                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st));
       MN_TRY(launch_bn_bwd_apply<T>(S0, (const T*)bl.out, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, S3, Mo, C, st));
     }
     // conv2
     MN_TRY(conv_wgrad<T>(bl.conv2, (const T*)bl.h, S1, B, st));
     MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st));
     // h = relu(bn1(y1))
-    MN_TRY(launch_channel_sums<T>(1, S4, (const T*)bl.h, (const T*)bl.y1, nullptr, Mo, C, partials, &nblk, st));
-    MN_TRY(launch_bn_bwd_finalize(partials, nblk, 2, 1, C, Mo, params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef, st));
+    MN_TRY(launch_bn_bwd_reduce<T>(S4, (const T*)bl.h, (const T*)bl.y1, nullptr, Mo, C,
+                                   params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
+                                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st));
     MN_TRY(launch_bn_bwd_apply<T>(S4, (const T*)bl.h, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st));
     // conv1 (+ downsample conv): d zin
     MN_TRY(conv_wgrad<T>(bl.conv1, zin, S1, B, st));
@@ -397,10 +401,10 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
   {
     BNL& b0 = bns[convs[0].bn];
     const long long M0 = (long long)B * Hc * Wc;
-    int nblk = 0;
     MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S1, B, Hc, Wc, Hp, Wp, 64, st));
-    MN_TRY(launch_channel_sums<T>(1, S1, nullptr, (const T*)y0, nullptr, M0, 64, partials, &nblk, st));
-    MN_TRY(launch_bn_bwd_finalize(partials, nblk, 2, 1, 64, M0, params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef, st));
+    MN_TRY(launch_bn_bwd_reduce<T>(S1, nullptr, (const T*)y0, nullptr, M0, 64,
+                                   params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef,
+                                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st));
     MN_TRY(launch_bn_bwd_apply<T>(S1, nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st));
     MN_TRY(conv_wgrad<T>(0, (const T*)A0, S2, B, st));
   }

@@ -56,7 +56,7 @@ struct Net {
   void *A0, *y0, *z0; uint8_t* amax0;
   void* scratch[5]; long long scratch_elems;
   void *w_krsc, *w_dg; float* dw_krsc; WeightDesc* d_wdescs;
-  float* partials;
+  double* bn_accum; unsigned int* bn_counter;
   float *feat, *fcpre, *hdrop, *mask, *dh, *dfeat, *dpredf;
   float* bn_small;               // backing store of the BN small arrays
   float *sq_partials, *sq_out;
