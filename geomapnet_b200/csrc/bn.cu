@@ -46,6 +46,7 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
   const long long rstep = (long long)gridDim.x * rows_par;
+#pragma unroll 4
   for (long long r = (long long)blockIdx.x * rows_par + ty; r < M; r += rstep) {
     const long long off = r * C + tx * 8;
     if (MODE == 0) {
@@ -212,13 +213,21 @@ k_bn_apply(const T* __restrict__ y, const float* __restrict__ scale, const float
            const T* __restrict__ res, const float* __restrict__ scale2, const float* __restrict__ shift2,
            T* __restrict__ z, long long nvec, int C, int relu) {
   const int cv = C >> 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cv) * 8;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // the grid stride (gridDim*256) is a multiple of cv, so this thread always sees the same 8 channels
+  const int c0 = (int)(i0 % cv) * 8;
+  float sc[8], sh[8], sc2[8], sh2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = __ldg(scale + c0 + k); sh[k] = __ldg(shift + c0 + k);
+    if (RES == 2) { sc2[k] = __ldg(scale2 + c0 + k); sh2[k] = __ldg(shift2 + c0 + k); }
+  }
+#pragma unroll 2
+  for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     Vec8<T> v; v.load(y + i * 8);
     float o[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = v.v[k] * __ldg(scale + c0 + k) + __ldg(shift + c0 + k);
+    for (int k = 0; k < 8; ++k) o[k] = v.v[k] * sc[k] + sh[k];
     if (RES == 1) {
       Vec8<T> r; r.load(res + i * 8);
 #pragma unroll
@@ -226,7 +235,7 @@ k_bn_apply(const T* __restrict__ y, const float* __restrict__ scale, const float
     } else if (RES == 2) {
       Vec8<T> r; r.load(res + i * 8);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] += r.v[k] * __ldg(scale2 + c0 + k) + __ldg(shift2 + c0 + k);
+      for (int k = 0; k < 8; ++k) o[k] += r.v[k] * sc2[k] + sh2[k];
     }
     Vec8<T> w;
 #pragma unroll
@@ -388,9 +397,16 @@ k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T*
                const float* __restrict__ coefd, T* __restrict__ dyd, T* __restrict__ gout, long long nvec,
                int C) {
   const int cv = C >> 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cv) * 8;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 % cv) * 8;          // loop invariant (grid stride is a multiple of cv)
+  float cA[8], cB[8], cC[8], dA[8], dB[8], dC[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    cA[k] = __ldg(coef + c0 + k); cB[k] = __ldg(coef + C + c0 + k); cC[k] = __ldg(coef + 2 * C + c0 + k);
+    if (DS) { dA[k] = __ldg(coefd + c0 + k); dB[k] = __ldg(coefd + C + c0 + k); dC[k] = __ldg(coefd + 2 * C + c0 + k); }
+  }
+#pragma unroll 2
+  for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     Vec8<T> g, yy; g.load(dout + i * 8); yy.load(y + i * 8);
     if (zmask != nullptr) {
       Vec8<T> z; z.load(zmask + i * 8);
@@ -399,15 +415,13 @@ k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T*
     }
     Vec8<T> o;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      o.v[k] = __ldg(coef + c0 + k) * g.v[k] + __ldg(coef + C + c0 + k) * yy.v[k] + __ldg(coef + 2 * C + c0 + k);
+    for (int k = 0; k < 8; ++k) o.v[k] = cA[k] * g.v[k] + cB[k] * yy.v[k] + cC[k];
     o.store(dy + i * 8);
     if (DS) {
       Vec8<T> y2; y2.load(yd + i * 8);
       Vec8<T> o2;
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        o2.v[k] = __ldg(coefd + c0 + k) * g.v[k] + __ldg(coefd + C + c0 + k) * y2.v[k] + __ldg(coefd + 2 * C + c0 + k);
+      for (int k = 0; k < 8; ++k) o2.v[k] = dA[k] * g.v[k] + dB[k] * y2.v[k] + dC[k];
       o2.store(dyd + i * 8);
     }
     if (GOUT) g.store(gout + i * 8);

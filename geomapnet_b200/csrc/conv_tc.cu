@@ -20,6 +20,8 @@
 //       with fp32 red.global.add into the flat wgrad buffer.
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "kernels.h"
@@ -101,7 +103,7 @@ struct WgradParams {
   WgradChunk chunks[72];
 };
 
-static const int kStagesConv = 5;
+static constexpr int conv_stages(int BN) { return BN <= 128 ? 5 : 4; }
 
 // ---------------------------------------------------------------------------------
 // fprop / dgrad kernel
@@ -112,11 +114,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
           const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
           bf16* __restrict__ out) {
-  constexpr int STAGES = kStagesConv;
+  constexpr int STAGES = conv_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;        // 128 pixels x 64 ch bf16
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = 2 * BN;         // double-buffered accumulator: 128 / 256 / 512 columns
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -431,6 +433,17 @@ static void pick_box(int Wd, int Hd, int pixels, int* TW, int* TH, int* TN) {
   *TW = tw; *TH = th; *TN = tn;
 }
 
+// N-tile: wider tiles re-use the A operand more (the engines are L2-bandwidth bound), but
+// must still leave enough tiles to occupy the 148 SMs.
+static int pick_bn(int Cout, long long M) {
+  static int force = -1;
+  if (force < 0) { const char* e = getenv("MAPNET_TC_BN"); force = e ? atoi(e) : 0; }
+  if (force == 64 || (force == 128 && Cout % 128 == 0) || (force == 256 && Cout % 256 == 0)) return force;
+  if (Cout % 256 == 0 && (M / 128) * (Cout / 256) >= 120) return 256;
+  if (Cout % 128 == 0) return 128;
+  return 64;
+}
+
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int posmod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
 
@@ -444,7 +457,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
   if (kind == 0) {
     // ---------------- fprop ----------------
-    p->BN = (g.Co % 128 == 0) ? 128 : 64;
+    p->BN = pick_bn(g.Co, g.M_out());
     ConvLaunch L; memset(&L, 0, sizeof(L));
     ConvParams& P = L.P;
     P.Nimg = g.B; P.Hs = g.Ho; P.Ws = g.Wo;
@@ -471,7 +484,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     p->launches.push_back(L);
   } else if (kind == 1) {
     // ---------------- dgrad: gather over dY [B,Ho,Wo,Co], output dX [B,Hi,Wi,Ci] ----------------
-    p->BN = (g.Ci % 128 == 0) ? 128 : 64;
+    p->BN = pick_bn(g.Ci, g.M_in());
     for (int a = 0; a < s; ++a)
       for (int b = 0; b < s; ++b) {
         ConvLaunch L; memset(&L, 0, sizeof(L));
@@ -570,9 +583,11 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       }
       p->c_in0 = in0;
     }
-    const size_t smem = (size_t)kStagesConv * (128 * 128 + p->BN * 128) + 1024;
+    const size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024;
     if (!p->smem_attr_set) {
-      if (p->BN == 64) MN_TRY(set_smem(k_tc_conv<64>, smem)); else MN_TRY(set_smem(k_tc_conv<128>, smem));
+      if (p->BN == 64) MN_TRY(set_smem(k_tc_conv<64>, smem));
+      else if (p->BN == 128) MN_TRY(set_smem(k_tc_conv<128>, smem));
+      else MN_TRY(set_smem(k_tc_conv<256>, smem));
       p->smem_attr_set = true;
     }
     for (auto& L : p->launches) {
@@ -580,8 +595,10 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       const int grid = total < nsm ? total : nsm;
       if (p->BN == 64)
         k_tc_conv<64><<<grid, 192, smem, st>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out);
-      else
+      else if (p->BN == 128)
         k_tc_conv<128><<<grid, 192, smem, st>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out);
+      else
+        k_tc_conv<256><<<grid, 192, smem, st>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out);
       MN_LAUNCH_CHECK();
     }
     return 0;

@@ -41,8 +41,38 @@ __global__ void k_pack_weights(const WeightDesc* __restrict__ descs, const float
       v = params[d.p_off + (((long long)co * d.Ci_real + ci) * d.KH + kh) * d.KW + kw];
       if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
       w_krsc[d.k_off + e] = cvt_w<TW>(v);
-      if (w_dg != nullptr) w_dg[d.k_off + ((long long)ci * KK + tap) * d.Co + co] = cvt_w<TW>(v);
     }
+  }
+}
+
+// w_dg[ci][tap][co] = w_krsc[co][tap][ci]: 32x32 shared-memory tile transpose per filter tap,
+// coalesced on both sides (the dgrad engines want Cout as the contiguous K dimension)
+template <typename TW>
+__global__ void __launch_bounds__(256)
+k_transpose_dg(const WeightDesc* __restrict__ descs, const TW* __restrict__ w_krsc, TW* __restrict__ w_dg) {
+  const WeightDesc d = descs[blockIdx.y];
+  if (d.im2col_k > 0) return;          // the stem has no dgrad
+  const int KK = d.KH * d.KW;
+  const int tco = d.Co >> 5, tci = d.Ci >> 5;
+  const int ntiles = tco * tci * KK;
+  __shared__ TW tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tap = t % KK;
+    const int cit = (t / KK) % tci;
+    const int cot = t / (KK * tci);
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int co = cot * 32 + r, ci = cit * 32 + tx;
+      tile[r][tx] = w_krsc[d.k_off + ((long long)co * KK + tap) * d.Ci + ci];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int ci = cit * 32 + r, co = cot * 32 + tx;
+      w_dg[d.k_off + ((long long)ci * KK + tap) * d.Co + co] = tile[tx][r];
+    }
+    __syncthreads();
   }
 }
 
@@ -52,6 +82,11 @@ int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* param
   dim3 grid(cdiv(max_elems, 256) < 512 ? cdiv(max_elems, 256) : 512, nconv);
   k_pack_weights<TW><<<grid, 256, 0, st>>>(d_descs, params, w_krsc, w_dg, round_bf16);
   MN_LAUNCH_CHECK();
+  if (w_dg != nullptr) {
+    dim3 g2(592, nconv);
+    k_transpose_dg<TW><<<g2, 256, 0, st>>>(d_descs, w_krsc, w_dg);
+    MN_LAUNCH_CHECK();
+  }
   return 0;
 }
 template int launch_pack_weights<float>(const WeightDesc*, int, const float*, float*, float*, int, int, cudaStream_t);
@@ -92,43 +127,50 @@ int launch_unpack_wgrads(const WeightDesc* d_descs, int nconv, const float* dw_k
   return 0;
 }
 
+// One block per output row (b, oh): the 7 input rows x 3 channels it needs are staged in
+// shared memory with coalesced loads (3-pixel zero halo left/right, zero rows above/below
+// the image), then every thread emits 16-byte slices of the patch matrix (coalesced).
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_stem_im2col(const float* __restrict__ x, T* __restrict__ A, int B, int H, int W, int Ho, int Wo, int Kpad) {
-  // one thread per (pixel, 8 consecutive k): Kpad % 8 == 0
+  extern __shared__ float sx[];          // [3*7][W + 6]
+  const int WP = W + 6;
+  const int b = blockIdx.x / Ho, oh = blockIdx.x - b * Ho;
+  for (int i = threadIdx.x; i < 21 * WP; i += blockDim.x) {
+    const int r = i / WP, col = i - r * WP;
+    const int c = r / 7, kh = r - c * 7;
+    const int ih = oh * 2 - 3 + kh, iw = col - 3;
+    float v = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((long long)b * 3 + c) * H + ih) * W + iw);
+    sx[i] = v;
+  }
+  __syncthreads();
   const int kv = Kpad >> 3;
-  const long long nvec = (long long)B * Ho * Wo * kv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k0 = (int)(i % kv) * 8;
-    long long p = i / kv;
-    const int ow = (int)(p % Wo); p /= Wo;
-    const int oh = (int)(p % Ho);
-    const int b = (int)(p / Ho);
+  T* Arow = A + ((long long)b * Ho + oh) * Wo * Kpad;
+  for (int i = threadIdx.x; i < Wo * kv; i += blockDim.x) {
+    const int ow = i / kv, k0 = (i - ow * kv) * 8;
     Vec8<T> o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = k0 + j;
       float v = 0.f;
       if (k < 147) {
-        const int c = k % 3, t = k / 3;
+        const int t = k / 3, c = k - t * 3;
         const int kh = t / 7, kw = t - kh * 7;
-        const int ih = oh * 2 - 3 + kh, iw = ow * 2 - 3 + kw;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((long long)b * 3 + c) * H + ih) * W + iw);
+        v = sx[(c * 7 + kh) * WP + ow * 2 + kw];
       }
       o.v[j] = v;
     }
-    o.store(A + i * 8);
+    o.store(Arow + (long long)i * 8);
   }
 }
 
 template <typename T>
 int launch_stem_im2col(const float* x_nchw, T* A, int B, int H, int W, int Ho, int Wo, int Kpad, cudaStream_t st) {
   MN_CHECK(Kpad % 8 == 0 && Kpad >= 147, "stem_im2col: bad Kpad");
-  const long long nvec = (long long)B * Ho * Wo * (Kpad >> 3);
-  long long grid = (nvec + 255) / 256;
-  if (grid > 148LL * 32) grid = 148LL * 32;
-  k_stem_im2col<T><<<(int)grid, 256, 0, st>>>(x_nchw, A, B, H, W, Ho, Wo, Kpad);
+  const size_t smem = (size_t)21 * (W + 6) * sizeof(float);
+  MN_CHECK(smem <= 48 * 1024, "stem_im2col: image width %d too large", W);
+  k_stem_im2col<T><<<B * Ho, 256, smem, st>>>(x_nchw, A, B, H, W, Ho, Wo, Kpad);
   MN_LAUNCH_CHECK();
   return 0;
 }
