@@ -32,6 +32,56 @@ WORKLOADS = {
 }
 
 
+def usable_cores():
+    """Host threads this process can really use: CPU affinity capped by the cgroup quota
+    (os.cpu_count() over-reports inside containers and oversubscription wrecks the CPU arm)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    cap = os.environ.get("BENCH_CPU_THREADS")
+    if cap:
+        n = max(1, int(cap))
+    return n
+
+
+def tune_cpu_threads(kind):
+    """Pick the torch thread count that makes the CPU arm FASTEST on this host (all usable
+    cores is not always best: NUMA / SMT oversubscription).  A 4-frame step per candidate."""
+    import torch
+    from oracle import weights, mapnet_oracle as O
+    n = usable_cores()
+    cands = sorted({c for c in (n, n // 2, 64, 32, 16, 8) if 1 <= c <= n}, reverse=True)
+    st = weights.make_state(7)
+    cfg = dict(kind="posenet", N=4, T=1, H=256, W=256)
+    x, targ = weights.make_inputs(cfg, 5)
+    sv = dict(sax=0.0, saq=-3.0, srx=0.0, srq=-3.0)
+    best, best_t = n, None
+    for c in cands:
+        torch.set_num_threads(c)
+        O.train_step("posenet", st, x, targ, sv)             # warm
+        t0 = time.time()
+        O.train_step("posenet", st, x, targ, sv)
+        dt = time.time() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -125,8 +175,7 @@ def run_reference(args, cfg, rank, world):
         return
     import torch
     from oracle import weights, mapnet_oracle as O
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
+    cores = tune_cpu_threads(cfg["kind"])
     st = weights.make_state(7)
     sv = dict(sax=0.0, saq=-3.0, srx=0.0, srq=-3.0)
     # bounded sample: each timed step is one full step of the workload at a reduced
@@ -135,9 +184,11 @@ def run_reference(args, cfg, rank, world):
     scfg = dict(cfg, N=n_tuples)
     batches = make_batches(scfg, args.steps + args.warmup, 100)
     times = []
+    tr = O.OracleTrainer(cfg["kind"], st, sv, lr=cfg["lr"], weight_decay=cfg["wd"], max_grad_norm=cfg["clip"],
+                         droprate=args.droprate)
     for i, (x, targ) in enumerate(batches):
         t0 = time.time()
-        O.train_step(cfg["kind"], st, x, targ, sv, lr=cfg["lr"], weight_decay=cfg["wd"], max_grad_norm=cfg["clip"])
+        tr.step(x, targ)
         dt = time.time() - t0
         if i >= args.warmup:
             times.append(dt)
@@ -148,7 +199,8 @@ def run_reference(args, cfg, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "frames_per_step": frames(scfg),
-                   "note": "oracle port of the reference CPU path (torch CPU ops, all host threads)"},
+                   "note": "oracle port of the reference CPU path (torch CPU ops); thread count = fastest of "
+                           "{all usable cores, half, 64, 32, 16, 8} on this host, %d usable" % usable_cores()},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": "%d-frame steps of %s (bounded sample of the %d-frame workload)"
                                    % (frames(scfg), args.workload, frames(cfg))},
@@ -310,17 +362,18 @@ def run_b200(args, cfg, rank, local_rank, world):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import weights
-        cores = os.cpu_count()
-        torch.set_num_threads(cores)
+        cores = tune_cpu_threads(cfg["kind"])
         st = weights.make_state(7)
         sv = dict(sax=0.0, saq=-3.0, srx=0.0, srq=-3.0)
         n_tuples = min(cfg["N"], max(1, args.ref_frames // cfg["T"]))
         scfg = dict(cfg, N=n_tuples)
         cb = make_batches(scfg, 3, 300)
         ts = []
+        tr = O.OracleTrainer(cfg["kind"], st, sv, lr=cfg["lr"], weight_decay=cfg["wd"], max_grad_norm=cfg["clip"],
+                             droprate=args.droprate)
         for i, (x, targ) in enumerate(cb):
             t0 = time.time()
-            O.train_step(cfg["kind"], st, x, targ, sv, lr=cfg["lr"], weight_decay=cfg["wd"], max_grad_norm=cfg["clip"])
+            tr.step(x, targ)
             if i >= 1:
                 ts.append(time.time() - t0)
         cpu = {"value": frames(scfg) / (sum(ts) / len(ts)), "unit": "images/s", "cores": cores, "kind": "port",

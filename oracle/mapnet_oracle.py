@@ -362,6 +362,51 @@ def train_step(kind, st, x, targ, svals, learn=(True, True), lr=1e-4, weight_dec
     return out
 
 
+class OracleTrainer(object):
+    """Persistent-state version of train_step for TIMING the CPU path (bench.py's
+    cpu_baseline / --impl reference): parameters, Adam state and criterion scalars live
+    across steps exactly as in common/train.py (no per-step cloning), so a timed step is
+    only forward + loss + zero_grad + backward + [clip] + Adam.step (train.py:339-361)."""
+
+    def __init__(self, kind, st, svals, learn=(True, True), lr=1e-4, weight_decay=5e-4, max_grad_norm=0.0,
+                 droprate=0.0):
+        self.kind, self.max_grad_norm, self.droprate = kind, max_grad_norm, droprate
+        params, bufs = split_state(st)
+        self.P = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in params.items())
+        self.full = OrderedDict(self.P)
+        for k, v in bufs.items():
+            self.full[k] = v.detach().clone()
+        self.S = OrderedDict()
+        for name in (("sax", "saq") if kind == "posenet" else ("sax", "saq", "srx", "srq")):
+            trainable = learn[0] if name in ("sax", "saq") else learn[1]
+            self.S[name] = torch.tensor([svals[name]], dtype=torch.float32, requires_grad=trainable)
+        groups = [{"params": list(self.P.values())}]
+        sl = [v for v in self.S.values() if v.requires_grad]
+        if sl:
+            groups.append({"params": sl})
+        self.opt = torch.optim.Adam(groups, lr=lr, weight_decay=weight_decay)
+
+    def step(self, x, targ):
+        bufs_out = {}
+        mask = None
+        if self.droprate > 0:
+            B = x.shape[0] if x.dim() == 4 else x.shape[0] * x.shape[1]
+            keep = (torch.rand(B, self.full["feature_extractor.fc.bias"].numel()) >= self.droprate).float()
+            mask = keep / (1.0 - self.droprate)
+        x = x.clone().requires_grad_(True)                               # train.py:339
+        pred = model_forward("posenet" if self.kind == "posenet" else "mapnet", self.full, x, training=True,
+                             drop_mask=mask, bufs_out=bufs_out)
+        loss = criterion(self.kind, pred, targ, self.S)
+        self.opt.zero_grad()
+        loss.backward()
+        if self.max_grad_norm > 0.0:
+            torch.nn.utils.clip_grad_norm_(list(self.P.values()), self.max_grad_norm)
+        self.opt.step()
+        for k, v in bufs_out.items():
+            self.full[k] = v
+        return float(loss.item())                                         # train.py:361
+
+
 class _NanFilter(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred):
