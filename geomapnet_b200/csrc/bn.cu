@@ -11,6 +11,8 @@
 namespace mapnet {
 
 static const int kEwThreads = 256;
+static const int kReplicas = 32;        // accumulator replicas (must match Net's allocation)
+static const int kAccStride = 3 * 512;  // doubles per replica
 
 // ---------------------------------------------------------------------------
 // per-channel sums over pixels, finalize fused into the LAST block to arrive:
@@ -18,8 +20,9 @@ static const int kEwThreads = 256;
 //   MODE 1: (sum g, sum g*y)            -> d gamma, d beta, dy = A*g + B*y + C coefficients
 //   MODE 2: (sum g, sum g*y, sum g*yd)  -> the same for the main AND the downsample BN
 //   g = dout * [z > 0]
-// Block partials are combined with fp64 atomics into a [3][C] accumulator (reset by
-// the finalizing block), so no separate finalize launch and no long serial loop.
+// Block partials are combined with fp64 atomics into kReplicas x [3][C] accumulators
+// (block b -> replica b % kReplicas: same-address atomics serialise at ~30 ns each, the
+// replicas keep that chain short); the finalizing block sums the replicas and resets them.
 // ---------------------------------------------------------------------------
 struct BnFin {
   // forward (MODE 0)
@@ -79,7 +82,7 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
   for (int idx = threadIdx.x; idx < NACC * C; idx += kEwThreads) {
     float s = 0.f;
     for (int t = 0; t < rows_par; ++t) s += sm[(size_t)t * NACC * C + idx];
-    atomicAdd(accum + idx, (double)s);
+    atomicAdd(accum + (size_t)(blockIdx.x % kReplicas) * kAccStride + idx, (double)s);
   }
   // ---- last block finalizes ----
   __shared__ unsigned int s_last;
@@ -89,9 +92,22 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // sum the replicas into shared memory (reuse the reduction buffer: NACC*C doubles <= 12 KB... held as
+  // doubles in a separate static array to keep precision)
+  __shared__ double s_tot[3 * 512];
+  const int nrep = (gridDim.x < (unsigned)kReplicas) ? (int)gridDim.x : kReplicas;
+  for (int idx = threadIdx.x; idx < NACC * C; idx += kEwThreads) {
+    double t = 0.0;
+    for (int r = 0; r < nrep; ++r) {
+      t += __ldcg(accum + (size_t)r * kAccStride + idx);
+      accum[(size_t)r * kAccStride + idx] = 0.0;
+    }
+    s_tot[idx] = t;
+  }
+  __syncthreads();
   const double invM = 1.0 / (double)M;
   for (int c = threadIdx.x; c < C; c += kEwThreads) {
-    const double s0 = __ldcg(accum + c), s1 = __ldcg(accum + C + c);
+    const double s0 = s_tot[c], s1 = s_tot[C + c];
     if (MODE == 0) {
       const double m = s0 * invM;
       double var = s1 * invM - m * m;
@@ -118,7 +134,7 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
         f.coef[c] = (float)A; f.coef[C + c] = (float)Bc; f.coef[2 * C + c] = (float)Cc;
       }
       if (MODE == 2) {
-        const double s1d = __ldcg(accum + 2 * C + c);
+        const double s1d = s_tot[2 * C + c];
         const double mu = (double)f.mean2[c], is = (double)f.invstd2[c];
         const double s2 = is * (s1d - mu * s0);
         f.dgamma2[c] = (float)s2;
@@ -130,8 +146,6 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
       }
     }
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < NACC * C; idx += kEwThreads) accum[idx] = 0.0;
   if (threadIdx.x == 0) *counter = 0u;
 }
 

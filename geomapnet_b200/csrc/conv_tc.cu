@@ -108,7 +108,10 @@ static constexpr int conv_stages(int BN) { return BN <= 128 ? 5 : 4; }
 // ---------------------------------------------------------------------------------
 // fprop / dgrad kernel
 // ---------------------------------------------------------------------------------
-template <int BN>
+// CL = thread-block cluster size along M: the CL CTAs of a cluster work on CL consecutive
+// M tiles of the same N tile and share the weight tile -- each loads 1/CL of it and TMA-
+// multicasts it to all (the engines are L2-bandwidth bound, this cuts the B traffic by CL).
+template <int BN, int CL>
 __global__ void __launch_bounds__(192, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -130,28 +133,37 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();          // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  const int total_tiles = P.n_tiles_m * P.n_tiles_n;
+  // work items: (group of CL consecutive M tiles, N tile); every CTA of a cluster walks the
+  // same sequence, CTA r takes M tile group*CL + r (possibly past the end: a dummy tile whose
+  // loads are zero-filled by TMA and whose epilogue stores nothing)
+  const int n_groups = (P.n_tiles_m + CL - 1) / CL;
+  const int total_tiles = n_groups * P.n_tiles_n;
+  const int first_tile = blockIdx.x / CL;
+  const int tile_step = gridDim.x / CL;
   const int kblocks = P.num_taps * P.cblocks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int tn = tile % P.n_tiles_n;
-        int tm = tile / P.n_tiles_n;
+        int tm = (tile / P.n_tiles_n) * CL + (int)crank;
         const int tw = tm % P.tiles_w; tm /= P.tiles_w;
         const int th = tm % P.tiles_h;
         const int tb = tm / P.tiles_h;
@@ -164,7 +176,13 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
             mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
             tma_load_4d(sa, mA, full0 + 8 * stage, cb * 64, jw0 + tap.dw, jh0 + tap.dh, n0);
-            tma_load_2d(sa + A_BYTES, &mapB, full0 + 8 * stage, tap.kidx * P.Cs + cb * 64, tn * BN);
+            if (CL == 1) {
+              tma_load_2d(sa + A_BYTES, &mapB, full0 + 8 * stage, tap.kidx * P.Cs + cb * 64, tn * BN);
+            } else {
+              constexpr int BROWS = BN / CL;      // this CTA's slice of the weight tile
+              tma_load_2d_mc(sa + A_BYTES + crank * (BROWS * 128), &mapB, full0 + 8 * stage,
+                             tap.kidx * P.Cs + cb * 64, tn * BN + (int)crank * BROWS, CMASK);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -176,7 +194,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     constexpr uint64_t DESC_BASE = make_smem_desc_base(16, 1024);
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       mbar_wait(tempty0 + 8 * as, aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
@@ -191,7 +209,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             mma_bf16(d_tmem, smem_desc(DESC_BASE, sa + k * 32), smem_desc(DESC_BASE, sb + k * 32), IDESC,
                      (kb > 0 || k > 0) ? 1u : 0u);
           }
-          mma_commit(empty0 + 8 * stage);
+          if (CL == 1) mma_commit(empty0 + 8 * stage); else mma_commit_mc(empty0 + 8 * stage, CMASK);
           if (kb == kblocks - 1) mma_commit(tfull0 + 8 * as);
         }
         __syncwarp();
@@ -205,9 +223,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int q = warp & 3;
     const int m = q * 32 + lane;                 // row of the tile = TMEM lane
     int as = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int tn = tile % P.n_tiles_n;
-      int tm = tile / P.n_tiles_n;
+      int tm = (tile / P.n_tiles_n) * CL + (int)crank;
       const int tw = tm % P.tiles_w; tm /= P.tiles_w;
       const int th = tm % P.tiles_h;
       const int tb = tm / P.tiles_h;
@@ -271,6 +289,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();          // no CTA exits while a peer may still multicast into it
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
@@ -412,7 +431,7 @@ struct TcConvPlan {
   ConvGeom g;
   int kind;
   const bf16* wmat;
-  int BN;
+  int BN, CL;
   std::vector<ConvLaunch> launches;     // fprop: 1; dgrad: 1 (stride 1) or 4 (stride 2)
   // wgrad
   WgradParams WP;
@@ -444,6 +463,12 @@ static int pick_bn(int Cout, long long M) {
   return 64;
 }
 
+static int pick_cl() {
+  static int cl = -1;
+  if (cl < 0) { const char* e = getenv("MAPNET_TC_CLUSTER"); cl = e ? atoi(e) : 2; if (cl != 1 && cl != 2 && cl != 4) cl = 2; }
+  return cl;
+}
+
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int posmod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
 
@@ -454,6 +479,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   MN_CHECK(g.KH == g.KW && (g.KH == 1 || g.KH == 3), "tc conv: kernel %dx%d unsupported", g.KH, g.KW);
   TcConvPlan* p = new TcConvPlan();
   p->g = g; p->kind = kind; p->wmat = wmat; p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false;
+  p->CL = pick_cl();
   const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
   if (kind == 0) {
     // ---------------- fprop ----------------
@@ -574,32 +600,37 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
         if (p->kind == 0) {
           for (int i = 0; i < L.n_maps; ++i)
             MN_TRY(encode_view(&L.mapA[i], in0, g.B, g.Hi, g.Wi, g.Ci, g.stride, L.pa[i], L.pb[i], L.P.TW, L.P.TH, L.P.TN));
-          MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Ci, g.Co, p->BN));
+          MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Ci, g.Co, p->BN / p->CL));
         } else {
           MN_TRY(encode_view(&L.mapA[0], in0, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, L.P.TW, L.P.TH, L.P.TN));
-          MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Co, g.Ci, p->BN));
+          MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Co, g.Ci, p->BN / p->CL));
         }
         for (int i = L.n_maps; i < 4; ++i) L.mapA[i] = L.mapA[0];
       }
       p->c_in0 = in0;
     }
     const size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024;
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*) = nullptr;
+#define PICK(BNv, CLv) if (p->BN == BNv && p->CL == CLv) kern = k_tc_conv<BNv, CLv>;
+    PICK(64, 1) PICK(128, 1) PICK(256, 1) PICK(64, 2) PICK(128, 2) PICK(256, 2) PICK(64, 4) PICK(128, 4) PICK(256, 4)
+#undef PICK
+    MN_CHECK(kern != nullptr, "tc conv: no kernel for BN=%d CL=%d", p->BN, p->CL);
     if (!p->smem_attr_set) {
-      if (p->BN == 64) MN_TRY(set_smem(k_tc_conv<64>, smem));
-      else if (p->BN == 128) MN_TRY(set_smem(k_tc_conv<128>, smem));
-      else MN_TRY(set_smem(k_tc_conv<256>, smem));
+      MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       p->smem_attr_set = true;
     }
     for (auto& L : p->launches) {
-      const int total = L.P.n_tiles_m * L.P.n_tiles_n;
-      const int grid = total < nsm ? total : nsm;
-      if (p->BN == 64)
-        k_tc_conv<64><<<grid, 192, smem, st>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out);
-      else if (p->BN == 128)
-        k_tc_conv<128><<<grid, 192, smem, st>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out);
-      else
-        k_tc_conv<256><<<grid, 192, smem, st>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out);
-      MN_LAUNCH_CHECK();
+      const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n;
+      const int max_clusters = (p->CL == 4) ? 32 : nsm / p->CL;
+      const int nclusters = groups < max_clusters ? groups : max_clusters;
+      cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(nclusters * p->CL); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = p->CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out));
+      ++g_launch_count;
     }
     return 0;
   }

@@ -134,8 +134,15 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_stem_im2col(const float* __restrict__ x, T* __restrict__ A, int B, int H, int W, int Ho, int Wo, int Kpad) {
   extern __shared__ float sx[];          // [3*7][W + 6]
+  __shared__ int lut[192];               // k -> offset of (c,kh,kw) inside sx (-1: zero padding of K)
   const int WP = W + 6;
   const int b = blockIdx.x / Ho, oh = blockIdx.x - b * Ho;
+  if (threadIdx.x < 192) {
+    const int k = threadIdx.x;
+    int off = -1;
+    if (k < 147) { const int t = k / 3, c = k - t * 3; const int kh = t / 7, kw = t - kh * 7; off = (c * 7 + kh) * WP + kw; }
+    lut[k] = off;
+  }
   for (int i = threadIdx.x; i < 21 * WP; i += blockDim.x) {
     const int r = i / WP, col = i - r * WP;
     const int c = r / 7, kh = r - c * 7;
@@ -152,14 +159,8 @@ k_stem_im2col(const float* __restrict__ x, T* __restrict__ A, int B, int H, int 
     Vec8<T> o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = k0 + j;
-      float v = 0.f;
-      if (k < 147) {
-        const int t = k / 3, c = k - t * 3;
-        const int kh = t / 7, kw = t - kh * 7;
-        v = sx[(c * 7 + kh) * WP + ow * 2 + kw];
-      }
-      o.v[j] = v;
+      const int off = lut[k0 + j];
+      o.v[j] = (off >= 0) ? sx[off + ow * 2] : 0.f;
     }
     o.store(Arow + (long long)i * 8);
   }

@@ -152,9 +152,9 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   for (auto& c : convs) wd.push_back(c.wd);
   MN_TRY(alloc((void**)&d_wdescs, wd.size() * sizeof(WeightDesc)));
   MN_CUDA(cudaMemcpy(d_wdescs, wd.data(), wd.size() * sizeof(WeightDesc), cudaMemcpyHostToDevice));
-  MN_TRY(alloc((void**)&bn_accum, 3 * 512 * sizeof(double) + 64));
-  MN_CUDA(cudaMemset(bn_accum, 0, 3 * 512 * sizeof(double) + 64));
-  bn_counter = (unsigned int*)(bn_accum + 3 * 512);
+  MN_TRY(alloc((void**)&bn_accum, 32 * 3 * 512 * sizeof(double) + 64));      // kReplicas x [3][512] (bn.cu)
+  MN_CUDA(cudaMemset(bn_accum, 0, 32 * 3 * 512 * sizeof(double) + 64));
+  bn_counter = (unsigned int*)(bn_accum + 32 * 3 * 512);
   long long small = 0;
   for (auto& b : bns) small += 7LL * b.C;
   MN_TRY(alloc((void**)&bn_small, (size_t)small * sizeof(float)));

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 # CPU result deviates from an fp64 run of the same graph by ~1.2e-3 (worst per-tensor norm,
 # measured with oracle fp64 on posenet_tiny); test_fp32_error_is_at_reference_noise_floor
 # checks the product against that fp64 arbiter, here the bound is 1e-2.
-TOL_FP32 = dict(loss=1e-4, pred=1e-4, grad=1e-2, grad_head=1.5e-1, post=1e-4, sgrad=1e-4)
+TOL_FP32 = dict(loss=1e-4, pred=1e-4, grad=1e-2, grad_head=1.5e-1, post=1e-4, sgrad=1e-3)
 # bf16 tensor-core path vs the fp32 reference at the BASELINE sizes: plain bf16 operands
 # (8-bit mantissa) and bf16-stored activations through 36 conv+BN layers cannot meet
 # 1e-4; an fp32-graph emulation of the same rounding points (oracle emulate="bf16")
