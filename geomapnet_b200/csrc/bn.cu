@@ -172,6 +172,46 @@ static int launch_sums(int mode, const T* a, const T* zmask, const T* y, const T
   return 0;
 }
 
+// finalize for statistics accumulated by the tcgen05 conv epilogue (conv_tc.cu): sum the
+// replicas, produce mean / invstd / scale / shift, update the running stats, reset the replicas
+__global__ void __launch_bounds__(512)
+k_bn_finalize_accum(long long M, int C, BnFin f, double* __restrict__ accum) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int r = 0; r < kReplicas; ++r) {
+    double* a = accum + (size_t)r * kAccStride;
+    s0 += a[c]; s1 += a[C + c];
+    a[c] = 0.0; a[C + c] = 0.0;
+  }
+  const double invM = 1.0 / (double)M;
+  const double m = s0 * invM;
+  double var = s1 * invM - m * m;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)m;
+  const float invstd = (float)(1.0 / sqrt(var + 1e-5));
+  const double unbiased = (M > 1) ? var * (double)M / (double)(M - 1) : var;
+  f.run_mean[c] = 0.9f * f.run_mean[c] + 0.1f * mean;
+  f.run_var[c] = 0.9f * f.run_var[c] + 0.1f * (float)unbiased;
+  f.mean[c] = mean;
+  f.invstd[c] = invstd;
+  const float sc = f.gamma[c] * invstd;
+  f.scale[c] = sc;
+  f.shift[c] = f.beta[c] - mean * sc;
+}
+
+int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float* beta, float* run_mean,
+                             float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift,
+                             double* accum, cudaStream_t st) {
+  MN_CHECK(C <= 512, "bn_finalize_accum: C=%d", C);
+  BnFin f; memset(&f, 0, sizeof(f));
+  f.gamma = gamma; f.beta = beta; f.run_mean = run_mean; f.run_var = run_var; f.mean = mean_out;
+  f.invstd = invstd_out; f.scale = scale; f.shift = shift; f.training = 1;
+  k_bn_finalize_accum<<<1, 512, 0, st>>>(M, C, f, accum);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
 // eval-mode scale/shift from the running statistics (no batch statistics)
 __global__ void k_bn_eval_scale(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ run_mean, const float* __restrict__ run_var,

@@ -103,6 +103,24 @@ struct WgradParams {
   WgradChunk chunks[72];
 };
 
+// BN statistic accumulators: kStatReplicas x [2][<=512] doubles (same buffer bn.cu uses)
+static const int kStatReplicas = 32;
+static const int kStatStride = 3 * 512;
+
+// x[32] per lane -> lane L ends with sum over the warp's lanes of x[L] (in x[0])
+__device__ __forceinline__ void warp_transpose_reduce(float (&x)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const float send = up ? x[k] : x[k + s];
+      const float keep = up ? x[k + s] : x[k];
+      x[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
 static constexpr int conv_stages(int BN) { return BN <= 128 ? 5 : 4; }
 
 // ---------------------------------------------------------------------------------
@@ -116,7 +134,7 @@ __global__ void __launch_bounds__(192, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
           const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
-          bf16* __restrict__ out) {
+          bf16* __restrict__ out, double* __restrict__ stats) {
   constexpr int STAGES = conv_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;        // 128 pixels x 64 ch bf16
   constexpr uint32_t B_BYTES = BN * 128;
@@ -223,8 +241,25 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int q = warp & 3;
     const int m = q * 32 + lane;                 // row of the tile = TMEM lane
     int as = 0; uint32_t aphase = 0;
+    // fused BatchNorm statistics (fprop only): lane L keeps the running column sums of column
+    // cc*32+L over all rows this warp has stored, flushed with fp64 atomics per N tile
+    float st_sum[BN / 32], st_sq[BN / 32];
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
+    int st_tn = -1;
+    auto flush_stats = [&](int tn_flush) {
+      double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        const int c = tn_flush * BN + i * 32 + lane;
+        atomicAdd(acc + c, (double)st_sum[i]);
+        atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
+        st_sum[i] = 0.f; st_sq[i] = 0.f;
+      }
+    };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int tn = tile % P.n_tiles_n;
+      if (stats != nullptr && tn != st_tn) { if (st_tn >= 0) flush_stats(st_tn); st_tn = tn; }
       int tm = (tile / P.n_tiles_n) * CL + (int)crank;
       const int tw = tm % P.tiles_w; tm /= P.tiles_w;
       const int th = tm % P.tiles_h;
@@ -282,9 +317,24 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             op[j] = o;
           }
         }
+        if (stats != nullptr) {
+          // statistics of the values AS STORED (bf16-rounded); rows outside the tensor count as 0
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            x[i] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
+          float y2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y2[i] = x[i] * x[i];
+          warp_transpose_reduce(x, lane);
+          warp_transpose_reduce(y2, lane);
+          st_sum[cc] += x[0];
+          st_sq[cc] += y2[0];
+        }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
   }
   // ---- teardown ----
   tc_fence_before();
@@ -590,7 +640,8 @@ static int encode_view(CUtensorMap* m, const bf16* base, int N, int Hd, int Wd, 
   return encode_act_map(m, vb, C, Wq > 0 ? Wq : 1, Hq > 0 ? Hq : 1, N, (long long)C * 4, rowb * 2, imgb, bw, bh, bn);
 }
 
-int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st) {
+int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st,
+                double* stats) {
   MN_CHECK(p != nullptr, "tc_conv_run: null plan");
   const ConvGeom& g = p->g;
   int nsm = 148;
@@ -610,7 +661,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       p->c_in0 = in0;
     }
     const size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024;
-    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*) = nullptr;
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*, double*) = nullptr;
 #define PICK(BNv, CLv) if (p->BN == BNv && p->CL == CLv) kern = k_tc_conv<BNv, CLv>;
     PICK(64, 1) PICK(128, 1) PICK(256, 1) PICK(64, 2) PICK(128, 2) PICK(256, 2) PICK(64, 4) PICK(128, 4) PICK(256, 4)
 #undef PICK
@@ -629,7 +680,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = p->CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out));
+      MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out, stats));
       ++g_launch_count;
     }
     return 0;

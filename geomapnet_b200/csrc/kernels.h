@@ -50,7 +50,13 @@ struct TcConvPlan;   // opaque: tile shapes, tap tables and cached TMA tensor ma
 int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wmat);
 void tc_plan_destroy(TcConvPlan* p);
 // fprop: in0 = x, out = y (bf16);  dgrad: in0 = dy, out = dx (bf16);  wgrad: in0 = x, in1 = dy, out = fp32 dW (accumulated)
-int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st);
+// stats != nullptr (fprop, no residual): per-channel sum / sum of squares of the stored output are
+// accumulated into the replica accumulators for the fused BatchNorm statistics
+int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st,
+                double* stats = nullptr);
+int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float* beta, float* run_mean,
+                             float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift,
+                             double* accum, cudaStream_t st);
 
 // ---- layout.cu -----------------------------------------------------------------
 struct WeightDesc {   // one conv's weight in the flat parameter buffer and in the packed matrices

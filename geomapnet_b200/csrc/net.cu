@@ -218,12 +218,13 @@ static double conv_flops(const ConvGeom& g, int B, bool stem) {
 }
 
 template <typename T>
-int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st) {
+int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st, bool with_stats) {
   ConvGeom g = convs[ci].g; g.B = B;
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
-  if (precision == PREC_BF16_TC) r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st);
+  if (precision == PREC_BF16_TC)
+    r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st, with_stats ? bn_accum : nullptr);
   else r = launch_conv_simt_fprop<T>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
   prof_end(st, e0, 0, conv_flops(g, B, ci == 0));
   return r;
@@ -275,6 +276,9 @@ template <typename T>
 int Net::bn_forward(int bi, const T* y, long long M, const float* params, float* bufs, int training,
                     cudaStream_t st) {
   BNL& b = bns[bi];
+  if (precision == PREC_BF16_TC && training)   // sums were accumulated by the conv epilogue
+    return launch_bn_finalize_accum(M, b.C, params + b.g_off, params + b.b_off, bufs + b.rm_off, bufs + b.rv_off,
+                                    b.mean, b.invstd, b.scale, b.shift, bn_accum, st);
   return launch_bn_stats<T>(y, M, b.C, params + b.g_off, params + b.b_off, bufs + b.rm_off, bufs + b.rv_off,
                             b.mean, b.invstd, b.scale, b.shift, training, bn_accum, bn_counter, st);
 }
@@ -292,7 +296,7 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
                                       precision == PREC_BF16_SIMT, st));
   // stem: im2col -> GEMM -> BN -> ReLU -> maxpool
   MN_TRY(launch_stem_im2col<T>(x, (T*)A0, B, H, W, Hc, Wc, kStemK, st));
-  MN_TRY(conv_fprop<T>(0, (const T*)A0, nullptr, (T*)y0, B, st));
+  MN_TRY(conv_fprop<T>(0, (const T*)A0, nullptr, (T*)y0, B, st, training != 0));
   MN_TRY(bn_forward<T>(convs[0].bn, (const T*)y0, (long long)B * Hc * Wc, params, bufs, training, st));
   {
     BNL& b = bns[convs[0].bn];
@@ -303,14 +307,14 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
     const long long Mo = (long long)B * bl.Ho * bl.Wo;
     BNL& b1 = bns[convs[bl.conv1].bn];
     BNL& b2 = bns[convs[bl.conv2].bn];
-    MN_TRY(conv_fprop<T>(bl.conv1, zin, nullptr, (T*)bl.y1, B, st));
+    MN_TRY(conv_fprop<T>(bl.conv1, zin, nullptr, (T*)bl.y1, B, st, training != 0));
     MN_TRY(bn_forward<T>(convs[bl.conv1].bn, (const T*)bl.y1, Mo, params, bufs, training, st));
     MN_TRY(launch_bn_apply<T>((const T*)bl.y1, b1.scale, b1.shift, 0, nullptr, nullptr, nullptr, (T*)bl.h, Mo, bl.Cout, 1, st));
-    MN_TRY(conv_fprop<T>(bl.conv2, (const T*)bl.h, nullptr, (T*)bl.y2, B, st));
+    MN_TRY(conv_fprop<T>(bl.conv2, (const T*)bl.h, nullptr, (T*)bl.y2, B, st, training != 0));
     MN_TRY(bn_forward<T>(convs[bl.conv2].bn, (const T*)bl.y2, Mo, params, bufs, training, st));
     if (bl.convd >= 0) {
       BNL& bd = bns[convs[bl.convd].bn];
-      MN_TRY(conv_fprop<T>(bl.convd, zin, nullptr, (T*)bl.yd, B, st));
+      MN_TRY(conv_fprop<T>(bl.convd, zin, nullptr, (T*)bl.yd, B, st, training != 0));
       MN_TRY(bn_forward<T>(convs[bl.convd].bn, (const T*)bl.yd, Mo, params, bufs, training, st));
       MN_TRY(launch_bn_apply<T>((const T*)bl.y2, b2.scale, b2.shift, 2, (const T*)bl.yd, bd.scale, bd.shift, (T*)bl.out, Mo, bl.Cout, 1, st));
     } else {

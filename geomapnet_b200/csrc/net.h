@@ -92,7 +92,8 @@ struct Net {
                                       float* pred, cudaStream_t st);
   template <typename T> int backward_t(const float* dpred, const float* params, float* grads, int filter_nans,
                                        cudaStream_t st);
-  template <typename T> int conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st);
+  template <typename T> int conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st,
+                                       bool with_stats = false);
   template <typename T> int conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st);
   template <typename T> int conv_wgrad(int ci, const T* x, const T* dy, int B, cudaStream_t st);
   template <typename T> int bn_forward(int bi, const T* y, long long M, const float* params, float* bufs,
