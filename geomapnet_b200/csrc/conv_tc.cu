@@ -121,7 +121,8 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&x)[32], int lane) 
   }
 }
 
-static constexpr int conv_stages(int BN) { return BN <= 128 ? 5 : 4; }
+// as many stages as fit in 227 KB: the engines are bound by bytes in flight x L2 latency
+static constexpr int conv_stages(int BN) { return BN <= 64 ? 9 : (BN <= 128 ? 6 : 4); }
 
 // ---------------------------------------------------------------------------------
 // fprop / dgrad kernel
@@ -353,7 +354,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
            const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapX3,
            const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ WgradParams P,
            float* __restrict__ dw) {
-  constexpr int STAGES = (BN <= 128) ? 5 : 4;
+  constexpr int STAGES = conv_stages(BN);
   constexpr uint32_t CHUNK_BYTES = 64 * 128;     // 64 pixels x 64 ch bf16
   constexpr uint32_t A_BYTES = 2 * CHUNK_BYTES;
   constexpr uint32_t B_BYTES = (BN / 64) * CHUNK_BYTES;
@@ -694,7 +695,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     MN_TRY(encode_view(&p->mapDY, in1, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, P.TW, P.TH, P.TN));
     p->c_in0 = in0; p->c_in1 = in1;
   }
-  const int stages = (p->BN <= 128) ? 5 : 4;
+  const int stages = conv_stages(p->BN);
   const size_t smem = (size_t)stages * (2 * 8192 + (p->BN / 64) * 8192) + 1024;
   if (!p->smem_attr_set) {
     if (p->BN == 64) MN_TRY(set_smem(k_tc_wgrad<64>, smem));

@@ -7,6 +7,7 @@
 #include "net.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace mapnet {
 
@@ -129,6 +130,7 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_CHECK(precision >= 0 && precision <= 2, "create: bad precision %d", precision);
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0;
+  { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   build_table();
   if (max_B == 0) return 0;      // spec-only handle: parameter table, no device memory
   const size_t es = elt();
@@ -224,7 +226,7 @@ int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStre
   MN_TRY(prof_begin(st, &e0));
   int r;
   if (precision == PREC_BF16_TC)
-    r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st, with_stats ? bn_accum : nullptr);
+    r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st, (with_stats && fuse_stats) ? bn_accum : nullptr);
   else r = launch_conv_simt_fprop<T>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
   prof_end(st, e0, 0, conv_flops(g, B, ci == 0));
   return r;
@@ -276,7 +278,7 @@ template <typename T>
 int Net::bn_forward(int bi, const T* y, long long M, const float* params, float* bufs, int training,
                     cudaStream_t st) {
   BNL& b = bns[bi];
-  if (precision == PREC_BF16_TC && training)   // sums were accumulated by the conv epilogue
+  if (fuse_stats && training)   // sums were accumulated by the conv epilogue
     return launch_bn_finalize_accum(M, b.C, params + b.g_off, params + b.b_off, bufs + b.rm_off, bufs + b.rv_off,
                                     b.mean, b.invstd, b.scale, b.shift, bn_accum, st);
   return launch_bn_stats<T>(y, M, b.C, params + b.g_off, params + b.b_off, bufs + b.rm_off, bufs + b.rv_off,

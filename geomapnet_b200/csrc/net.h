@@ -71,6 +71,7 @@ struct Net {
   // optional per-conv-launch timing (bench.py roofline): CUDA events around every conv call
   struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
   int profile_on;
+  int fuse_stats;                // BN statistics accumulated in the tcgen05 conv epilogue (env MAPNET_TC_FUSE_STATS)
   std::vector<ProfRec> prof;
   int prof_begin(cudaStream_t st, cudaEvent_t* e0);
   void prof_end(cudaStream_t st, cudaEvent_t e0, int cls, double flops);
