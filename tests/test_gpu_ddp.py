@@ -1,0 +1,79 @@
+"""Multi-GPU data parallel on real devices (NCCL): every rank's post-allreduce gradient
+equals the sum of the per-rank gradients (then 1/world in FusedAdam), parameters stay
+identical across ranks after the step.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import weights
+    from helpers import make_product_model, make_product_criterion
+    from geomapnet_b200.common.optimizer import Optimizer
+    from geomapnet_b200.ddp import FlatDataParallel, shard_tuples
+    st = weights.make_state(7 + rank)          # different initial weights: broadcast must fix that
+    cfg = dict(kind="mapnet", N=4, T=3, H=64, W=64)
+    x, targ = weights.make_inputs(cfg, 7)
+    xs, ts = shard_tuples(x, rank, world).cuda(), shard_tuples(targ, rank, world).cuda()
+    model, net = make_product_model(st, "mapnet", "fp32")
+    crit = make_product_criterion("mapnet")
+    opt = Optimizer([{"params": model.parameters()}, {"params": list(crit.parameters())}], "adam", 1e-4, 5e-4)
+    model.train()
+    model(xs)                                   # materialise the flat buffers on the device
+    dp = FlatDataParallel(model, crit)
+    dp.broadcast_parameters()
+    flat, _ = net.flat_parameters()
+    ref0 = flat.clone(); dist.broadcast(ref0, src=0)
+    ok = torch.equal(flat, ref0)
+    loss = crit(model(xs), ts)
+    opt.learner.zero_grad()
+    loss.backward()
+    _, g = net.flat_parameters()
+    g_local = g.clone()
+    sax_local = crit.sax.grad.clone()
+    scale = dp.allreduce_grads()
+    gathered = [torch.zeros_like(g_local) for _ in range(world)]
+    dist.all_gather(gathered, g_local)
+    want = sum(gathered)
+    ok = ok and abs(scale - 1.0 / world) < 1e-12
+    ok = ok and float((g - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    sg = [torch.zeros_like(sax_local) for _ in range(world)]
+    dist.all_gather(sg, sax_local)
+    ok = ok and abs(float(crit.sax.grad) - float(sum(sg))) <= 1e-5 * abs(float(sum(sg))) + 1e-7
+    opt.learner.step(grad_scale=scale)
+    after = flat.clone(); dist.broadcast(after, src=0)
+    ok = ok and torch.equal(flat, after)        # replicas stay in lock-step
+    torch.cuda.synchronize()
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_flat_allreduce_nccl_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
