@@ -247,7 +247,7 @@ def run_b200(args, cfg, rank, local_rank, world):
     model.cuda(); crit.cuda(); model.train()
     dp = None
 
-    def step(x, targ):
+    def eager_step(x, targ):
         out = model(x)
         loss = crit(out, targ)
         opt.learner.zero_grad()
@@ -261,10 +261,20 @@ def run_b200(args, cfg, rank, local_rank, world):
     nb = max(2, min(4, args.steps))
     dev_batches = make_batches(cfg, nb, 1000 * (rank + 1), device=dev)
     # first step: builds the arena / flattens parameters
-    step(*dev_batches[0])
+    eager_step(*dev_batches[0])
     if world > 1:
         dp = FlatDataParallel(model, crit)
         dp.broadcast_parameters()
+    L = _lib.lib()
+    step = eager_step
+    graph_launches = None
+    if args.graph:
+        # the same modules, captured once as two CUDA graphs and replayed (geomapnet_b200/graph.py)
+        from geomapnet_b200.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(model, crit, opt, dev_batches[0][0], dev_batches[0][1], dp=dp,
+                                 max_grad_norm=cfg["clip"], warmup=2)
+        graph_launches = gstep.kernels_per_step
+        step = gstep
 
     def barrier():
         if world > 1:
@@ -278,7 +288,6 @@ def run_b200(args, cfg, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    L = _lib.lib()
     # ---------------- value: inputs resident in HBM ----------------
     for i in range(args.warmup):
         step(*dev_batches[i % nb])
@@ -297,6 +306,8 @@ def run_b200(args, cfg, rank, local_rank, world):
     barrier()
     t_wall1 = time.time()
     launches = (L.mapnet_launch_count() - lc0) // max(1, args.steps)
+    if args.graph:
+        launches = graph_launches       # kernels inside the replayed graphs (counted while capturing)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     value = world * frames(cfg) / (ms_step / 1000.0)
@@ -308,9 +319,12 @@ def run_b200(args, cfg, rank, local_rank, world):
 
     def e2e_step(i):
         xh, th = host_batches[i % nb]
-        xd.copy_(xh, non_blocking=True)        # common/train.py:341,347  (.cuda(async=True))
-        td.copy_(th, non_blocking=True)
-        loss = step(xd, td)
+        if args.graph:
+            loss = step(xh, th)                # H2D straight into the graph's static input buffers
+        else:
+            xd.copy_(xh, non_blocking=True)    # common/train.py:341,347  (.cuda(async=True))
+            td.copy_(th, non_blocking=True)
+            loss = step(xd, td)
         return loss.item()                      # common/train.py:361  D2H + sync every step
 
     for i in range(min(2, args.warmup)):
@@ -324,6 +338,22 @@ def run_b200(args, cfg, rank, local_rank, world):
     barrier()
     e2e_ms = max_over_ranks(f0.elapsed_time(f1)) / args.steps
     e2e_val = world * frames(cfg) / (e2e_ms / 1000.0)
+
+    # eager (no CUDA graph) step through the plain nn.Module calls, for transparency
+    eager_ms = None
+    if args.graph:
+        net._graph_rng = False
+        for i in range(3):
+            eager_step(*dev_batches[i % nb])
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for i in range(args.steps):
+            eager_step(*dev_batches[i % nb])
+        h1.record()
+        barrier()
+        eager_ms = max_over_ranks(h0.elapsed_time(h1)) / args.steps
+        step = eager_step
     h2d = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 4
     if sampler:
         sampler.stop()
@@ -331,14 +361,16 @@ def run_b200(args, cfg, rank, local_rank, world):
     # ---------------- roofline of the dominant kernel class (conv engines), rank 0 ----------------
     roof = None
     peaks = _peaks()
+    import ctypes
+    trunk = net._trunks[(dev.index, cfg["H"], cfg["W"])]
+    psteps = 3
+    if rank == 0:
+        _lib.check(L.mapnet_profile(trunk.h, 1), "mapnet_profile")
+    for i in range(psteps):                 # every rank steps (the allreduce is a collective)
+        step(*dev_batches[i % nb])
+    barrier()
     if rank == 0:
         B = frames(cfg)
-        trunk = net._trunks[(dev.index, cfg["H"], cfg["W"])]
-        import ctypes
-        _lib.check(L.mapnet_profile(trunk.h, 1), "mapnet_profile")
-        psteps = 3
-        for i in range(psteps):
-            step(*dev_batches[i % nb])
         ms3 = (ctypes.c_double * 3)(); fl3 = (ctypes.c_double * 3)(); n3 = (ctypes.c_int * 3)()
         _lib.check(L.mapnet_profile_read(trunk.h, ms3, fl3, n3), "mapnet_profile_read")
         _lib.check(L.mapnet_profile(trunk.h, 0), "mapnet_profile")
@@ -390,6 +422,7 @@ def run_b200(args, cfg, rank, local_rank, world):
                        "global_frames": world * frames(cfg), "image": "%dx%d" % (cfg["H"], cfg["W"]),
                        "criterion": cfg["kind"], "optimizer": "adam (fused, flat)", "droprate": args.droprate,
                        "parallelism": "dp%d" % world, "precision": args.precision,
+                       "cuda_graph": bool(args.graph), "eager_ms_per_step": eager_ms,
                        "l2": "per-step working set (activations + gradients, >3 GB) exceeds the 126 MB L2; "
                              "%d distinct input batches rotate" % nb},
             "e2e": {"value": e2e_val, "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
@@ -415,6 +448,8 @@ def main():
     ap.add_argument("--droprate", type=float, default=0.5)       # every reference .ini uses 0.5
     ap.add_argument("--ref-frames", type=int, default=32, help="frames per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="run the step eagerly instead of replaying it as CUDA graphs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

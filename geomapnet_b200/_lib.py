@@ -49,6 +49,9 @@ def lib():
     L.mapnet_sqnorm.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     L.mapnet_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                    c_float, c_float, c_int64, c_float, c_void_p, c_float, c_void_p]
+    L.mapnet_adam_step_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
+                                       c_float, c_float, c_void_p, c_float, c_void_p, c_float, c_void_p]
+    L.mapnet_adam_step_dev.restype = c_int
     L.mapnet_test_conv.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]
     L.mapnet_launch_count.restype = ctypes.c_ulonglong
@@ -67,7 +70,8 @@ def lib():
 EXPORTED = ["mapnet_last_error", "mapnet_abi_version", "mapnet_trunk_create", "mapnet_trunk_destroy",
             "mapnet_param_count", "mapnet_param_info", "mapnet_params_numel", "mapnet_bufs_numel",
             "mapnet_forward", "mapnet_backward", "mapnet_loss_fwd_bwd", "mapnet_sqnorm", "mapnet_adam_step",
-            "mapnet_test_conv", "mapnet_launch_count", "mapnet_profile", "mapnet_profile_read"]
+            "mapnet_test_conv", "mapnet_launch_count", "mapnet_profile", "mapnet_profile_read",
+            "mapnet_adam_step_dev"]
 
 
 def check(rc, what):

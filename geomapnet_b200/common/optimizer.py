@@ -64,6 +64,10 @@ class FusedAdam(optim.Optimizer):
                 if "step" not in st:
                     st["step"] = torch.tensor(0.0)
             r["m"], r["v"] = m, v
+            # device-side step counter (keeps captured CUDA graphs correct on replay)
+            st0 = self.state[r["params"][0]]
+            r["step_host"] = int(float(st0["step"]))
+            r["step_dev"] = torch.full((1,), r["step_host"], dtype=torch.int32, device=first.device)
             del old
         self._runs[gi] = (key, runs)
         return runs
@@ -109,18 +113,27 @@ class FusedAdam(optim.Optimizer):
                 b1, b2 = group["betas"]
                 for r in runs:
                     p0 = r["params"][0]
-                    stp = self.state[p0]["step"]
-                    step = int(float(stp)) + 1
-                    stp_new = torch.tensor(float(step))
+                    r["step_host"] += 1
+                    stp_new = torch.tensor(float(r["step_host"]))
                     for p in r["params"]:
                         self.state[p]["step"] = stp_new
-                    _lib.check(L.mapnet_adam_step(
+                    _lib.check(L.mapnet_adam_step_dev(
                         p0.data_ptr(), p0.grad.data_ptr(), r["m"].data_ptr(), r["v"].data_ptr(), r["n"],
                         float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                        float(group["weight_decay"]), step, float(grad_scale),
+                        float(group["weight_decay"]), r["step_dev"].data_ptr(), float(grad_scale),
                         ctypes.c_void_p(sq_ptr) if sq_ptr else None, float(max_grad_norm or 0.0), st),
-                        "mapnet_adam_step")
+                        "mapnet_adam_step_dev")
         return loss
+
+    def advance_host_step(self, n=1):
+        """After replaying a captured graph that contains step(): the device counters advanced,
+        bring the host mirrors (state['step'], used by state_dict()) in line."""
+        for key, runs in self._runs.values():
+            for r in runs:
+                r["step_host"] += n
+                stp_new = torch.tensor(float(r["step_host"]))
+                for p in r["params"]:
+                    self.state[p]["step"] = stp_new
 
 
 class Optimizer:

@@ -49,10 +49,19 @@ int launch_sqnorm(const float* g, long long n, float* partials, float* out_sq, c
 // torch.optim.Adam (amsgrad=False, maximize=False) single-tensor math:
 //   g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g
 //   p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void k_inc_i32(int* c) { *c += 1; }
+
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
        long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-       float gscale, const float* __restrict__ sqnorm, float max_norm) {
+       float gscale, const float* __restrict__ sqnorm, float max_norm, const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {
+    // CUDA-graph friendly: the step count lives on the device (bias corrections cannot be
+    // baked into a captured launch)
+    const double t = (double)(*step_dev);
+    bc1 = (float)(1.0 - pow((double)b1, t));
+    bc2_sqrt = sqrtf((float)(1.0 - pow((double)b2, t)));
+  }
   float coef = gscale;
   if (sqnorm != nullptr) {
     // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
@@ -94,12 +103,16 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                 float eps, float wd, float bc1, float bc2, float gscale, const float* sqnorm_or_null,
-                float max_norm, cudaStream_t st) {
+                float max_norm, int* step_dev, cudaStream_t st) {
   long long grid = ((n >> 2) + 255) / 256;
   if (grid > 148LL * 8) grid = 148LL * 8;
   if (grid < 1) grid = 1;
+  if (step_dev != nullptr) {
+    k_inc_i32<<<1, 1, 0, st>>>(step_dev);
+    MN_LAUNCH_CHECK();
+  }
   k_adam<<<(int)grid, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), gscale,
-                                    sqnorm_or_null, max_norm);
+                                    sqnorm_or_null, max_norm, step_dev);
   MN_LAUNCH_CHECK();
   return 0;
 }

@@ -91,7 +91,15 @@ int mapnet_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   return launch_adam(p, g, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
-                     sqnorm, max_norm, (cudaStream_t)stream);
+                     sqnorm, max_norm, nullptr, (cudaStream_t)stream);
+}
+
+int mapnet_adam_step_dev(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, int32_t* step_counter,
+                         float grad_scale, const float* sqnorm, float max_norm, void* stream) {
+  MN_CHECK(p && g && exp_avg && exp_avg_sq && step_counter && n > 0, "adam_step_dev: bad argument");
+  return launch_adam(p, g, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, grad_scale,
+                     sqnorm, max_norm, step_counter, (cudaStream_t)stream);
 }
 
 unsigned long long mapnet_launch_count(void) { return g_launch_count; }

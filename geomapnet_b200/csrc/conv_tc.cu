@@ -346,6 +346,212 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 }
 
 // ---------------------------------------------------------------------------------
+// 2-SM variant (tcgen05 cta_group::2): a CTA pair computes a 256 x BN tile.  Each CTA
+// stages its own 128 pixel rows of A and only HALF of the weight tile; one MMA issued by
+// the leader spans both CTAs' shared memory and TMEM.  Per-SM bytes per FLOP drop to what
+// a 256x256 GEMM tile needs -- the engines are bound by shared-memory ingest, not by math.
+// ---------------------------------------------------------------------------------
+static constexpr int conv2_stages(int BN) { return BN <= 128 ? 8 : 6; }
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+           const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
+           bf16* __restrict__ out, double* __restrict__ stats) {
+  constexpr int STAGES = conv2_stages(BN);
+  constexpr uint32_t A_BYTES = 128 * 128;
+  constexpr uint32_t BH_BYTES = (BN / 2) * 128;      // this CTA's half of the weight tile
+  constexpr uint32_t STAGE_BYTES = A_BYTES + BH_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = (crank == 0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
+    // full: leader's arrive.expect_tx + peer's remote arrive; empty / tfull: one multicast commit;
+    // tempty: 4 epilogue warps of each CTA arrive on the LEADER's barrier
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_base_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int n_groups = (P.n_tiles_m + 1) / 2;
+  const int total_tiles = n_groups * P.n_tiles_n;
+  const int first_tile = blockIdx.x / 2;
+  const int tile_step = gridDim.x / 2;
+  const int kblocks = P.num_taps * P.cblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int tn = tile % P.n_tiles_n;
+        int tm = (tile / P.n_tiles_n) * 2 + (int)crank;
+        const int tw = tm % P.tiles_w; tm /= P.tiles_w;
+        const int th = tm % P.tiles_h;
+        const int tb = tm / P.tiles_h;
+        const int jw0 = tw * P.TW, jh0 = th * P.TH, n0 = tb * P.TN;
+        for (int t = 0; t < P.num_taps; ++t) {
+          const TapDesc tap = P.taps[t];
+          const CUtensorMap* mA = (tap.map == 0) ? &mapA0 : (tap.map == 1) ? &mapA1 : (tap.map == 2) ? &mapA2 : &mapA3;
+          for (int cb = 0; cb < P.cblocks; ++cb) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            const uint32_t lfull = mapa(full0 + 8 * stage, 0);      // the LEADER's full barrier
+            if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
+            else mbar_arrive_cluster(lfull);
+            tma_load_4d_2sm(sa, mA, lfull, cb * 64, jw0 + tap.dw, jh0 + tap.dh, n0);
+            tma_load_2d_2sm(sa + A_BYTES, &mapB, lfull, tap.kidx * P.Cs + cb * 64, tn * BN + (int)crank * (BN / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t IDESC = make_idesc_bf16(256, BN, 0, 0);
+      constexpr uint64_t DESC_BASE = make_smem_desc_base(16, 1024);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              mma_bf16_2sm(d_tmem, smem_desc(DESC_BASE, sa + k * 32), smem_desc(DESC_BASE, sb + k * 32), IDESC,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit_2sm(empty0 + 8 * stage, 3);
+            if (kb == kblocks - 1) mma_commit_2sm(tfull0 + 8 * as, 3);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs; own TMEM half) =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int as = 0; uint32_t aphase = 0;
+    float st_sum[BN / 32], st_sq[BN / 32];
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
+    int st_tn = -1;
+    auto flush_stats = [&](int tn_flush) {
+      double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        const int c = tn_flush * BN + i * 32 + lane;
+        atomicAdd(acc + c, (double)st_sum[i]);
+        atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
+        st_sum[i] = 0.f; st_sq[i] = 0.f;
+      }
+    };
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int tn = tile % P.n_tiles_n;
+      if (stats != nullptr && tn != st_tn) { if (st_tn >= 0) flush_stats(st_tn); st_tn = tn; }
+      int tm = (tile / P.n_tiles_n) * 2 + (int)crank;
+      const int tw = tm % P.tiles_w; tm /= P.tiles_w;
+      const int th = tm % P.tiles_h;
+      const int tb = tm / P.tiles_h;
+      const int lw = m % P.TW;
+      const int lh = (m / P.TW) % P.TH;
+      const int ln = m / (P.TW * P.TH);
+      const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
+      const bool valid = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
+      const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
+      const long long obase = pix * P.Cout + tn * BN;
+      mbar_wait(tfull0 + 8 * as, aphase);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
+        tmem_ld_wait();
+        if (cc == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa(tempty0 + 8 * as, 0));
+        }
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(residual + obase + cc * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 r = rp[j];
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 t = __bfloat1622float2(h[i]);
+                f[j * 8 + 2 * i] += t.x; f[j * 8 + 2 * i + 1] += t.y;
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(out + obase + cc * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[j * 8 + 2 * i], f[j * 8 + 2 * i + 1]);
+            op[j] = o;
+          }
+        }
+        if (stats != nullptr) {
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            x[i] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
+          float y2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y2[i] = x[i] * x[i];
+          warp_transpose_reduce(x, lane);
+          warp_transpose_reduce(y2, lane);
+          st_sum[cc] += x[0];
+          st_sq[cc] += y2[0];
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------
 // wgrad kernel: one CTA per (M-tile of 2 X chunks, N-tile of BN couts, K split)
 // ---------------------------------------------------------------------------------
 template <int BN>
@@ -483,6 +689,7 @@ struct TcConvPlan {
   int kind;
   const bf16* wmat;
   int BN, CL;
+  bool two_cta;                         // cta_group::2 kernel (256 x BN pair tiles)
   std::vector<ConvLaunch> launches;     // fprop: 1; dgrad: 1 (stride 1) or 4 (stride 2)
   // wgrad
   WgradParams WP;
@@ -520,6 +727,12 @@ static int pick_cl() {
   return cl;
 }
 
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MAPNET_TC_2CTA"); v = e ? (atoi(e) != 0) : 0; }
+  return v != 0;
+}
+
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int posmod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
 
@@ -531,10 +744,12 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   TcConvPlan* p = new TcConvPlan();
   p->g = g; p->kind = kind; p->wmat = wmat; p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false;
   p->CL = pick_cl();
+  p->two_cta = false;
   const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
   if (kind == 0) {
     // ---------------- fprop ----------------
     p->BN = pick_bn(g.Co, g.M_out());
+    if (use_2cta() && g.Co % 128 == 0) { p->two_cta = true; p->BN = (g.Co % 256 == 0) ? 256 : 128; p->CL = 2; }
     ConvLaunch L; memset(&L, 0, sizeof(L));
     ConvParams& P = L.P;
     P.Nimg = g.B; P.Hs = g.Ho; P.Ws = g.Wo;
@@ -562,6 +777,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   } else if (kind == 1) {
     // ---------------- dgrad: gather over dY [B,Ho,Wo,Co], output dX [B,Hi,Wi,Ci] ----------------
     p->BN = pick_bn(g.Ci, g.M_in());
+    if (use_2cta() && g.Ci % 128 == 0) { p->two_cta = true; p->BN = (g.Ci % 256 == 0) ? 256 : 128; p->CL = 2; }
     for (int a = 0; a < s; ++a)
       for (int b = 0; b < s; ++b) {
         ConvLaunch L; memset(&L, 0, sizeof(L));
@@ -661,9 +877,13 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       }
       p->c_in0 = in0;
     }
-    const size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024;
+    size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024;
     void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*, double*) = nullptr;
-#define PICK(BNv, CLv) if (p->BN == BNv && p->CL == CLv) kern = k_tc_conv<BNv, CLv>;
+    if (p->two_cta) {
+      smem = (size_t)conv2_stages(p->BN) * (128 * 128 + (p->BN / 2) * 128) + 1024;
+      kern = (p->BN == 256) ? k_tc_conv2<256> : k_tc_conv2<128>;
+    }
+#define PICK(BNv, CLv) if (!p->two_cta && p->BN == BNv && p->CL == CLv) kern = k_tc_conv<BNv, CLv>;
     PICK(64, 1) PICK(128, 1) PICK(256, 1) PICK(64, 2) PICK(128, 2) PICK(256, 2) PICK(64, 4) PICK(128, 4) PICK(256, 4)
 #undef PICK
     MN_CHECK(kern != nullptr, "tc conv: no kernel for BN=%d CL=%d", p->BN, p->CL);

@@ -179,8 +179,12 @@ int launch_dpred_filter(const float* in, float* out, int n, int filter, cudaStre
 }
 
 // counter-based dropout mask: mask = (u >= p) / (1-p), u from splitmix64(seed, offset+i)
+__global__ void k_inc_u64(unsigned long long* c) { *c += 1ULL; }
+
 __global__ void k_dropout_mask(float* __restrict__ mask, long long n, float p, unsigned long long seed,
-                               unsigned long long offset) {
+                               unsigned long long offset, const unsigned long long* __restrict__ ctr,
+                               unsigned long long ctr_stride) {
+  if (ctr != nullptr) offset = (*ctr) * ctr_stride;      // device-side step counter (graph replay)
   const float keep_scale = 1.0f / (1.0f - p);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -193,10 +197,14 @@ __global__ void k_dropout_mask(float* __restrict__ mask, long long n, float p, u
   }
 }
 int launch_dropout_mask(float* mask, long long n, float p, unsigned long long seed, unsigned long long offset,
-                        cudaStream_t st) {
+                        unsigned long long* ctr_dev, unsigned long long ctr_stride, cudaStream_t st) {
   long long grid = (n + 255) / 256; if (grid > 592) grid = 592;
-  k_dropout_mask<<<(int)grid, 256, 0, st>>>(mask, n, p, seed, offset);
+  k_dropout_mask<<<(int)grid, 256, 0, st>>>(mask, n, p, seed, offset, ctr_dev, ctr_stride);
   MN_LAUNCH_CHECK();
+  if (ctr_dev != nullptr) {
+    k_inc_u64<<<1, 1, 0, st>>>(ctr_dev);
+    MN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

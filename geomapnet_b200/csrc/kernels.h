@@ -84,7 +84,7 @@ int launch_small_gemm(int epi, const float* A, long long sam, long long sak, con
 int launch_colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
 int launch_dpred_filter(const float* in, float* out, int n, int filter, cudaStream_t st);
 int launch_dropout_mask(float* mask, long long n, float p, unsigned long long seed, unsigned long long offset,
-                        cudaStream_t st);
+                        unsigned long long* ctr_dev, unsigned long long ctr_stride, cudaStream_t st);
 int launch_head_dh(const float* dpred, const float* wx, const float* wq, const float* mask, const float* fcpre,
                    float* dh, int B, int F, cudaStream_t st);
 
@@ -96,6 +96,6 @@ int launch_loss(int mode, const float* pred, const float* targ, int N, int Tp, i
 int launch_sqnorm(const float* g, long long n, float* partials, float* out_sq, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                 float eps, float wd, float bc1, float bc2, float gscale, const float* sqnorm_or_null,
-                float max_norm, cudaStream_t st);
+                float max_norm, int* step_dev, cudaStream_t st);
 
 }  // namespace mapnet

@@ -174,6 +174,8 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_TRY(alloc((void**)&dpredf, (size_t)Bm * 6 * 4));
   MN_TRY(alloc((void**)&sq_partials, 1024 * 4));
   MN_TRY(alloc((void**)&sq_out, 16));
+  MN_TRY(alloc((void**)&drop_ctr, 16));
+  MN_CUDA(cudaMemset(drop_ctr, 0, 16));
   return 0;
 }
 
@@ -328,7 +330,10 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
   MN_TRY(launch_gap<T>(zin, feat, B, Hf * Wf, 512, st));
   const float* mk = nullptr;
   if (droprate > 0.f) {
-    MN_TRY(launch_dropout_mask(mask, (long long)B * feat_dim, droprate, seed, step * (unsigned long long)max_B * feat_dim, st));
+    const unsigned long long stride = (unsigned long long)max_B * feat_dim;
+    const bool dev_ctr = (step == ~0ULL);
+    MN_TRY(launch_dropout_mask(mask, (long long)B * feat_dim, droprate, seed, dev_ctr ? 0ULL : step * stride,
+                               dev_ctr ? drop_ctr : nullptr, stride, st));
     mk = mask;
   }
   // hdrop = relu(feat @ Wfc^T + b) * mask ; fcpre kept for the ReLU gate

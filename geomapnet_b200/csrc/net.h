@@ -60,6 +60,7 @@ struct Net {
   float *feat, *fcpre, *hdrop, *mask, *dh, *dfeat, *dpredf;
   float* bn_small;               // backing store of the BN small arrays
   float *sq_partials, *sq_out;
+  unsigned long long* drop_ctr;  // device-side dropout step counter (graph capture)
 
   // tensor-core plans (precision == PREC_BF16_TC), rebuilt when B changes
   std::vector<TcConvPlan*> tc_fprop, tc_dgrad, tc_wgrad;

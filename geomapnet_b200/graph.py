@@ -1,0 +1,80 @@
+"""CUDA-graph capture of the training step (common/train.py:339-361).
+
+The step is ~290 short kernel launches; replaying it as two CUDA graphs removes the
+host launch cost and most of the inter-kernel gaps (Blackwell guideline 9).  Graph 1 =
+forward + criterion + zero_grad + backward, graph 2 = [clip +] Adam; the gradient
+allreduce of data-parallel runs sits between them, outside capture.
+
+    step = GraphedTrainStep(model, criterion, optimizer, x_example, targ_example)
+    loss = step(x, targ)            # x, targ: CUDA tensors (copied into static buffers)
+
+Everything captured is the same product code that runs eagerly (the reference-facing
+modules and the C ABI underneath); counters that change per step (Adam bias
+correction, dropout offset) live in device memory so replays stay correct.
+"""
+import torch
+
+__all__ = ["GraphedTrainStep"]
+
+
+class GraphedTrainStep(object):
+    def __init__(self, model, criterion, optimizer, x_example, targ_example, dp=None, max_grad_norm=0.0,
+                 warmup=3):
+        self.model, self.criterion, self.dp = model, criterion, dp
+        self.learner = optimizer.learner if hasattr(optimizer, "learner") else optimizer
+        self.max_grad_norm = float(max_grad_norm or 0.0)
+        self.posenet = model.mapnet if hasattr(model, "mapnet") else model
+        self.posenet._graph_rng = True
+        dev = x_example.device
+        self.x = torch.empty_like(x_example)
+        self.t = torch.empty_like(targ_example)
+        self.x.copy_(x_example); self.t.copy_(targ_example)
+        self.scale = 1.0 / dp.world if dp is not None else 1.0
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):       # builds arenas, tensor maps, optimizer plans
+                self._fwd_bwd()
+                if dp is not None:
+                    dp.allreduce_grads()
+                self._opt()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        lc = _lib.lib().mapnet_launch_count()
+        self.g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g1):
+            self.loss = self._fwd_bwd()
+        self.g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g2):
+            self._opt()
+        self.kernels_per_step = int(_lib.lib().mapnet_launch_count() - lc)   # library kernels in the two graphs
+        # the capture passes ran the host-side counters once each without executing kernels
+        self._fix_host_counters()
+
+    def _fwd_bwd(self):
+        out = self.model(self.x)
+        loss = self.criterion(out, self.t)
+        self.learner.zero_grad()
+        loss.backward()
+        return loss.detach()
+
+    def _opt(self):
+        self.learner.step(grad_scale=self.scale, max_grad_norm=self.max_grad_norm)
+
+    def _fix_host_counters(self):
+        # capture executed Python bookkeeping (host step mirrors) but launched nothing
+        if hasattr(self.learner, "advance_host_step"):
+            self.learner.advance_host_step(-1)
+
+    def __call__(self, x, targ):
+        self.x.copy_(x, non_blocking=True)
+        self.t.copy_(targ, non_blocking=True)
+        self.g1.replay()
+        if self.dp is not None:
+            self.dp.allreduce_grads()
+        self.g2.replay()
+        if hasattr(self.learner, "advance_host_step"):
+            self.learner.advance_host_step(1)
+        return self.loss

@@ -123,6 +123,7 @@ class PoseNet(nn.Module):
         self._step = 0
         self._seed = int(seed) if seed is not None else int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
         self._last_shape = None
+        self._graph_rng = False      # True: dropout counter lives on the device (CUDA-graph capture)
 
     # ------------------------------------------------------------------ tree
     def _build_tree(self):
@@ -244,7 +245,8 @@ class PoseNet(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().mapnet_forward(
                 trunk.h, xd.data_ptr(), self._flat.data_ptr(), self._bufs.data_ptr(), B, training,
-                float(self.droprate), self._seed, self._step, pred.data_ptr(), _lib.stream_ptr()),
+                float(self.droprate), self._seed, 0xFFFFFFFFFFFFFFFF if self._graph_rng else self._step,
+                pred.data_ptr(), _lib.stream_ptr()),
                 "mapnet_forward")
         if training:
             self._nbt += 1

@@ -65,7 +65,8 @@ int64_t mapnet_bufs_numel(mapnet_trunk_t* h);   /* floats in bufs_flat          
 
 /* ---- forward: x [B,3,H,W] -> pred [B,6].  training!=0: BN batch statistics + running-
  * stat update in bufs_flat; activations are kept for mapnet_backward.  droprate>0
- * applies dropout with a counter-based mask from (seed, step). */
+ * applies dropout with a counter-based mask from (seed, step); step == UINT64_MAX uses and
+ * advances a device-side counter owned by the handle (CUDA-graph capturable). */
 int mapnet_forward(mapnet_trunk_t* h, const float* x, const float* params_flat, float* bufs_flat, int B,
                    int training, float droprate, uint64_t seed, uint64_t step, float* pred, void* stream);
 
@@ -88,6 +89,13 @@ int mapnet_sqnorm(const float* g, int64_t n, float* scratch1024, float* out_sq, 
 int mapnet_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                      float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                      const float* sqnorm, float max_norm, void* stream);
+
+/* CUDA-graph capturable variant: the step count lives in device memory (*step_counter is
+ * incremented, then used for the bias corrections), so a captured launch stays correct
+ * on every replay. */
+int mapnet_adam_step_dev(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, int32_t* step_counter,
+                         float grad_scale, const float* sqnorm, float max_norm, void* stream);
 
 /* ---- measurement support (bench.py): number of kernels this library has launched so
  * far in this process, and per-class conv timing with CUDA events on the launching

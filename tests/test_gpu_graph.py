@@ -1,0 +1,55 @@
+"""CUDA-graph replay of the training step gives the same parameters as the eager step."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_graphed_step_matches_eager():
+    from oracle import weights
+    from helpers import make_product_model, make_product_criterion
+    from geomapnet_b200.common.optimizer import Optimizer
+    from geomapnet_b200.graph import GraphedTrainStep
+    st = weights.make_state(7)
+    cfg = dict(kind="mapnet", N=2, T=3, H=64, W=64)
+    batches = [weights.make_inputs(cfg, 20 + i) for i in range(4)]
+    finals = []
+    for use_graph in (False, True):
+        model, net = make_product_model(st, "mapnet", "fp32")
+        crit = make_product_criterion("mapnet")
+        opt = Optimizer([{"params": model.parameters()}, {"params": list(crit.parameters())}], "adam", 1e-3, 5e-4)
+        model.train()
+        losses = []
+        if use_graph:
+            # warm-up steps inside GraphedTrainStep must not change the weights of this comparison:
+            # construct it on a scratch copy of the first batch, then restore the state
+            x0, t0 = batches[0]
+            g = GraphedTrainStep(model, crit, opt, x0.cuda(), t0.cuda(), max_grad_norm=5.0, warmup=1)
+            net.load_state_dict({k: v.clone() for k, v in st.items()})
+            for p_ in crit.parameters():
+                p_.data.copy_(torch.tensor([0.0 if n_ in ("sax", "srx") else -3.0 for n_ in ["x"]][0]))
+            crit.sax.data.fill_(0.0); crit.saq.data.fill_(-3.0); crit.srx.data.fill_(0.0); crit.srq.data.fill_(-3.0)
+            # reset optimizer moments and step counters
+            for grp, runs in opt.learner._runs.values():
+                for r in runs:
+                    r["m"].zero_(); r["v"].zero_(); r["step_dev"].zero_(); r["step_host"] = 0
+            for x, t in batches:
+                losses.append(float(g(x.cuda(), t.cuda())))
+        else:
+            for x, t in batches:
+                out = model(x.cuda()); loss = crit(out, t.cuda())
+                opt.learner.zero_grad(); loss.backward(); opt.learner.step(max_grad_norm=5.0)
+                losses.append(float(loss))
+        torch.cuda.synchronize()
+        finals.append((losses, {k: v.detach().cpu().clone() for k, v in net.state_dict().items()},
+                       [float(p) for p in crit.parameters()]))
+    (la, sa, ca), (lb, sb, cb) = finals
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 1e-4 * abs(a), (la, lb)
+    for k in sa:
+        if sa[k].dtype.is_floating_point:
+            assert float((sa[k] - sb[k]).abs().max()) <= 1e-3 * float(sa[k].abs().max()) + 1e-6, k
+        else:
+            assert torch.equal(sa[k], sb[k]), k
+    for a, b in zip(ca, cb):
+        assert abs(a - b) < 1e-4
