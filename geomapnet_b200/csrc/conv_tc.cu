@@ -451,6 +451,10 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (kblocks == 0 && lane == 0) {       // no filter tap reaches this output class: D = 0
+          mbar_arrive(tfull0 + 8 * as);
+          mbar_arrive_cluster(mapa(tfull0 + 8 * as, 1));
+        }
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -492,8 +496,13 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 #pragma unroll
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
-        tmem_ld_wait();
+        if (kblocks > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
         if (cc == BN / 32 - 1) {
           tc_fence_before();
           __syncwarp();

@@ -30,6 +30,7 @@ class GraphedTrainStep(object):
         self.t = torch.empty_like(targ_example)
         self.x.copy_(x_example); self.t.copy_(targ_example)
         self.scale = 1.0 / dp.world if dp is not None else 1.0
+        snap = self._snapshot()
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(cur)
@@ -52,6 +53,46 @@ class GraphedTrainStep(object):
         self.kernels_per_step = int(_lib.lib().mapnet_launch_count() - lc)   # library kernels in the two graphs
         # the capture passes ran the host-side counters once each without executing kernels
         self._fix_host_counters()
+        # construction must not train: put parameters, BN buffers, criterion scalars and the
+        # optimizer moments / step counters back to what they were before the warm-up steps
+        self._restore(snap)
+
+    def _snapshot(self):
+        snap = {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()},
+                "crit": {k: v.detach().clone() for k, v in self.criterion.state_dict().items()},
+                "opt": {}}
+        for p, st in self.learner.state.items():
+            snap["opt"][p] = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+        return snap
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            sd = self.model.state_dict()
+            for k, v in snap["model"].items():
+                sd[k].copy_(v)
+            cd = self.criterion.state_dict()
+            for k, v in snap["crit"].items():
+                cd[k].copy_(v)
+            for p, st in self.learner.state.items():
+                old = snap["opt"].get(p)
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if k in st:
+                        if old is not None and k in old:
+                            st[k].copy_(old[k])
+                        else:
+                            st[k].zero_()
+            if hasattr(self.learner, "_runs"):
+                for key, runs in self.learner._runs.values():
+                    for r in runs:
+                        p0 = r["params"][0]
+                        old = snap["opt"].get(p0)
+                        step0 = int(float(old["step"])) if (old is not None and "step" in old) else 0
+                        r["step_host"] = step0
+                        r["step_dev"].fill_(step0)
+                        t = torch.tensor(float(step0))
+                        for p in r["params"]:
+                            self.learner.state[p]["step"] = t
+        torch.cuda.synchronize()
 
     def _fwd_bwd(self):
         out = self.model(self.x)

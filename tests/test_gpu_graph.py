@@ -21,20 +21,15 @@ def test_graphed_step_matches_eager():
         model.train()
         losses = []
         if use_graph:
-            # warm-up steps inside GraphedTrainStep must not change the weights of this comparison:
-            # construct it on a scratch copy of the first batch, then restore the state
             x0, t0 = batches[0]
-            g = GraphedTrainStep(model, crit, opt, x0.cuda(), t0.cuda(), max_grad_norm=5.0, warmup=1)
-            net.load_state_dict({k: v.clone() for k, v in st.items()})
-            for p_ in crit.parameters():
-                p_.data.copy_(torch.tensor([0.0 if n_ in ("sax", "srx") else -3.0 for n_ in ["x"]][0]))
-            crit.sax.data.fill_(0.0); crit.saq.data.fill_(-3.0); crit.srx.data.fill_(0.0); crit.srq.data.fill_(-3.0)
-            # reset optimizer moments and step counters
-            for grp, runs in opt.learner._runs.values():
-                for r in runs:
-                    r["m"].zero_(); r["v"].zero_(); r["step_dev"].zero_(); r["step_host"] = 0
+            # construction warms up and captures but must leave the training state untouched
+            g = GraphedTrainStep(model, crit, opt, x0.cuda(), t0.cuda(), max_grad_norm=5.0, warmup=2)
+            for k, v in net.state_dict().items():
+                assert torch.equal(v.cpu(), st[k]), "GraphedTrainStep construction changed %s" % k
             for x, t in batches:
                 losses.append(float(g(x.cuda(), t.cuda())))
+            sd = opt.learner.state_dict()
+            assert float(sd["state"][0]["step"]) == len(batches)
         else:
             for x, t in batches:
                 out = model(x.cuda()); loss = crit(out, t.cuda())

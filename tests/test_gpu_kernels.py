@@ -42,7 +42,8 @@ def _run_conv(precision, kind, x_nhwc, other_nhwc, wmat, out, geom):
 
 CASES = [(2, 16, 16, 64, 64, 3, 1), (2, 16, 16, 64, 128, 3, 2), (2, 16, 16, 64, 128, 1, 2),
          (3, 9, 11, 128, 128, 3, 1), (2, 18, 22, 64, 128, 3, 2), (1, 8, 8, 256, 512, 3, 2),
-         (2, 8, 8, 512, 512, 3, 1), (1, 32, 32, 192, 64, 1, 1), (4, 64, 64, 64, 64, 3, 1)]
+         (2, 8, 8, 512, 512, 3, 1), (1, 32, 32, 192, 64, 1, 1), (4, 64, 64, 64, 64, 3, 1),
+         (2, 16, 16, 128, 256, 1, 2), (3, 17, 13, 128, 256, 3, 2)]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16_simt", "bf16"])
