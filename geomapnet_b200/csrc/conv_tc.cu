@@ -732,14 +732,45 @@ static int pick_bn(int Cout, long long M) {
 
 static int pick_cl() {
   static int cl = -1;
-  if (cl < 0) { const char* e = getenv("MAPNET_TC_CLUSTER"); cl = e ? atoi(e) : 2; if (cl != 1 && cl != 2 && cl != 4) cl = 2; }
+  if (cl < 0) { const char* e = getenv("MAPNET_TC_CLUSTER"); cl = e ? atoi(e) : 1; if (cl != 1 && cl != 2 && cl != 4) cl = 1; }
   return cl;
 }
 
-static bool use_2cta() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MAPNET_TC_2CTA"); v = e ? (atoi(e) != 0) : 0; }
-  return v != 0;
+static int use_2cta() {     // -1 auto (cost model), 0 never, 1 whenever the channel count allows
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("MAPNET_TC_2CTA"); v = e ? atoi(e) : -1; }
+  return v;
+}
+
+// Tile configuration by a small cost model.  Measured on B200 (profiles/): a CTA ingests
+// ~43 B/cycle through TMA regardless of pipeline depth or multicast, so a k-block costs
+// max(bytes staged per CTA / 43, MMA cycles); candidates differ in bytes per k-block and
+// in how many CTAs (or CTA pairs) they can keep busy.
+struct TileChoice { int BN; bool two_cta; };
+static TileChoice choose_tiles(int Cout, long long Mpix, int kblocks) {
+  const int forced_bn = []() { const char* e = getenv("MAPNET_TC_BN"); return e ? atoi(e) : 0; }();
+  const int mode2 = use_2cta();
+  const long long mtiles = (Mpix + 127) / 128;
+  TileChoice best = {64, false};
+  double best_t = 1e30;
+  for (int two = 0; two <= 1; ++two) {
+    if (two && mode2 == 0) continue;
+    if (!two && mode2 == 1 && Cout % 128 == 0) continue;
+    for (int bn = 64; bn <= 256; bn *= 2) {
+      if (Cout % bn != 0) continue;
+      if (two && bn < 128) continue;
+      if (forced_bn && bn != forced_bn && Cout % forced_bn == 0 && !(two && forced_bn < 128)) continue;
+      const long long items = (two ? (mtiles + 1) / 2 : mtiles) * (Cout / bn);
+      const int slots = two ? 74 : 148;
+      const long long waves = (items + slots - 1) / slots;
+      const double bytes = 16384.0 + (two ? bn * 64.0 : bn * 128.0);
+      const double mma = 2.0 * bn;                       // 4 x (128 x bn x 16) at 8192 FLOP/cycle/SM
+      const double per_kb = (bytes / 43.0 > mma) ? bytes / 43.0 : mma;
+      const double t = (double)waves * (kblocks * per_kb + 1500.0 + 8.0 * bn);   // + prologue / exposed epilogue
+      if (t < best_t) { best_t = t; best.BN = bn; best.two_cta = (two != 0); }
+    }
+  }
+  return best;
 }
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -757,8 +788,11 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
   if (kind == 0) {
     // ---------------- fprop ----------------
-    p->BN = pick_bn(g.Co, g.M_out());
-    if (use_2cta() && g.Co % 128 == 0) { p->two_cta = true; p->BN = (g.Co % 256 == 0) ? 256 : 128; p->CL = 2; }
+    {
+      const TileChoice tc = choose_tiles(g.Co, g.M_out(), KK * (g.Ci / 64));
+      p->BN = tc.BN; p->two_cta = tc.two_cta;
+      if (tc.two_cta) p->CL = 2;
+    }
     ConvLaunch L; memset(&L, 0, sizeof(L));
     ConvParams& P = L.P;
     P.Nimg = g.B; P.Hs = g.Ho; P.Ws = g.Wo;
@@ -785,8 +819,12 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     p->launches.push_back(L);
   } else if (kind == 1) {
     // ---------------- dgrad: gather over dY [B,Ho,Wo,Co], output dX [B,Hi,Wi,Ci] ----------------
-    p->BN = pick_bn(g.Ci, g.M_in());
-    if (use_2cta() && g.Ci % 128 == 0) { p->two_cta = true; p->BN = (g.Ci % 256 == 0) ? 256 : 128; p->CL = 2; }
+    {
+      // stride-2 dgrad runs as s*s parity classes of ~M/4 pixels and <= KK taps each; size the tiles for one class
+      const TileChoice tc = choose_tiles(g.Ci, g.M_in() / (s * s), ((KK + s * s - 1) / (s * s)) * (g.Co / 64));
+      p->BN = tc.BN; p->two_cta = tc.two_cta;
+      if (tc.two_cta) p->CL = 2;
+    }
     for (int a = 0; a < s; ++a)
       for (int b = 0; b < s; ++b) {
         ConvLaunch L; memset(&L, 0, sizeof(L));
