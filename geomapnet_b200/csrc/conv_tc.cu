@@ -561,6 +561,238 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------
+// Halo-resident 3x3 / stride-1 engine (fprop and dgrad of 29 of the 36 convs).
+//
+// Measured (profiles/): the 4-D im2col TMA box costs ~4 cycles per 128-byte pixel row, and the
+// per-tap engine above re-stages the same pixels 9 times -- the tensor pipe idles 2/3 of the
+// time.  Here the activation tile is staged ONCE per 64-channel block together with its halo:
+// pixels are addressed in a padded linear space q = h*P + (w+1), P = W+2 (TMA's out-of-bounds
+// zero fill provides the halo columns / rows), an M tile is 128 consecutive q, and the nine
+// filter taps are nine SHIFTED shared-memory matrix descriptors into the same patch
+// (row m of tap (kh,kw) = patch row m + (kh-1)*P + (kw-1)).  Rows that fall on halo columns
+// compute garbage that is never stored (W/(W+2) of the MMA rows are useful).
+// For Cin=64 the whole weight matrix (72 KB) stays resident in shared memory.
+// ---------------------------------------------------------------------------------
+struct HaloParams {
+  int Nimg, H, W, P, tiles_per_img, n_tiles_m, n_tiles_n;
+  int cblocks, Cs, Cout;
+  int R, patch_bytes;           // patch box rows, bytes per patch buffer (multiple of 1024)
+  int NP, NB;                   // patch / weight ring depths
+  int b_stationary;             // weights loaded once per CTA (9*cblocks tiles)
+  int dq[9], kidx[9];           // per tap: shift in padded-linear space, K index of its weight slice
+  int use_base_offset;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ HaloParams P, const bf16* __restrict__ residual, bf16* __restrict__ out,
+               double* __restrict__ stats) {
+  constexpr uint32_t B_BYTES = BN * 128;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr int MAXNP = 4, MAXNB = 12;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + P.NP * P.patch_bytes;
+  __shared__ __align__(8) uint64_t bars[2 * MAXNP + 2 * MAXNB + 5];
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t pfull0 = smem_u32(&bars[0]), pempty0 = smem_u32(&bars[MAXNP]);
+  const uint32_t bfull0 = smem_u32(&bars[2 * MAXNP]), bempty0 = smem_u32(&bars[2 * MAXNP + MAXNB]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * MAXNP + 2 * MAXNB]), tempty0 = tfull0 + 16;
+  const uint32_t bstat = tfull0 + 32;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA); prefetch_tmap(&mapB);
+    for (int i = 0; i < MAXNP; ++i) { mbar_init(pfull0 + 8 * i, 1); mbar_init(pempty0 + 8 * i, 1); }
+    for (int i = 0; i < MAXNB; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    mbar_init(bstat, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int total_tiles = P.n_tiles_m * P.n_tiles_n;
+  const int ntaps_total = 9 * P.cblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (P.b_stationary) {
+        // (stationary weights imply a single N tile)
+        mbar_expect_tx(bstat, (uint32_t)ntaps_total * B_BYTES);
+        for (int cb = 0; cb < P.cblocks; ++cb)
+          for (int t = 0; t < 9; ++t)
+            tma_load_2d(b_base + (cb * 9 + t) * B_BYTES, &mapB, bstat, P.kidx[t] * P.Cs + cb * 64, 0);
+      }
+      int ps = 0; uint32_t pphase = 0;
+      int bs = 0; uint32_t bphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tn = tile % P.n_tiles_n;
+        const int tm = tile / P.n_tiles_n;
+        const int n = tm / P.tiles_per_img, t = tm - n * P.tiles_per_img;
+        const int q0 = t * 128;
+        const int a = q0 - P.P - 1;
+        const int h_lo = (a >= 0) ? a / P.P : -((-a + P.P - 1) / P.P);
+        for (int cb = 0; cb < P.cblocks; ++cb) {
+          mbar_wait(pempty0 + 8 * ps, pphase ^ 1);
+          mbar_expect_tx(pfull0 + 8 * ps, (uint32_t)(P.R * P.P * 128));
+          tma_load_4d(smem_base + ps * P.patch_bytes, &mapA, pfull0 + 8 * ps, cb * 64, -1, h_lo, n);
+          if (++ps == P.NP) { ps = 0; pphase ^= 1; }
+          if (!P.b_stationary) {
+            for (int tp = 0; tp < 9; ++tp) {
+              mbar_wait(bempty0 + 8 * bs, bphase ^ 1);
+              mbar_expect_tx(bfull0 + 8 * bs, B_BYTES);
+              tma_load_2d(b_base + bs * B_BYTES, &mapB, bfull0 + 8 * bs, P.kidx[tp] * P.Cs + cb * 64, tn * BN);
+              if (++bs == P.NB) { bs = 0; bphase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint64_t DESC_BASE = make_smem_desc_base(16, 1024);
+    int ps = 0; uint32_t pphase = 0;
+    int bs = 0; uint32_t bphase = 0;
+    int as = 0; uint32_t aphase = 0;
+    if (P.b_stationary) mbar_wait(bstat, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tm = tile / P.n_tiles_n;
+      const int t = tm % P.tiles_per_img;
+      const int q0 = t * 128;
+      const int a = q0 - P.P - 1;
+      const int h_lo = (a >= 0) ? a / P.P : -((-a + P.P - 1) / P.P);
+      const int row0 = q0 - h_lo * P.P;          // patch row of tile row 0 for the centre tap
+      mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int cb = 0; cb < P.cblocks; ++cb) {
+        mbar_wait(pfull0 + 8 * ps, pphase);
+        tc_fence_after();
+        const uint32_t patch = smem_base + ps * P.patch_bytes;
+        for (int tp = 0; tp < 9; ++tp) {
+          uint32_t sb;
+          if (P.b_stationary) sb = b_base + (cb * 9 + tp) * B_BYTES;
+          else { mbar_wait(bfull0 + 8 * bs, bphase); tc_fence_after(); sb = b_base + bs * B_BYTES; }
+          if (lane == 0) {
+            const uint32_t sa = patch + (uint32_t)(row0 + P.dq[tp]) * 128u;
+            uint64_t abase = DESC_BASE;
+            if (P.use_base_offset) abase |= (uint64_t)((sa >> 7) & 7u) << 49;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_bf16(d_tmem, smem_desc(abase, sa + k * 32), smem_desc(DESC_BASE, sb + k * 32), IDESC,
+                       (cb > 0 || tp > 0 || k > 0) ? 1u : 0u);
+            if (!P.b_stationary) mma_commit(bempty0 + 8 * bs);
+            if (tp == 8) mma_commit(pempty0 + 8 * ps);
+            if (tp == 8 && cb == P.cblocks - 1) mma_commit(tfull0 + 8 * as);
+          }
+          __syncwarp();
+          if (!P.b_stationary) { if (++bs == P.NB) { bs = 0; bphase ^= 1; } }
+        }
+        if (++ps == P.NP) { ps = 0; pphase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int as = 0; uint32_t aphase = 0;
+    float st_sum[BN / 32], st_sq[BN / 32];
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
+    int st_tn = -1;
+    auto flush_stats = [&](int tn_flush) {
+      double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        const int c = tn_flush * BN + i * 32 + lane;
+        atomicAdd(acc + c, (double)st_sum[i]);
+        atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
+        st_sum[i] = 0.f; st_sq[i] = 0.f;
+      }
+    };
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tn = tile % P.n_tiles_n;
+      if (stats != nullptr && tn != st_tn) { if (st_tn >= 0) flush_stats(st_tn); st_tn = tn; }
+      const int tm = tile / P.n_tiles_n;
+      const int n = tm / P.tiles_per_img, t = tm - n * P.tiles_per_img;
+      const int qq = t * 128 + m;
+      const int h = qq / P.P, j = qq - h * P.P;
+      const bool valid = (j >= 1) && (j <= P.W) && (h < P.H);
+      const long long pix = ((long long)n * P.H + h) * P.W + (j - 1);
+      const long long obase = pix * P.Cout + tn * BN;
+      mbar_wait(tfull0 + 8 * as, aphase);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
+        tmem_ld_wait();
+        if (cc == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+        }
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(residual + obase + cc * 32);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint4 r = rp[jj];
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 tt = __bfloat1622float2(hh[i]);
+                f[jj * 8 + 2 * i] += tt.x; f[jj * 8 + 2 * i + 1] += tt.y;
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(out + obase + cc * 32);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            uint4 o;
+            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(f[jj * 8 + 2 * i], f[jj * 8 + 2 * i + 1]);
+            op[jj] = o;
+          }
+        }
+        if (stats != nullptr) {
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            x[i] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
+          float y2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y2[i] = x[i] * x[i];
+          warp_transpose_reduce(x, lane);
+          warp_transpose_reduce(y2, lane);
+          st_sum[cc] += x[0];
+          st_sq[cc] += y2[0];
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------
 // wgrad kernel: one CTA per (M-tile of 2 X chunks, N-tile of BN couts, K split)
 // ---------------------------------------------------------------------------------
 template <int BN>
@@ -683,6 +915,141 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------
+// 2-SM wgrad: a CTA pair accumulates a 256 x BN block of dW (4 X chunks x BN couts); each CTA
+// stages 2 X chunks and half of the dY columns.
+// ---------------------------------------------------------------------------------
+static constexpr int wgrad2_stages(int BN) { return BN <= 128 ? 8 : 6; }
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
+            const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapX3,
+            const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ WgradParams P,
+            float* __restrict__ dw) {
+  constexpr int STAGES = wgrad2_stages(BN);
+  constexpr uint32_t CHUNK_BYTES = 64 * 128;
+  constexpr uint32_t A_BYTES = 2 * CHUNK_BYTES;
+  constexpr int NBCH = BN / 128;                       // dY chunks (64 couts) staged by this CTA
+  constexpr uint32_t B_BYTES = NBCH * CHUNK_BYTES;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (BN <= 128) ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull = smem_u32(&bars[2 * STAGES]);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = (crank == 0);
+
+  int u = blockIdx.x / 2;
+  const int split = u % P.splits; u /= P.splits;
+  const int nt = u % P.n_ntiles;
+  const int mt = u / P.n_ntiles;
+  const int c_lo = mt * 4 + 2 * (int)crank;            // this CTA's first X chunk
+  const int n_valid = (c_lo + 1 < P.n_chunks) ? 2 : ((c_lo < P.n_chunks) ? 1 : 0);
+  const int t_beg = split * P.tiles_per_split;
+  int t_end = t_beg + P.tiles_per_split; if (t_end > P.n_pix_tiles) t_end = P.n_pix_tiles;
+  const int ksteps = (t_end > t_beg) ? (t_end - t_beg) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapX0); prefetch_tmap(&mapDY);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, 1); }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_base_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const int ca = (n_valid >= 1) ? c_lo : 0;
+      const int cb2 = (n_valid == 2) ? c_lo + 1 : ca;
+      const WgradChunk ch0 = P.chunks[ca];
+      const WgradChunk ch1 = P.chunks[cb2];
+      const CUtensorMap* m0 = (ch0.map == 0) ? &mapX0 : (ch0.map == 1) ? &mapX1 : (ch0.map == 2) ? &mapX2 : &mapX3;
+      const CUtensorMap* m1 = (ch1.map == 0) ? &mapX0 : (ch1.map == 1) ? &mapX1 : (ch1.map == 2) ? &mapX2 : &mapX3;
+      for (int t = t_beg; t < t_end; ++t) {
+        int tt = t;
+        const int tw = tt % P.tiles_w; tt /= P.tiles_w;
+        const int th = tt % P.tiles_h;
+        const int tb = tt / P.tiles_h;
+        const int ow0 = tw * P.TW, oh0 = th * P.TH, n0 = tb * P.TN;
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        const uint32_t lfull = mapa(full0 + 8 * stage, 0);
+        if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
+        else mbar_arrive_cluster(lfull);
+        tma_load_4d_2sm(sa, m0, lfull, ch0.c0, ow0 + ch0.dw, oh0 + ch0.dh, n0);
+        tma_load_4d_2sm(sa + CHUNK_BYTES, m1, lfull, ch1.c0, ow0 + ch1.dw, oh0 + ch1.dh, n0);
+#pragma unroll
+        for (int j = 0; j < NBCH; ++j)
+          tma_load_4d_2sm(sa + A_BYTES + j * CHUNK_BYTES, &mapDY, lfull,
+                          nt * BN + (int)crank * (BN / 2) + j * 64, ow0, oh0, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint32_t IDESC = make_idesc_bf16(256, BN, 1, 1);
+      constexpr uint64_t DESC_BASE = make_smem_desc_base(CHUNK_BYTES, 1024);
+      int stage = 0; uint32_t phase = 0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_bf16_2sm(tmem_base, smem_desc(DESC_BASE, sa + k * 2048), smem_desc(DESC_BASE, sb + k * 2048), IDESC,
+                         (ks > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit_2sm(empty0 + 8 * stage, 3);
+          if (ks == ksteps - 1) mma_commit_2sm(tfull, 3);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (ksteps > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int j = m >> 6, ci_l = m & 63;
+    const bool valid = j < n_valid;
+    const WgradChunk ch = P.chunks[valid ? c_lo + j : 0];
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int co = nt * BN + cc * 32 + i;
+          if (co < P.Co)
+            atomicAdd(dw + ((long long)co * P.KK + ch.tap) * P.Ci + ch.c0 + ci_l, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------
 // host plans
 // ---------------------------------------------------------------------------------
 struct ConvLaunch {
@@ -699,6 +1066,10 @@ struct TcConvPlan {
   const bf16* wmat;
   int BN, CL;
   bool two_cta;                         // cta_group::2 kernel (256 x BN pair tiles)
+  bool halo;                            // halo-resident 3x3/s1 engine
+  HaloParams HP;
+  CUtensorMap hmapA, hmapB;
+  size_t halo_smem;
   std::vector<ConvLaunch> launches;     // fprop: 1; dgrad: 1 (stride 1) or 4 (stride 2)
   // wgrad
   WgradParams WP;
@@ -785,7 +1156,56 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   p->g = g; p->kind = kind; p->wmat = wmat; p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false;
   p->CL = pick_cl();
   p->two_cta = false;
+  p->halo = false;
   const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
+  {
+    static int halo_mode = -1, halo_bo = -1;
+    if (halo_mode < 0) { const char* e = getenv("MAPNET_TC_HALO"); halo_mode = e ? atoi(e) : 1; }
+    if (halo_bo < 0) { const char* e = getenv("MAPNET_TC_HALO_BASEOFF"); halo_bo = e ? atoi(e) : 1; }
+    if (halo_mode && (kind == 0 || kind == 1) && g.KH == 3 && s == 1 && g.Wi + 2 <= 256) {
+      // fprop: gather x [B,H,W,Ci] -> y [.,Co]; dgrad: gather dy [B,H,W,Co] -> dx [.,Ci] (same spatial dims)
+      const int Cs = (kind == 0) ? g.Ci : g.Co, Cn = (kind == 0) ? g.Co : g.Ci;
+      HaloParams& H = p->HP; memset(&H, 0, sizeof(H));
+      H.Nimg = g.B; H.H = g.Hi; H.W = g.Wi; H.P = g.Wi + 2;
+      H.tiles_per_img = cdiv((long long)g.Hi * H.P, 128);
+      H.n_tiles_m = g.B * H.tiles_per_img;
+      H.cblocks = Cs / 64; H.Cs = Cs; H.Cout = Cn;
+      // rows needed: from floor((q0-P-1)/P) to floor((q0+127+P+1)/P) for any q0 = 128 t
+      H.R = (128 + 2 * H.P + 2 + H.P - 1) / H.P + 1;
+      if (H.R > g.Hi + 3) H.R = g.Hi + 3;
+      if (H.R <= 256) {
+        H.patch_bytes = (int)(((long long)H.R * H.P * 128 + 1023) / 1024 * 1024);
+        // N tile: the patch cost is per tile, so prefer wide N; keep >= ~120 tiles when possible
+        int bn = (Cn % 256 == 0 && H.n_tiles_m >= 120) ? 256 : ((Cn % 128 == 0) ? 128 : 64);
+        { const char* e = getenv("MAPNET_TC_BN"); int f = e ? atoi(e) : 0; if ((f == 64 || f == 128 || f == 256) && Cn % f == 0) bn = f; }
+        const long long wbytes = 9LL * H.cblocks * bn * 128;
+        const long long budget = 226LL * 1024 - 2048;
+        H.b_stationary = (Cn == bn && wbytes + 2LL * H.patch_bytes <= budget) ? 1 : 0;
+        long long left = budget - (H.b_stationary ? wbytes : 0);
+        if (H.b_stationary) { H.NP = (int)(left / H.patch_bytes); H.NB = 0; }
+        else {
+          H.NP = 2; left -= 2LL * H.patch_bytes;
+          H.NB = (int)(left / (bn * 128));
+          while (H.NB > 12) { if (H.NP < 4 && left - H.patch_bytes >= 6LL * bn * 128) { H.NP++; left -= H.patch_bytes; H.NB = (int)(left / (bn * 128)); } else H.NB = 12; }
+        }
+        if (H.NP > 4) H.NP = 4;
+        if (H.NP >= 2 && (H.b_stationary || H.NB >= 3)) {
+          p->halo = true; p->BN = bn;
+          H.n_tiles_n = Cn / bn;
+          H.use_base_offset = halo_bo;
+          for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+              const int t = kh * 3 + kw;
+              H.kidx[t] = t;
+              H.dq[t] = (kind == 0) ? ((kh - 1) * H.P + (kw - 1)) : ((1 - kh) * H.P + (1 - kw));
+            }
+          p->halo_smem = (size_t)H.NP * H.patch_bytes + (size_t)(H.b_stationary ? 9 * H.cblocks : H.NB) * bn * 128 + 1024;
+          *out = p;
+          return 0;
+        }
+      }
+    }
+  }
   if (kind == 0) {
     // ---------------- fprop ----------------
     {
@@ -858,7 +1278,10 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     P.n_pix_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
     P.n_chunks = KK * (g.Ci / 64);
     MN_CHECK(P.n_chunks <= 72, "tc wgrad: too many chunks");
-    P.n_mtiles = cdiv(P.n_chunks, 2); P.n_ntiles = g.Co / p->BN;
+    p->two_cta = (use_2cta() != 0) && (g.Co % 128 == 0);
+    if (p->two_cta) p->BN = (g.Co % 256 == 0) ? 256 : 128;
+    P.BN = p->BN;
+    P.n_mtiles = cdiv(P.n_chunks, p->two_cta ? 4 : 2); P.n_ntiles = g.Co / p->BN;
     p->w_nmaps = 0;
     int ci = 0;
     for (int kh = 0; kh < g.KH; ++kh)
@@ -877,7 +1300,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
           }
         }
     const int units = P.n_mtiles * P.n_ntiles;
-    int splits = (148 * 2) / units; if (splits < 1) splits = 1;
+    int splits = (p->two_cta ? 74 * 2 : 148 * 2) / units; if (splits < 1) splits = 1;
     if (splits > P.n_pix_tiles) splits = P.n_pix_tiles;
     P.tiles_per_split = cdiv(P.n_pix_tiles, splits);
     P.splits = cdiv(P.n_pix_tiles, P.tiles_per_split);
@@ -909,6 +1332,27 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
   MN_CHECK(p != nullptr, "tc_conv_run: null plan");
   const ConvGeom& g = p->g;
   int nsm = 148;
+  if (p->halo) {
+    HaloParams& H = p->HP;
+    if (p->c_in0 != in0) {
+      const int Cs = H.Cs;
+      MN_TRY(encode_act_map(&p->hmapA, in0, Cs, H.W, H.H, H.Nimg, (long long)Cs * 2, (long long)H.W * Cs * 2,
+                            (long long)H.H * H.W * Cs * 2, H.P, H.R, 1));
+      MN_TRY(encode_w_map(&p->hmapB, p->wmat, 9 * Cs, H.Cout, p->BN));
+      p->c_in0 = in0;
+    }
+    void (*kern)(CUtensorMap, CUtensorMap, HaloParams, const bf16*, bf16*, double*) =
+        (p->BN == 64) ? k_tc_conv_halo<64> : (p->BN == 128 ? k_tc_conv_halo<128> : k_tc_conv_halo<256>);
+    if (!p->smem_attr_set) {
+      MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->halo_smem));
+      p->smem_attr_set = true;
+    }
+    const int total = H.n_tiles_m * H.n_tiles_n;
+    const int grid = total < nsm ? total : nsm;
+    kern<<<grid, 192, p->halo_smem, st>>>(p->hmapA, p->hmapB, H, residual, (bf16*)out, stats);
+    MN_LAUNCH_CHECK();
+    return 0;
+  }
   if (p->kind == 0 || p->kind == 1) {
     if (p->c_in0 != in0) {
       for (auto& L : p->launches) {
@@ -961,6 +1405,25 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     for (int i = p->w_nmaps; i < 4; ++i) p->mapX[i] = p->mapX[0];
     MN_TRY(encode_view(&p->mapDY, in1, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, P.TW, P.TH, P.TN));
     p->c_in0 = in0; p->c_in1 = in1;
+  }
+  if (p->two_cta) {
+    const size_t smem2 = (size_t)wgrad2_stages(p->BN) * (2 * 8192 + (p->BN / 128) * 8192) + 1024;
+    void (*k2)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, WgradParams, float*) =
+        (p->BN == 256) ? k_tc_wgrad2<256> : k_tc_wgrad2<128>;
+    if (!p->smem_attr_set) {
+      MN_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      p->smem_attr_set = true;
+    }
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(P.n_mtiles * P.n_ntiles * P.splits * 2); cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem2; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MN_CUDA(cudaLaunchKernelEx(&cfg, k2, p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out));
+    ++g_launch_count;
+    return 0;
   }
   const int stages = conv_stages(p->BN);
   const size_t smem = (size_t)stages * (2 * 8192 + (p->BN / 64) * 8192) + 1024;
