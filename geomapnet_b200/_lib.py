@@ -59,6 +59,9 @@ def lib():
     L.mapnet_profile.restype = c_int
     L.mapnet_profile_read.argtypes = [c_void_p, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]
     L.mapnet_profile_read.restype = c_int
+    L.mapnet_bench_conv.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int, POINTER(c_float)]
+    L.mapnet_bench_conv.restype = c_int
     for name in ("mapnet_trunk_create", "mapnet_trunk_destroy", "mapnet_param_count", "mapnet_param_info",
                  "mapnet_forward", "mapnet_backward", "mapnet_loss_fwd_bwd", "mapnet_sqnorm",
                  "mapnet_adam_step", "mapnet_test_conv"):
@@ -71,7 +74,7 @@ EXPORTED = ["mapnet_last_error", "mapnet_abi_version", "mapnet_trunk_create", "m
             "mapnet_param_count", "mapnet_param_info", "mapnet_params_numel", "mapnet_bufs_numel",
             "mapnet_forward", "mapnet_backward", "mapnet_loss_fwd_bwd", "mapnet_sqnorm", "mapnet_adam_step",
             "mapnet_test_conv", "mapnet_launch_count", "mapnet_profile", "mapnet_profile_read",
-            "mapnet_adam_step_dev"]
+            "mapnet_adam_step_dev", "mapnet_bench_conv"]
 
 
 def check(rc, what):

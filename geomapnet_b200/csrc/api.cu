@@ -141,4 +141,31 @@ int mapnet_test_conv(int precision, int kind, int B, int Hi, int Wi, int Ci, int
   return r;
 }
 
+// micro-benchmark of one tcgen05 conv launch configuration (plan built once, CUDA-event timing)
+int mapnet_bench_conv(int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride, const void* in0,
+                      const void* in1, const void* wmat, void* out, int iters, float* host_ms) {
+  MN_TRY(require_device());
+  ConvGeom g;
+  g.B = B; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Co = Co; g.KH = g.KW = k; g.stride = stride; g.pad = (k - 1) / 2;
+  g.Ho = (Hi + 2 * g.pad - k) / stride + 1; g.Wo = (Wi + 2 * g.pad - k) / stride + 1;
+  TcConvPlan* plan = nullptr;
+  MN_TRY(tc_plan_create(&plan, g, kind, (const bf16*)wmat));
+  cudaStream_t st = 0;
+  int r = 0;
+  for (int i = 0; i < 3 && r == 0; ++i) r = tc_conv_run(plan, (const bf16*)in0, (const bf16*)in1, nullptr, out, st);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters && r == 0; ++i) r = tc_conv_run(plan, (const bf16*)in0, (const bf16*)in1, nullptr, out, st);
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaEventSynchronize(e1);
+  if (r == 0 && e != cudaSuccess) { set_last_error("bench_conv: %s", cudaGetErrorString(e)); r = 1; }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (host_ms) *host_ms = ms / (iters > 0 ? iters : 1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  tc_plan_destroy(plan);
+  return r;
+}
+
 }  // extern "C"

@@ -89,6 +89,7 @@ struct ConvParams {
   TapDesc taps[9];
   // output tensor [Nimg, Hout, Wout, Cout]; pixel (n, jh*os+oa, jw*os+ob)
   int Hout, Wout, Cout, os, oa, ob;
+  int debug;     // micro-benchmark only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
 };
 
 struct WgradChunk { int dh, dw, map, c0, tap; };   // one 64-channel slice of X at one filter tap
@@ -193,6 +194,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           for (int cb = 0; cb < P.cblocks; ++cb) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            if (P.debug == 2) { mbar_arrive(full0 + 8 * stage); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
             mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
             tma_load_4d(sa, mA, full0 + 8 * stage, cb * 64, jw0 + tap.dw, jh0 + tap.dh, n0);
             if (CL == 1) {
@@ -223,13 +225,18 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         if (lane == 0) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
+          if (P.debug == 1) {
+            mbar_arrive(empty0 + 8 * stage);
+            if (kb == kblocks - 1) mbar_arrive(tfull0 + 8 * as);
+          } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            mma_bf16(d_tmem, smem_desc(DESC_BASE, sa + k * 32), smem_desc(DESC_BASE, sb + k * 32), IDESC,
-                     (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              mma_bf16(d_tmem, smem_desc(DESC_BASE, sa + k * 32), smem_desc(DESC_BASE, sb + k * 32), IDESC,
+                       (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            if (CL == 1) mma_commit(empty0 + 8 * stage); else mma_commit_mc(empty0 + 8 * stage, CMASK);
+            if (kb == kblocks - 1) mma_commit(tfull0 + 8 * as);
           }
-          if (CL == 1) mma_commit(empty0 + 8 * stage); else mma_commit_mc(empty0 + 8 * stage, CMASK);
-          if (kb == kblocks - 1) mma_commit(tfull0 + 8 * as);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -581,6 +588,7 @@ struct HaloParams {
   int b_stationary;             // weights loaded once per CTA (9*cblocks tiles)
   int dq[9], kidx[9];           // per tap: shift in padded-linear space, K index of its weight slice
   int use_base_offset;
+  int debug;                    // micro-benchmark only: 1 = skip MMAs, 2 = skip TMA loads
 };
 
 template <int BN>
@@ -641,14 +649,20 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int h_lo = (a >= 0) ? a / P.P : -((-a + P.P - 1) / P.P);
         for (int cb = 0; cb < P.cblocks; ++cb) {
           mbar_wait(pempty0 + 8 * ps, pphase ^ 1);
-          mbar_expect_tx(pfull0 + 8 * ps, (uint32_t)(P.R * P.P * 128));
-          tma_load_4d(smem_base + ps * P.patch_bytes, &mapA, pfull0 + 8 * ps, cb * 64, -1, h_lo, n);
+          if (P.debug == 2) mbar_arrive(pfull0 + 8 * ps);
+          else {
+            mbar_expect_tx(pfull0 + 8 * ps, (uint32_t)(P.R * P.P * 128));
+            tma_load_4d(smem_base + ps * P.patch_bytes, &mapA, pfull0 + 8 * ps, cb * 64, -1, h_lo, n);
+          }
           if (++ps == P.NP) { ps = 0; pphase ^= 1; }
           if (!P.b_stationary) {
             for (int tp = 0; tp < 9; ++tp) {
               mbar_wait(bempty0 + 8 * bs, bphase ^ 1);
-              mbar_expect_tx(bfull0 + 8 * bs, B_BYTES);
-              tma_load_2d(b_base + bs * B_BYTES, &mapB, bfull0 + 8 * bs, P.kidx[tp] * P.Cs + cb * 64, tn * BN);
+              if (P.debug == 2) mbar_arrive(bfull0 + 8 * bs);
+              else {
+                mbar_expect_tx(bfull0 + 8 * bs, B_BYTES);
+                tma_load_2d(b_base + bs * B_BYTES, &mapB, bfull0 + 8 * bs, P.kidx[tp] * P.Cs + cb * 64, tn * BN);
+              }
               if (++bs == P.NB) { bs = 0; bphase ^= 1; }
             }
           }
@@ -685,13 +699,19 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t sa = patch + (uint32_t)(row0 + P.dq[tp]) * 128u;
             uint64_t abase = DESC_BASE;
             if (P.use_base_offset) abase |= (uint64_t)((sa >> 7) & 7u) << 49;
+            if (P.debug == 1) {
+              if (!P.b_stationary) mbar_arrive(bempty0 + 8 * bs);
+              if (tp == 8) mbar_arrive(pempty0 + 8 * ps);
+              if (tp == 8 && cb == P.cblocks - 1) mbar_arrive(tfull0 + 8 * as);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_bf16(d_tmem, smem_desc(abase, sa + k * 32), smem_desc(DESC_BASE, sb + k * 32), IDESC,
-                       (cb > 0 || tp > 0 || k > 0) ? 1u : 0u);
-            if (!P.b_stationary) mma_commit(bempty0 + 8 * bs);
-            if (tp == 8) mma_commit(pempty0 + 8 * ps);
-            if (tp == 8 && cb == P.cblocks - 1) mma_commit(tfull0 + 8 * as);
+              for (int k = 0; k < 4; ++k)
+                mma_bf16(d_tmem, smem_desc(abase, sa + k * 32), smem_desc(DESC_BASE, sb + k * 32), IDESC,
+                         (cb > 0 || tp > 0 || k > 0) ? 1u : 0u);
+              if (!P.b_stationary) mma_commit(bempty0 + 8 * bs);
+              if (tp == 8) mma_commit(pempty0 + 8 * ps);
+              if (tp == 8 && cb == P.cblocks - 1) mma_commit(tfull0 + 8 * as);
+            }
           }
           __syncwarp();
           if (!P.b_stationary) { if (++bs == P.NB) { bs = 0; bphase ^= 1; } }
@@ -1161,7 +1181,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   {
     static int halo_mode = -1, halo_bo = -1;
     if (halo_mode < 0) { const char* e = getenv("MAPNET_TC_HALO"); halo_mode = e ? atoi(e) : 1; }
-    if (halo_bo < 0) { const char* e = getenv("MAPNET_TC_HALO_BASEOFF"); halo_bo = e ? atoi(e) : 1; }
+    if (halo_bo < 0) { const char* e = getenv("MAPNET_TC_HALO_BASEOFF"); halo_bo = e ? atoi(e) : 0; }   // measured: swizzle follows absolute smem address bits, base_offset must stay 0
     if (halo_mode && (kind == 0 || kind == 1) && g.KH == 3 && s == 1 && g.Wi + 2 <= 256) {
       // fprop: gather x [B,H,W,Ci] -> y [.,Co]; dgrad: gather dy [B,H,W,Co] -> dx [.,Ci] (same spatial dims)
       const int Cs = (kind == 0) ? g.Ci : g.Co, Cn = (kind == 0) ? g.Co : g.Ci;
@@ -1193,6 +1213,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
           p->halo = true; p->BN = bn;
           H.n_tiles_n = Cn / bn;
           H.use_base_offset = halo_bo;
+          { const char* e = getenv("MAPNET_TC_DEBUG"); H.debug = e ? atoi(e) : 0; }
           for (int kh = 0; kh < 3; ++kh)
             for (int kw = 0; kw < 3; ++kw) {
               const int t = kh * 3 + kw;
@@ -1215,6 +1236,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     }
     ConvLaunch L; memset(&L, 0, sizeof(L));
     ConvParams& P = L.P;
+    { const char* e = getenv("MAPNET_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
     P.Nimg = g.B; P.Hs = g.Ho; P.Ws = g.Wo;
     pick_box(g.Wo, g.Ho, 128, &P.TW, &P.TH, &P.TN);
     P.tiles_w = cdiv(g.Wo, P.TW); P.tiles_h = cdiv(g.Ho, P.TH); P.tiles_n = cdiv(g.B, P.TN);

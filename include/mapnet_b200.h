@@ -108,6 +108,10 @@ int mapnet_profile_read(mapnet_trunk_t* h, double* host_ms3, double* host_flops3
 int mapnet_test_conv(int precision, int kind /*0 fprop 1 dgrad 2 wgrad*/, int B, int Hi, int Wi, int Ci, int Co,
                      int k, int stride, const void* in0, const void* in1, const void* wmat, void* out, void* stream);
 
+/* micro-benchmark of one tensor-core conv configuration (tools/bench_conv.py): average ms per launch */
+int mapnet_bench_conv(int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride, const void* in0,
+                      const void* in1, const void* wmat, void* out, int iters, float* host_ms);
+
 #ifdef __cplusplus
 }
 #endif
