@@ -282,6 +282,13 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       const long long obase = pix * P.Cout + tn * BN;
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
+      if (P.debug == 3) {           // micro-benchmark: no epilogue work at all
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        continue;
+      }
 #pragma unroll
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t v[32];
@@ -298,7 +305,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         }
-        if (valid) {
+        if (valid && P.debug != 4) {
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
