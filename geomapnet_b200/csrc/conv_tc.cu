@@ -144,13 +144,13 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   constexpr uint32_t TMEM_COLS = 2 * BN;         // double-buffered accumulator: 128 / 256 / 512 columns
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = __shfl_sync(0xffffffffu, (smem_u32(smem_raw) + 1023u) & ~1023u, 0);
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_smem;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+  const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(&bars[0]), 0), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull0 = __shfl_sync(0xffffffffu, smem_u32(&bars[2 * STAGES]), 0), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
@@ -166,7 +166,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   __syncthreads();
   if (CL > 1) cluster_sync();          // peers' barriers are initialised before any multicast
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
 
   // work items: (group of CL consecutive M tiles, N tile); every CTA of a cluster walks the
   // same sequence, CTA r takes M tile group*CL + r (possibly past the end: a dummy tile whose
@@ -179,7 +179,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int tn = tile % P.n_tiles_n;
@@ -222,7 +222,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           if (P.debug == 1) {
@@ -241,7 +241,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (kblocks == 0 && lane == 0) mbar_arrive(tfull0 + 8 * as);
+      if (kblocks == 0 && elect_one()) mbar_arrive(tfull0 + 8 * as);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
@@ -379,12 +379,12 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   constexpr uint32_t STAGE_BYTES = A_BYTES + BH_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = __shfl_sync(0xffffffffu, (smem_u32(smem_raw) + 1023u) & ~1023u, 0);
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_smem;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
-  const int warp = threadIdx.x >> 5;
+  const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(&bars[0]), 0), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull0 = __shfl_sync(0xffffffffu, smem_u32(&bars[2 * STAGES]), 0), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const bool leader = (crank == 0);
@@ -402,7 +402,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   __syncthreads();
   cluster_sync();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
 
   const int n_groups = (P.n_tiles_m + 1) / 2;
   const int total_tiles = n_groups * P.n_tiles_n;
@@ -412,7 +412,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int tn = tile % P.n_tiles_n;
@@ -451,7 +451,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
             const uint32_t sb = sa + A_BYTES;
 #pragma unroll
@@ -465,7 +465,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (kblocks == 0 && lane == 0) {       // no filter tap reaches this output class: D = 0
+        if (kblocks == 0 && elect_one()) {       // no filter tap reaches this output class: D = 0
           mbar_arrive(tfull0 + 8 * as);
           mbar_arrive_cluster(mapa(tfull0 + 8 * as, 1));
         }
@@ -607,15 +607,15 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr int MAXNP = 4, MAXNB = 12;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = __shfl_sync(0xffffffffu, (smem_u32(smem_raw) + 1023u) & ~1023u, 0);
   const uint32_t b_base = smem_base + P.NP * P.patch_bytes;
   __shared__ __align__(8) uint64_t bars[2 * MAXNP + 2 * MAXNB + 5];
   __shared__ uint32_t tmem_base_smem;
-  const uint32_t pfull0 = smem_u32(&bars[0]), pempty0 = smem_u32(&bars[MAXNP]);
-  const uint32_t bfull0 = smem_u32(&bars[2 * MAXNP]), bempty0 = smem_u32(&bars[2 * MAXNP + MAXNB]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * MAXNP + 2 * MAXNB]), tempty0 = tfull0 + 16;
+  const uint32_t pfull0 = __shfl_sync(0xffffffffu, smem_u32(&bars[0]), 0), pempty0 = smem_u32(&bars[MAXNP]);
+  const uint32_t bfull0 = __shfl_sync(0xffffffffu, smem_u32(&bars[2 * MAXNP]), 0), bempty0 = smem_u32(&bars[2 * MAXNP + MAXNB]);
+  const uint32_t tfull0 = __shfl_sync(0xffffffffu, smem_u32(&bars[2 * MAXNP + 2 * MAXNB]), 0), tempty0 = tfull0 + 16;
   const uint32_t bstat = tfull0 + 32;
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -630,14 +630,14 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
 
   const int total_tiles = P.n_tiles_m * P.n_tiles_n;
   const int ntaps_total = 9 * P.cblocks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       if (P.b_stationary) {
         // (stationary weights imply a single N tile)
         mbar_expect_tx(bstat, (uint32_t)ntaps_total * B_BYTES);
@@ -702,7 +702,7 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           uint32_t sb;
           if (P.b_stationary) sb = b_base + (cb * 9 + tp) * B_BYTES;
           else { mbar_wait(bfull0 + 8 * bs, bphase); tc_fence_after(); sb = b_base + bs * B_BYTES; }
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sa = patch + (uint32_t)(row0 + P.dq[tp]) * 128u;
             uint64_t abase = DESC_BASE;
             if (P.use_base_offset) abase |= (uint64_t)((sa >> 7) & 7u) << 49;
@@ -835,12 +835,12 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = __shfl_sync(0xffffffffu, (smem_u32(smem_raw) + 1023u) & ~1023u, 0);
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
   __shared__ uint32_t tmem_base_smem;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
-  const uint32_t tfull = smem_u32(&bars[2 * STAGES]);
-  const int warp = threadIdx.x >> 5;
+  const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(&bars[0]), 0), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull = __shfl_sync(0xffffffffu, smem_u32(&bars[2 * STAGES]), 0);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   // unit decode
@@ -864,10 +864,10 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       const WgradChunk ch0 = P.chunks[c_lo];
       const WgradChunk ch1 = P.chunks[(n_valid_chunks == 2) ? c_lo + 1 : c_lo];
@@ -898,7 +898,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     for (int ks = 0; ks < ksteps; ++ks) {
       mbar_wait(full0 + 8 * stage, phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sa = smem_base + stage * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
 #pragma unroll
@@ -961,12 +961,12 @@ k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ C
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = (BN <= 128) ? 128 : 256;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = __shfl_sync(0xffffffffu, (smem_u32(smem_raw) + 1023u) & ~1023u, 0);
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
   __shared__ uint32_t tmem_base_smem;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
-  const uint32_t tfull = smem_u32(&bars[2 * STAGES]);
-  const int warp = threadIdx.x >> 5;
+  const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(&bars[0]), 0), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull = __shfl_sync(0xffffffffu, smem_u32(&bars[2 * STAGES]), 0);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const bool leader = (crank == 0);
@@ -992,10 +992,10 @@ k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ C
   __syncthreads();
   cluster_sync();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       const int ca = (n_valid >= 1) ? c_lo : 0;
       const int cb2 = (n_valid == 2) ? c_lo + 1 : ca;
@@ -1031,7 +1031,7 @@ k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ C
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
