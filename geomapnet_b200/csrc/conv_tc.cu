@@ -101,6 +101,7 @@ struct WgradParams {
   int n_ntiles, BN;        // Co tiles of BN columns
   int splits, tiles_per_split;
   int Ci, Co, KK;          // dW layout [Co][KK][Ci]
+  int debug;               // micro-benchmark only: 3 = skip the atomic epilogue
   WgradChunk chunks[72];
 };
 
@@ -921,7 +922,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     mbar_wait(tfull, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
+    for (int cc = 0; cc < ((P.debug == 3) ? 0 : BN / 32); ++cc) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
       tmem_ld_wait();
@@ -1140,10 +1141,10 @@ static int use_2cta() {     // -1 auto (cost model), 0 never, 1 whenever the cha
   return v;
 }
 
-// Tile configuration by a small cost model.  Measured on B200 (profiles/): a CTA ingests
-// ~43 B/cycle through TMA regardless of pipeline depth or multicast, so a k-block costs
-// max(bytes staged per CTA / 43, MMA cycles); candidates differ in bytes per k-block and
-// in how many CTAs (or CTA pairs) they can keep busy.
+// Tile configuration by a small cost model fitted to tools/bench_conv.py on B200
+// (profiles/r01_conv_microbench.txt): a k-block (4 MMAs + barrier round trip) costs the issuing
+// warp ~600 cycles for N <= 128 and ~980 for N = 256 on one CTA, ~490 / ~1075 on a CTA pair;
+// TMA alone sustains ~55 B/cycle per CTA; a kernel needs waves x (k-blocks x max(...) + ~2000).
 struct TileChoice { int BN; bool two_cta; };
 static TileChoice choose_tiles(int Cout, long long Mpix, int kblocks) {
   const int forced_bn = []() { const char* e = getenv("MAPNET_TC_BN"); return e ? atoi(e) : 0; }();
@@ -1162,9 +1163,9 @@ static TileChoice choose_tiles(int Cout, long long Mpix, int kblocks) {
       const int slots = two ? 74 : 148;
       const long long waves = (items + slots - 1) / slots;
       const double bytes = 16384.0 + (two ? bn * 64.0 : bn * 128.0);
-      const double mma = 2.0 * bn;                       // 4 x (128 x bn x 16) at 8192 FLOP/cycle/SM
-      const double per_kb = (bytes / 43.0 > mma) ? bytes / 43.0 : mma;
-      const double t = (double)waves * (kblocks * per_kb + 1500.0 + 8.0 * bn);   // + prologue / exposed epilogue
+      const double issue = two ? (bn <= 128 ? 490.0 : 1075.0) : (bn <= 64 ? 580.0 : (bn <= 128 ? 600.0 : 980.0));
+      const double per_kb = (bytes / 55.0 > issue) ? bytes / 55.0 : issue;
+      const double t = (double)waves * (kblocks * per_kb + 2000.0);
       if (t < best_t) { best_t = t; best.BN = bn; best.two_cta = (two != 0); }
     }
   }
@@ -1216,7 +1217,11 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
           while (H.NB > 12) { if (H.NP < 4 && left - H.patch_bytes >= 6LL * bn * 128) { H.NP++; left -= H.patch_bytes; H.NB = (int)(left / (bn * 128)); } else H.NB = 12; }
         }
         if (H.NP > 4) H.NP = 4;
-        if (H.NP >= 2 && (H.b_stationary || H.NB >= 3)) {
+        static int halo_all = -1;
+        if (halo_all < 0) { const char* e = getenv("MAPNET_TC_HALO_ALL"); halo_all = e ? atoi(e) : 0; }
+        // measured (tools/bench_conv.py): the halo engine wins only with stationary weights (Cin = 64);
+        // elsewhere the big patch box is slower than per-tap boxes and the weights dominate
+        if (H.NP >= 2 && (H.b_stationary || (halo_all && H.NB >= 3))) {
           p->halo = true; p->BN = bn;
           H.n_tiles_n = Cn / bn;
           H.use_base_offset = halo_bo;
@@ -1299,6 +1304,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   } else {
     // ---------------- wgrad ----------------
     WgradParams& P = p->WP; memset(&P, 0, sizeof(P));
+    { const char* e = getenv("MAPNET_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
     p->BN = (g.Co % 256 == 0) ? 256 : ((g.Co % 128 == 0) ? 128 : 64);
     MN_CHECK(p->BN == 64 || p->BN == 128 || p->BN == 256, "tc wgrad: Co=%d unsupported", g.Co);
     P.BN = p->BN; P.Nimg = g.B; P.Ho = g.Ho; P.Wo = g.Wo; P.Ci = g.Ci; P.Co = g.Co; P.KK = KK;
