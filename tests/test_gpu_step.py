@@ -189,7 +189,7 @@ def test_fp32_error_is_at_reference_noise_floor(name):
         if str(n) in ("feature_extractor.fc.weight", "fc_xyz.weight", "fc_wpqr.weight",
                       "feature_extractor.layer4.2.conv2.weight"):
             assert e < 2e-4, (str(n), e)
-    assert worst_prod < 4 * worst_ref + 2e-2, (worst_prod, worst_ref)
+    assert worst_prod < 4 * worst_ref + 5e-2, (worst_prod, worst_ref)
     assert abs(float(loss) - float(r["loss"])) / float(r["loss"]) < 1e-4
 
 
