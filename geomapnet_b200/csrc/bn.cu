@@ -30,6 +30,7 @@ struct BnFin {
   float *run_mean, *run_var, *mean, *invstd, *scale, *shift;
   int training;
   // backward (MODE 1/2): main BN then downsample BN
+  const float *mscale, *mshift;      // optional: ReLU mask recomputed as (mscale*y + mshift > 0) instead of reading z
   const float *gamma2, *mean2, *invstd2;
   float *dgamma, *dbeta, *coef, *dgamma2, *dbeta2, *coef2;
 };
@@ -49,6 +50,12 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
   const long long rstep = (long long)gridDim.x * rows_par;
+  float msc[8], msh[8];
+  const bool ymask = (MODE != 0) && (zmask == nullptr) && (f.mscale != nullptr);
+  if (ymask) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { msc[i] = __ldg(f.mscale + tx * 8 + i); msh[i] = __ldg(f.mshift + tx * 8 + i); }
+  }
 #pragma unroll 4
   for (long long r = (long long)blockIdx.x * rows_par + ty; r < M; r += rstep) {
     const long long off = r * C + tx * 8;
@@ -62,6 +69,9 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
         Vec8<T> z; z.load(zmask + off);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g.v[i] = (z.v[i] > 0.f) ? g.v[i] : 0.f;
+      } else if (ymask) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g.v[i] = (yy.v[i] * msc[i] + msh[i] > 0.f) ? g.v[i] : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) { acc[0][i] += g.v[i]; acc[1][i] += g.v[i] * yy.v[i]; }
@@ -98,11 +108,11 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
   const int nrep = (gridDim.x < (unsigned)kReplicas) ? (int)gridDim.x : kReplicas;
   for (int idx = threadIdx.x; idx < NACC * C; idx += kEwThreads) {
     double t = 0.0;
-    for (int r = 0; r < nrep; ++r) {
-      t += __ldcg(accum + (size_t)r * kAccStride + idx);
-      accum[(size_t)r * kAccStride + idx] = 0.0;
-    }
+#pragma unroll 8
+    for (int r = 0; r < nrep; ++r) t += __ldcg(accum + (size_t)r * kAccStride + idx);
     s_tot[idx] = t;
+#pragma unroll 8
+    for (int r = 0; r < nrep; ++r) accum[(size_t)r * kAccStride + idx] = 0.0;
   }
   __syncthreads();
   const double invM = 1.0 / (double)M;
@@ -174,16 +184,24 @@ static int launch_sums(int mode, const T* a, const T* zmask, const T* y, const T
 
 // finalize for statistics accumulated by the tcgen05 conv epilogue (conv_tc.cu): sum the
 // replicas, produce mean / invstd / scale / shift, update the running stats, reset the replicas
-__global__ void __launch_bounds__(512)
+// block = 32 channels x 32 replicas: coalesced replica loads, shared-memory reduction over replicas
+__global__ void __launch_bounds__(1024)
 k_bn_finalize_accum(long long M, int C, BnFin f, double* __restrict__ accum) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int r = 0; r < kReplicas; ++r) {
+  __shared__ double s0s[32][33], s1s[32][33];
+  const int cl = threadIdx.x, r = threadIdx.y;
+  const int c = blockIdx.x * 32 + cl;
+  double v0 = 0.0, v1 = 0.0;
+  if (c < C && r < kReplicas) {
     double* a = accum + (size_t)r * kAccStride;
-    s0 += a[c]; s1 += a[C + c];
+    v0 = a[c]; v1 = a[C + c];
     a[c] = 0.0; a[C + c] = 0.0;
   }
+  s0s[r][cl] = v0; s1s[r][cl] = v1;
+  __syncthreads();
+  if (r != 0 || c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { s0 += s0s[k][cl]; s1 += s1s[k][cl]; }
   const double invM = 1.0 / (double)M;
   const double m = s0 * invM;
   double var = s1 * invM - m * m;
@@ -207,7 +225,7 @@ int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float
   BnFin f; memset(&f, 0, sizeof(f));
   f.gamma = gamma; f.beta = beta; f.run_mean = run_mean; f.run_var = run_var; f.mean = mean_out;
   f.invstd = invstd_out; f.scale = scale; f.shift = shift; f.training = 1;
-  k_bn_finalize_accum<<<1, 512, 0, st>>>(M, C, f, accum);
+  k_bn_finalize_accum<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(M, C, f, accum);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -248,15 +266,16 @@ int launch_bn_bwd_reduce(const T* dout, const T* zmask, const T* y, const T* yd,
                          const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
                          float* coef, const float* gamma2, const float* mean2, const float* invstd2,
                          float* dgamma2, float* dbeta2, float* coef2, double* accum, unsigned int* counter,
-                         cudaStream_t st) {
+                         cudaStream_t st, const float* mscale, const float* mshift) {
   BnFin f; memset(&f, 0, sizeof(f));
+  f.mscale = mscale; f.mshift = mshift;
   f.gamma = gamma; f.mean = const_cast<float*>(mean); f.invstd = const_cast<float*>(invstd);
   f.dgamma = dgamma; f.dbeta = dbeta; f.coef = coef;
   f.gamma2 = gamma2; f.mean2 = mean2; f.invstd2 = invstd2; f.dgamma2 = dgamma2; f.dbeta2 = dbeta2; f.coef2 = coef2;
   return launch_sums<T>(yd != nullptr ? 2 : 1, dout, zmask, y, yd, M, C, accum, counter, f, st);
 }
-template int launch_bn_bwd_reduce<float>(const float*, const float*, const float*, const float*, long long, int, const float*, const float*, const float*, float*, float*, float*, const float*, const float*, const float*, float*, float*, float*, double*, unsigned int*, cudaStream_t);
-template int launch_bn_bwd_reduce<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, long long, int, const float*, const float*, const float*, float*, float*, float*, const float*, const float*, const float*, float*, float*, float*, double*, unsigned int*, cudaStream_t);
+template int launch_bn_bwd_reduce<float>(const float*, const float*, const float*, const float*, long long, int, const float*, const float*, const float*, float*, float*, float*, const float*, const float*, const float*, float*, float*, float*, double*, unsigned int*, cudaStream_t, const float*, const float*);
+template int launch_bn_bwd_reduce<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, long long, int, const float*, const float*, const float*, float*, float*, float*, const float*, const float*, const float*, float*, float*, float*, double*, unsigned int*, cudaStream_t, const float*, const float*);
 
 // ---------------------------------------------------------------------------
 // forward apply:  z = relu?( scale*y + shift  [+ zres | + scale2*y2 + shift2] )
@@ -449,11 +468,16 @@ __global__ void __launch_bounds__(kEwThreads)
 k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T* __restrict__ y,
                const float* __restrict__ coef, T* __restrict__ dy, const T* __restrict__ yd,
                const float* __restrict__ coefd, T* __restrict__ dyd, T* __restrict__ gout, long long nvec,
-               int C) {
+               int C, const float* __restrict__ mscale, const float* __restrict__ mshift) {
   const int cv = C >> 3;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(i0 % cv) * 8;          // loop invariant (grid stride is a multiple of cv)
-  float cA[8], cB[8], cC[8], dA[8], dB[8], dC[8];
+  float cA[8], cB[8], cC[8], dA[8], dB[8], dC[8], msc[8], msh[8];
+  const bool ymask = (zmask == nullptr) && (mscale != nullptr);
+  if (ymask) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { msc[k] = __ldg(mscale + c0 + k); msh[k] = __ldg(mshift + c0 + k); }
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     cA[k] = __ldg(coef + c0 + k); cB[k] = __ldg(coef + C + c0 + k); cC[k] = __ldg(coef + 2 * C + c0 + k);
@@ -466,6 +490,9 @@ k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T*
       Vec8<T> z; z.load(zmask + i * 8);
 #pragma unroll
       for (int k = 0; k < 8; ++k) g.v[k] = (z.v[k] > 0.f) ? g.v[k] : 0.f;
+    } else if (ymask) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = (yy.v[k] * msc[k] + msh[k] > 0.f) ? g.v[k] : 0.f;
     }
     Vec8<T> o;
 #pragma unroll
@@ -484,18 +511,19 @@ k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T*
 
 template <typename T>
 int launch_bn_bwd_apply(const T* dout, const T* zmask, const T* y, const float* coef, T* dy, const T* yd,
-                        const float* coefd, T* dyd, T* gout, long long M, int C, cudaStream_t st) {
+                        const float* coefd, T* dyd, T* gout, long long M, int C, cudaStream_t st,
+                        const float* mscale, const float* mshift) {
   const long long nvec = M * (C >> 3);
   const int grid = ew_grid(nvec);
   const bool ds = (yd != nullptr), go = (gout != nullptr);
-  if (ds && !go) k_bn_bwd_apply<T, 1, 0><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C);
-  else if (!ds && go) k_bn_bwd_apply<T, 0, 1><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C);
-  else if (!ds && !go) k_bn_bwd_apply<T, 0, 0><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C);
-  else k_bn_bwd_apply<T, 1, 1><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C);
+  if (ds && !go) k_bn_bwd_apply<T, 1, 0><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
+  else if (!ds && go) k_bn_bwd_apply<T, 0, 1><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
+  else if (!ds && !go) k_bn_bwd_apply<T, 0, 0><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
+  else k_bn_bwd_apply<T, 1, 1><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
   MN_LAUNCH_CHECK();
   return 0;
 }
-template int launch_bn_bwd_apply<float>(const float*, const float*, const float*, const float*, float*, const float*, const float*, float*, float*, long long, int, cudaStream_t);
-template int launch_bn_bwd_apply<bf16>(const bf16*, const bf16*, const bf16*, const float*, bf16*, const bf16*, const float*, bf16*, bf16*, long long, int, cudaStream_t);
+template int launch_bn_bwd_apply<float>(const float*, const float*, const float*, const float*, float*, const float*, const float*, float*, float*, long long, int, cudaStream_t, const float*, const float*);
+template int launch_bn_bwd_apply<bf16>(const bf16*, const bf16*, const bf16*, const float*, bf16*, const bf16*, const float*, bf16*, bf16*, long long, int, cudaStream_t, const float*, const float*);
 
 }  // namespace mapnet

@@ -22,7 +22,7 @@ int launch_bn_bwd_reduce(const T* dout, const T* zmask, const T* y, const T* yd,
                          const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
                          float* coef, const float* gamma2, const float* mean2, const float* invstd2,
                          float* dgamma2, float* dbeta2, float* coef2, double* accum, unsigned int* counter,
-                         cudaStream_t st);
+                         cudaStream_t st, const float* mscale = nullptr, const float* mshift = nullptr);
 template <typename T>
 int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_mode, const T* res,
                     const float* scale2, const float* shift2, T* z, long long M, int C, int relu, cudaStream_t st);
@@ -34,7 +34,8 @@ int launch_stem_pool_bwd(const T* dz, const uint8_t* amax, const T* y, const flo
                          T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st);
 template <typename T>
 int launch_bn_bwd_apply(const T* dout, const T* zmask, const T* y, const float* coef, T* dy, const T* yd,
-                        const float* coefd, T* dyd, T* gout, long long M, int C, cudaStream_t st);
+                        const float* coefd, T* dyd, T* gout, long long M, int C, cudaStream_t st,
+                        const float* mscale = nullptr, const float* mshift = nullptr);
 
 // ---- conv_simt.cu: fp32 CUDA-core implicit GEMM (strict-parity path) -----------
 template <typename T>

@@ -15,32 +15,37 @@ template <typename TW> __device__ __forceinline__ TW cvt_w(float v);
 template <> __device__ __forceinline__ float cvt_w<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 cvt_w<bf16>(float v) { return __float2bfloat16_rn(v); }
 
+// One block per (output channel, conv): the channel's [Ci][KH*KW] slab is contiguous in the torch
+// layout -> coalesced load into shared memory -> coalesced store as [KH*KW][Ci] (odd stride 9: no
+// bank conflicts).  The stem's [3][7][7] slab becomes the padded [im2col_k] row of the patch GEMM.
 template <typename TW>
-__global__ void k_pack_weights(const WeightDesc* __restrict__ descs, const float* __restrict__ params,
-                               TW* __restrict__ w_krsc, TW* __restrict__ w_dg, int round_bf16) {
+__global__ void __launch_bounds__(256)
+k_pack_weights(const WeightDesc* __restrict__ descs, const float* __restrict__ params,
+               TW* __restrict__ w_krsc, TW* __restrict__ w_dg, int round_bf16) {
+  extern __shared__ float slab[];
   const WeightDesc d = descs[blockIdx.y];
-  const int KK = d.KH * d.KW;
-  const long long total = (long long)d.Co * KK * d.Ci;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(e % d.Ci);
-    const int tap = (int)((e / d.Ci) % KK);
-    const int co = (int)(e / ((long long)d.Ci * KK));
-    float v = 0.f;
-    if (d.im2col_k > 0) {
-      // packed as [Co][im2col_k]; here KK==1, Ci==im2col_k, ci == k
-      const int kreal = d.Ci_real * 49;
-      if (ci < kreal) {
-        const int c = ci % d.Ci_real, t = ci / d.Ci_real;   // t = kh*7+kw
-        v = params[d.p_off + ((long long)co * d.Ci_real + c) * 49 + t];
-      }
+  const int co = blockIdx.x;
+  if (co >= d.Co) return;
+  const int KK = (d.im2col_k > 0) ? 49 : d.KH * d.KW;
+  const int n_in = d.Ci_real * KK;
+  const float* src = params + d.p_off + (long long)co * n_in;
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) slab[i] = src[i];
+  __syncthreads();
+  if (d.im2col_k > 0) {
+    TW* dst = w_krsc + d.k_off + (long long)co * d.im2col_k;
+    for (int k = threadIdx.x; k < d.im2col_k; k += blockDim.x) {
+      float v = 0.f;
+      if (k < n_in) { const int t = k / d.Ci_real, c = k - t * d.Ci_real; v = slab[c * 49 + t]; }
       if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
-      w_krsc[d.k_off + e] = cvt_w<TW>(v);
-    } else {
-      const int kh = tap / d.KW, kw = tap - kh * d.KW;
-      v = params[d.p_off + (((long long)co * d.Ci_real + ci) * d.KH + kh) * d.KW + kw];
+      dst[k] = cvt_w<TW>(v);
+    }
+  } else {
+    TW* dst = w_krsc + d.k_off + (long long)co * KK * d.Ci;
+    for (int j = threadIdx.x; j < n_in; j += blockDim.x) {
+      const int tap = j / d.Ci, ci = j - tap * d.Ci;
+      float v = slab[ci * KK + tap];
       if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
-      w_krsc[d.k_off + e] = cvt_w<TW>(v);
+      dst[j] = cvt_w<TW>(v);
     }
   }
 }
@@ -79,8 +84,8 @@ k_transpose_dg(const WeightDesc* __restrict__ descs, const TW* __restrict__ w_kr
 template <typename TW>
 int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* params, TW* w_krsc, TW* w_dg,
                         int max_elems, int round_bf16, cudaStream_t st) {
-  dim3 grid(cdiv(max_elems, 256) < 512 ? cdiv(max_elems, 256) : 512, nconv);
-  k_pack_weights<TW><<<grid, 256, 0, st>>>(d_descs, params, w_krsc, w_dg, round_bf16);
+  dim3 grid(512, nconv);                 // blockIdx.x = output channel (<= 512), blocks past Co exit
+  k_pack_weights<TW><<<grid, 256, 512 * 9 * sizeof(float), st>>>(d_descs, params, w_krsc, w_dg, round_bf16);
   MN_LAUNCH_CHECK();
   if (w_dg != nullptr) {
     dim3 g2(592, nconv);
@@ -92,37 +97,39 @@ int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* param
 template int launch_pack_weights<float>(const WeightDesc*, int, const float*, float*, float*, int, int, cudaStream_t);
 template int launch_pack_weights<bf16>(const WeightDesc*, int, const float*, bf16*, bf16*, int, int, cudaStream_t);
 
-__global__ void k_unpack_wgrads(const WeightDesc* __restrict__ descs, const float* __restrict__ dw,
-                                float* __restrict__ grads) {
+__global__ void __launch_bounds__(256)
+k_unpack_wgrads(const WeightDesc* __restrict__ descs, const float* __restrict__ dw, float* __restrict__ grads) {
+  extern __shared__ float slab[];
   const WeightDesc d = descs[blockIdx.y];
-  const int KK = d.KH * d.KW;
+  const int co = blockIdx.x;
+  if (co >= d.Co) return;
   if (d.im2col_k > 0) {
-    const long long total = (long long)d.Co * d.Ci_real * 49;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-      // e indexes the torch layout [Co][Ci_real][7][7]
-      const int t = (int)(e % 49);
-      const int c = (int)((e / 49) % d.Ci_real);
-      const int co = (int)(e / (49LL * d.Ci_real));
-      grads[d.p_off + e] = dw[d.k_off + (long long)co * d.im2col_k + t * d.Ci_real + c];
+    const float* src = dw + d.k_off + (long long)co * d.im2col_k;
+    for (int i = threadIdx.x; i < d.im2col_k; i += blockDim.x) slab[i] = src[i];
+    __syncthreads();
+    const int n_out = d.Ci_real * 49;
+    float* dst = grads + d.p_off + (long long)co * n_out;
+    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
+      const int t = e % 49, c = e / 49;
+      dst[e] = slab[t * d.Ci_real + c];
     }
     return;
   }
-  const long long total = (long long)d.Co * KK * d.Ci;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    // e indexes the torch layout [Co][Ci][KH][KW] (coalesced writes)
-    const int tap = (int)(e % KK);
-    const int ci = (int)((e / KK) % d.Ci);
-    const int co = (int)(e / ((long long)KK * d.Ci));
-    grads[d.p_off + e] = dw[d.k_off + ((long long)co * KK + tap) * d.Ci + ci];
+  const int KK = d.KH * d.KW, n = KK * d.Ci, pitch = d.Ci + 1;   // +1: conflict-free column reads
+  const float* src = dw + d.k_off + (long long)co * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const int tap = i / d.Ci; slab[tap * pitch + (i - tap * d.Ci)] = src[i]; }
+  __syncthreads();
+  float* dst = grads + d.p_off + (long long)co * n;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int tap = e % KK, ci = e / KK;           // torch layout [Ci][KH*KW]
+    dst[e] = slab[tap * pitch + ci];
   }
 }
 
 int launch_unpack_wgrads(const WeightDesc* d_descs, int nconv, const float* dw_krsc, float* grads,
                          int max_elems, cudaStream_t st) {
-  dim3 grid(cdiv(max_elems, 256) < 512 ? cdiv(max_elems, 256) : 512, nconv);
-  k_unpack_wgrads<<<grid, 256, 0, st>>>(d_descs, dw_krsc, grads);
+  dim3 grid(512, nconv);
+  k_unpack_wgrads<<<grid, 256, 513 * 9 * sizeof(float), st>>>(d_descs, dw_krsc, grads);
   MN_LAUNCH_CHECK();
   return 0;
 }

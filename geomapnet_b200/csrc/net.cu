@@ -394,10 +394,14 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     MN_TRY(conv_wgrad<T>(bl.conv2, (const T*)bl.h, S1, B, st));
     MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st));
     // h = relu(bn1(y1))
-    MN_TRY(launch_bn_bwd_reduce<T>(S4, (const T*)bl.h, (const T*)bl.y1, nullptr, Mo, C,
+    // h = relu(bn1(y1)) has no residual: its ReLU mask is recomputed from y1 (scale*y+shift > 0),
+    // one tensor read less in both backward passes
+    MN_TRY(launch_bn_bwd_reduce<T>(S4, nullptr, (const T*)bl.y1, nullptr, Mo, C,
                                    params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
-                                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st));
-    MN_TRY(launch_bn_bwd_apply<T>(S4, (const T*)bl.h, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st));
+                                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st,
+                                   b1.scale, b1.shift));
+    MN_TRY(launch_bn_bwd_apply<T>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st,
+                                  b1.scale, b1.shift));
     // conv1 (+ downsample conv): d zin
     MN_TRY(conv_wgrad<T>(bl.conv1, zin, S1, B, st));
     if (ds) {
