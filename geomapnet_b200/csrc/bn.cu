@@ -82,6 +82,9 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
       }
     }
   }
+  // replicas actually used by this launch: small grids need few (the finalizing block walks them all)
+  int nrep = (int)gridDim.x / 16;
+  nrep = nrep < 4 ? 4 : (nrep > kReplicas ? kReplicas : nrep);
   // reduce across ty through shared memory (rows_par <= 32)
   extern __shared__ float sm[];               // [rows_par][NACC][C]
 #pragma unroll
@@ -92,7 +95,7 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
   for (int idx = threadIdx.x; idx < NACC * C; idx += kEwThreads) {
     float s = 0.f;
     for (int t = 0; t < rows_par; ++t) s += sm[(size_t)t * NACC * C + idx];
-    atomicAdd(accum + (size_t)(blockIdx.x % kReplicas) * kAccStride + idx, (double)s);
+    atomicAdd(accum + (size_t)(blockIdx.x % nrep) * kAccStride + idx, (double)s);
   }
   // ---- last block finalizes ----
   __shared__ unsigned int s_last;
@@ -105,7 +108,6 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
   // sum the replicas into shared memory (reuse the reduction buffer: NACC*C doubles <= 12 KB... held as
   // doubles in a separate static array to keep precision)
   __shared__ double s_tot[3 * 512];
-  const int nrep = (gridDim.x < (unsigned)kReplicas) ? (int)gridDim.x : kReplicas;
   for (int idx = threadIdx.x; idx < NACC * C; idx += kEwThreads) {
     double t = 0.0;
 #pragma unroll 8
