@@ -1,5 +1,11 @@
 mkdir -p gpurun_out
-echo "=== ddp test"; timeout 200 python -m pytest tests/test_gpu_ddp.py -m gpu -q 2>&1 | tail -2
-echo "=== 2-GPU bench"; timeout 250 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -n 4 gpurun_out/bench_n2.err | cut -c1-200; python -c "
-import json; d=json.load(open('gpurun_out/bench_n2.json')); print('n2', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['n_gpus'], d['config']['eager_ms_per_step'])"
-echo "=== 2-GPU reference arm"; timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | cut -c1-300
+echo "=== warm launch list (cache-control none)"
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 1150 -c 300 --csv --log-file gpurun_out/launches_warm.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/bench_ncu_warm.log 2>&1
+tail -n 2 gpurun_out/bench_ncu_warm.log | cut -c1-200
+python - <<'PY'
+import csv
+lines=[l for l in open('gpurun_out/launches_warm.csv') if not l.startswith('==')]
+rows=list(csv.DictReader(lines))
+tot=sum(float(r['Metric Value'].replace(',','')) for r in rows)
+print('launches',len(rows),'sum_us',tot/1000)
+PY
