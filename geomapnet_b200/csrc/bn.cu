@@ -24,6 +24,14 @@ static const int kAccStride = 3 * 512;  // doubles per replica
 // (block b -> replica b % kReplicas: same-address atomics serialise at ~30 ns each, the
 // replicas keep that chain short); the finalizing block sums the replicas and resets them.
 // ---------------------------------------------------------------------------
+// 8 consecutive per-channel floats (32-byte aligned: channel offsets are multiples of 8) as two
+// 128-bit loads; scalar loads here cost 8 L1 wavefronts per warp instruction once C >= 256
+__device__ __forceinline__ void ld8(const float* __restrict__ p, float* o) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
 struct BnFin {
   // forward (MODE 0)
   const float *gamma, *beta;
@@ -52,10 +60,7 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
   const long long rstep = (long long)gridDim.x * rows_par;
   float msc[8], msh[8];
   const bool ymask = (MODE != 0) && (zmask == nullptr) && (f.mscale != nullptr);
-  if (ymask) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { msc[i] = __ldg(f.mscale + tx * 8 + i); msh[i] = __ldg(f.mshift + tx * 8 + i); }
-  }
+  if (ymask) { ld8(f.mscale + tx * 8, msc); ld8(f.mshift + tx * 8, msh); }
 #pragma unroll 4
   for (long long r = (long long)blockIdx.x * rows_par + ty; r < M; r += rstep) {
     const long long off = r * C + tx * 8;
@@ -232,6 +237,63 @@ int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float
   return 0;
 }
 
+// finalize for the backward reductions accumulated by the dgrad epilogue (conv_tc.cu, EpiBwd):
+// same arithmetic as MODE 1 / 2 of k_channel_sums
+__global__ void __launch_bounds__(1024)
+k_bn_bwd_finalize_accum(long long M, int C, BnFin f, double* __restrict__ accum, int nacc) {
+  __shared__ double ss[3][32][33];
+  const int cl = threadIdx.x, r = threadIdx.y;
+  const int c = blockIdx.x * 32 + cl;
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  if (c < C && r < kReplicas) {
+    double* a = accum + (size_t)r * kAccStride;
+    v0 = a[c]; v1 = a[C + c];
+    a[c] = 0.0; a[C + c] = 0.0;
+    if (nacc == 3) { v2 = a[2 * C + c]; a[2 * C + c] = 0.0; }
+  }
+  ss[0][r][cl] = v0; ss[1][r][cl] = v1; ss[2][r][cl] = v2;
+  __syncthreads();
+  if (r != 0 || c >= C) return;
+  double s0 = 0.0, s1 = 0.0, s1d = 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { s0 += ss[0][k][cl]; s1 += ss[1][k][cl]; s1d += ss[2][k][cl]; }
+  const double invM = 1.0 / (double)M;
+  {
+    const double mu = (double)f.mean[c], is = (double)f.invstd[c];
+    const double s2 = is * (s1 - mu * s0);          // sum g * xhat
+    f.dgamma[c] = (float)s2;
+    f.dbeta[c] = (float)s0;
+    const double A = (double)f.gamma[c] * is;
+    const double Bc = -A * is * s2 * invM;
+    const double Cc = -A * s0 * invM - Bc * mu;
+    f.coef[c] = (float)A; f.coef[C + c] = (float)Bc; f.coef[2 * C + c] = (float)Cc;
+  }
+  if (nacc == 3) {
+    const double mu = (double)f.mean2[c], is = (double)f.invstd2[c];
+    const double s2 = is * (s1d - mu * s0);
+    f.dgamma2[c] = (float)s2;
+    f.dbeta2[c] = (float)s0;
+    const double A = (double)f.gamma2[c] * is;
+    const double Bc = -A * is * s2 * invM;
+    const double Cc = -A * s0 * invM - Bc * mu;
+    f.coef2[c] = (float)A; f.coef2[C + c] = (float)Bc; f.coef2[2 * C + c] = (float)Cc;
+  }
+}
+
+int launch_bn_bwd_finalize_accum(long long M, int C, const float* gamma, const float* mean, const float* invstd,
+                                 float* dgamma, float* dbeta, float* coef, const float* gamma2, const float* mean2,
+                                 const float* invstd2, float* dgamma2, float* dbeta2, float* coef2, double* accum,
+                                 cudaStream_t st) {
+  MN_CHECK(C <= 512, "bn_bwd_finalize_accum: C=%d", C);
+  BnFin f; memset(&f, 0, sizeof(f));
+  f.gamma = gamma; f.mean = const_cast<float*>(mean); f.invstd = const_cast<float*>(invstd);
+  f.dgamma = dgamma; f.dbeta = dbeta; f.coef = coef;
+  f.gamma2 = gamma2; f.mean2 = mean2; f.invstd2 = invstd2; f.dgamma2 = dgamma2; f.dbeta2 = dbeta2; f.coef2 = coef2;
+  k_bn_bwd_finalize_accum<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(M, C, f, accum, gamma2 != nullptr ? 3 : 2);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
 // eval-mode scale/shift from the running statistics (no batch statistics)
 __global__ void k_bn_eval_scale(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ run_mean, const float* __restrict__ run_var,
@@ -292,12 +354,9 @@ k_bn_apply(const T* __restrict__ y, const float* __restrict__ scale, const float
   // the grid stride (gridDim*256) is a multiple of cv, so this thread always sees the same 8 channels
   const int c0 = (int)(i0 % cv) * 8;
   float sc[8], sh[8], sc2[8], sh2[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    sc[k] = __ldg(scale + c0 + k); sh[k] = __ldg(shift + c0 + k);
-    if (RES == 2) { sc2[k] = __ldg(scale2 + c0 + k); sh2[k] = __ldg(shift2 + c0 + k); }
-  }
-#pragma unroll 2
+  ld8(scale + c0, sc); ld8(shift + c0, sh);
+  if (RES == 2) { ld8(scale2 + c0, sc2); ld8(shift2 + c0, sh2); }
+#pragma unroll 4
   for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     Vec8<T> v; v.load(y + i * 8);
     float o[8];
@@ -321,7 +380,9 @@ k_bn_apply(const T* __restrict__ y, const float* __restrict__ scale, const float
 
 static int ew_grid(long long n) {
   long long g = (n + kEwThreads - 1) / kEwThreads;
-  const long long cap = 148LL * 16;
+  // few fat threads: the per-thread channel-parameter prologue is amortised over >= 4 vectors and
+  // 148*4 blocks x 256 threads x 4 loads in flight cover the HBM latency-bandwidth product
+  const long long cap = 148LL * 4;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
@@ -361,8 +422,7 @@ k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const floa
 #pragma unroll
     for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
     float sc[8], sh[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + c0 + k); sh[k] = __ldg(shift + c0 + k); }
+    ld8(scale + c0, sc); ld8(shift + c0, sh);
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int ih = oh * 2 - 1 + kh;
@@ -443,10 +503,12 @@ k_stem_pool_bwd(const T* __restrict__ dz, const uint8_t* __restrict__ amax, cons
       }
     }
     Vec8<T> yy; yy.load(y + i * 8);
+    float sc[8], sh[8];
+    ld8(scale + c0, sc); ld8(shift + c0, sh);
     Vec8<T> o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float a = yy.v[k] * __ldg(scale + c0 + k) + __ldg(shift + c0 + k);
+      const float a = yy.v[k] * sc[k] + sh[k];
       o.v[k] = (a > 0.f) ? acc[k] : 0.f;
     }
     o.store(g + i * 8);
@@ -476,16 +538,10 @@ k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T*
   const int c0 = (int)(i0 % cv) * 8;          // loop invariant (grid stride is a multiple of cv)
   float cA[8], cB[8], cC[8], dA[8], dB[8], dC[8], msc[8], msh[8];
   const bool ymask = (zmask == nullptr) && (mscale != nullptr);
-  if (ymask) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { msc[k] = __ldg(mscale + c0 + k); msh[k] = __ldg(mshift + c0 + k); }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    cA[k] = __ldg(coef + c0 + k); cB[k] = __ldg(coef + C + c0 + k); cC[k] = __ldg(coef + 2 * C + c0 + k);
-    if (DS) { dA[k] = __ldg(coefd + c0 + k); dB[k] = __ldg(coefd + C + c0 + k); dC[k] = __ldg(coefd + 2 * C + c0 + k); }
-  }
-#pragma unroll 2
+  if (ymask) { ld8(mscale + c0, msc); ld8(mshift + c0, msh); }
+  ld8(coef + c0, cA); ld8(coef + C + c0, cB); ld8(coef + 2 * C + c0, cC);
+  if (DS) { ld8(coefd + c0, dA); ld8(coefd + C + c0, dB); ld8(coefd + 2 * C + c0, dC); }
+#pragma unroll 4
   for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     Vec8<T> g, yy; g.load(dout + i * 8); yy.load(y + i * 8);
     if (zmask != nullptr) {

@@ -123,6 +123,107 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&x)[32], int lane) 
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Shared epilogue of the fprop / dgrad engines: one 32-column chunk of one accumulator row.
+//   f = acc (+ residual)                                  every mode
+//   dgrad with E.y:  f = gate ? f : 0                     the consumer BN's ReLU gate, so the stored
+//                                                         gradient is already masked
+//   store bf16(f)
+//   statistics of the values AS STORED (rows outside the tensor count as 0):
+//     fprop:  (sum f, sum f^2)                            BatchNorm batch statistics
+//     dgrad:  (sum g, sum g*y [, sum g*yd])               BatchNorm backward reductions of the BN
+//                                                         (and downsample BN) that consumes g
+// which removes the separate reduction pass over dY and Y of every BatchNorm backward.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row32(const bf16* __restrict__ p, float (&o)[32]) {
+  const uint4* rp = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 r = rp[j];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      o[j * 8 + 2 * i] = t.x; o[j * 8 + 2 * i + 1] = t.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const bool valid, const bool do_store,
+                                          const long long off, const int col0, const bf16* __restrict__ residual,
+                                          bf16* __restrict__ out, const bool stats_on, const EpiBwd& E,
+                                          const int lane, float& s0, float& s1, float& s2) {
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  const bool bwd = (E.y != nullptr);
+  float yv[32];
+  if (valid) {
+    if (residual != nullptr) {
+      float r[32];
+      load_row32(residual + off, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] += r[i];
+    }
+    if (bwd) {
+      load_row32(E.y + off, yv);
+      if (E.zmask != nullptr) {
+        float z[32];
+        load_row32(E.zmask + off, z);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = (z[i] > 0.f) ? f[i] : 0.f;
+      } else if (E.mscale != nullptr) {
+        const float4* sc = reinterpret_cast<const float4*>(E.mscale + col0);
+        const float4* sh = reinterpret_cast<const float4*>(E.mshift + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = __ldg(sc + j), b = __ldg(sh + j);
+          f[4 * j + 0] = (yv[4 * j + 0] * a.x + b.x > 0.f) ? f[4 * j + 0] : 0.f;
+          f[4 * j + 1] = (yv[4 * j + 1] * a.y + b.y > 0.f) ? f[4 * j + 1] : 0.f;
+          f[4 * j + 2] = (yv[4 * j + 2] * a.z + b.z > 0.f) ? f[4 * j + 2] : 0.f;
+          f[4 * j + 3] = (yv[4 * j + 3] * a.w + b.w > 0.f) ? f[4 * j + 3] : 0.f;
+        }
+      }
+    }
+  }
+  __nv_bfloat162 hq[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hq[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  if (valid && do_store) {
+    uint4* op = reinterpret_cast<uint4*>(out + off);
+    const uint4* src = reinterpret_cast<const uint4*>(hq);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[j] = src[j];
+  }
+  if (stats_on) {
+    float x[32], w[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 t = __bfloat1622float2(hq[i]);
+      x[2 * i] = valid ? t.x : 0.f; x[2 * i + 1] = valid ? t.y : 0.f;
+    }
+    if (bwd) {
+      if (E.yd != nullptr) {
+        float u[32];
+        if (valid) load_row32(E.yd + off, u);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) u[i] = valid ? x[i] * u[i] : 0.f;
+        warp_transpose_reduce(u, lane);
+        s2 += u[0];
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] = valid ? x[i] * yv[i] : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] = x[i] * x[i];
+    }
+    warp_transpose_reduce(x, lane);
+    warp_transpose_reduce(w, lane);
+    s0 += x[0];
+    s1 += w[0];
+  }
+}
+
 // as many stages as fit in 227 KB: the engines are bound by bytes in flight x L2 latency
 static constexpr int conv_stages(int BN) { return BN <= 64 ? 9 : (BN <= 128 ? 6 : 4); }
 
@@ -137,7 +238,7 @@ __global__ void __launch_bounds__(192, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
           const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
-          bf16* __restrict__ out, double* __restrict__ stats) {
+          bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E) {
   constexpr int STAGES = conv_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;        // 128 pixels x 64 ch bf16
   constexpr uint32_t B_BYTES = BN * 128;
@@ -252,9 +353,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     int as = 0; uint32_t aphase = 0;
     // fused BatchNorm statistics (fprop only): lane L keeps the running column sums of column
     // cc*32+L over all rows this warp has stored, flushed with fp64 atomics per N tile
-    float st_sum[BN / 32], st_sq[BN / 32];
+    float st_sum[BN / 32], st_sq[BN / 32], st_x3[BN / 32];
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
+    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f; }
     int st_tn = -1;
     auto flush_stats = [&](int tn_flush) {
       double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
@@ -263,7 +364,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const int c = tn_flush * BN + i * 32 + lane;
         atomicAdd(acc + c, (double)st_sum[i]);
         atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
-        st_sum[i] = 0.f; st_sq[i] = 0.f;
+        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)st_x3[i]);
+        st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f;
       }
     };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -306,47 +408,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         }
-        if (valid && P.debug != 4) {
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(residual + obase + cc * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 r = rp[j];
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 t = __bfloat1622float2(h[i]);
-                f[j * 8 + 2 * i] += t.x; f[j * 8 + 2 * i + 1] += t.y;
-              }
-            }
-          }
-          uint4* op = reinterpret_cast<uint4*>(out + obase + cc * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[j * 8 + 2 * i], f[j * 8 + 2 * i + 1]);
-            op[j] = o;
-          }
-        }
-        if (stats != nullptr) {
-          // statistics of the values AS STORED (bf16-rounded); rows outside the tensor count as 0
-          float x[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            x[i] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
-          float y2[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) y2[i] = x[i] * x[i];
-          warp_transpose_reduce(x, lane);
-          warp_transpose_reduce(y2, lane);
-          st_sum[cc] += x[0];
-          st_sq[cc] += y2[0];
-        }
+        epi_chunk(v, valid, P.debug != 4, obase + cc * 32, tn * BN + cc * 32, residual, out, stats != nullptr, E, lane,
+                  st_sum[cc], st_sq[cc], st_x3[cc]);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -373,7 +436,7 @@ __global__ void __launch_bounds__(192, 1)
 k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
            const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
-           bf16* __restrict__ out, double* __restrict__ stats) {
+           bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E) {
   constexpr int STAGES = conv2_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;
   constexpr uint32_t BH_BYTES = (BN / 2) * 128;      // this CTA's half of the weight tile
@@ -478,9 +541,9 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const int q = warp & 3;
     const int m = q * 32 + lane;
     int as = 0; uint32_t aphase = 0;
-    float st_sum[BN / 32], st_sq[BN / 32];
+    float st_sum[BN / 32], st_sq[BN / 32], st_x3[BN / 32];
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
+    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f; }
     int st_tn = -1;
     auto flush_stats = [&](int tn_flush) {
       double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
@@ -489,7 +552,8 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const int c = tn_flush * BN + i * 32 + lane;
         atomicAdd(acc + c, (double)st_sum[i]);
         atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
-        st_sum[i] = 0.f; st_sq[i] = 0.f;
+        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)st_x3[i]);
+        st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f;
       }
     };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -523,46 +587,8 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa(tempty0 + 8 * as, 0));
         }
-        if (valid) {
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(residual + obase + cc * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 r = rp[j];
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 t = __bfloat1622float2(h[i]);
-                f[j * 8 + 2 * i] += t.x; f[j * 8 + 2 * i + 1] += t.y;
-              }
-            }
-          }
-          uint4* op = reinterpret_cast<uint4*>(out + obase + cc * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[j * 8 + 2 * i], f[j * 8 + 2 * i + 1]);
-            op[j] = o;
-          }
-        }
-        if (stats != nullptr) {
-          float x[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            x[i] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
-          float y2[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) y2[i] = x[i] * x[i];
-          warp_transpose_reduce(x, lane);
-          warp_transpose_reduce(y2, lane);
-          st_sum[cc] += x[0];
-          st_sq[cc] += y2[0];
-        }
+        epi_chunk(v, valid, true, obase + cc * 32, tn * BN + cc * 32, residual, out, stats != nullptr, E, lane,
+                  st_sum[cc], st_sq[cc], st_x3[cc]);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -603,7 +629,7 @@ template <int BN>
 __global__ void __launch_bounds__(192, 1)
 k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ HaloParams P, const bf16* __restrict__ residual, bf16* __restrict__ out,
-               double* __restrict__ stats) {
+               double* __restrict__ stats, const EpiBwd E) {
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr int MAXNP = 4, MAXNB = 12;
@@ -733,9 +759,9 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int q = warp & 3;
     const int m = q * 32 + lane;
     int as = 0; uint32_t aphase = 0;
-    float st_sum[BN / 32], st_sq[BN / 32];
+    float st_sum[BN / 32], st_sq[BN / 32], st_x3[BN / 32];
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
+    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f; }
     int st_tn = -1;
     auto flush_stats = [&](int tn_flush) {
       double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
@@ -744,7 +770,8 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int c = tn_flush * BN + i * 32 + lane;
         atomicAdd(acc + c, (double)st_sum[i]);
         atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
-        st_sum[i] = 0.f; st_sq[i] = 0.f;
+        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)st_x3[i]);
+        st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f;
       }
     };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -769,46 +796,8 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         }
-        if (valid) {
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(residual + obase + cc * 32);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const uint4 r = rp[jj];
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 tt = __bfloat1622float2(hh[i]);
-                f[jj * 8 + 2 * i] += tt.x; f[jj * 8 + 2 * i + 1] += tt.y;
-              }
-            }
-          }
-          uint4* op = reinterpret_cast<uint4*>(out + obase + cc * 32);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            uint4 o;
-            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(f[jj * 8 + 2 * i], f[jj * 8 + 2 * i + 1]);
-            op[jj] = o;
-          }
-        }
-        if (stats != nullptr) {
-          float x[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            x[i] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
-          float y2[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) y2[i] = x[i] * x[i];
-          warp_transpose_reduce(x, lane);
-          warp_transpose_reduce(y2, lane);
-          st_sum[cc] += x[0];
-          st_sq[cc] += y2[0];
-        }
+        epi_chunk(v, valid, true, obase + cc * 32, tn * BN + cc * 32, residual, out, stats != nullptr, E, lane,
+                  st_sum[cc], st_sq[cc], st_x3[cc]);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -1363,8 +1352,13 @@ static int encode_view(CUtensorMap* m, const bf16* base, int N, int Hd, int Wd, 
 }
 
 int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st,
-                double* stats) {
+                double* stats, const EpiBwd* bwd) {
   MN_CHECK(p != nullptr, "tc_conv_run: null plan");
+  EpiBwd E; memset(&E, 0, sizeof(E));
+  if (bwd != nullptr) {
+    MN_CHECK(p->kind == 1 && stats != nullptr && bwd->y != nullptr, "tc_conv_run: backward statistics need a dgrad plan, accumulators and Y");
+    E = *bwd;
+  }
   const ConvGeom& g = p->g;
   int nsm = 148;
   if (p->halo) {
@@ -1376,7 +1370,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       MN_TRY(encode_w_map(&p->hmapB, p->wmat, 9 * Cs, H.Cout, p->BN));
       p->c_in0 = in0;
     }
-    void (*kern)(CUtensorMap, CUtensorMap, HaloParams, const bf16*, bf16*, double*) =
+    void (*kern)(CUtensorMap, CUtensorMap, HaloParams, const bf16*, bf16*, double*, EpiBwd) =
         (p->BN == 64) ? k_tc_conv_halo<64> : (p->BN == 128 ? k_tc_conv_halo<128> : k_tc_conv_halo<256>);
     if (!p->smem_attr_set) {
       MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->halo_smem));
@@ -1384,7 +1378,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     }
     const int total = H.n_tiles_m * H.n_tiles_n;
     const int grid = total < nsm ? total : nsm;
-    kern<<<grid, 192, p->halo_smem, st>>>(p->hmapA, p->hmapB, H, residual, (bf16*)out, stats);
+    kern<<<grid, 192, p->halo_smem, st>>>(p->hmapA, p->hmapB, H, residual, (bf16*)out, stats, E);
     MN_LAUNCH_CHECK();
     return 0;
   }
@@ -1404,7 +1398,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       p->c_in0 = in0;
     }
     size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024;
-    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*, double*) = nullptr;
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*, double*, EpiBwd) = nullptr;
     if (p->two_cta) {
       smem = (size_t)conv2_stages(p->BN) * (128 * 128 + (p->BN / 2) * 128) + 1024;
       kern = (p->BN == 256) ? k_tc_conv2<256> : k_tc_conv2<128>;
@@ -1427,7 +1421,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = p->CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out, stats));
+      MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out, stats, E));
       ++g_launch_count;
     }
     return 0;

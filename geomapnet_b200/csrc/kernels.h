@@ -53,8 +53,23 @@ void tc_plan_destroy(TcConvPlan* p);
 // fprop: in0 = x, out = y (bf16);  dgrad: in0 = dy, out = dx (bf16);  wgrad: in0 = x, in1 = dy, out = fp32 dW (accumulated)
 // stats != nullptr (fprop, no residual): per-channel sum / sum of squares of the stored output are
 // accumulated into the replica accumulators for the fused BatchNorm statistics
+// bwd != nullptr (dgrad only, with stats): the stored gradient is gated by the consumer BN's ReLU
+// (zmask > 0, or mscale*y + mshift > 0) and (sum g, sum g*y [, sum g*yd]) are accumulated: the
+// reductions of that BN's backward, fused into the producer of its incoming gradient
+struct EpiBwd {
+  const bf16* y;        // consumer BN input (forward conv output), shaped like the dgrad output
+  const bf16* zmask;    // post-ReLU tensor whose sign gates the gradient, or null
+  const bf16* yd;       // downsample-branch BN input (third sum), or null
+  const float* mscale;  // gate recomputed from y when zmask is null
+  const float* mshift;
+};
 int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st,
-                double* stats = nullptr);
+                double* stats = nullptr, const EpiBwd* bwd = nullptr);
+// finalize of the dgrad-fused reductions: d gamma, d beta and the dy = A*g + B*y + C coefficients
+int launch_bn_bwd_finalize_accum(long long M, int C, const float* gamma, const float* mean, const float* invstd,
+                                 float* dgamma, float* dbeta, float* coef, const float* gamma2, const float* mean2,
+                                 const float* invstd2, float* dgamma2, float* dbeta2, float* coef2, double* accum,
+                                 cudaStream_t st);
 int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float* beta, float* run_mean,
                              float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift,
                              double* accum, cudaStream_t st);

@@ -131,6 +131,7 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0;
   { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
+  { const char* e = getenv("MAPNET_TC_FUSE_BWD"); fuse_bwd = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   build_table();
   if (max_B == 0) return 0;      // spec-only handle: parameter table, no device memory
   const size_t es = elt();
@@ -234,12 +235,13 @@ int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStre
   return r;
 }
 template <typename T>
-int Net::conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st) {
+int Net::conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd) {
   ConvGeom g = convs[ci].g; g.B = B;
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
-  if (precision == PREC_BF16_TC) r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, nullptr, (const bf16*)residual, dx, st);
+  if (precision == PREC_BF16_TC)
+    r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, nullptr, (const bf16*)residual, dx, st, bwd ? bn_accum : nullptr, bwd);
   else r = launch_conv_simt_dgrad<T>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
   prof_end(st, e0, 1, conv_flops(g, B, false));
   return r;
@@ -368,6 +370,10 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
   MN_TRY(launch_gap_bwd<T>(dfeat, S0, B, Hf * Wf, 512, st));
 
   // ---- residual blocks, last to first ----
+  // fuse_bwd (tcgen05 path): the dgrad that PRODUCES a BatchNorm's incoming gradient gates it with that
+  // BN's ReLU and accumulates its backward reductions in the epilogue (conv_tc.cu, EpiBwd), so only a tiny
+  // finalize and the apply pass remain.  `pre` = S0 arrives gated with the BN2 sums of this block pending.
+  bool pre = false;
   for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
     BlockL& bl = blocks[bi];
     const T* zin = (bi == 0) ? (const T*)z0 : (const T*)blocks[bi - 1].out;
@@ -376,14 +382,27 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     BNL& b1 = bns[convs[bl.conv1].bn];
     BNL& b2 = bns[convs[bl.conv2].bn];
     const bool ds = bl.convd >= 0;
+    const T* gres = S3;       // gated d out, the gradient of the identity branch
     // out = relu(bn2(y2) + idt): g = dout*[out>0]; BN2 (and downsample BN) backward
     if (ds) {
       BNL& bd = bns[convs[bl.convd].bn];
-      MN_TRY(launch_bn_bwd_reduce<T>(S0, (const T*)bl.out, (const T*)bl.y2, (const T*)bl.yd, Mo, C,
-                                     params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
-                                     params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef,
-                                     bn_accum, bn_counter, st));
-      MN_TRY(launch_bn_bwd_apply<T>(S0, (const T*)bl.out, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st));
+      if (pre) {
+        MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
+                                            params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef,
+                                            bn_accum, st));
+        MN_TRY(launch_bn_bwd_apply<T>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st));
+      } else {
+        MN_TRY(launch_bn_bwd_reduce<T>(S0, (const T*)bl.out, (const T*)bl.y2, (const T*)bl.yd, Mo, C,
+                                       params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
+                                       params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef,
+                                       bn_accum, bn_counter, st));
+        MN_TRY(launch_bn_bwd_apply<T>(S0, (const T*)bl.out, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st));
+      }
+    } else if (pre) {
+      MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
+                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
+      MN_TRY(launch_bn_bwd_apply<T>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st));
+      gres = S0;              // already gated; conv1's dgrad adds it in place
     } else {
       MN_TRY(launch_bn_bwd_reduce<T>(S0, (const T*)bl.out, (const T*)bl.y2, nullptr, Mo, C,
                                      params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
@@ -392,25 +411,42 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     }
     // conv2
     MN_TRY(conv_wgrad<T>(bl.conv2, (const T*)bl.h, S1, B, st));
-    MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st));
-    // h = relu(bn1(y1))
     // h = relu(bn1(y1)) has no residual: its ReLU mask is recomputed from y1 (scale*y+shift > 0),
     // one tensor read less in both backward passes
-    MN_TRY(launch_bn_bwd_reduce<T>(S4, nullptr, (const T*)bl.y1, nullptr, Mo, C,
-                                   params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
-                                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st,
-                                   b1.scale, b1.shift));
-    MN_TRY(launch_bn_bwd_apply<T>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st,
-                                  b1.scale, b1.shift));
-    // conv1 (+ downsample conv): d zin
+    if (fuse_bwd) {
+      EpiBwd e1; memset(&e1, 0, sizeof(e1));
+      e1.y = (const bf16*)bl.y1; e1.mscale = b1.scale; e1.mshift = b1.shift;
+      MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st, &e1));
+      MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
+                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
+      MN_TRY(launch_bn_bwd_apply<T>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st));
+    } else {
+      MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st));
+      MN_TRY(launch_bn_bwd_reduce<T>(S4, nullptr, (const T*)bl.y1, nullptr, Mo, C,
+                                     params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
+                                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st,
+                                     b1.scale, b1.shift));
+      MN_TRY(launch_bn_bwd_apply<T>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st,
+                                    b1.scale, b1.shift));
+    }
+    // conv1 (+ downsample conv): d zin; with fuse_bwd it is gated by the previous block's output ReLU
+    // and carries that block's BN2 (+ downsample BN) reductions
+    const bool next_pre = fuse_bwd && bi > 0;
+    EpiBwd e2; memset(&e2, 0, sizeof(e2));
+    if (next_pre) {
+      BlockL& pb = blocks[bi - 1];
+      e2.y = (const bf16*)pb.y2; e2.zmask = (const bf16*)pb.out;
+      e2.yd = (pb.convd >= 0) ? (const bf16*)pb.yd : nullptr;
+    }
     MN_TRY(conv_wgrad<T>(bl.conv1, zin, S1, B, st));
     if (ds) {
       MN_TRY(conv_wgrad<T>(bl.convd, zin, S2, B, st));
       MN_TRY(conv_dgrad<T>(bl.convd, S2, nullptr, S0, B, st));
-      MN_TRY(conv_dgrad<T>(bl.conv1, S1, S0, S0, B, st));
+      MN_TRY(conv_dgrad<T>(bl.conv1, S1, S0, S0, B, st, next_pre ? &e2 : nullptr));
     } else {
-      MN_TRY(conv_dgrad<T>(bl.conv1, S1, S3, S0, B, st));
+      MN_TRY(conv_dgrad<T>(bl.conv1, S1, gres, S0, B, st, next_pre ? &e2 : nullptr));
     }
+    pre = next_pre;
   }
   // ---- stem: maxpool -> ReLU -> BN -> conv (no input gradient: nothing consumes it) ----
   {

@@ -72,6 +72,7 @@ struct Net {
   // optional per-conv-launch timing (bench.py roofline): CUDA events around every conv call
   struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
   int profile_on;
+  int fuse_bwd;                  // BN backward reductions accumulated in the dgrad epilogue (env MAPNET_TC_FUSE_BWD)
   int fuse_stats;                // BN statistics accumulated in the tcgen05 conv epilogue (env MAPNET_TC_FUSE_STATS)
   std::vector<ProfRec> prof;
   int prof_begin(cudaStream_t st, cudaEvent_t* e0);
@@ -96,7 +97,7 @@ struct Net {
                                        cudaStream_t st);
   template <typename T> int conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st,
                                        bool with_stats = false);
-  template <typename T> int conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st);
+  template <typename T> int conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd = nullptr);
   template <typename T> int conv_wgrad(int ci, const T* x, const T* dy, int B, cudaStream_t st);
   template <typename T> int bn_forward(int bi, const T* y, long long M, const float* params, float* bufs,
                                        int training, cudaStream_t st);

@@ -117,6 +117,39 @@ def test_tensor_core_path_matches_cuda_core_path_on_bf16(name):
         assert v == v and v < 2.0, (el, ep, eg)
 
 
+@pytest.mark.parametrize("name", ["posenet_b8_256", "posenet_ragged", "mapnet_tiny"])
+def test_dgrad_fused_bn_backward_matches_separate_reduction(name):
+    """MAPNET_TC_FUSE_BWD=1 (default): the dgrad epilogue gates the gradient with the consumer
+    BN's ReLU and accumulates that BN's backward reductions; =0: separate k_channel_sums pass.
+    Same forward, same masks, the backward is linear given the masks: only the summation order
+    of the per-channel sums differs."""
+    from oracle import weights
+    g, cfg = load_golden(name)
+    st = weights.make_state(int(g["seed"]))
+    x, targ = weights.make_inputs(cfg, int(g["seed"]))
+    res = {}
+    old = os.environ.get("MAPNET_TC_FUSE_BWD")
+    try:
+        for mode in ("1", "0"):
+            os.environ["MAPNET_TC_FUSE_BWD"] = mode      # read when the trunk is created
+            model, net = make_product_model(st, cfg["kind"], "bf16")
+            crit = make_product_criterion(cfg["kind"])
+            model.train()
+            loss, pred, grads, _ = product_step(model, net, crit, x, targ, do_step=False)
+            res[mode] = (float(loss), {k: v.float().cpu() for k, v in grads.items()})
+    finally:
+        if old is None:
+            os.environ.pop("MAPNET_TC_FUSE_BWD", None)
+        else:
+            os.environ["MAPNET_TC_FUSE_BWD"] = old
+    (la, ga), (lb, gb) = res["1"], res["0"]
+    assert abs(la - lb) <= 1e-5 * abs(lb), (la, lb)
+    errs = {k: float((ga[k] - gb[k]).norm() / (gb[k].norm() + 1e-20)) for k in gb}
+    worst = max(errs, key=errs.get)
+    print("fused-vs-separate BN backward", name, worst, errs[worst])
+    assert errs[worst] < 5e-2, (worst, errs[worst])
+
+
 def test_eval_mode_forward_matches_oracle():
     """model.eval(): BN running statistics, no state change (validation path,
     common/train.py:214-256)."""

@@ -1,11 +1,14 @@
 mkdir -p gpurun_out
-echo "=== warm launch list (cache-control none)"
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 1150 -c 300 --csv --log-file gpurun_out/launches_warm.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/bench_ncu_warm.log 2>&1
-tail -n 2 gpurun_out/bench_ncu_warm.log | cut -c1-200
+echo "=== gpu tests"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+echo "=== bench fused"; timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench24.json 2> gpurun_out/bench24.err; tail -n 3 gpurun_out/bench24.err | cut -c1-300
 python - <<'PY'
-import csv
-lines=[l for l in open('gpurun_out/launches_warm.csv') if not l.startswith('==')]
-rows=list(csv.DictReader(lines))
-tot=sum(float(r['Metric Value'].replace(',','')) for r in rows)
-print('launches',len(rows),'sum_us',tot/1000)
+import json
+d=json.load(open('gpurun_out/bench24.json')); r=d['roofline']
+print('fused', d['value'], d['ms_per_step'], 'eager', d['config'].get('eager_ms_per_step'), 'e2e', d['e2e']['value'], d['gpu_launches'], r['conv_ms_per_step'], {k:round(v['tflops']) for k,v in r['per_class'].items()})
+PY
+echo "=== bench unfused bwd"; MAPNET_TC_FUSE_BWD=0 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench24u.json 2> gpurun_out/bench24u.err; tail -n 3 gpurun_out/bench24u.err | cut -c1-300
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench24u.json')); r=d['roofline']
+print('unfused', d['value'], d['ms_per_step'], 'eager', d['config'].get('eager_ms_per_step'), 'e2e', d['e2e']['value'], d['gpu_launches'], r['conv_ms_per_step'], {k:round(v['tflops']) for k,v in r['per_class'].items()})
 PY
