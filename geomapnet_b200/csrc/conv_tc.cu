@@ -124,7 +124,7 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&x)[32], int lane) 
 }
 
 // ---------------------------------------------------------------------------------
-// Shared epilogue of the fprop / dgrad engines: one 32-column chunk of one accumulator row.
+// Shared epilogue of the fprop / dgrad engines: one 32-column chunk of a warp's 32 accumulator rows.
 //   f = acc (+ residual)                                  every mode
 //   dgrad with E.y:  f = gate ? f : 0                     the consumer BN's ReLU gate, so the stored
 //                                                         gradient is already masked
@@ -134,98 +134,154 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&x)[32], int lane) 
 //     dgrad:  (sum g, sum g*y [, sum g*yd])               BatchNorm backward reductions of the BN
 //                                                         (and downsample BN) that consumes g
 // which removes the separate reduction pass over dY and Y of every BatchNorm backward.
+//
+// tcgen05.ld hands lane L the 32 fp32 columns of accumulator row L: touching global memory in that
+// layout costs one L1 wavefront per lane per 16 bytes (measured: with three extra tensors the
+// epilogue, not the MMAs, bounded the dgrad).  The accumulator chunk is therefore transposed once
+// through a per-warp shared-memory scratch (row stride 36 floats: conflict-free both ways) into the
+// COALESCED layout -- lane L owns 8 consecutive columns (16 bytes of bf16) p = L&3 of rows
+// 8i + (L>>2), i = 0..3 -- in which every global load and store instruction covers 8 rows x 64
+// contiguous bytes, and everything else (residual, gate, statistics) happens in that layout.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void load_row32(const bf16* __restrict__ p, float (&o)[32]) {
-  const uint4* rp = reinterpret_cast<const uint4*>(p);
+static constexpr int kEpiRowStride = 36;                 // floats per scratch row (32 + 4 pad)
+static constexpr int kEpiScratchFloats = 32 * kEpiRowStride;
+
+struct EpiRegs { uint4 r[4], y[4], z[4], d[4]; };
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 r = rp[j];
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    o[2 * i] = t.x; o[2 * i + 1] = t.y;
+  }
+}
+
+// x[8] per lane -> the sum over the 8 lanes that share (lane & 3), column (lane >> 2) of the 8 in x[0]
+__device__ __forceinline__ void group_reduce8(float (&x)[8], int lane) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 t = __bfloat1622float2(h[i]);
-      o[j * 8 + 2 * i] = t.x; o[j * 8 + 2 * i + 1] = t.y;
+  for (int s = 4; s >= 1; s >>= 1) {          // lane bits 4, 3, 2 <-> column bits 2, 1, 0
+    const bool up = (lane & (s << 2)) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const float send = up ? x[k] : x[k + s];
+      const float keep = up ? x[k + s] : x[k];
+      x[k] = keep + __shfl_xor_sync(0xffffffffu, send, s << 2);
     }
   }
 }
 
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const bool valid, const bool do_store,
-                                          const long long off, const int col0, const bf16* __restrict__ residual,
-                                          bf16* __restrict__ out, const bool stats_on, const EpiBwd& E,
-                                          const int lane, float& s0, float& s1, float& s2) {
-  float f[32];
+// issue this chunk's global loads (they do not depend on the accumulator): call before the TMEM load
+__device__ __forceinline__ void epi_issue_loads(EpiRegs& G, const long long (&rowoff)[4], const bool (&rvalid)[4],
+                                                const int coff, const bf16* residual, const EpiBwd& E, const int lane) {
+  const int po = coff + 8 * (lane & 3);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  for (int i = 0; i < 4; ++i) {
+    G.r[i] = make_uint4(0u, 0u, 0u, 0u); G.y[i] = G.r[i]; G.z[i] = G.r[i]; G.d[i] = G.r[i];
+    if (rvalid[i]) {
+      const long long off = rowoff[i] + po;
+      if (residual != nullptr) G.r[i] = *reinterpret_cast<const uint4*>(residual + off);   // may alias `out`: plain load
+      if (E.y != nullptr) {
+        G.y[i] = __ldg(reinterpret_cast<const uint4*>(E.y + off));
+        if (E.zmask != nullptr) G.z[i] = __ldg(reinterpret_cast<const uint4*>(E.zmask + off));
+        if (E.yd != nullptr) G.d[i] = __ldg(reinterpret_cast<const uint4*>(E.yd + off));
+      }
+    }
+  }
+}
+
+// statistics land on lane L for column  col0 + epi_stat_col(L)
+__device__ __forceinline__ int epi_stat_col(int lane) { return 8 * (lane & 3) + (lane >> 2); }
+
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float* __restrict__ scr, const EpiRegs& G,
+                                          const long long (&rowoff)[4], const bool (&rvalid)[4], const int coff,
+                                          const int col0, const bool has_res, bf16* out, const bool do_store,
+                                          const bool stats_on, const EpiBwd& E, const int lane, float& s0, float& s1,
+                                          float& s2) {
+  // stage the accumulator rows
+  {
+    float4* dst = reinterpret_cast<float4*>(scr + lane * kEpiRowStride);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                           __uint_as_float(v[4 * j + 3]));
+  }
+  __syncwarp();
+  const int p = lane & 3, rr = lane >> 2;
   const bool bwd = (E.y != nullptr);
-  float yv[32];
-  if (valid) {
-    if (residual != nullptr) {
-      float r[32];
-      load_row32(residual + off, r);
+  const bool ygate = bwd && (E.zmask == nullptr) && (E.mscale != nullptr);
+  float msc[8], msh[8];
+  if (ygate) {
+    const float4* a = reinterpret_cast<const float4*>(E.mscale + col0 + 8 * p);
+    const float4* b = reinterpret_cast<const float4*>(E.mshift + col0 + 8 * p);
+    const float4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
+    msc[0] = a0.x; msc[1] = a0.y; msc[2] = a0.z; msc[3] = a0.w; msc[4] = a1.x; msc[5] = a1.y; msc[6] = a1.z; msc[7] = a1.w;
+    msh[0] = b0.x; msh[1] = b0.y; msh[2] = b0.z; msh[3] = b0.w; msh[4] = b1.x; msh[5] = b1.y; msh[6] = b1.z; msh[7] = b1.w;
+  }
+  float c0[8], c1[8], c2[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] += r[i];
+  for (int k = 0; k < 8; ++k) { c0[k] = 0.f; c1[k] = 0.f; c2[k] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4* src = reinterpret_cast<const float4*>(scr + (8 * i + rr) * kEpiRowStride + 8 * p);
+    const float4 lo = src[0], hi = src[1];
+    if (!rvalid[i]) continue;
+    float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    float yv[8];
+    if (has_res) {
+      float r[8];
+      unpack8(G.r[i], r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += r[k];
     }
     if (bwd) {
-      load_row32(E.y + off, yv);
+      unpack8(G.y[i], yv);
       if (E.zmask != nullptr) {
-        float z[32];
-        load_row32(E.zmask + off, z);
+        float z[8];
+        unpack8(G.z[i], z);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = (z[i] > 0.f) ? f[i] : 0.f;
-      } else if (E.mscale != nullptr) {
-        const float4* sc = reinterpret_cast<const float4*>(E.mscale + col0);
-        const float4* sh = reinterpret_cast<const float4*>(E.mshift + col0);
+        for (int k = 0; k < 8; ++k) f[k] = (z[k] > 0.f) ? f[k] : 0.f;
+      } else if (ygate) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 a = __ldg(sc + j), b = __ldg(sh + j);
-          f[4 * j + 0] = (yv[4 * j + 0] * a.x + b.x > 0.f) ? f[4 * j + 0] : 0.f;
-          f[4 * j + 1] = (yv[4 * j + 1] * a.y + b.y > 0.f) ? f[4 * j + 1] : 0.f;
-          f[4 * j + 2] = (yv[4 * j + 2] * a.z + b.z > 0.f) ? f[4 * j + 2] : 0.f;
-          f[4 * j + 3] = (yv[4 * j + 3] * a.w + b.w > 0.f) ? f[4 * j + 3] : 0.f;
+        for (int k = 0; k < 8; ++k) f[k] = (yv[k] * msc[k] + msh[k] > 0.f) ? f[k] : 0.f;
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    if (do_store) *reinterpret_cast<uint4*>(out + rowoff[i] + coff + 8 * p) = o;
+    if (stats_on) {
+      float x[8];
+      unpack8(o, x);
+      if (bwd) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c0[k] += x[k]; c1[k] += x[k] * yv[k]; }
+        if (E.yd != nullptr) {
+          float u[8];
+          unpack8(G.d[i], u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) c2[k] += x[k] * u[k];
         }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c0[k] += x[k]; c1[k] += x[k] * x[k]; }
       }
     }
   }
-  __nv_bfloat162 hq[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) hq[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  if (valid && do_store) {
-    uint4* op = reinterpret_cast<uint4*>(out + off);
-    const uint4* src = reinterpret_cast<const uint4*>(hq);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) op[j] = src[j];
-  }
+  __syncwarp();                                // scratch may be overwritten by the next chunk
   if (stats_on) {
-    float x[32], w[32];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float2 t = __bfloat1622float2(hq[i]);
-      x[2 * i] = valid ? t.x : 0.f; x[2 * i + 1] = valid ? t.y : 0.f;
-    }
-    if (bwd) {
-      if (E.yd != nullptr) {
-        float u[32];
-        if (valid) load_row32(E.yd + off, u);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) u[i] = valid ? x[i] * u[i] : 0.f;
-        warp_transpose_reduce(u, lane);
-        s2 += u[0];
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) w[i] = valid ? x[i] * yv[i] : 0.f;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) w[i] = x[i] * x[i];
-    }
-    warp_transpose_reduce(x, lane);
-    warp_transpose_reduce(w, lane);
-    s0 += x[0];
-    s1 += w[0];
+    group_reduce8(c0, lane);
+    group_reduce8(c1, lane);
+    s0 += c0[0];
+    s1 += c1[0];
+    if (bwd && E.yd != nullptr) { group_reduce8(c2, lane); s2 += c2[0]; }
   }
 }
 
 // as many stages as fit in 227 KB: the engines are bound by bytes in flight x L2 latency
-static constexpr int conv_stages(int BN) { return BN <= 64 ? 9 : (BN <= 128 ? 6 : 4); }
+static constexpr int conv_stages(int BN) { return BN <= 64 ? 8 : (BN <= 128 ? 6 : 4); }   // + 18 KB epilogue scratch
+static constexpr int wgrad_stages(int BN) { return BN <= 64 ? 9 : (BN <= 128 ? 6 : 4); }
 
 // ---------------------------------------------------------------------------------
 // fprop / dgrad kernel
@@ -349,7 +405,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
     const int q = warp & 3;
-    const int m = q * 32 + lane;                 // row of the tile = TMEM lane
+    __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
+    float* scr = epi_scratch[q];
     int as = 0; uint32_t aphase = 0;
     // fused BatchNorm statistics (fprop only): lane L keeps the running column sums of column
     // cc*32+L over all rows this warp has stored, flushed with fp64 atomics per N tile
@@ -361,7 +418,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) {
-        const int c = tn_flush * BN + i * 32 + lane;
+        const int c = tn_flush * BN + i * 32 + epi_stat_col(lane);
         atomicAdd(acc + c, (double)st_sum[i]);
         atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
         if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)st_x3[i]);
@@ -375,14 +432,22 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       const int tw = tm % P.tiles_w; tm /= P.tiles_w;
       const int th = tm % P.tiles_h;
       const int tb = tm / P.tiles_h;
-      // pixel of this thread inside the TN x TH x TW box (w fastest)
-      const int lw = m % P.TW;
-      const int lh = (m / P.TW) % P.TH;
-      const int ln = m / (P.TW * P.TH);
-      const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
-      const bool valid = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
-      const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
-      const long long obase = pix * P.Cout + tn * BN;
+      // the 4 rows this lane owns in the coalesced layout: tile row q*32 + 8i + (lane>>2)
+      long long rowoff[4]; bool rvalid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = q * 32 + 8 * i + (lane >> 2);
+        const int lw = m % P.TW;
+        const int lh = (m / P.TW) % P.TH;
+        const int ln = m / (P.TW * P.TH);
+        const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
+        rvalid[i] = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
+        const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
+        rowoff[i] = pix * P.Cout + tn * BN;
+      }
+      // the first chunk's operand loads do not depend on the accumulator: in flight while the MMAs finish
+      EpiRegs G;
+      epi_issue_loads(G, rowoff, rvalid, 0, residual, E, lane);
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
       if (P.debug == 3) {           // micro-benchmark: no epilogue work at all
@@ -394,6 +459,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       }
 #pragma unroll
       for (int cc = 0; cc < BN / 32; ++cc) {
+        if (cc > 0) epi_issue_loads(G, rowoff, rvalid, cc * 32, residual, E, lane);
         uint32_t v[32];
         if (kblocks > 0) {
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
@@ -408,8 +474,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         }
-        epi_chunk(v, valid, P.debug != 4, obase + cc * 32, tn * BN + cc * 32, residual, out, stats != nullptr, E, lane,
-                  st_sum[cc], st_sq[cc], st_x3[cc]);
+        epi_chunk(v, scr, G, rowoff, rvalid, cc * 32, tn * BN + cc * 32, residual != nullptr, out, P.debug != 4,
+                  stats != nullptr, E, lane, st_sum[cc], st_sq[cc], st_x3[cc]);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -539,7 +605,8 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   } else {
     // ===================== epilogue (both CTAs; own TMEM half) =====================
     const int q = warp & 3;
-    const int m = q * 32 + lane;
+    __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
+    float* scr = epi_scratch[q];
     int as = 0; uint32_t aphase = 0;
     float st_sum[BN / 32], st_sq[BN / 32], st_x3[BN / 32];
 #pragma unroll
@@ -549,7 +616,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) {
-        const int c = tn_flush * BN + i * 32 + lane;
+        const int c = tn_flush * BN + i * 32 + epi_stat_col(lane);
         atomicAdd(acc + c, (double)st_sum[i]);
         atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
         if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)st_x3[i]);
@@ -563,17 +630,27 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       const int tw = tm % P.tiles_w; tm /= P.tiles_w;
       const int th = tm % P.tiles_h;
       const int tb = tm / P.tiles_h;
-      const int lw = m % P.TW;
-      const int lh = (m / P.TW) % P.TH;
-      const int ln = m / (P.TW * P.TH);
-      const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
-      const bool valid = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
-      const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
-      const long long obase = pix * P.Cout + tn * BN;
+      // the 4 rows this lane owns in the coalesced layout: tile row q*32 + 8i + (lane>>2)
+      long long rowoff[4]; bool rvalid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = q * 32 + 8 * i + (lane >> 2);
+        const int lw = m % P.TW;
+        const int lh = (m / P.TW) % P.TH;
+        const int ln = m / (P.TW * P.TH);
+        const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
+        rvalid[i] = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
+        const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
+        rowoff[i] = pix * P.Cout + tn * BN;
+      }
+      // the first chunk's operand loads do not depend on the accumulator: in flight while the MMAs finish
+      EpiRegs G;
+      epi_issue_loads(G, rowoff, rvalid, 0, residual, E, lane);
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < BN / 32; ++cc) {
+        if (cc > 0) epi_issue_loads(G, rowoff, rvalid, cc * 32, residual, E, lane);
         uint32_t v[32];
         if (kblocks > 0) {
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
@@ -587,8 +664,8 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa(tempty0 + 8 * as, 0));
         }
-        epi_chunk(v, valid, true, obase + cc * 32, tn * BN + cc * 32, residual, out, stats != nullptr, E, lane,
-                  st_sum[cc], st_sq[cc], st_x3[cc]);
+        epi_chunk(v, scr, G, rowoff, rvalid, cc * 32, tn * BN + cc * 32, residual != nullptr, out, true,
+                  stats != nullptr, E, lane, st_sum[cc], st_sq[cc], st_x3[cc]);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -757,7 +834,8 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;
-    const int m = q * 32 + lane;
+    __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
+    float* scr = epi_scratch[q];
     int as = 0; uint32_t aphase = 0;
     float st_sum[BN / 32], st_sq[BN / 32], st_x3[BN / 32];
 #pragma unroll
@@ -767,7 +845,7 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) {
-        const int c = tn_flush * BN + i * 32 + lane;
+        const int c = tn_flush * BN + i * 32 + epi_stat_col(lane);
         atomicAdd(acc + c, (double)st_sum[i]);
         atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
         if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)st_x3[i]);
@@ -779,15 +857,23 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (stats != nullptr && tn != st_tn) { if (st_tn >= 0) flush_stats(st_tn); st_tn = tn; }
       const int tm = tile / P.n_tiles_n;
       const int n = tm / P.tiles_per_img, t = tm - n * P.tiles_per_img;
-      const int qq = t * 128 + m;
-      const int h = qq / P.P, j = qq - h * P.P;
-      const bool valid = (j >= 1) && (j <= P.W) && (h < P.H);
-      const long long pix = ((long long)n * P.H + h) * P.W + (j - 1);
-      const long long obase = pix * P.Cout + tn * BN;
+      long long rowoff[4]; bool rvalid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int qq = t * 128 + q * 32 + 8 * i + (lane >> 2);
+        const int h = qq / P.P, j = qq - h * P.P;
+        rvalid[i] = (j >= 1) && (j <= P.W) && (h < P.H);
+        const long long pix = ((long long)n * P.H + h) * P.W + (j - 1);
+        rowoff[i] = pix * P.Cout + tn * BN;
+      }
+      // the first chunk's operand loads do not depend on the accumulator: in flight while the MMAs finish
+      EpiRegs G;
+      epi_issue_loads(G, rowoff, rvalid, 0, residual, E, lane);
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < BN / 32; ++cc) {
+        if (cc > 0) epi_issue_loads(G, rowoff, rvalid, cc * 32, residual, E, lane);
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
         tmem_ld_wait();
@@ -796,8 +882,8 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         }
-        epi_chunk(v, valid, true, obase + cc * 32, tn * BN + cc * 32, residual, out, stats != nullptr, E, lane,
-                  st_sum[cc], st_sq[cc], st_x3[cc]);
+        epi_chunk(v, scr, G, rowoff, rvalid, cc * 32, tn * BN + cc * 32, residual != nullptr, out, true,
+                  stats != nullptr, E, lane, st_sum[cc], st_sq[cc], st_x3[cc]);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -818,7 +904,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
            const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapX3,
            const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ WgradParams P,
            float* __restrict__ dw) {
-  constexpr int STAGES = conv_stages(BN);
+  constexpr int STAGES = wgrad_stages(BN);
   constexpr uint32_t CHUNK_BYTES = 64 * 128;     // 64 pixels x 64 ch bf16
   constexpr uint32_t A_BYTES = 2 * CHUNK_BYTES;
   constexpr uint32_t B_BYTES = (BN / 64) * CHUNK_BYTES;
@@ -1196,7 +1282,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
         int bn = (Cn % 256 == 0 && H.n_tiles_m >= 120) ? 256 : ((Cn % 128 == 0) ? 128 : 64);
         { const char* e = getenv("MAPNET_TC_BN"); int f = e ? atoi(e) : 0; if ((f == 64 || f == 128 || f == 256) && Cn % f == 0) bn = f; }
         const long long wbytes = 9LL * H.cblocks * bn * 128;
-        const long long budget = 226LL * 1024 - 2048;
+        const long long budget = 226LL * 1024 - 2048 - 4 * kEpiScratchFloats * 4;    // static epilogue scratch
         H.b_stationary = (Cn == bn && wbytes + 2LL * H.patch_bytes <= budget) ? 1 : 0;
         long long left = budget - (H.b_stationary ? wbytes : 0);
         if (H.b_stationary) { H.NP = (int)(left / H.patch_bytes); H.NB = 0; }
@@ -1454,7 +1540,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     ++g_launch_count;
     return 0;
   }
-  const int stages = conv_stages(p->BN);
+  const int stages = wgrad_stages(p->BN);
   const size_t smem = (size_t)stages * (2 * 8192 + (p->BN / 64) * 8192) + 1024;
   if (!p->smem_attr_set) {
     if (p->BN == 64) MN_TRY(set_smem(k_tc_wgrad<64>, smem));
