@@ -410,19 +410,23 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     int as = 0; uint32_t aphase = 0;
     // fused BatchNorm statistics (fprop only): lane L keeps the running column sums of column
     // cc*32+L over all rows this warp has stored, flushed with fp64 atomics per N tile
-    float st_sum[BN / 32], st_sq[BN / 32], st_x3[BN / 32];
-#pragma unroll
-    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f; }
+    // running column sums of this warp, [statistic][chunk][lane] (lane <-> column epi_stat_col(lane)); kept in
+    // shared memory so that the chunk loop can stay ROLLED: unrolled, the epilogue alone was > 100 KB of
+    // SASS and the four epilogue warps stalled on instruction fetch (ncu: stall_no_inst dominant)
+    __shared__ float epi_stats[4][3][BN / 32][32];
+    float (*stw)[BN / 32][32] = epi_stats[q];
+#pragma unroll 1
+    for (int i = 0; i < BN / 32; ++i) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
     int st_tn = -1;
     auto flush_stats = [&](int tn_flush) {
       double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < BN / 32; ++i) {
         const int c = tn_flush * BN + i * 32 + epi_stat_col(lane);
-        atomicAdd(acc + c, (double)st_sum[i]);
-        atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
-        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)st_x3[i]);
-        st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f;
+        atomicAdd(acc + c, (double)stw[0][i][lane]);
+        atomicAdd(acc + P.Cout + c, (double)stw[1][i][lane]);
+        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)stw[2][i][lane]);
+        stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f;
       }
     };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -457,7 +461,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         if (++as == 2) { as = 0; aphase ^= 1; }
         continue;
       }
-#pragma unroll
+#pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         if (cc > 0) epi_issue_loads(G, rowoff, rvalid, cc * 32, residual, E, lane);
         uint32_t v[32];
@@ -475,7 +479,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         }
         epi_chunk(v, scr, G, rowoff, rvalid, cc * 32, tn * BN + cc * 32, residual != nullptr, out, P.debug != 4,
-                  stats != nullptr, E, lane, st_sum[cc], st_sq[cc], st_x3[cc]);
+                  stats != nullptr, E, lane, stw[0][cc][lane], stw[1][cc][lane], stw[2][cc][lane]);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -608,19 +612,23 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
     float* scr = epi_scratch[q];
     int as = 0; uint32_t aphase = 0;
-    float st_sum[BN / 32], st_sq[BN / 32], st_x3[BN / 32];
-#pragma unroll
-    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f; }
+    // running column sums of this warp, [statistic][chunk][lane] (lane <-> column epi_stat_col(lane)); kept in
+    // shared memory so that the chunk loop can stay ROLLED: unrolled, the epilogue alone was > 100 KB of
+    // SASS and the four epilogue warps stalled on instruction fetch (ncu: stall_no_inst dominant)
+    __shared__ float epi_stats[4][3][BN / 32][32];
+    float (*stw)[BN / 32][32] = epi_stats[q];
+#pragma unroll 1
+    for (int i = 0; i < BN / 32; ++i) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
     int st_tn = -1;
     auto flush_stats = [&](int tn_flush) {
       double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < BN / 32; ++i) {
         const int c = tn_flush * BN + i * 32 + epi_stat_col(lane);
-        atomicAdd(acc + c, (double)st_sum[i]);
-        atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
-        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)st_x3[i]);
-        st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f;
+        atomicAdd(acc + c, (double)stw[0][i][lane]);
+        atomicAdd(acc + P.Cout + c, (double)stw[1][i][lane]);
+        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)stw[2][i][lane]);
+        stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f;
       }
     };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -648,7 +656,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       epi_issue_loads(G, rowoff, rvalid, 0, residual, E, lane);
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         if (cc > 0) epi_issue_loads(G, rowoff, rvalid, cc * 32, residual, E, lane);
         uint32_t v[32];
@@ -665,7 +673,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           if (lane == 0) mbar_arrive_cluster(mapa(tempty0 + 8 * as, 0));
         }
         epi_chunk(v, scr, G, rowoff, rvalid, cc * 32, tn * BN + cc * 32, residual != nullptr, out, true,
-                  stats != nullptr, E, lane, st_sum[cc], st_sq[cc], st_x3[cc]);
+                  stats != nullptr, E, lane, stw[0][cc][lane], stw[1][cc][lane], stw[2][cc][lane]);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -837,19 +845,23 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
     float* scr = epi_scratch[q];
     int as = 0; uint32_t aphase = 0;
-    float st_sum[BN / 32], st_sq[BN / 32], st_x3[BN / 32];
-#pragma unroll
-    for (int i = 0; i < BN / 32; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f; }
+    // running column sums of this warp, [statistic][chunk][lane] (lane <-> column epi_stat_col(lane)); kept in
+    // shared memory so that the chunk loop can stay ROLLED: unrolled, the epilogue alone was > 100 KB of
+    // SASS and the four epilogue warps stalled on instruction fetch (ncu: stall_no_inst dominant)
+    __shared__ float epi_stats[4][3][BN / 32][32];
+    float (*stw)[BN / 32][32] = epi_stats[q];
+#pragma unroll 1
+    for (int i = 0; i < BN / 32; ++i) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
     int st_tn = -1;
     auto flush_stats = [&](int tn_flush) {
       double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < BN / 32; ++i) {
         const int c = tn_flush * BN + i * 32 + epi_stat_col(lane);
-        atomicAdd(acc + c, (double)st_sum[i]);
-        atomicAdd(acc + P.Cout + c, (double)st_sq[i]);
-        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)st_x3[i]);
-        st_sum[i] = 0.f; st_sq[i] = 0.f; st_x3[i] = 0.f;
+        atomicAdd(acc + c, (double)stw[0][i][lane]);
+        atomicAdd(acc + P.Cout + c, (double)stw[1][i][lane]);
+        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)stw[2][i][lane]);
+        stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f;
       }
     };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -871,7 +883,7 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       epi_issue_loads(G, rowoff, rvalid, 0, residual, E, lane);
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         if (cc > 0) epi_issue_loads(G, rowoff, rvalid, cc * 32, residual, E, lane);
         uint32_t v[32];
@@ -883,7 +895,7 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         }
         epi_chunk(v, scr, G, rowoff, rvalid, cc * 32, tn * BN + cc * 32, residual != nullptr, out, true,
-                  stats != nullptr, E, lane, st_sum[cc], st_sq[cc], st_x3[cc]);
+                  stats != nullptr, E, lane, stw[0][cc][lane], stw[1][cc][lane], stw[2][cc][lane]);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -1282,7 +1294,9 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
         int bn = (Cn % 256 == 0 && H.n_tiles_m >= 120) ? 256 : ((Cn % 128 == 0) ? 128 : 64);
         { const char* e = getenv("MAPNET_TC_BN"); int f = e ? atoi(e) : 0; if ((f == 64 || f == 128 || f == 256) && Cn % f == 0) bn = f; }
         const long long wbytes = 9LL * H.cblocks * bn * 128;
-        const long long budget = 226LL * 1024 - 2048 - 4 * kEpiScratchFloats * 4;    // static epilogue scratch
+        // 227 KB per CTA minus the alignment slack and the kernel's static shared memory (epilogue scratch,
+        // per-warp statistics, barriers)
+        const long long budget = 227LL * 1024 - 1024 - (4LL * kEpiScratchFloats * 4 + 1536LL * (bn / 32) + 512);
         H.b_stationary = (Cn == bn && wbytes + 2LL * H.patch_bytes <= budget) ? 1 : 0;
         long long left = budget - (H.b_stationary ? wbytes : 0);
         if (H.b_stationary) { H.NP = (int)(left / H.patch_bytes); H.NB = 0; }

@@ -1,5 +1,7 @@
 mkdir -p gpurun_out
-echo "=== gpu tests"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+echo "=== conv kernel tests"; timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q 2>&1 | tail -3
+for dbg in 0 3; do echo "=== bench_conv DEBUG=$dbg"; MAPNET_TC_DEBUG=$dbg timeout 120 python tools/bench_conv.py 64 2>&1 | tail -7; done
+echo "=== gpu step tests"; timeout 600 python -m pytest tests/test_gpu_step.py tests/test_gpu_graph.py -m gpu -x -q 2>&1 | tail -3
 echo "=== bench fused"; timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench24.json 2> gpurun_out/bench24.err; tail -n 3 gpurun_out/bench24.err | cut -c1-300
 python - <<'PY'
 import json
