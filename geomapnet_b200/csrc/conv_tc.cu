@@ -146,6 +146,17 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&x)[32], int lane) 
 static constexpr int kEpiRowStride = 36;                 // floats per scratch row (32 + 4 pad)
 static constexpr int kEpiScratchFloats = 32 * kEpiRowStride;
 
+// Epilogue variants (template flags): the flags are launch-uniform, and specialising on them keeps every
+// variant's chunk body straight-line code (runtime flags cost ~3x: branches fence the scheduler and the
+// four epilogue warps are latency-, not throughput-bound).
+enum : int {
+  EPI_RES = 1,      // + residual
+  EPI_STATS = 2,    // fprop: (sum f, sum f^2)
+  EPI_BWD = 4,      // dgrad: gate + (sum g, sum g*y); gate = mscale*y+mshift > 0 unless EPI_ZMASK
+  EPI_ZMASK = 8,    // gate = zmask > 0
+  EPI_YD = 16,      // third sum over the downsample-branch BN input
+};
+
 struct EpiRegs { uint4 r[4], y[4], z[4], d[4]; };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
@@ -171,33 +182,30 @@ __device__ __forceinline__ void group_reduce8(float (&x)[8], int lane) {
   }
 }
 
-// issue this chunk's global loads (they do not depend on the accumulator): call before the TMEM load
-__device__ __forceinline__ void epi_issue_loads(EpiRegs& G, const long long (&rowoff)[4], const bool (&rvalid)[4],
-                                                const int coff, const bf16* residual, const EpiBwd& E, const int lane) {
-  const int po = coff + 8 * (lane & 3);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    G.r[i] = make_uint4(0u, 0u, 0u, 0u); G.y[i] = G.r[i]; G.z[i] = G.r[i]; G.d[i] = G.r[i];
-    if (rvalid[i]) {
-      const long long off = rowoff[i] + po;
-      if (residual != nullptr) G.r[i] = *reinterpret_cast<const uint4*>(residual + off);   // may alias `out`: plain load
-      if (E.y != nullptr) {
-        G.y[i] = __ldg(reinterpret_cast<const uint4*>(E.y + off));
-        if (E.zmask != nullptr) G.z[i] = __ldg(reinterpret_cast<const uint4*>(E.zmask + off));
-        if (E.yd != nullptr) G.d[i] = __ldg(reinterpret_cast<const uint4*>(E.yd + off));
-      }
-    }
-  }
-}
-
 // statistics land on lane L for column  col0 + epi_stat_col(L)
 __device__ __forceinline__ int epi_stat_col(int lane) { return 8 * (lane & 3) + (lane >> 2); }
 
+// issue one chunk's operand loads (they do not depend on the accumulator).  Rows outside the tensor have
+// their offset clamped to row 0 by the caller, so no load needs a guard.
+template <int F>
+__device__ __forceinline__ void epi_issue_loads(EpiRegs& G, const long long (&rowoff)[4], const int coff,
+                                                const bf16* residual, const EpiBwd& E, const int lane) {
+  const int po = coff + 8 * (lane & 3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long off = rowoff[i] + po;
+    if (F & EPI_RES) G.r[i] = *reinterpret_cast<const uint4*>(residual + off);   // may alias `out`: plain load
+    if (F & EPI_BWD) G.y[i] = __ldg(reinterpret_cast<const uint4*>(E.y + off));
+    if (F & EPI_ZMASK) G.z[i] = __ldg(reinterpret_cast<const uint4*>(E.zmask + off));
+    if (F & EPI_YD) G.d[i] = __ldg(reinterpret_cast<const uint4*>(E.yd + off));
+  }
+}
+
+template <int F>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float* __restrict__ scr, const EpiRegs& G,
-                                          const long long (&rowoff)[4], const bool (&rvalid)[4], const int coff,
-                                          const int col0, const bool has_res, bf16* out, const bool do_store,
-                                          const bool stats_on, const EpiBwd& E, const int lane, float& s0, float& s1,
-                                          float& s2) {
+                                          const long long (&rowoff)[4], const bool (&rstore)[4], const float (&rw)[4],
+                                          const int coff, const int col0, bf16* out, const EpiBwd& E, const int lane,
+                                          float& s0, float& s1, float& s2) {
   // stage the accumulator rows
   {
     float4* dst = reinterpret_cast<float4*>(scr + lane * kEpiRowStride);
@@ -208,10 +216,14 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float* __rest
   }
   __syncwarp();
   const int p = lane & 3, rr = lane >> 2;
-  const bool bwd = (E.y != nullptr);
-  const bool ygate = bwd && (E.zmask == nullptr) && (E.mscale != nullptr);
+  float4 lo[4], hi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4* src = reinterpret_cast<const float4*>(scr + (8 * i + rr) * kEpiRowStride + 8 * p);
+    lo[i] = src[0]; hi[i] = src[1];
+  }
   float msc[8], msh[8];
-  if (ygate) {
+  if ((F & EPI_BWD) && !(F & EPI_ZMASK)) {
     const float4* a = reinterpret_cast<const float4*>(E.mscale + col0 + 8 * p);
     const float4* b = reinterpret_cast<const float4*>(E.mshift + col0 + 8 * p);
     const float4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
@@ -223,25 +235,22 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float* __rest
   for (int k = 0; k < 8; ++k) { c0[k] = 0.f; c1[k] = 0.f; c2[k] = 0.f; }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4* src = reinterpret_cast<const float4*>(scr + (8 * i + rr) * kEpiRowStride + 8 * p);
-    const float4 lo = src[0], hi = src[1];
-    if (!rvalid[i]) continue;
-    float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    float f[8] = {lo[i].x, lo[i].y, lo[i].z, lo[i].w, hi[i].x, hi[i].y, hi[i].z, hi[i].w};
     float yv[8];
-    if (has_res) {
+    if (F & EPI_RES) {
       float r[8];
       unpack8(G.r[i], r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] += r[k];
     }
-    if (bwd) {
+    if (F & EPI_BWD) {
       unpack8(G.y[i], yv);
-      if (E.zmask != nullptr) {
+      if (F & EPI_ZMASK) {
         float z[8];
         unpack8(G.z[i], z);
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = (z[k] > 0.f) ? f[k] : 0.f;
-      } else if (ygate) {
+      } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = (yv[k] * msc[k] + msh[k] > 0.f) ? f[k] : 0.f;
       }
@@ -250,14 +259,17 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float* __rest
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
     for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-    if (do_store) *reinterpret_cast<uint4*>(out + rowoff[i] + coff + 8 * p) = o;
-    if (stats_on) {
+    if (rstore[i]) *reinterpret_cast<uint4*>(out + rowoff[i] + coff + 8 * p) = o;
+    if (F & (EPI_STATS | EPI_BWD)) {
+      // the values AS STORED; rw = 1 for rows inside the tensor, 0 outside
       float x[8];
       unpack8(o, x);
-      if (bwd) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] *= rw[i];
+      if (F & EPI_BWD) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) { c0[k] += x[k]; c1[k] += x[k] * yv[k]; }
-        if (E.yd != nullptr) {
+        if (F & EPI_YD) {
           float u[8];
           unpack8(G.d[i], u);
 #pragma unroll
@@ -270,13 +282,88 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float* __rest
     }
   }
   __syncwarp();                                // scratch may be overwritten by the next chunk
-  if (stats_on) {
+  if (F & (EPI_STATS | EPI_BWD)) {
     group_reduce8(c0, lane);
     group_reduce8(c1, lane);
     s0 += c0[0];
     s1 += c1[0];
-    if (bwd && E.yd != nullptr) { group_reduce8(c2, lane); s2 += c2[0]; }
+    if (F & EPI_YD) { group_reduce8(c2, lane); s2 += c2[0]; }
   }
+}
+
+// One accumulator tile (this warp's 32 rows x BN columns): wait for the MMAs, walk the 32-column chunks,
+// hand the TMEM stage back after the last TMEM read.  `release` performs the tempty arrive.
+template <int F, int BN, typename Release>
+__device__ __forceinline__ void epi_tile(const uint32_t tmem_addr, const bool has_acc, const uint32_t tfull_bar,
+                                         const uint32_t tfull_phase, Release release, float* __restrict__ scr,
+                                         float (*stw)[BN / 32][32], const long long (&rowoff)[4],
+                                         const bool (&rvalid)[4], const bool do_store, const int tn,
+                                         const bf16* residual, bf16* out, const EpiBwd& E, const int lane) {
+  bool rstore[4]; float rw[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { rstore[i] = rvalid[i] && do_store; rw[i] = rvalid[i] ? 1.f : 0.f; }
+  // the first chunk's operand loads are in flight while the MMAs finish
+  EpiRegs G;
+  epi_issue_loads<F>(G, rowoff, 0, residual, E, lane);
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int cc = 0; cc < BN / 32; ++cc) {
+    if (cc > 0) epi_issue_loads<F>(G, rowoff, cc * 32, residual, E, lane);
+    uint32_t v[32];
+    if (has_acc) {
+      tmem_ld32(tmem_addr + cc * 32, v);
+      tmem_ld_wait();
+    } else {                                   // no filter tap reaches this output class: D = 0
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0u;
+    }
+    if (cc == BN / 32 - 1) {
+      // all TMEM reads of this accumulator stage are complete: hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) release();
+    }
+    epi_chunk<F>(v, scr, G, rowoff, rstore, rw, cc * 32, tn * BN + cc * 32, out, E, lane, stw[0][cc][lane],
+                 stw[1][cc][lane], stw[2][cc][lane]);
+  }
+}
+
+// launch-uniform dispatch over the variants the network uses
+template <int BN, typename Release>
+__device__ __forceinline__ void epi_tile_dispatch(const int mode, const uint32_t tmem_addr, const bool has_acc,
+                                                  const uint32_t tfull_bar, const uint32_t tfull_phase, Release release,
+                                                  float* __restrict__ scr, float (*stw)[BN / 32][32],
+                                                  const long long (&rowoff)[4], const bool (&rvalid)[4],
+                                                  const bool do_store, const int tn, const bf16* residual, bf16* out,
+                                                  const EpiBwd& E, const int lane) {
+#define MN_EPI_CASE(Fv) case (Fv): epi_tile<(Fv), BN>(tmem_addr, has_acc, tfull_bar, tfull_phase, release, scr, stw, rowoff, \
+                                                      rvalid, do_store, tn, residual, out, E, lane); break;
+  switch (mode) {
+    MN_EPI_CASE(0)
+    MN_EPI_CASE(EPI_RES)
+    MN_EPI_CASE(EPI_STATS)
+    MN_EPI_CASE(EPI_BWD)
+    MN_EPI_CASE(EPI_BWD | EPI_RES)
+    MN_EPI_CASE(EPI_BWD | EPI_ZMASK)
+    MN_EPI_CASE(EPI_BWD | EPI_ZMASK | EPI_RES)
+    MN_EPI_CASE(EPI_BWD | EPI_ZMASK | EPI_YD)
+    MN_EPI_CASE(EPI_BWD | EPI_ZMASK | EPI_RES | EPI_YD)
+    default: __trap();
+  }
+#undef MN_EPI_CASE
+}
+
+__device__ __forceinline__ int epi_mode_of(const bf16* residual, const double* stats, const EpiBwd& E) {
+  int m = (residual != nullptr) ? EPI_RES : 0;
+  if (E.y != nullptr) {
+    m |= EPI_BWD;
+    if (E.zmask != nullptr) m |= EPI_ZMASK;
+    if (E.yd != nullptr) m |= EPI_YD;
+  } else if (stats != nullptr) {
+    m |= EPI_STATS;
+  }
+  return m;
 }
 
 // as many stages as fit in 227 KB: the engines are bound by bytes in flight x L2 latency
@@ -407,6 +494,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int q = warp & 3;
     __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
     float* scr = epi_scratch[q];
+    const int epi_mode = epi_mode_of(residual, stats, E);
     int as = 0; uint32_t aphase = 0;
     // fused BatchNorm statistics (fprop only): lane L keeps the running column sums of column
     // cc*32+L over all rows this warp has stored, flushed with fp64 atomics per N tile
@@ -447,40 +535,20 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
         rvalid[i] = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
         const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
-        rowoff[i] = pix * P.Cout + tn * BN;
+        rowoff[i] = (rvalid[i] ? pix * P.Cout : 0) + tn * BN;     // outside rows: clamped, loads stay in bounds
       }
-      // the first chunk's operand loads do not depend on the accumulator: in flight while the MMAs finish
-      EpiRegs G;
-      epi_issue_loads(G, rowoff, rvalid, 0, residual, E, lane);
-      mbar_wait(tfull0 + 8 * as, aphase);
-      tc_fence_after();
       if (P.debug == 3) {           // micro-benchmark: no epilogue work at all
+        mbar_wait(tfull0 + 8 * as, aphase);
+        tc_fence_after();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         if (++as == 2) { as = 0; aphase ^= 1; }
         continue;
       }
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        if (cc > 0) epi_issue_loads(G, rowoff, rvalid, cc * 32, residual, E, lane);
-        uint32_t v[32];
-        if (kblocks > 0) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
-        if (cc == BN / 32 - 1) {
-          // all TMEM reads of this accumulator stage are complete: hand it back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8 * as);
-        }
-        epi_chunk(v, scr, G, rowoff, rvalid, cc * 32, tn * BN + cc * 32, residual != nullptr, out, P.debug != 4,
-                  stats != nullptr, E, lane, stw[0][cc][lane], stw[1][cc][lane], stw[2][cc][lane]);
-      }
+      epi_tile_dispatch<BN>(epi_mode, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, kblocks > 0, tfull0 + 8 * as,
+                            aphase, [&]() { mbar_arrive(tempty0 + 8 * as); }, scr, stw, rowoff, rvalid, P.debug != 4, tn,
+                            residual, out, E, lane);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
@@ -611,6 +679,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const int q = warp & 3;
     __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
     float* scr = epi_scratch[q];
+    const int epi_mode = epi_mode_of(residual, stats, E);
     int as = 0; uint32_t aphase = 0;
     // running column sums of this warp, [statistic][chunk][lane] (lane <-> column epi_stat_col(lane)); kept in
     // shared memory so that the chunk loop can stay ROLLED: unrolled, the epilogue alone was > 100 KB of
@@ -649,32 +718,11 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
         rvalid[i] = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
         const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
-        rowoff[i] = pix * P.Cout + tn * BN;
+        rowoff[i] = (rvalid[i] ? pix * P.Cout : 0) + tn * BN;     // outside rows: clamped, loads stay in bounds
       }
-      // the first chunk's operand loads do not depend on the accumulator: in flight while the MMAs finish
-      EpiRegs G;
-      epi_issue_loads(G, rowoff, rvalid, 0, residual, E, lane);
-      mbar_wait(tfull0 + 8 * as, aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        if (cc > 0) epi_issue_loads(G, rowoff, rvalid, cc * 32, residual, E, lane);
-        uint32_t v[32];
-        if (kblocks > 0) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
-        if (cc == BN / 32 - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa(tempty0 + 8 * as, 0));
-        }
-        epi_chunk(v, scr, G, rowoff, rvalid, cc * 32, tn * BN + cc * 32, residual != nullptr, out, true,
-                  stats != nullptr, E, lane, stw[0][cc][lane], stw[1][cc][lane], stw[2][cc][lane]);
-      }
+      epi_tile_dispatch<BN>(epi_mode, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, kblocks > 0, tfull0 + 8 * as,
+                            aphase, [&]() { mbar_arrive_cluster(mapa(tempty0 + 8 * as, 0)); }, scr, stw, rowoff, rvalid, true, tn,
+                            residual, out, E, lane);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
@@ -844,6 +892,7 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int q = warp & 3;
     __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
     float* scr = epi_scratch[q];
+    const int epi_mode = epi_mode_of(residual, stats, E);
     int as = 0; uint32_t aphase = 0;
     // running column sums of this warp, [statistic][chunk][lane] (lane <-> column epi_stat_col(lane)); kept in
     // shared memory so that the chunk loop can stay ROLLED: unrolled, the epilogue alone was > 100 KB of
@@ -876,27 +925,11 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int h = qq / P.P, j = qq - h * P.P;
         rvalid[i] = (j >= 1) && (j <= P.W) && (h < P.H);
         const long long pix = ((long long)n * P.H + h) * P.W + (j - 1);
-        rowoff[i] = pix * P.Cout + tn * BN;
+        rowoff[i] = (rvalid[i] ? pix * P.Cout : 0) + tn * BN;     // outside rows: clamped, loads stay in bounds
       }
-      // the first chunk's operand loads do not depend on the accumulator: in flight while the MMAs finish
-      EpiRegs G;
-      epi_issue_loads(G, rowoff, rvalid, 0, residual, E, lane);
-      mbar_wait(tfull0 + 8 * as, aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        if (cc > 0) epi_issue_loads(G, rowoff, rvalid, cc * 32, residual, E, lane);
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
-        tmem_ld_wait();
-        if (cc == BN / 32 - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8 * as);
-        }
-        epi_chunk(v, scr, G, rowoff, rvalid, cc * 32, tn * BN + cc * 32, residual != nullptr, out, true,
-                  stats != nullptr, E, lane, stw[0][cc][lane], stw[1][cc][lane], stw[2][cc][lane]);
-      }
+      epi_tile_dispatch<BN>(epi_mode, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, true, tfull0 + 8 * as,
+                            aphase, [&]() { mbar_arrive(tempty0 + 8 * as); }, scr, stw, rowoff, rvalid, true, tn,
+                            residual, out, E, lane);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
@@ -910,13 +943,15 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // ---------------------------------------------------------------------------------
 // wgrad kernel: one CTA per (M-tile of 2 X chunks, N-tile of BN couts, K split)
 // ---------------------------------------------------------------------------------
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
+// OCC = CTAs per SM: with 2, each CTA gets half the stages and the fp32-atomic epilogue of one CTA
+// (~40% of a CTA's life) overlaps the other CTA's MMAs instead of idling the tensor pipe
+template <int BN, int OCC>
+__global__ void __launch_bounds__(192, OCC)
 k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
            const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapX3,
            const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ WgradParams P,
            float* __restrict__ dw) {
-  constexpr int STAGES = wgrad_stages(BN);
+  constexpr int STAGES = wgrad_stages(BN) / OCC;
   constexpr uint32_t CHUNK_BYTES = 64 * 128;     // 64 pixels x 64 ch bf16
   constexpr uint32_t A_BYTES = 2 * CHUNK_BYTES;
   constexpr uint32_t B_BYTES = (BN / 64) * CHUNK_BYTES;
@@ -1035,13 +1070,13 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
 // ---------------------------------------------------------------------------------
 static constexpr int wgrad2_stages(int BN) { return BN <= 128 ? 8 : 6; }
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int OCC>
+__global__ void __launch_bounds__(192, OCC)
 k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
             const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapX3,
             const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ WgradParams P,
             float* __restrict__ dw) {
-  constexpr int STAGES = wgrad2_stages(BN);
+  constexpr int STAGES = wgrad2_stages(BN) / OCC;
   constexpr uint32_t CHUNK_BYTES = 64 * 128;
   constexpr uint32_t A_BYTES = 2 * CHUNK_BYTES;
   constexpr int NBCH = BN / 128;                       // dY chunks (64 couts) staged by this CTA
@@ -1457,7 +1492,11 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
   EpiBwd E; memset(&E, 0, sizeof(E));
   if (bwd != nullptr) {
     MN_CHECK(p->kind == 1 && stats != nullptr && bwd->y != nullptr, "tc_conv_run: backward statistics need a dgrad plan, accumulators and Y");
+    MN_CHECK(bwd->zmask != nullptr || (bwd->mscale != nullptr && bwd->mshift != nullptr), "tc_conv_run: backward statistics need a gate (zmask or mscale/mshift)");
+    MN_CHECK(bwd->yd == nullptr || bwd->zmask != nullptr, "tc_conv_run: the downsample sum is only built for zmask-gated gradients");
     E = *bwd;
+  } else {
+    MN_CHECK(stats == nullptr || residual == nullptr, "tc_conv_run: fprop statistics with a fused residual are not built");
   }
   const ConvGeom& g = p->g;
   int nsm = 148;
@@ -1535,10 +1574,13 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     MN_TRY(encode_view(&p->mapDY, in1, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, P.TW, P.TH, P.TN));
     p->c_in0 = in0; p->c_in1 = in1;
   }
+  static int occ = -1;
+  if (occ < 0) { const char* e = getenv("MAPNET_TC_WGRAD_OCC"); occ = (e && atoi(e) == 2) ? 2 : 1; }
   if (p->two_cta) {
-    const size_t smem2 = (size_t)wgrad2_stages(p->BN) * (2 * 8192 + (p->BN / 128) * 8192) + 1024;
+    const size_t smem2 = (size_t)(wgrad2_stages(p->BN) / occ) * (2 * 8192 + (p->BN / 128) * 8192) + 1024;
     void (*k2)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, WgradParams, float*) =
-        (p->BN == 256) ? k_tc_wgrad2<256> : k_tc_wgrad2<128>;
+        (occ == 2) ? ((p->BN == 256) ? k_tc_wgrad2<256, 2> : k_tc_wgrad2<128, 2>)
+                   : ((p->BN == 256) ? k_tc_wgrad2<256, 1> : k_tc_wgrad2<128, 1>);
     if (!p->smem_attr_set) {
       MN_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       p->smem_attr_set = true;
@@ -1554,18 +1596,17 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     ++g_launch_count;
     return 0;
   }
-  const int stages = wgrad_stages(p->BN);
+  const int stages = wgrad_stages(p->BN) / occ;
   const size_t smem = (size_t)stages * (2 * 8192 + (p->BN / 64) * 8192) + 1024;
+  void (*k1)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, WgradParams, float*) =
+      (occ == 2) ? ((p->BN == 64) ? k_tc_wgrad<64, 2> : (p->BN == 128 ? k_tc_wgrad<128, 2> : k_tc_wgrad<256, 2>))
+                 : ((p->BN == 64) ? k_tc_wgrad<64, 1> : (p->BN == 128 ? k_tc_wgrad<128, 1> : k_tc_wgrad<256, 1>));
   if (!p->smem_attr_set) {
-    if (p->BN == 64) MN_TRY(set_smem(k_tc_wgrad<64>, smem));
-    else if (p->BN == 128) MN_TRY(set_smem(k_tc_wgrad<128>, smem));
-    else MN_TRY(set_smem(k_tc_wgrad<256>, smem));
+    MN_TRY(set_smem(k1, smem));
     p->smem_attr_set = true;
   }
   const int grid = P.n_mtiles * P.n_ntiles * P.splits;
-  if (p->BN == 64) k_tc_wgrad<64><<<grid, 192, smem, st>>>(p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out);
-  else if (p->BN == 128) k_tc_wgrad<128><<<grid, 192, smem, st>>>(p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out);
-  else k_tc_wgrad<256><<<grid, 192, smem, st>>>(p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out);
+  k1<<<grid, 192, smem, st>>>(p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out);
   MN_LAUNCH_CHECK();
   return 0;
 }
