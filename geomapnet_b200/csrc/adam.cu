@@ -10,6 +10,7 @@ namespace mapnet {
 
 __global__ void __launch_bounds__(256)
 k_sqnorm_partial(const float* __restrict__ g, long long n, float* __restrict__ partials) {
+  pdl_prologue();
   double acc = 0.0;
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
@@ -31,6 +32,7 @@ k_sqnorm_partial(const float* __restrict__ g, long long n, float* __restrict__ p
 }
 __global__ void k_sqnorm_final(const float* __restrict__ partials, int nblk, float* __restrict__ out,
                                int accumulate) {
+  pdl_prologue();
   double s = 0.0;
   for (int i = threadIdx.x; i < nblk; i += 32) s += (double)partials[i];
   s = warp_sum_d(s);
@@ -39,9 +41,9 @@ __global__ void k_sqnorm_final(const float* __restrict__ partials, int nblk, flo
 
 int launch_sqnorm(const float* g, long long n, float* partials, float* out_sq, cudaStream_t st) {
   const int nblk = 296;
-  k_sqnorm_partial<<<nblk, 256, 0, st>>>(g, n, partials);
+  MN_LAUNCH(k_sqnorm_partial, nblk, 256, 0, st, g, n, partials);
   MN_LAUNCH_CHECK();
-  k_sqnorm_final<<<1, 32, 0, st>>>(partials, nblk, out_sq, 0);
+  MN_LAUNCH(k_sqnorm_final, 1, 32, 0, st, partials, nblk, out_sq, 0);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -49,12 +51,14 @@ int launch_sqnorm(const float* g, long long n, float* partials, float* out_sq, c
 // torch.optim.Adam (amsgrad=False, maximize=False) single-tensor math:
 //   g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g
 //   p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
-__global__ void k_inc_i32(int* c) { *c += 1; }
+__global__ void k_inc_i32(int* c) {
+  pdl_prologue(); *c += 1; }
 
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
        long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
        float gscale, const float* __restrict__ sqnorm, float max_norm, const int* __restrict__ step_dev) {
+  pdl_prologue();
   if (step_dev != nullptr) {
     // CUDA-graph friendly: the step count lives on the device (bias corrections cannot be
     // baked into a captured launch)
@@ -108,11 +112,10 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
   if (grid > 148LL * 8) grid = 148LL * 8;
   if (grid < 1) grid = 1;
   if (step_dev != nullptr) {
-    k_inc_i32<<<1, 1, 0, st>>>(step_dev);
+    MN_LAUNCH(k_inc_i32, 1, 1, 0, st, step_dev);
     MN_LAUNCH_CHECK();
   }
-  k_adam<<<(int)grid, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), gscale,
-                                    sqnorm_or_null, max_norm, step_dev);
+  MN_LAUNCH(k_adam, (int)grid, 256, 0, st, p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), gscale, sqnorm_or_null, max_norm, step_dev);
   MN_LAUNCH_CHECK();
   return 0;
 }

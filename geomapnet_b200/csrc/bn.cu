@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kEwThreads)
 k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __restrict__ y,
                const T* __restrict__ yd, long long M, int C, double* __restrict__ accum,
                unsigned int* __restrict__ counter, BnFin f) {
+  pdl_prologue();
   constexpr int NACC = (MODE == 2) ? 3 : 2;
   const int cv = C >> 3;                      // channel vectors per pixel
   const int rows_par = kEwThreads / cv;       // pixels processed in parallel by the block
@@ -182,9 +183,9 @@ static int launch_sums(int mode, const T* a, const T* zmask, const T* y, const T
   const int rows_par = kEwThreads / (C >> 3);
   const int nacc = (mode == 2) ? 3 : 2;
   const size_t smem = (size_t)rows_par * nacc * C * sizeof(float);
-  if (mode == 0) k_channel_sums<T, 0><<<grid, kEwThreads, smem, st>>>(a, nullptr, nullptr, nullptr, M, C, accum, counter, f);
-  else if (mode == 1) k_channel_sums<T, 1><<<grid, kEwThreads, smem, st>>>(a, zmask, y, nullptr, M, C, accum, counter, f);
-  else k_channel_sums<T, 2><<<grid, kEwThreads, smem, st>>>(a, zmask, y, yd, M, C, accum, counter, f);
+  if (mode == 0) MN_LAUNCH((k_channel_sums<T, 0>), grid, kEwThreads, smem, st, a, nullptr, nullptr, nullptr, M, C, accum, counter, f);
+  else if (mode == 1) MN_LAUNCH((k_channel_sums<T, 1>), grid, kEwThreads, smem, st, a, zmask, y, nullptr, M, C, accum, counter, f);
+  else MN_LAUNCH((k_channel_sums<T, 2>), grid, kEwThreads, smem, st, a, zmask, y, yd, M, C, accum, counter, f);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -194,6 +195,7 @@ static int launch_sums(int mode, const T* a, const T* zmask, const T* y, const T
 // block = 32 channels x 32 replicas: coalesced replica loads, shared-memory reduction over replicas
 __global__ void __launch_bounds__(1024)
 k_bn_finalize_accum(long long M, int C, BnFin f, double* __restrict__ accum) {
+  pdl_prologue();
   __shared__ double s0s[32][33], s1s[32][33];
   const int cl = threadIdx.x, r = threadIdx.y;
   const int c = blockIdx.x * 32 + cl;
@@ -232,7 +234,7 @@ int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float
   BnFin f; memset(&f, 0, sizeof(f));
   f.gamma = gamma; f.beta = beta; f.run_mean = run_mean; f.run_var = run_var; f.mean = mean_out;
   f.invstd = invstd_out; f.scale = scale; f.shift = shift; f.training = 1;
-  k_bn_finalize_accum<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(M, C, f, accum);
+  MN_LAUNCH(k_bn_finalize_accum, cdiv(C, 32), dim3(32, 32), 0, st, M, C, f, accum);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -241,6 +243,7 @@ int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float
 // same arithmetic as MODE 1 / 2 of k_channel_sums
 __global__ void __launch_bounds__(1024)
 k_bn_bwd_finalize_accum(long long M, int C, BnFin f, double* __restrict__ accum, int nacc) {
+  pdl_prologue();
   __shared__ double ss[3][32][33];
   const int cl = threadIdx.x, r = threadIdx.y;
   const int c = blockIdx.x * 32 + cl;
@@ -289,7 +292,7 @@ int launch_bn_bwd_finalize_accum(long long M, int C, const float* gamma, const f
   f.gamma = gamma; f.mean = const_cast<float*>(mean); f.invstd = const_cast<float*>(invstd);
   f.dgamma = dgamma; f.dbeta = dbeta; f.coef = coef;
   f.gamma2 = gamma2; f.mean2 = mean2; f.invstd2 = invstd2; f.dgamma2 = dgamma2; f.dbeta2 = dbeta2; f.coef2 = coef2;
-  k_bn_bwd_finalize_accum<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(M, C, f, accum, gamma2 != nullptr ? 3 : 2);
+  MN_LAUNCH(k_bn_bwd_finalize_accum, cdiv(C, 32), dim3(32, 32), 0, st, M, C, f, accum, gamma2 != nullptr ? 3 : 2);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -299,6 +302,7 @@ __global__ void k_bn_eval_scale(int C, const float* __restrict__ gamma, const fl
                                 const float* __restrict__ run_mean, const float* __restrict__ run_var,
                                 float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                 float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float mean = run_mean[c];
@@ -313,7 +317,7 @@ int launch_bn_stats(const T* y, long long M, int C, const float* gamma, const fl
                     float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift, int training,
                     double* accum, unsigned int* counter, cudaStream_t st) {
   if (!training) {
-    k_bn_eval_scale<<<cdiv(C, 128), 128, 0, st>>>(C, gamma, beta, run_mean, run_var, mean_out, invstd_out, scale, shift);
+    MN_LAUNCH(k_bn_eval_scale, cdiv(C, 128), 128, 0, st, C, gamma, beta, run_mean, run_var, mean_out, invstd_out, scale, shift);
     MN_LAUNCH_CHECK();
     return 0;
   }
@@ -349,6 +353,7 @@ __global__ void __launch_bounds__(kEwThreads)
 k_bn_apply(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
            const T* __restrict__ res, const float* __restrict__ scale2, const float* __restrict__ shift2,
            T* __restrict__ z, long long nvec, int C, int relu) {
+  pdl_prologue();
   const int cv = C >> 3;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   // the grid stride (gridDim*256) is a multiple of cv, so this thread always sees the same 8 channels
@@ -392,9 +397,9 @@ int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_
                     cudaStream_t st) {
   const long long nvec = M * (C >> 3);
   const int grid = ew_grid(nvec);
-  if (res_mode == 0) k_bn_apply<T, 0><<<grid, kEwThreads, 0, st>>>(y, scale, shift, nullptr, nullptr, nullptr, z, nvec, C, relu);
-  else if (res_mode == 1) k_bn_apply<T, 1><<<grid, kEwThreads, 0, st>>>(y, scale, shift, res, nullptr, nullptr, z, nvec, C, relu);
-  else k_bn_apply<T, 2><<<grid, kEwThreads, 0, st>>>(y, scale, shift, res, scale2, shift2, z, nvec, C, relu);
+  if (res_mode == 0) MN_LAUNCH((k_bn_apply<T, 0>), grid, kEwThreads, 0, st, y, scale, shift, nullptr, nullptr, nullptr, z, nvec, C, relu);
+  else if (res_mode == 1) MN_LAUNCH((k_bn_apply<T, 1>), grid, kEwThreads, 0, st, y, scale, shift, res, nullptr, nullptr, z, nvec, C, relu);
+  else MN_LAUNCH((k_bn_apply<T, 2>), grid, kEwThreads, 0, st, y, scale, shift, res, scale2, shift2, z, nvec, C, relu);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -409,6 +414,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
             T* __restrict__ z, uint8_t* __restrict__ amax, int B, int H, int W, int Ho, int Wo, int C) {
+  pdl_prologue();
   const int cv = C >> 3;
   const long long nvec = (long long)B * Ho * Wo * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
@@ -454,7 +460,7 @@ template <typename T>
 int launch_stem_pool(const T* y, const float* scale, const float* shift, T* z, uint8_t* amax, int B, int H,
                      int W, int Ho, int Wo, int C, cudaStream_t st) {
   const long long nvec = (long long)B * Ho * Wo * (C >> 3);
-  k_stem_pool<T><<<ew_grid(nvec), kEwThreads, 0, st>>>(y, scale, shift, z, amax, B, H, W, Ho, Wo, C);
+  MN_LAUNCH(k_stem_pool<T>, ew_grid(nvec), kEwThreads, 0, st, y, scale, shift, z, amax, B, H, W, Ho, Wo, C);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -467,6 +473,7 @@ __global__ void __launch_bounds__(kEwThreads)
 k_stem_pool_bwd(const T* __restrict__ dz, const uint8_t* __restrict__ amax, const T* __restrict__ y,
                 const float* __restrict__ scale, const float* __restrict__ shift, T* __restrict__ g,
                 int B, int H, int W, int Ho, int Wo, int C) {
+  pdl_prologue();
   const int cv = C >> 3;
   const long long nvec = (long long)B * H * W * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
@@ -519,7 +526,7 @@ template <typename T>
 int launch_stem_pool_bwd(const T* dz, const uint8_t* amax, const T* y, const float* scale, const float* shift,
                          T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st) {
   const long long nvec = (long long)B * H * W * (C >> 3);
-  k_stem_pool_bwd<T><<<ew_grid(nvec), kEwThreads, 0, st>>>(dz, amax, y, scale, shift, g, B, H, W, Ho, Wo, C);
+  MN_LAUNCH(k_stem_pool_bwd<T>, ew_grid(nvec), kEwThreads, 0, st, dz, amax, y, scale, shift, g, B, H, W, Ho, Wo, C);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -533,6 +540,7 @@ k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T*
                const float* __restrict__ coef, T* __restrict__ dy, const T* __restrict__ yd,
                const float* __restrict__ coefd, T* __restrict__ dyd, T* __restrict__ gout, long long nvec,
                int C, const float* __restrict__ mscale, const float* __restrict__ mshift) {
+  pdl_prologue();
   const int cv = C >> 3;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(i0 % cv) * 8;          // loop invariant (grid stride is a multiple of cv)
@@ -574,10 +582,10 @@ int launch_bn_bwd_apply(const T* dout, const T* zmask, const T* y, const float* 
   const long long nvec = M * (C >> 3);
   const int grid = ew_grid(nvec);
   const bool ds = (yd != nullptr), go = (gout != nullptr);
-  if (ds && !go) k_bn_bwd_apply<T, 1, 0><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
-  else if (!ds && go) k_bn_bwd_apply<T, 0, 1><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
-  else if (!ds && !go) k_bn_bwd_apply<T, 0, 0><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
-  else k_bn_bwd_apply<T, 1, 1><<<grid, kEwThreads, 0, st>>>(dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
+  if (ds && !go) MN_LAUNCH((k_bn_bwd_apply<T, 1, 0>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
+  else if (!ds && go) MN_LAUNCH((k_bn_bwd_apply<T, 0, 1>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
+  else if (!ds && !go) MN_LAUNCH((k_bn_bwd_apply<T, 0, 0>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
+  else MN_LAUNCH((k_bn_bwd_apply<T, 1, 1>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
   MN_LAUNCH_CHECK();
   return 0;
 }

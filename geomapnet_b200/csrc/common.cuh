@@ -47,6 +47,37 @@ extern unsigned long long g_launch_count;   // kernels launched by this library 
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch -------------------------------------------
+// Every kernel of the library starts with pdl_prologue(): it lets the NEXT kernel in the stream be
+// scheduled early (its blocks then sit in griddepcontrol.wait) and itself waits until the PREVIOUS
+// kernel has completed and flushed.  Nothing touches global memory before the wait, so the
+// semantics are those of a serialized stream; what overlaps is launch latency, block scheduling
+// and per-block setup (barrier init, TMEM allocation, descriptor prefetch) -- worth it because a
+// training step is ~290 launches of 2-40 us each.  MAPNET_PDL=0 disables the launch attribute.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+int pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define MN_LAUNCH(kern, grid, block, smem, st, ...)                                        \
+  do {                                                                                     \
+    MN_CUDA(mapnet::launch_k(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)); \
+  } while (0)
+
 // ---- activation element access ---------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }

@@ -40,6 +40,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(NT)
 k_conv_simt(ConvGeom g, const T* __restrict__ src, const float* __restrict__ wmat,
             const T* __restrict__ residual, T* __restrict__ dst) {
+  pdl_prologue();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int t = threadIdx.x;
@@ -127,6 +128,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT)
 k_conv_simt_wgrad(ConvGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
                   long long kchunk) {
+  pdl_prologue();
   __shared__ float As[BK][BM + 4];   // [pixel][co]
   __shared__ float Bs[BK][BN + 4];   // [pixel][(tap,ci)]
   const int t = threadIdx.x;
@@ -194,7 +196,7 @@ template <typename T>
 int launch_conv_simt_fprop(const ConvGeom& g, const T* x, const float* w, const T* residual, T* y, cudaStream_t st) {
   MN_CHECK(g.Ci % 4 == 0, "conv_simt: Ci %% 4 != 0");
   dim3 grid(cdiv(g.M_out(), BM), cdiv(g.Co, BN));
-  k_conv_simt<T, 0><<<grid, NT, 0, st>>>(g, x, w, residual, y);
+  MN_LAUNCH((k_conv_simt<T, 0>), grid, NT, 0, st, g, x, w, residual, y);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -202,7 +204,7 @@ template <typename T>
 int launch_conv_simt_dgrad(const ConvGeom& g, const T* dy, const float* w_dg, const T* residual, T* dx, cudaStream_t st) {
   MN_CHECK(g.Co % 4 == 0, "conv_simt: Co %% 4 != 0");
   dim3 grid(cdiv(g.M_in(), BM), cdiv(g.Ci, BN));
-  k_conv_simt<T, 1><<<grid, NT, 0, st>>>(g, dy, w_dg, residual, dx);
+  MN_LAUNCH((k_conv_simt<T, 1>), grid, NT, 0, st, g, dy, w_dg, residual, dx);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -218,7 +220,7 @@ int launch_conv_simt_wgrad(const ConvGeom& g, const T* x, const T* dy, float* dw
   if (kchunk < 256) kchunk = 256;
   splits = (Kt + kchunk - 1) / kchunk;
   dim3 grid(gm, gn, (unsigned)splits);
-  k_conv_simt_wgrad<T><<<grid, NT, 0, st>>>(g, x, dy, dw, kchunk);
+  MN_LAUNCH(k_conv_simt_wgrad<T>, grid, NT, 0, st, g, x, dy, dw, kchunk);
   MN_LAUNCH_CHECK();
   return 0;
 }

@@ -412,6 +412,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   if (CL > 1) cluster_sync();          // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
+  pdl_prologue();      // nothing above touches global memory: setup overlaps the previous kernel's tail
 
   // work items: (group of CL consecutive M tiles, N tile); every CTA of a cluster walks the
   // same sequence, CTA r takes M tile group*CL + r (possibly past the end: a dummy tile whose
@@ -605,6 +606,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
+  pdl_prologue();      // nothing above touches global memory: setup overlaps the previous kernel's tail
 
   const int n_groups = (P.n_tiles_m + 1) / 2;
   const int total_tiles = n_groups * P.n_tiles_n;
@@ -791,6 +793,7 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
+  pdl_prologue();      // nothing above touches global memory: setup overlaps the previous kernel's tail
 
   const int total_tiles = P.n_tiles_m * P.n_tiles_n;
   const int ntaps_total = 9 * P.cblocks;
@@ -988,6 +991,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
+  pdl_prologue();      // nothing above touches global memory: setup overlaps the previous kernel's tail
 
   if (warp == 0) {
     if (elect_one()) {
@@ -1116,6 +1120,7 @@ k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ C
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
+  pdl_prologue();      // nothing above touches global memory: setup overlaps the previous kernel's tail
 
   if (warp == 0) {
     if (elect_one()) {
@@ -1517,7 +1522,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     }
     const int total = H.n_tiles_m * H.n_tiles_n;
     const int grid = total < nsm ? total : nsm;
-    kern<<<grid, 192, p->halo_smem, st>>>(p->hmapA, p->hmapB, H, residual, (bf16*)out, stats, E);
+    MN_LAUNCH(kern, grid, 192, p->halo_smem, st, p->hmapA, p->hmapB, H, residual, (bf16*)out, stats, E);
     MN_LAUNCH_CHECK();
     return 0;
   }
@@ -1556,10 +1561,12 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       const int nclusters = groups < max_clusters ? groups : max_clusters;
       cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3(nclusters * p->CL); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = p->CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
       MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out, stats, E));
       ++g_launch_count;
     }
@@ -1588,10 +1595,12 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(P.n_mtiles * P.n_ntiles * P.splits * 2); cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = smem2; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MN_CUDA(cudaLaunchKernelEx(&cfg, k2, p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out));
     ++g_launch_count;
     return 0;
@@ -1606,7 +1615,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     p->smem_attr_set = true;
   }
   const int grid = P.n_mtiles * P.n_ntiles * P.splits;
-  k1<<<grid, 192, smem, st>>>(p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out);
+  MN_LAUNCH(k1, grid, 192, smem, st, p->mapX[0], p->mapX[1], p->mapX[2], p->mapX[3], p->mapDY, P, (float*)out);
   MN_LAUNCH_CHECK();
   return 0;
 }

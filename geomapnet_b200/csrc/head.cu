@@ -11,6 +11,7 @@ namespace mapnet {
 // ---- global average pool ------------------------------------------------------
 template <typename T>
 __global__ void k_gap(const T* __restrict__ z, float* __restrict__ feat, int B, int HW, int C) {
+  pdl_prologue();
   const int cv = C >> 3;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * cv) return;
@@ -30,7 +31,7 @@ __global__ void k_gap(const T* __restrict__ z, float* __restrict__ feat, int B, 
 template <typename T>
 int launch_gap(const T* z, float* feat, int B, int HW, int C, cudaStream_t st) {
   const int n = B * (C >> 3);
-  k_gap<T><<<cdiv(n, 128), 128, 0, st>>>(z, feat, B, HW, C);
+  MN_LAUNCH(k_gap<T>, cdiv(n, 128), 128, 0, st, z, feat, B, HW, C);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -39,6 +40,7 @@ template int launch_gap<bf16>(const bf16*, float*, int, int, int, cudaStream_t);
 
 template <typename T>
 __global__ void k_gap_bwd(const float* __restrict__ dfeat, T* __restrict__ dz, int B, int HW, int C) {
+  pdl_prologue();
   const int cv = C >> 3;
   const long long nvec = (long long)B * HW * cv;
   const float inv = 1.0f / (float)HW;
@@ -56,7 +58,7 @@ template <typename T>
 int launch_gap_bwd(const float* dfeat, T* dz, int B, int HW, int C, cudaStream_t st) {
   const long long nvec = (long long)B * HW * (C >> 3);
   long long grid = (nvec + 255) / 256; if (grid > 148 * 8) grid = 148 * 8;
-  k_gap_bwd<T><<<(int)grid, 256, 0, st>>>(dfeat, dz, B, HW, C);
+  MN_LAUNCH(k_gap_bwd<T>, (int)grid, 256, 0, st, dfeat, dz, B, HW, C);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -73,6 +75,7 @@ k_small_gemm(const float* __restrict__ A, long long sam, long long sak, const fl
              long long sbn, long long sbk, float* __restrict__ C, int ldc, int M, int N, int K,
              const float* __restrict__ bias, float* __restrict__ aux, const float* __restrict__ mask,
              int kchunk) {
+  pdl_prologue();
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -142,15 +145,16 @@ int launch_small_gemm(int epi, const float* A, long long sam, long long sak, con
       MN_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
     }
   }
-  if (epi == 0) k_small_gemm<0><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask, kchunk);
-  else if (epi == 1) k_small_gemm<1><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask, kchunk);
-  else k_small_gemm<2><<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask, kchunk);
+  if (epi == 0) MN_LAUNCH(k_small_gemm<0>, grid, 256, 0, st, A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask, kchunk);
+  else if (epi == 1) MN_LAUNCH(k_small_gemm<1>, grid, 256, 0, st, A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask, kchunk);
+  else MN_LAUNCH(k_small_gemm<2>, grid, 256, 0, st, A, sam, sak, Bm, sbn, sbk, C, ldc, M, N, K, bias, aux, mask, kchunk);
   MN_LAUNCH_CHECK();
   return 0;
 }
 
 // column sums: out[n] = sum_m A[m*lda + n]
 __global__ void k_colsum(const float* __restrict__ A, int lda, int M, int N, float* __restrict__ out) {
+  pdl_prologue();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -158,7 +162,7 @@ __global__ void k_colsum(const float* __restrict__ A, int lda, int M, int N, flo
   out[n] = s;
 }
 int launch_colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st) {
-  k_colsum<<<cdiv(N, 128), 128, 0, st>>>(A, lda, M, N, out);
+  MN_LAUNCH(k_colsum, cdiv(N, 128), 128, 0, st, A, lda, M, N, out);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -166,6 +170,7 @@ int launch_colsum(const float* A, int lda, int M, int N, float* out, cudaStream_
 // dpred copy with the NaN filter of models/posenet.py:28-34 applied to the
 // rotation half (the gradient entering fc_wpqr).
 __global__ void k_dpred_filter(const float* __restrict__ in, float* __restrict__ out, int n, int filter) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = in[i];
@@ -173,17 +178,19 @@ __global__ void k_dpred_filter(const float* __restrict__ in, float* __restrict__
   out[i] = v;
 }
 int launch_dpred_filter(const float* in, float* out, int n, int filter, cudaStream_t st) {
-  k_dpred_filter<<<cdiv(n, 128), 128, 0, st>>>(in, out, n, filter);
+  MN_LAUNCH(k_dpred_filter, cdiv(n, 128), 128, 0, st, in, out, n, filter);
   MN_LAUNCH_CHECK();
   return 0;
 }
 
 // counter-based dropout mask: mask = (u >= p) / (1-p), u from splitmix64(seed, offset+i)
-__global__ void k_inc_u64(unsigned long long* c) { *c += 1ULL; }
+__global__ void k_inc_u64(unsigned long long* c) {
+  pdl_prologue(); *c += 1ULL; }
 
 __global__ void k_dropout_mask(float* __restrict__ mask, long long n, float p, unsigned long long seed,
                                unsigned long long offset, const unsigned long long* __restrict__ ctr,
                                unsigned long long ctr_stride) {
+  pdl_prologue();
   if (ctr != nullptr) offset = (*ctr) * ctr_stride;      // device-side step counter (graph replay)
   const float keep_scale = 1.0f / (1.0f - p);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -199,10 +206,10 @@ __global__ void k_dropout_mask(float* __restrict__ mask, long long n, float p, u
 int launch_dropout_mask(float* mask, long long n, float p, unsigned long long seed, unsigned long long offset,
                         unsigned long long* ctr_dev, unsigned long long ctr_stride, cudaStream_t st) {
   long long grid = (n + 255) / 256; if (grid > 592) grid = 592;
-  k_dropout_mask<<<(int)grid, 256, 0, st>>>(mask, n, p, seed, offset, ctr_dev, ctr_stride);
+  MN_LAUNCH(k_dropout_mask, (int)grid, 256, 0, st, mask, n, p, seed, offset, ctr_dev, ctr_stride);
   MN_LAUNCH_CHECK();
   if (ctr_dev != nullptr) {
-    k_inc_u64<<<1, 1, 0, st>>>(ctr_dev);
+    MN_LAUNCH(k_inc_u64, 1, 1, 0, st, ctr_dev);
     MN_LAUNCH_CHECK();
   }
   return 0;
@@ -215,6 +222,7 @@ namespace mapnet {
 __global__ void k_head_dh(const float* __restrict__ dpred, const float* __restrict__ wx,
                           const float* __restrict__ wq, const float* __restrict__ mask,
                           const float* __restrict__ fcpre, float* __restrict__ dh, int B, int F) {
+  pdl_prologue();
   const long long n = (long long)B * F;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -229,7 +237,7 @@ __global__ void k_head_dh(const float* __restrict__ dpred, const float* __restri
 int launch_head_dh(const float* dpred, const float* wx, const float* wq, const float* mask, const float* fcpre,
                    float* dh, int B, int F, cudaStream_t st) {
   long long grid = ((long long)B * F + 255) / 256; if (grid > 592) grid = 592;
-  k_head_dh<<<(int)grid, 256, 0, st>>>(dpred, wx, wq, mask, fcpre, dh, B, F);
+  MN_LAUNCH(k_head_dh, (int)grid, 256, 0, st, dpred, wx, wq, mask, fcpre, dh, B, F);
   MN_LAUNCH_CHECK();
   return 0;
 }

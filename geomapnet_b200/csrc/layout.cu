@@ -22,6 +22,7 @@ template <typename TW>
 __global__ void __launch_bounds__(256)
 k_pack_weights(const WeightDesc* __restrict__ descs, const float* __restrict__ params,
                TW* __restrict__ w_krsc, TW* __restrict__ w_dg, int round_bf16) {
+  pdl_prologue();
   extern __shared__ float slab[];
   const WeightDesc d = descs[blockIdx.y];
   const int co = blockIdx.x;
@@ -55,6 +56,7 @@ k_pack_weights(const WeightDesc* __restrict__ descs, const float* __restrict__ p
 template <typename TW>
 __global__ void __launch_bounds__(256)
 k_transpose_dg(const WeightDesc* __restrict__ descs, const TW* __restrict__ w_krsc, TW* __restrict__ w_dg) {
+  pdl_prologue();
   const WeightDesc d = descs[blockIdx.y];
   if (d.im2col_k > 0) return;          // the stem has no dgrad
   const int KK = d.KH * d.KW;
@@ -85,11 +87,11 @@ template <typename TW>
 int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* params, TW* w_krsc, TW* w_dg,
                         int max_elems, int round_bf16, cudaStream_t st) {
   dim3 grid(512, nconv);                 // blockIdx.x = output channel (<= 512), blocks past Co exit
-  k_pack_weights<TW><<<grid, 256, 512 * 9 * sizeof(float), st>>>(d_descs, params, w_krsc, w_dg, round_bf16);
+  MN_LAUNCH(k_pack_weights<TW>, grid, 256, 512 * 9 * sizeof(float), st, d_descs, params, w_krsc, w_dg, round_bf16);
   MN_LAUNCH_CHECK();
   if (w_dg != nullptr) {
     dim3 g2(592, nconv);
-    k_transpose_dg<TW><<<g2, 256, 0, st>>>(d_descs, w_krsc, w_dg);
+    MN_LAUNCH(k_transpose_dg<TW>, g2, 256, 0, st, d_descs, w_krsc, w_dg);
     MN_LAUNCH_CHECK();
   }
   return 0;
@@ -99,6 +101,7 @@ template int launch_pack_weights<bf16>(const WeightDesc*, int, const float*, bf1
 
 __global__ void __launch_bounds__(256)
 k_unpack_wgrads(const WeightDesc* __restrict__ descs, const float* __restrict__ dw, float* __restrict__ grads) {
+  pdl_prologue();
   extern __shared__ float slab[];
   const WeightDesc d = descs[blockIdx.y];
   const int co = blockIdx.x;
@@ -129,7 +132,7 @@ k_unpack_wgrads(const WeightDesc* __restrict__ descs, const float* __restrict__ 
 int launch_unpack_wgrads(const WeightDesc* d_descs, int nconv, const float* dw_krsc, float* grads,
                          int max_elems, cudaStream_t st) {
   dim3 grid(512, nconv);
-  k_unpack_wgrads<<<grid, 256, 513 * 9 * sizeof(float), st>>>(d_descs, dw_krsc, grads);
+  MN_LAUNCH(k_unpack_wgrads, grid, 256, 513 * 9 * sizeof(float), st, d_descs, dw_krsc, grads);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -140,6 +143,7 @@ int launch_unpack_wgrads(const WeightDesc* d_descs, int nconv, const float* dw_k
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_stem_im2col(const float* __restrict__ x, T* __restrict__ A, int B, int H, int W, int Ho, int Wo, int Kpad) {
+  pdl_prologue();
   extern __shared__ float sx[];          // [3*7][W + 6]
   __shared__ int lut[192];               // k -> offset of (c,kh,kw) inside sx (-1: zero padding of K)
   const int WP = W + 6;
@@ -178,7 +182,7 @@ int launch_stem_im2col(const float* x_nchw, T* A, int B, int H, int W, int Ho, i
   MN_CHECK(Kpad % 8 == 0 && Kpad >= 147, "stem_im2col: bad Kpad");
   const size_t smem = (size_t)21 * (W + 6) * sizeof(float);
   MN_CHECK(smem <= 48 * 1024, "stem_im2col: image width %d too large", W);
-  k_stem_im2col<T><<<B * Ho, 256, smem, st>>>(x_nchw, A, B, H, W, Ho, Wo, Kpad);
+  MN_LAUNCH(k_stem_im2col<T>, B * Ho, 256, smem, st, x_nchw, A, B, H, W, Ho, Wo, Kpad);
   MN_LAUNCH_CHECK();
   return 0;
 }

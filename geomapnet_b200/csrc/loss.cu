@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256)
 k_loss(int mode, const float* __restrict__ pred, const float* __restrict__ targ, int N, int Tp, int Tt,
        const float* __restrict__ s4, float* __restrict__ loss, float* __restrict__ dpred,
        float* __restrict__ ds4) {
+  pdl_prologue();
   __shared__ float red[8][4];
   float s[4] = {s4[0], s4[1], s4[2], s4[3]};
   const losscore::Cfg c = losscore::make_cfg(mode, N, Tp, Tt, s);
@@ -55,7 +56,7 @@ int launch_loss(int mode, const float* pred, const float* targ, int N, int Tp, i
   if (mode == losscore::MAPNET) MN_CHECK(Tt == Tp, "loss: mapnet mode wants targ [N,T,6] like pred");
   if (mode == losscore::ONLINE) MN_CHECK(Tp % 2 == 0 && Tt == Tp - 1, "loss: online mode wants pred [N,2T,6], targ [N,2T-1,6]");
   if (mode == losscore::ONLINE_GPS) MN_CHECK(Tp % 2 == 0 && Tt == Tp, "loss: online_gps mode wants pred, targ [N,2T,6]");
-  k_loss<<<1, 256, 0, st>>>(mode, pred, targ, N, Tp, Tt, s4, loss, dpred, ds4);
+  MN_LAUNCH(k_loss, 1, 256, 0, st, mode, pred, targ, N, Tp, Tt, s4, loss, dpred, ds4);
   MN_LAUNCH_CHECK();
   return 0;
 }

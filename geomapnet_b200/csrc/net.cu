@@ -13,6 +13,12 @@ namespace mapnet {
 
 // ---- error string ------------------------------------------------------------
 unsigned long long g_launch_count = 0;
+
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MAPNET_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v;
+}
 static thread_local char g_err[1024] = "";
 void set_last_error(const char* fmt, ...) {
   va_list ap;
