@@ -522,16 +522,117 @@ k_stem_pool_bwd(const T* __restrict__ dz, const uint8_t* __restrict__ amax, cons
   }
 }
 
+// Quad version (H, W even): one thread owns the 2x2 input pixels (2a..2a+1, 2b..2b+1) of 8 channels.
+// They are covered by exactly the four pooling windows (a..a+1, b..b+1), so dz / argmax are read
+// 4 times per quad instead of 9, and the reductions of the stem BatchNorm backward
+// (sum g, sum g*y) are accumulated on the way (accum != nullptr): no separate pass over g and y.
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+k_stem_pool_bwd_quad(const T* __restrict__ dz, const uint8_t* __restrict__ amax, const T* __restrict__ y,
+                     const float* __restrict__ scale, const float* __restrict__ shift, T* __restrict__ g,
+                     int B, int H, int W, int Ho, int Wo, int C, double* __restrict__ accum) {
+  pdl_prologue();
+  const int cv = C >> 3;
+  const int Hq = H >> 1, Wq = W >> 1;
+  const long long nq = (long long)B * Hq * Wq * cv;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 % cv) * 8;            // loop invariant: the grid stride is a multiple of cv
+  float sc[8], sh[8], s0[8], s1[8];
+  ld8(scale + c0, sc); ld8(shift + c0, sh);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
+  for (long long i = i0; i < nq; i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / cv;
+    const int qb = (int)(p % Wq); p /= Wq;
+    const int qa = (int)(p % Hq);
+    const int b = (int)(p / Hq);
+    // windows (qa + dh, qb + dw): gradient and argmax position (kh*3+kw inside the window)
+    float d[4][8]; uint2 pk[4];
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        const int oh = qa + dh, ow = qb + dw;
+        const int w = dh * 2 + dw;
+        if (oh < Ho && ow < Wo) {
+          const long long o = (((long long)b * Ho + oh) * Wo + ow) * C + c0;
+          pk[w] = *reinterpret_cast<const uint2*>(amax + o);
+          Vec8<T> t; t.load(dz + o);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[w][k] = t.v[k];
+        } else {
+          pk[w] = make_uint2(0xffffffffu, 0xffffffffu);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[w][k] = 0.f;
+        }
+      }
+    // pixel (r, c) of the quad sits at window position: w00 -> (1+r)*3 + (1+c); w01 (c == 1) -> (1+r)*3;
+    // w10 (r == 1) -> (1+c); w11 (r == c == 1) -> 0
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const long long off = (((long long)b * H + 2 * qa + r) * W + 2 * qb + c) * C + c0;
+        Vec8<T> yy; yy.load(y + off);
+        Vec8<T> o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int sft = (k & 3) * 8;
+          const uint32_t i00 = (((k < 4) ? pk[0].x : pk[0].y) >> sft) & 0xff;
+          const uint32_t i01 = (((k < 4) ? pk[1].x : pk[1].y) >> sft) & 0xff;
+          const uint32_t i10 = (((k < 4) ? pk[2].x : pk[2].y) >> sft) & 0xff;
+          const uint32_t i11 = (((k < 4) ? pk[3].x : pk[3].y) >> sft) & 0xff;
+          float a = (i00 == (uint32_t)((1 + r) * 3 + 1 + c)) ? d[0][k] : 0.f;
+          if (c == 1) a += (i01 == (uint32_t)((1 + r) * 3)) ? d[1][k] : 0.f;
+          if (r == 1) a += (i10 == (uint32_t)(1 + c)) ? d[2][k] : 0.f;
+          if (r == 1 && c == 1) a += (i11 == 0u) ? d[3][k] : 0.f;
+          const float act = yy.v[k] * sc[k] + sh[k];
+          o.v[k] = (act > 0.f) ? a : 0.f;
+        }
+        o.store(g + off);
+        if (accum != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float gs = to_f(from_f<T>(o.v[k]));       // the value as stored
+            s0[k] += gs; s1[k] += gs * yy.v[k];
+          }
+        }
+      }
+  }
+  if (accum == nullptr) return;
+  // block reduction over the threads that share a channel vector, then one fp64 atomic per channel
+  extern __shared__ float sm[];                 // [kEwThreads / cv][2][C]
+  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv, rows = kEwThreads / cv;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sm[(ty * 2 + 0) * C + tx * 8 + k] = s0[k]; sm[(ty * 2 + 1) * C + tx * 8 + k] = s1[k]; }
+  __syncthreads();
+  int nrep = (int)gridDim.x / 16;
+  nrep = nrep < 4 ? 4 : (nrep > kReplicas ? kReplicas : nrep);
+  for (int idx = threadIdx.x; idx < 2 * C; idx += kEwThreads) {
+    float t = 0.f;
+    for (int r = 0; r < rows; ++r) t += sm[r * 2 * C + idx];
+    atomicAdd(accum + (size_t)(blockIdx.x % nrep) * kAccStride + idx, (double)t);
+  }
+}
+
 template <typename T>
 int launch_stem_pool_bwd(const T* dz, const uint8_t* amax, const T* y, const float* scale, const float* shift,
-                         T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st) {
+                         T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st, double* accum) {
+  if ((H % 2) == 0 && (W % 2) == 0 && Ho == H / 2 && Wo == W / 2 && kEwThreads % (C >> 3) == 0) {
+    const long long nq = (long long)B * (H / 2) * (W / 2) * (C >> 3);
+    const size_t smem = accum ? (size_t)(kEwThreads / (C >> 3)) * 2 * C * sizeof(float) : 0;
+    MN_LAUNCH(k_stem_pool_bwd_quad<T>, ew_grid(nq), kEwThreads, smem, st, dz, amax, y, scale, shift, g, B, H, W, Ho, Wo, C, accum);
+    MN_LAUNCH_CHECK();
+    return 0;
+  }
+  MN_CHECK(accum == nullptr, "stem_pool_bwd: fused reductions need even H, W (got %dx%d)", H, W);
   const long long nvec = (long long)B * H * W * (C >> 3);
   MN_LAUNCH(k_stem_pool_bwd<T>, ew_grid(nvec), kEwThreads, 0, st, dz, amax, y, scale, shift, g, B, H, W, Ho, Wo, C);
   MN_LAUNCH_CHECK();
   return 0;
 }
-template int launch_stem_pool_bwd<float>(const float*, const uint8_t*, const float*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
-template int launch_stem_pool_bwd<bf16>(const bf16*, const uint8_t*, const bf16*, const float*, const float*, bf16*, int, int, int, int, int, int, cudaStream_t);
+template int launch_stem_pool_bwd<float>(const float*, const uint8_t*, const float*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t, double*);
+template int launch_stem_pool_bwd<bf16>(const bf16*, const uint8_t*, const bf16*, const float*, const float*, bf16*, int, int, int, int, int, int, cudaStream_t, double*);
 
 // backward apply: dy = A*g + B*y + C  [, dyd = Ad*g + Bd*yd + Cd] [, gout = g]
 template <typename T, int DS, int GOUT>

@@ -201,20 +201,21 @@ __device__ __forceinline__ void epi_issue_loads(EpiRegs& G, const long long (&ro
   }
 }
 
+// stage this lane's accumulator row (32 fp32) into the warp's scratch
+__device__ __forceinline__ void epi_stage(const uint32_t (&v)[32], float* __restrict__ scr, const int lane) {
+  float4* dst = reinterpret_cast<float4*>(scr + lane * kEpiRowStride);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                         __uint_as_float(v[4 * j + 3]));
+}
+
 template <int F>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float* __restrict__ scr, const EpiRegs& G,
+__device__ __forceinline__ void epi_chunk(float* __restrict__ scr, const EpiRegs& G,
                                           const long long (&rowoff)[4], const bool (&rstore)[4], const float (&rw)[4],
                                           const int coff, const int col0, bf16* out, const EpiBwd& E, const int lane,
                                           float& s0, float& s1, float& s2) {
-  // stage the accumulator rows
-  {
-    float4* dst = reinterpret_cast<float4*>(scr + lane * kEpiRowStride);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                           __uint_as_float(v[4 * j + 3]));
-  }
-  __syncwarp();
+  __syncwarp();                                // the staged rows are visible to the whole warp
   const int p = lane & 3, rr = lane >> 2;
   float4 lo[4], hi[4];
 #pragma unroll
@@ -307,24 +308,24 @@ __device__ __forceinline__ void epi_tile(const uint32_t tmem_addr, const bool ha
   epi_issue_loads<F>(G, rowoff, 0, residual, E, lane);
   mbar_wait(tfull_bar, tfull_phase);
   tc_fence_after();
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0u;      // has_acc == false: no filter tap reaches this output class, D = 0
+  if (has_acc) tmem_ld32(tmem_addr, v);
 #pragma unroll 1
   for (int cc = 0; cc < BN / 32; ++cc) {
     if (cc > 0) epi_issue_loads<F>(G, rowoff, cc * 32, residual, E, lane);
-    uint32_t v[32];
-    if (has_acc) {
-      tmem_ld32(tmem_addr + cc * 32, v);
-      tmem_ld_wait();
-    } else {                                   // no filter tap reaches this output class: D = 0
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0u;
-    }
+    if (has_acc) tmem_ld_wait();
     if (cc == BN / 32 - 1) {
       // all TMEM reads of this accumulator stage are complete: hand it back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) release();
     }
-    epi_chunk<F>(v, scr, G, rowoff, rstore, rw, cc * 32, tn * BN + cc * 32, out, E, lane, stw[0][cc][lane],
+    epi_stage(v, scr, lane);
+    // the next chunk's TMEM read overlaps this chunk's processing
+    if (has_acc && cc + 1 < BN / 32) tmem_ld32(tmem_addr + (cc + 1) * 32, v);
+    epi_chunk<F>(scr, G, rowoff, rstore, rw, cc * 32, tn * BN + cc * 32, out, E, lane, stw[0][cc][lane],
                  stw[1][cc][lane], stw[2][cc][lane]);
   }
 }

@@ -31,7 +31,7 @@ int launch_stem_pool(const T* y, const float* scale, const float* shift, T* z, u
                      int W, int Ho, int Wo, int C, cudaStream_t st);
 template <typename T>
 int launch_stem_pool_bwd(const T* dz, const uint8_t* amax, const T* y, const float* scale, const float* shift,
-                         T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st);
+                         T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st, double* accum = nullptr);
 template <typename T>
 int launch_bn_bwd_apply(const T* dout, const T* zmask, const T* y, const float* coef, T* dy, const T* yd,
                         const float* coefd, T* dyd, T* gout, long long M, int C, cudaStream_t st,

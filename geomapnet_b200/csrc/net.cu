@@ -137,6 +137,7 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0;
   { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
+  { const char* e = getenv("MAPNET_STEM_FUSE"); stem_fuse = (e ? atoi(e) != 0 : 1) && (Hc % 2 == 0) && (Wc % 2 == 0); }
   { const char* e = getenv("MAPNET_TC_FUSE_BWD"); fuse_bwd = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   build_table();
   if (max_B == 0) return 0;      // spec-only handle: parameter table, no device memory
@@ -458,10 +459,17 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
   {
     BNL& b0 = bns[convs[0].bn];
     const long long M0 = (long long)B * Hc * Wc;
-    MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S1, B, Hc, Wc, Hp, Wp, 64, st));
-    MN_TRY(launch_bn_bwd_reduce<T>(S1, nullptr, (const T*)y0, nullptr, M0, 64,
-                                   params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef,
-                                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st));
+    if (stem_fuse) {
+      // the pool/ReLU backward accumulates the stem BN's (sum g, sum g*y) while it has g and y in registers
+      MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S1, B, Hc, Wc, Hp, Wp, 64, st, bn_accum));
+      MN_TRY(launch_bn_bwd_finalize_accum(M0, 64, params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef,
+                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
+    } else {
+      MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S1, B, Hc, Wc, Hp, Wp, 64, st));
+      MN_TRY(launch_bn_bwd_reduce<T>(S1, nullptr, (const T*)y0, nullptr, M0, 64,
+                                     params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef,
+                                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st));
+    }
     MN_TRY(launch_bn_bwd_apply<T>(S1, nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st));
     MN_TRY(conv_wgrad<T>(0, (const T*)A0, S2, B, st));
   }

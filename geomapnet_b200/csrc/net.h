@@ -72,6 +72,7 @@ struct Net {
   // optional per-conv-launch timing (bench.py roofline): CUDA events around every conv call
   struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
   int profile_on;
+  int stem_fuse;                 // stem BN backward reductions inside the pool backward (env MAPNET_STEM_FUSE)
   int fuse_bwd;                  // BN backward reductions accumulated in the dgrad epilogue (env MAPNET_TC_FUSE_BWD)
   int fuse_stats;                // BN statistics accumulated in the tcgen05 conv epilogue (env MAPNET_TC_FUSE_STATS)
   std::vector<ProfRec> prof;
