@@ -7,6 +7,7 @@
 // (cuDNN BN fwd-training/bwd, THCUNN threshold, TH add, SpatialDilatedMaxPooling;
 // SURVEY.md section 2c) that /root/reference/models/posenet.py:66 runs.
 #include "kernels.h"
+#include "bn_fin.cuh"
 
 namespace mapnet {
 
@@ -32,16 +33,6 @@ __device__ __forceinline__ void ld8(const float* __restrict__ p, float* o) {
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
-struct BnFin {
-  // forward (MODE 0)
-  const float *gamma, *beta;
-  float *run_mean, *run_var, *mean, *invstd, *scale, *shift;
-  int training;
-  // backward (MODE 1/2): main BN then downsample BN
-  const float *mscale, *mshift;      // optional: ReLU mask recomputed as (mscale*y + mshift > 0) instead of reading z
-  const float *gamma2, *mean2, *invstd2;
-  float *dgamma, *dbeta, *coef, *dgamma2, *dbeta2, *coef2;
-};
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kEwThreads)
@@ -123,46 +114,10 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
     for (int r = 0; r < nrep; ++r) accum[(size_t)r * kAccStride + idx] = 0.0;
   }
   __syncthreads();
-  const double invM = 1.0 / (double)M;
   for (int c = threadIdx.x; c < C; c += kEwThreads) {
     const double s0 = s_tot[c], s1 = s_tot[C + c];
-    if (MODE == 0) {
-      const double m = s0 * invM;
-      double var = s1 * invM - m * m;
-      if (var < 0.0) var = 0.0;
-      const float mean = (float)m;
-      const float invstd = (float)(1.0 / sqrt(var + 1e-5));
-      const double unbiased = (M > 1) ? var * (double)M / (double)(M - 1) : var;
-      f.run_mean[c] = 0.9f * f.run_mean[c] + 0.1f * mean;
-      f.run_var[c] = 0.9f * f.run_var[c] + 0.1f * (float)unbiased;
-      f.mean[c] = mean;
-      f.invstd[c] = invstd;
-      const float sc = f.gamma[c] * invstd;
-      f.scale[c] = sc;
-      f.shift[c] = f.beta[c] - mean * sc;
-    } else {
-      {
-        const double mu = (double)f.mean[c], is = (double)f.invstd[c];
-        const double s2 = is * (s1 - mu * s0);          // sum g * xhat
-        f.dgamma[c] = (float)s2;
-        f.dbeta[c] = (float)s0;
-        const double A = (double)f.gamma[c] * is;
-        const double Bc = -A * is * s2 * invM;
-        const double Cc = -A * s0 * invM - Bc * mu;
-        f.coef[c] = (float)A; f.coef[C + c] = (float)Bc; f.coef[2 * C + c] = (float)Cc;
-      }
-      if (MODE == 2) {
-        const double s1d = s_tot[2 * C + c];
-        const double mu = (double)f.mean2[c], is = (double)f.invstd2[c];
-        const double s2 = is * (s1d - mu * s0);
-        f.dgamma2[c] = (float)s2;
-        f.dbeta2[c] = (float)s0;
-        const double A = (double)f.gamma2[c] * is;
-        const double Bc = -A * is * s2 * invM;
-        const double Cc = -A * s0 * invM - Bc * mu;
-        f.coef2[c] = (float)A; f.coef2[C + c] = (float)Bc; f.coef2[2 * C + c] = (float)Cc;
-      }
-    }
+    if (MODE == 0) bn_fin_forward(c, s0, s1, M, f);
+    else bn_fin_backward(c, C, s0, s1, (MODE == 2) ? s_tot[2 * C + c] : 0.0, M, f, MODE == 2);
   }
   if (threadIdx.x == 0) *counter = 0u;
 }
@@ -211,20 +166,7 @@ k_bn_finalize_accum(long long M, int C, BnFin f, double* __restrict__ accum) {
   double s0 = 0.0, s1 = 0.0;
 #pragma unroll
   for (int k = 0; k < 32; ++k) { s0 += s0s[k][cl]; s1 += s1s[k][cl]; }
-  const double invM = 1.0 / (double)M;
-  const double m = s0 * invM;
-  double var = s1 * invM - m * m;
-  if (var < 0.0) var = 0.0;
-  const float mean = (float)m;
-  const float invstd = (float)(1.0 / sqrt(var + 1e-5));
-  const double unbiased = (M > 1) ? var * (double)M / (double)(M - 1) : var;
-  f.run_mean[c] = 0.9f * f.run_mean[c] + 0.1f * mean;
-  f.run_var[c] = 0.9f * f.run_var[c] + 0.1f * (float)unbiased;
-  f.mean[c] = mean;
-  f.invstd[c] = invstd;
-  const float sc = f.gamma[c] * invstd;
-  f.scale[c] = sc;
-  f.shift[c] = f.beta[c] - mean * sc;
+  bn_fin_forward(c, s0, s1, M, f);
 }
 
 int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float* beta, float* run_mean,
@@ -260,27 +202,7 @@ k_bn_bwd_finalize_accum(long long M, int C, BnFin f, double* __restrict__ accum,
   double s0 = 0.0, s1 = 0.0, s1d = 0.0;
 #pragma unroll
   for (int k = 0; k < 32; ++k) { s0 += ss[0][k][cl]; s1 += ss[1][k][cl]; s1d += ss[2][k][cl]; }
-  const double invM = 1.0 / (double)M;
-  {
-    const double mu = (double)f.mean[c], is = (double)f.invstd[c];
-    const double s2 = is * (s1 - mu * s0);          // sum g * xhat
-    f.dgamma[c] = (float)s2;
-    f.dbeta[c] = (float)s0;
-    const double A = (double)f.gamma[c] * is;
-    const double Bc = -A * is * s2 * invM;
-    const double Cc = -A * s0 * invM - Bc * mu;
-    f.coef[c] = (float)A; f.coef[C + c] = (float)Bc; f.coef[2 * C + c] = (float)Cc;
-  }
-  if (nacc == 3) {
-    const double mu = (double)f.mean2[c], is = (double)f.invstd2[c];
-    const double s2 = is * (s1d - mu * s0);
-    f.dgamma2[c] = (float)s2;
-    f.dbeta2[c] = (float)s0;
-    const double A = (double)f.gamma2[c] * is;
-    const double Bc = -A * is * s2 * invM;
-    const double Cc = -A * s0 * invM - Bc * mu;
-    f.coef2[c] = (float)A; f.coef2[C + c] = (float)Bc; f.coef2[2 * C + c] = (float)Cc;
-  }
+  bn_fin_backward(c, C, s0, s1, s1d, M, f, nacc == 3);
 }
 
 int launch_bn_bwd_finalize_accum(long long M, int C, const float* gamma, const float* mean, const float* invstd,

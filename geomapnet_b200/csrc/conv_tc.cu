@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "bn_fin.cuh"
 #include "tc_ptx.cuh"
 
 namespace mapnet {
@@ -367,6 +368,56 @@ __device__ __forceinline__ int epi_mode_of(const bf16* residual, const double* s
   return m;
 }
 
+// ---- statistics flush + fused BatchNorm finalize (epilogue warps only: 128 threads, named barrier 1) ----
+static constexpr int kConvReplicas = 8;        // accumulator replicas the conv engines spread their flushes over
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Combine the four epilogue warps' running column sums of N tile `tn` in shared memory and add them to this
+// CTA's accumulator replica: one fp64 atomic per (statistic, column) per CTA.
+template <int BN>
+__device__ __forceinline__ void epi_flush(float (*all)[3][BN / 32][32], double* __restrict__ stats, const int Cout,
+                                          const int tn, const bool third, const int etid) {
+  epi_bar();                                    // every warp's sums for this N tile are in shared memory
+  double* acc = stats + (size_t)(blockIdx.x % kConvReplicas) * kStatStride;
+  const int nstat = third ? 3 : 2;
+#pragma unroll 1
+  for (int e = etid; e < nstat * BN; e += 128) {
+    const int j = e / BN, rem = e - j * BN, i = rem >> 5, l = rem & 31;
+    const float t = all[0][j][i][l] + all[1][j][i][l] + all[2][j][i][l] + all[3][j][i][l];
+    all[0][j][i][l] = 0.f; all[1][j][i][l] = 0.f; all[2][j][i][l] = 0.f; all[3][j][i][l] = 0.f;
+    atomicAdd(acc + (size_t)j * Cout + tn * BN + i * 32 + epi_stat_col(l), (double)t);
+  }
+  epi_bar();                                    // zeroed before any warp accumulates the next N tile
+}
+
+// The LAST CTA (over all launches that feed the accumulators) to finish its flushes turns the sums into the
+// BatchNorm quantities the next kernel needs -- no separate finalize launch.
+__device__ __forceinline__ void epi_finalize(const EpiFin& Fin, double* __restrict__ stats, const int C,
+                                             const int etid, unsigned int* s_flag) {
+  __threadfence();                              // this thread's atomics are ordered before the counter
+  epi_bar();
+  if (etid == 0) *s_flag = (atomicAdd(Fin.counter, 1u) == Fin.expected - 1u) ? 1u : 0u;
+  epi_bar();
+  if (*s_flag == 0u) return;
+  __threadfence();
+  const int nacc = (Fin.mode == 3) ? 3 : 2;
+#pragma unroll 1
+  for (int c = etid; c < C; c += 128) {
+    double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < kConvReplicas; ++r) {
+      double* a = stats + (size_t)r * kStatStride;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (j < nacc) { s[j] += __ldcg(a + (size_t)j * C + c); a[(size_t)j * C + c] = 0.0; }
+    }
+    if (Fin.mode == 1) bn_fin_forward(c, s[0], s[1], Fin.M, Fin.f);
+    else bn_fin_backward(c, C, s[0], s[1], s[2], Fin.M, Fin.f, nacc == 3);
+  }
+  if (etid == 0) *Fin.counter = 0u;
+}
+
 // as many stages as fit in 227 KB: the engines are bound by bytes in flight x L2 latency
 static constexpr int conv_stages(int BN) { return BN <= 64 ? 8 : (BN <= 128 ? 6 : 4); }   // + 18 KB epilogue scratch
 static constexpr int wgrad_stages(int BN) { return BN <= 64 ? 9 : (BN <= 128 ? 6 : 4); }
@@ -382,7 +433,7 @@ __global__ void __launch_bounds__(192, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
           const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
-          bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E) {
+          bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E, const EpiFin Fin) {
   constexpr int STAGES = conv_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;        // 128 pixels x 64 ch bf16
   constexpr uint32_t B_BYTES = BN * 128;
@@ -508,17 +559,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 #pragma unroll 1
     for (int i = 0; i < BN / 32; ++i) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
     int st_tn = -1;
-    auto flush_stats = [&](int tn_flush) {
-      double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
-#pragma unroll 1
-      for (int i = 0; i < BN / 32; ++i) {
-        const int c = tn_flush * BN + i * 32 + epi_stat_col(lane);
-        atomicAdd(acc + c, (double)stw[0][i][lane]);
-        atomicAdd(acc + P.Cout + c, (double)stw[1][i][lane]);
-        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)stw[2][i][lane]);
-        stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f;
-      }
-    };
+    const int etid = q * 32 + lane;
+    auto flush_stats = [&](int tn_flush) { epi_flush<BN>(epi_stats, stats, P.Cout, tn_flush, E.yd != nullptr, etid); };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int tn = tile % P.n_tiles_n;
       if (stats != nullptr && tn != st_tn) { if (st_tn >= 0) flush_stats(st_tn); st_tn = tn; }
@@ -554,6 +596,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
+    if (Fin.mode != 0) {
+      __shared__ unsigned int s_fin_flag;
+      epi_finalize(Fin, stats, P.Cout, etid, &s_fin_flag);
+    }
   }
   // ---- teardown ----
   tc_fence_before();
@@ -576,7 +622,7 @@ __global__ void __launch_bounds__(192, 1)
 k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
            const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
-           bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E) {
+           bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E, const EpiFin Fin) {
   constexpr int STAGES = conv2_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;
   constexpr uint32_t BH_BYTES = (BN / 2) * 128;      // this CTA's half of the weight tile
@@ -692,17 +738,8 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 #pragma unroll 1
     for (int i = 0; i < BN / 32; ++i) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
     int st_tn = -1;
-    auto flush_stats = [&](int tn_flush) {
-      double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
-#pragma unroll 1
-      for (int i = 0; i < BN / 32; ++i) {
-        const int c = tn_flush * BN + i * 32 + epi_stat_col(lane);
-        atomicAdd(acc + c, (double)stw[0][i][lane]);
-        atomicAdd(acc + P.Cout + c, (double)stw[1][i][lane]);
-        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)stw[2][i][lane]);
-        stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f;
-      }
-    };
+    const int etid = q * 32 + lane;
+    auto flush_stats = [&](int tn_flush) { epi_flush<BN>(epi_stats, stats, P.Cout, tn_flush, E.yd != nullptr, etid); };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int tn = tile % P.n_tiles_n;
       if (stats != nullptr && tn != st_tn) { if (st_tn >= 0) flush_stats(st_tn); st_tn = tn; }
@@ -729,6 +766,10 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
+    if (Fin.mode != 0) {
+      __shared__ unsigned int s_fin_flag;
+      epi_finalize(Fin, stats, P.Cout, etid, &s_fin_flag);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -765,7 +806,7 @@ template <int BN>
 __global__ void __launch_bounds__(192, 1)
 k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ HaloParams P, const bf16* __restrict__ residual, bf16* __restrict__ out,
-               double* __restrict__ stats, const EpiBwd E) {
+               double* __restrict__ stats, const EpiBwd E, const EpiFin Fin) {
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr int MAXNP = 4, MAXNB = 12;
@@ -906,17 +947,8 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll 1
     for (int i = 0; i < BN / 32; ++i) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
     int st_tn = -1;
-    auto flush_stats = [&](int tn_flush) {
-      double* acc = stats + (size_t)(blockIdx.x % kStatReplicas) * kStatStride;
-#pragma unroll 1
-      for (int i = 0; i < BN / 32; ++i) {
-        const int c = tn_flush * BN + i * 32 + epi_stat_col(lane);
-        atomicAdd(acc + c, (double)stw[0][i][lane]);
-        atomicAdd(acc + P.Cout + c, (double)stw[1][i][lane]);
-        if (E.yd != nullptr) atomicAdd(acc + 2 * P.Cout + c, (double)stw[2][i][lane]);
-        stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f;
-      }
-    };
+    const int etid = q * 32 + lane;
+    auto flush_stats = [&](int tn_flush) { epi_flush<BN>(epi_stats, stats, P.Cout, tn_flush, E.yd != nullptr, etid); };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tn = tile % P.n_tiles_n;
       if (stats != nullptr && tn != st_tn) { if (st_tn >= 0) flush_stats(st_tn); st_tn = tn; }
@@ -937,6 +969,10 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
+    if (Fin.mode != 0) {
+      __shared__ unsigned int s_fin_flag;
+      epi_finalize(Fin, stats, P.Cout, etid, &s_fin_flag);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1493,8 +1529,14 @@ static int encode_view(CUtensorMap* m, const bf16* base, int N, int Hd, int Wd, 
 }
 
 int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st,
-                double* stats, const EpiBwd* bwd) {
+                double* stats, const EpiBwd* bwd, const EpiFin* fin) {
   MN_CHECK(p != nullptr, "tc_conv_run: null plan");
+  EpiFin F; memset(&F, 0, sizeof(F));
+  if (fin != nullptr && fin->mode != 0) {
+    MN_CHECK(stats != nullptr && fin->counter != nullptr && p->kind != 2, "tc_conv_run: fused finalize needs statistics accumulators");
+    MN_CHECK((fin->mode == 1) == (bwd == nullptr), "tc_conv_run: finalize mode %d does not match the statistics kind", fin->mode);
+    F = *fin;
+  }
   EpiBwd E; memset(&E, 0, sizeof(E));
   if (bwd != nullptr) {
     MN_CHECK(p->kind == 1 && stats != nullptr && bwd->y != nullptr, "tc_conv_run: backward statistics need a dgrad plan, accumulators and Y");
@@ -1515,7 +1557,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       MN_TRY(encode_w_map(&p->hmapB, p->wmat, 9 * Cs, H.Cout, p->BN));
       p->c_in0 = in0;
     }
-    void (*kern)(CUtensorMap, CUtensorMap, HaloParams, const bf16*, bf16*, double*, EpiBwd) =
+    void (*kern)(CUtensorMap, CUtensorMap, HaloParams, const bf16*, bf16*, double*, EpiBwd, EpiFin) =
         (p->BN == 64) ? k_tc_conv_halo<64> : (p->BN == 128 ? k_tc_conv_halo<128> : k_tc_conv_halo<256>);
     if (!p->smem_attr_set) {
       MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->halo_smem));
@@ -1523,7 +1565,8 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     }
     const int total = H.n_tiles_m * H.n_tiles_n;
     const int grid = total < nsm ? total : nsm;
-    MN_LAUNCH(kern, grid, 192, p->halo_smem, st, p->hmapA, p->hmapB, H, residual, (bf16*)out, stats, E);
+    F.expected = (unsigned int)grid;
+    MN_LAUNCH(kern, grid, 192, p->halo_smem, st, p->hmapA, p->hmapB, H, residual, (bf16*)out, stats, E, F);
     MN_LAUNCH_CHECK();
     return 0;
   }
@@ -1543,7 +1586,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       p->c_in0 = in0;
     }
     size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024;
-    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*, double*, EpiBwd) = nullptr;
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*, double*, EpiBwd, EpiFin) = nullptr;
     if (p->two_cta) {
       smem = (size_t)conv2_stages(p->BN) * (128 * 128 + (p->BN / 2) * 128) + 1024;
       kern = (p->BN == 256) ? k_tc_conv2<256> : k_tc_conv2<128>;
@@ -1555,6 +1598,12 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     if (!p->smem_attr_set) {
       MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       p->smem_attr_set = true;
+    }
+    F.expected = 0;
+    for (auto& L : p->launches) {     // the sums of a stride-2 dgrad come from all its parity launches
+      const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n;
+      const int max_clusters = (p->CL == 4) ? 32 : nsm / p->CL;
+      F.expected += (unsigned int)((groups < max_clusters ? groups : max_clusters) * p->CL);
     }
     for (auto& L : p->launches) {
       const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n;
@@ -1568,7 +1617,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-      MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out, stats, E));
+      MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out, stats, E, F));
       ++g_launch_count;
     }
     return 0;

@@ -63,8 +63,11 @@ struct EpiBwd {
   const float* mscale;  // gate recomputed from y when zmask is null
   const float* mshift;
 };
+// fin != nullptr (with stats): the last CTA to flush its sums also finalizes them (bn_fin.cuh) -- forward:
+// mean / invstd / scale / shift / running statistics; backward: d gamma, d beta, dy coefficients
+struct EpiFin;
 int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* residual, void* out, cudaStream_t st,
-                double* stats = nullptr, const EpiBwd* bwd = nullptr);
+                double* stats = nullptr, const EpiBwd* bwd = nullptr, const EpiFin* fin = nullptr);
 // finalize of the dgrad-fused reductions: d gamma, d beta and the dy = A*g + B*y + C coefficients
 int launch_bn_bwd_finalize_accum(long long M, int C, const float* gamma, const float* mean, const float* invstd,
                                  float* dgamma, float* dbeta, float* coef, const float* gamma2, const float* mean2,

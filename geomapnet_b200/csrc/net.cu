@@ -5,6 +5,7 @@
 // torchvision resnet34 (BasicBlock [3,4,6,3]; conv-BN-ReLU-conv-BN-(+id|1x1s2
 // conv+BN)-ReLU) with training-mode BatchNorm.
 #include "net.h"
+#include "bn_fin.cuh"
 
 #include <stdarg.h>
 #include <stdlib.h>
@@ -138,6 +139,7 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0;
   { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   { const char* e = getenv("MAPNET_STEM_FUSE"); stem_fuse = (e ? atoi(e) != 0 : 1) && (Hc % 2 == 0) && (Wc % 2 == 0); }
+  { const char* e = getenv("MAPNET_TC_FUSE_FIN"); fuse_fin = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   { const char* e = getenv("MAPNET_TC_FUSE_BWD"); fuse_bwd = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   build_table();
   if (max_B == 0) return 0;      // spec-only handle: parameter table, no device memory
@@ -230,25 +232,26 @@ static double conv_flops(const ConvGeom& g, int B, bool stem) {
 }
 
 template <typename T>
-int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st, bool with_stats) {
+int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st, bool with_stats, const EpiFin* fin) {
   ConvGeom g = convs[ci].g; g.B = B;
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
   if (precision == PREC_BF16_TC)
-    r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st, (with_stats && fuse_stats) ? bn_accum : nullptr);
+    r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st, (with_stats && fuse_stats) ? bn_accum : nullptr,
+                    nullptr, (with_stats && fuse_stats) ? fin : nullptr);
   else r = launch_conv_simt_fprop<T>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
   prof_end(st, e0, 0, conv_flops(g, B, ci == 0));
   return r;
 }
 template <typename T>
-int Net::conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd) {
+int Net::conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd, const EpiFin* fin) {
   ConvGeom g = convs[ci].g; g.B = B;
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
   if (precision == PREC_BF16_TC)
-    r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, nullptr, (const bf16*)residual, dx, st, bwd ? bn_accum : nullptr, bwd);
+    r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, nullptr, (const bf16*)residual, dx, st, bwd ? bn_accum : nullptr, bwd, bwd ? fin : nullptr);
   else r = launch_conv_simt_dgrad<T>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
   prof_end(st, e0, 1, conv_flops(g, B, false));
   return r;
@@ -289,11 +292,37 @@ template <typename T>
 int Net::bn_forward(int bi, const T* y, long long M, const float* params, float* bufs, int training,
                     cudaStream_t st) {
   BNL& b = bns[bi];
+  if (fuse_stats && training && fuse_fin) return 0;   // the conv's last CTA finalized the statistics
   if (fuse_stats && training)   // sums were accumulated by the conv epilogue
     return launch_bn_finalize_accum(M, b.C, params + b.g_off, params + b.b_off, bufs + b.rm_off, bufs + b.rv_off,
                                     b.mean, b.invstd, b.scale, b.shift, bn_accum, st);
   return launch_bn_stats<T>(y, M, b.C, params + b.g_off, params + b.b_off, bufs + b.rm_off, bufs + b.rv_off,
                             b.mean, b.invstd, b.scale, b.shift, training, bn_accum, bn_counter, st);
+}
+
+// finalize descriptors for the conv kernels (conv_tc.cu: the last CTA finalizes the sums it helped accumulate)
+EpiFin Net::fin_forward(int bi, long long M, const float* params, float* bufs) {
+  EpiFin F; memset(&F, 0, sizeof(F));
+  if (!(fuse_fin && fuse_stats)) return F;
+  BNL& b = bns[bi];
+  F.mode = 1; F.counter = bn_counter; F.M = M;
+  F.f.gamma = params + b.g_off; F.f.beta = params + b.b_off; F.f.run_mean = bufs + b.rm_off; F.f.run_var = bufs + b.rv_off;
+  F.f.mean = b.mean; F.f.invstd = b.invstd; F.f.scale = b.scale; F.f.shift = b.shift; F.f.training = 1;
+  return F;
+}
+EpiFin Net::fin_backward(int bi, int bi_ds, long long M, const float* params, float* grads) {
+  EpiFin F; memset(&F, 0, sizeof(F));
+  if (!(fuse_fin && fuse_bwd)) return F;
+  BNL& b = bns[bi];
+  F.mode = (bi_ds >= 0) ? 3 : 2; F.counter = bn_counter; F.M = M;
+  F.f.gamma = params + b.g_off; F.f.mean = b.mean; F.f.invstd = b.invstd;
+  F.f.dgamma = grads + b.g_off; F.f.dbeta = grads + b.b_off; F.f.coef = b.coef;
+  if (bi_ds >= 0) {
+    BNL& d = bns[bi_ds];
+    F.f.gamma2 = params + d.g_off; F.f.mean2 = d.mean; F.f.invstd2 = d.invstd;
+    F.f.dgamma2 = grads + d.g_off; F.f.dbeta2 = grads + d.b_off; F.f.coef2 = d.coef;
+  }
+  return F;
 }
 
 // ---- forward -------------------------------------------------------------------
@@ -309,7 +338,10 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
                                       precision == PREC_BF16_SIMT, st));
   // stem: im2col -> GEMM -> BN -> ReLU -> maxpool
   MN_TRY(launch_stem_im2col<T>(x, (T*)A0, B, H, W, Hc, Wc, kStemK, st));
-  MN_TRY(conv_fprop<T>(0, (const T*)A0, nullptr, (T*)y0, B, st, training != 0));
+  {
+    const EpiFin f0 = fin_forward(convs[0].bn, (long long)B * Hc * Wc, params, bufs);
+    MN_TRY(conv_fprop<T>(0, (const T*)A0, nullptr, (T*)y0, B, st, training != 0, &f0));
+  }
   MN_TRY(bn_forward<T>(convs[0].bn, (const T*)y0, (long long)B * Hc * Wc, params, bufs, training, st));
   {
     BNL& b = bns[convs[0].bn];
@@ -320,14 +352,17 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
     const long long Mo = (long long)B * bl.Ho * bl.Wo;
     BNL& b1 = bns[convs[bl.conv1].bn];
     BNL& b2 = bns[convs[bl.conv2].bn];
-    MN_TRY(conv_fprop<T>(bl.conv1, zin, nullptr, (T*)bl.y1, B, st, training != 0));
+    const EpiFin f1 = fin_forward(convs[bl.conv1].bn, Mo, params, bufs);
+    const EpiFin f2 = fin_forward(convs[bl.conv2].bn, Mo, params, bufs);
+    MN_TRY(conv_fprop<T>(bl.conv1, zin, nullptr, (T*)bl.y1, B, st, training != 0, &f1));
     MN_TRY(bn_forward<T>(convs[bl.conv1].bn, (const T*)bl.y1, Mo, params, bufs, training, st));
     MN_TRY(launch_bn_apply<T>((const T*)bl.y1, b1.scale, b1.shift, 0, nullptr, nullptr, nullptr, (T*)bl.h, Mo, bl.Cout, 1, st));
-    MN_TRY(conv_fprop<T>(bl.conv2, (const T*)bl.h, nullptr, (T*)bl.y2, B, st, training != 0));
+    MN_TRY(conv_fprop<T>(bl.conv2, (const T*)bl.h, nullptr, (T*)bl.y2, B, st, training != 0, &f2));
     MN_TRY(bn_forward<T>(convs[bl.conv2].bn, (const T*)bl.y2, Mo, params, bufs, training, st));
     if (bl.convd >= 0) {
       BNL& bd = bns[convs[bl.convd].bn];
-      MN_TRY(conv_fprop<T>(bl.convd, zin, nullptr, (T*)bl.yd, B, st, training != 0));
+      const EpiFin fd = fin_forward(convs[bl.convd].bn, Mo, params, bufs);
+      MN_TRY(conv_fprop<T>(bl.convd, zin, nullptr, (T*)bl.yd, B, st, training != 0, &fd));
       MN_TRY(bn_forward<T>(convs[bl.convd].bn, (const T*)bl.yd, Mo, params, bufs, training, st));
       MN_TRY(launch_bn_apply<T>((const T*)bl.y2, b2.scale, b2.shift, 2, (const T*)bl.yd, bd.scale, bd.shift, (T*)bl.out, Mo, bl.Cout, 1, st));
     } else {
@@ -394,9 +429,10 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     if (ds) {
       BNL& bd = bns[convs[bl.convd].bn];
       if (pre) {
-        MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
-                                            params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef,
-                                            bn_accum, st));
+        if (!fuse_fin)
+          MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
+                                              params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef,
+                                              bn_accum, st));
         MN_TRY(launch_bn_bwd_apply<T>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st));
       } else {
         MN_TRY(launch_bn_bwd_reduce<T>(S0, (const T*)bl.out, (const T*)bl.y2, (const T*)bl.yd, Mo, C,
@@ -406,8 +442,9 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
         MN_TRY(launch_bn_bwd_apply<T>(S0, (const T*)bl.out, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st));
       }
     } else if (pre) {
-      MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
-                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
+      if (!fuse_fin)
+        MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
+                                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
       MN_TRY(launch_bn_bwd_apply<T>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st));
       gres = S0;              // already gated; conv1's dgrad adds it in place
     } else {
@@ -423,9 +460,11 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     if (fuse_bwd) {
       EpiBwd e1; memset(&e1, 0, sizeof(e1));
       e1.y = (const bf16*)bl.y1; e1.mscale = b1.scale; e1.mshift = b1.shift;
-      MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st, &e1));
-      MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
-                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
+      const EpiFin fb1 = fin_backward(convs[bl.conv1].bn, -1, Mo, params, grads);
+      MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st, &e1, &fb1));
+      if (!fuse_fin)
+        MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
+                                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
       MN_TRY(launch_bn_bwd_apply<T>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st));
     } else {
       MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st));
@@ -440,18 +479,20 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     // and carries that block's BN2 (+ downsample BN) reductions
     const bool next_pre = fuse_bwd && bi > 0;
     EpiBwd e2; memset(&e2, 0, sizeof(e2));
+    EpiFin fb2; memset(&fb2, 0, sizeof(fb2));
     if (next_pre) {
       BlockL& pb = blocks[bi - 1];
       e2.y = (const bf16*)pb.y2; e2.zmask = (const bf16*)pb.out;
       e2.yd = (pb.convd >= 0) ? (const bf16*)pb.yd : nullptr;
+      fb2 = fin_backward(convs[pb.conv2].bn, (pb.convd >= 0) ? convs[pb.convd].bn : -1, (long long)B * pb.Ho * pb.Wo, params, grads);
     }
     MN_TRY(conv_wgrad<T>(bl.conv1, zin, S1, B, st));
     if (ds) {
       MN_TRY(conv_wgrad<T>(bl.convd, zin, S2, B, st));
       MN_TRY(conv_dgrad<T>(bl.convd, S2, nullptr, S0, B, st));
-      MN_TRY(conv_dgrad<T>(bl.conv1, S1, S0, S0, B, st, next_pre ? &e2 : nullptr));
+      MN_TRY(conv_dgrad<T>(bl.conv1, S1, S0, S0, B, st, next_pre ? &e2 : nullptr, &fb2));
     } else {
-      MN_TRY(conv_dgrad<T>(bl.conv1, S1, gres, S0, B, st, next_pre ? &e2 : nullptr));
+      MN_TRY(conv_dgrad<T>(bl.conv1, S1, gres, S0, B, st, next_pre ? &e2 : nullptr, &fb2));
     }
     pre = next_pre;
   }

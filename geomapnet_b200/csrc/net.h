@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "bn_fin.cuh"
 
 namespace mapnet {
 
@@ -73,6 +74,7 @@ struct Net {
   struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
   int profile_on;
   int stem_fuse;                 // stem BN backward reductions inside the pool backward (env MAPNET_STEM_FUSE)
+  int fuse_fin;                  // BN finalize inside the last CTA of the accumulating conv (env MAPNET_TC_FUSE_FIN)
   int fuse_bwd;                  // BN backward reductions accumulated in the dgrad epilogue (env MAPNET_TC_FUSE_BWD)
   int fuse_stats;                // BN statistics accumulated in the tcgen05 conv epilogue (env MAPNET_TC_FUSE_STATS)
   std::vector<ProfRec> prof;
@@ -97,8 +99,10 @@ struct Net {
   template <typename T> int backward_t(const float* dpred, const float* params, float* grads, int filter_nans,
                                        cudaStream_t st);
   template <typename T> int conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st,
-                                       bool with_stats = false);
-  template <typename T> int conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd = nullptr);
+                                       bool with_stats = false, const EpiFin* fin = nullptr);
+  template <typename T> int conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd = nullptr, const EpiFin* fin = nullptr);
+  EpiFin fin_forward(int bi, long long M, const float* params, float* bufs);
+  EpiFin fin_backward(int bi, int bi_ds, long long M, const float* params, float* grads);
   template <typename T> int conv_wgrad(int ci, const T* x, const T* dy, int B, cudaStream_t st);
   template <typename T> int bn_forward(int bi, const T* y, long long M, const float* params, float* bufs,
                                        int training, cudaStream_t st);
