@@ -77,6 +77,30 @@ static int encode_w_map(CUtensorMap* m, const void* base, int K, int rows, int b
   return 0;
 }
 
+bool tc_overlapped_view_supported() {
+  static int ok = -1;
+  if (ok < 0) {
+    // encode only (nothing is dereferenced): 64-element rows that start 16 elements apart
+    CUtensorMap m;
+    auto fn = get_encode_fn();
+    ok = 0;
+    if (fn != nullptr) {
+      cuuint64_t dims[4] = {64, 128, 131, 2};
+      cuuint64_t strides[3] = {32, 132 * 32, 131ull * 132 * 32};
+      cuuint32_t box[4] = {64, 16, 8, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      void* base = nullptr;
+      if (cudaMalloc(&base, 4096) == cudaSuccess) {
+        CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        ok = (r == CUDA_SUCCESS) ? 1 : 0;
+        cudaFree(base);
+      }
+    }
+  }
+  return ok == 1;
+}
+
 // ---------------------------------------------------------------------------------
 // device parameter blocks
 // ---------------------------------------------------------------------------------
@@ -1343,7 +1367,9 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   *out = nullptr;
   MN_CHECK(g.stride == 1 || g.stride == 2, "tc conv: stride %d unsupported", g.stride);
   MN_CHECK(g.Ci % 64 == 0 && g.Co % 64 == 0, "tc conv: channels must be multiples of 64 (Ci=%d Co=%d)", g.Ci, g.Co);
-  MN_CHECK(g.KH == g.KW && (g.KH == 1 || g.KH == 3), "tc conv: kernel %dx%d unsupported", g.KH, g.KW);
+  MN_CHECK((g.KH == g.KW && (g.KH == 1 || g.KH == 3)) || (g.KH == 4 && g.KW == 1 && g.stride == 1 && g.pad == 0 && kind != 1),
+           "tc conv: kernel %dx%d unsupported", g.KH, g.KW);
+  MN_CHECK(g.in_pix_stride == 0 || (g.stride == 1 && kind != 1), "tc conv: strided input views only for stride-1 fprop / wgrad");
   TcConvPlan* p = new TcConvPlan();
   p->g = g; p->kind = kind; p->wmat = wmat; p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false;
   p->CL = pick_cl();
@@ -1520,7 +1546,9 @@ static int set_smem(K kernel, size_t bytes) {
 
 // activation map (optionally a stride-2 parity view) over [N, Hd, Wd, C]
 static int encode_view(CUtensorMap* m, const bf16* base, int N, int Hd, int Wd, int C, int s, int a, int b, int bw,
-                       int bh, int bn) {
+                       int bh, int bn, const ConvGeom* gv = nullptr) {
+  if (gv != nullptr && gv->in_pix_stride != 0)      // explicit (possibly overlapping) strides, stride-1 only
+    return encode_act_map(m, base, C, Wd, Hd, N, gv->in_pix_stride, gv->in_row_stride, gv->in_img_stride, bw, bh, bn);
   const long long rowb = (long long)Wd * C * 2, imgb = (long long)Hd * rowb;
   if (s == 1) return encode_act_map(m, base, C, Wd, Hd, N, (long long)C * 2, rowb, imgb, bw, bh, bn);
   const int Hq = cdiv(Hd - a, 2), Wq = cdiv(Wd - b, 2);
@@ -1575,7 +1603,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       for (auto& L : p->launches) {
         if (p->kind == 0) {
           for (int i = 0; i < L.n_maps; ++i)
-            MN_TRY(encode_view(&L.mapA[i], in0, g.B, g.Hi, g.Wi, g.Ci, g.stride, L.pa[i], L.pb[i], L.P.TW, L.P.TH, L.P.TN));
+            MN_TRY(encode_view(&L.mapA[i], in0, g.B, g.Hi, g.Wi, g.Ci, g.stride, L.pa[i], L.pb[i], L.P.TW, L.P.TH, L.P.TN, &g));
           MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Ci, g.Co, p->BN / p->CL));
         } else {
           MN_TRY(encode_view(&L.mapA[0], in0, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, L.P.TW, L.P.TH, L.P.TN));
@@ -1626,7 +1654,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
   WgradParams& P = p->WP;
   if (p->c_in0 != in0 || p->c_in1 != in1) {
     for (int i = 0; i < p->w_nmaps; ++i)
-      MN_TRY(encode_view(&p->mapX[i], in0, g.B, g.Hi, g.Wi, g.Ci, g.stride, p->wpa[i], p->wpb[i], P.TW, P.TH, P.TN));
+      MN_TRY(encode_view(&p->mapX[i], in0, g.B, g.Hi, g.Wi, g.Ci, g.stride, p->wpa[i], p->wpb[i], P.TW, P.TH, P.TN, &g));
     for (int i = p->w_nmaps; i < 4; ++i) p->mapX[i] = p->mapX[0];
     MN_TRY(encode_view(&p->mapDY, in1, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, P.TW, P.TH, P.TN));
     p->c_in0 = in0; p->c_in1 = in1;

@@ -7,6 +7,10 @@ namespace mapnet {
 // Geometry of one convolution (NHWC activations, weights [Co][KH][KW][Ci] "KRSC").
 struct ConvGeom {
   int B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad;
+  // tensor-core path only: byte strides of the INPUT view when it is not a dense [B,Hi,Wi,Ci] tensor
+  // (0 = dense).  The stem uses an overlapped view of its space-to-depth image: a "pixel" is 64
+  // consecutive elements and consecutive pixels start 16 elements apart (layout.cu, k_stem_s2d).
+  long long in_pix_stride = 0, in_row_stride = 0, in_img_stride = 0;
   __host__ __device__ long long M_out() const { return (long long)B * Ho * Wo; }
   __host__ __device__ long long M_in() const { return (long long)B * Hi * Wi; }
   __host__ __device__ int Kdim() const { return KH * KW * Ci; }
@@ -77,18 +81,26 @@ int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float
                              float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift,
                              double* accum, cudaStream_t st);
 
+// true when the driver accepts a tiled tensor map whose second dimension's stride is smaller than the
+// first dimension's extent (overlapping windows) -- what the space-to-depth stem view needs
+bool tc_overlapped_view_supported();
+
 // ---- layout.cu -----------------------------------------------------------------
 struct WeightDesc {   // one conv's weight in the flat parameter buffer and in the packed matrices
   long long p_off;    // float offset in params_flat ([Co,Ci_real,KH,KW] torch layout)
   long long k_off;    // element offset in the KRSC / dgrad packed buffers
   int Co, Ci, Ci_real, KH, KW;   // Ci = packed (padded) channels per tap
   int im2col_k;       // >0: stem conv stored as [Co][im2col_k] with k=(kh*KW+kw)*Ci_real+ci
+  int s2d;            // stem, space-to-depth K order: k = kh2*64 + kw2*16 + (pr*2+pc)*3 + ci, (kh,kw) = (2*kh2+pr-1, 2*kw2+pc-1)
 };
 template <typename TW>
 int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* params, TW* w_krsc, TW* w_dg,
                         int max_elems, int round_bf16, cudaStream_t st);
 int launch_unpack_wgrads(const WeightDesc* d_descs, int nconv, const float* dw_krsc, float* grads,
                          int max_elems, cudaStream_t st);
+// space-to-depth image of the stem input: S[b][bh][bw][16] bf16, channel (pr*2+pc)*3+c of block (bh,bw)
+// = x[b][c][2*bh+pr-4][2*bw+pc-4] (0 outside the image, channels 12..15 = 0), row pitch Wsp blocks
+int launch_stem_s2d(const float* x_nchw, bf16* S, int B, int H, int W, int Hs, int Wsp, cudaStream_t st);
 template <typename T>
 int launch_stem_im2col(const float* x_nchw, T* A, int B, int H, int W, int Ho, int Wo, int Kpad, cudaStream_t st);
 

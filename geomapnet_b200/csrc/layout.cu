@@ -36,7 +36,14 @@ k_pack_weights(const WeightDesc* __restrict__ descs, const float* __restrict__ p
     TW* dst = w_krsc + d.k_off + (long long)co * d.im2col_k;
     for (int k = threadIdx.x; k < d.im2col_k; k += blockDim.x) {
       float v = 0.f;
-      if (k < n_in) { const int t = k / d.Ci_real, c = k - t * d.Ci_real; v = slab[c * 49 + t]; }
+      if (d.s2d) {
+        const int kh2 = k >> 6, kw2 = (k >> 4) & 3, ch = k & 15;
+        if (ch < 12) {
+          const int q = ch / 3, c = ch - q * 3;
+          const int kh = 2 * kh2 + (q >> 1) - 1, kw = 2 * kw2 + (q & 1) - 1;
+          if (kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = slab[c * 49 + kh * 7 + kw];
+        }
+      } else if (k < n_in) { const int t = k / d.Ci_real, c = k - t * d.Ci_real; v = slab[c * 49 + t]; }
       if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
       dst[k] = cvt_w<TW>(v);
     }
@@ -114,7 +121,13 @@ k_unpack_wgrads(const WeightDesc* __restrict__ descs, const float* __restrict__ 
     float* dst = grads + d.p_off + (long long)co * n_out;
     for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
       const int t = e % 49, c = e / 49;
-      dst[e] = slab[t * d.Ci_real + c];
+      if (d.s2d) {
+        const int kh = t / 7, kw = t - kh * 7;
+        const int k = ((kh + 1) >> 1) * 64 + ((kw + 1) >> 1) * 16 + ((((kh + 1) & 1) << 1) | ((kw + 1) & 1)) * 3 + c;
+        dst[e] = slab[k];
+      } else {
+        dst[e] = slab[t * d.Ci_real + c];
+      }
     }
     return;
   }
@@ -188,5 +201,54 @@ int launch_stem_im2col(const float* x_nchw, T* A, int B, int H, int W, int Ho, i
 }
 template int launch_stem_im2col<float>(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 template int launch_stem_im2col<bf16>(const float*, bf16*, int, int, int, int, int, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------------
+// stem, tensor-core path: space-to-depth instead of a materialised im2col matrix.
+// The 7x7/s2/p3 conv on 3 channels is a 4x4/s1 conv on the 2x2 space-to-depth image (12 channels, padded
+// to 16; the 7x7 kernel is the 8x8 kernel whose first row and column are zero).  With 16 channels per
+// block, the 4 blocks x 16 channels a filter row touches are 64 CONTIGUOUS elements, so the im2col
+// operand is an overlapped TMA view of S (pixel stride 16 elements, extent 64): a 4-tap conv with
+// "Cin" = 64 that the generic engines run unchanged.  35 MB written and read instead of 403 MB.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_stem_s2d(const float* __restrict__ x, bf16* __restrict__ S, int B, int H, int W, int Hs, int Wsp) {
+  pdl_prologue();
+  const long long n = (long long)B * Hs * Wsp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int bw = (int)(i % Wsp);
+    const long long r = i / Wsp;
+    const int bh = (int)(r % Hs), b = (int)(r / Hs);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+      const int ih = 2 * bh + pr - 4;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int pc = 0; pc < 2; ++pc) {
+        const int iw = 2 * bw + pc - 4;
+        if (iw < 0 || iw >= W) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(pr * 2 + pc) * 3 + c] = __ldg(x + (((long long)b * 3 + c) * H + ih) * W + iw);
+      }
+    }
+    uint4 o[2];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    uint4* dst = reinterpret_cast<uint4*>(S + i * 16);
+    dst[0] = o[0]; dst[1] = o[1];
+  }
+}
+
+int launch_stem_s2d(const float* x_nchw, bf16* S, int B, int H, int W, int Hs, int Wsp, cudaStream_t st) {
+  const long long n = (long long)B * Hs * Wsp;
+  long long grid = (n + 255) / 256;
+  if (grid > 148LL * 8) grid = 148LL * 8;
+  MN_LAUNCH(k_stem_s2d, (int)grid, 256, 0, st, x_nchw, S, B, H, W, Hs, Wsp);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
 
 }  // namespace mapnet

@@ -30,6 +30,7 @@ void set_last_error(const char* fmt, ...) {
 const char* get_last_error() { return g_err; }
 
 static const int kStages[4][3] = {{64, 3, 1}, {128, 4, 2}, {256, 6, 2}, {512, 3, 2}};
+static int s2d_wsp(int wc) { return (wc + 3 + 3) / 4 * 4; }   // blocks per row of the space-to-depth image (128 B aligned rows)
 static const int kStemK = 192;   // 7*7*3 = 147 padded to a multiple of 64 (tensor-core K block)
 
 static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
@@ -75,7 +76,15 @@ void Net::build_table() {
     c.wd.p_off = table[pidx].offset;
     c.wd.k_off = wk_total;
     c.wd.Co = Co; c.wd.Ci_real = stem ? 3 : Ci;
-    if (stem) {
+    c.wd.s2d = 0;
+    if (stem && stem_s2d) {
+      // 4 taps (filter rows of the space-to-depth image) x 64 contiguous elements (4 blocks x 16 channels)
+      const int hc = conv_out(Hi, 7, 2, 3), wc = conv_out(Wi, 7, 2, 3);
+      c.wd.Ci = 64; c.wd.KH = 4; c.wd.KW = 1; c.wd.im2col_k = 256; c.wd.s2d = 1;
+      c.g.Hi = hc + 3; c.g.Wi = wc; c.g.Ci = 64; c.g.Co = Co; c.g.KH = 4; c.g.KW = 1; c.g.stride = 1; c.g.pad = 0;
+      c.g.Ho = hc; c.g.Wo = wc;
+      c.g.in_pix_stride = 16 * 2; c.g.in_row_stride = (long long)s2d_wsp(wc) * 32; c.g.in_img_stride = (long long)(hc + 3) * c.g.in_row_stride;
+    } else if (stem) {
       c.wd.Ci = kStemK; c.wd.KH = c.wd.KW = 1; c.wd.im2col_k = kStemK;
       c.g.Hi = conv_out(Hi, 7, 2, 3); c.g.Wi = conv_out(Wi, 7, 2, 3);   // GEMM view: 1x1 conv over the patch matrix
       c.g.Ho = c.g.Hi; c.g.Wo = c.g.Wi; c.g.Ci = kStemK; c.g.Co = Co; c.g.KH = c.g.KW = 1; c.g.stride = 1; c.g.pad = 0;
@@ -138,8 +147,13 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0;
   { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
+  { const char* e = getenv("MAPNET_STEM_S2D");
+    stem_s2d = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1) && (max_B == 0 || tc_overlapped_view_supported()); }
+  Hc = conv_out(H, 7, 2, 3); Wc = conv_out(W, 7, 2, 3);        // (build_table sets them again)
   { const char* e = getenv("MAPNET_STEM_FUSE"); stem_fuse = (e ? atoi(e) != 0 : 1) && (Hc % 2 == 0) && (Wc % 2 == 0); }
-  { const char* e = getenv("MAPNET_TC_FUSE_FIN"); fuse_fin = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
+  // measured on B200 (posenet_bs64): finalizing inside the conv's last CTA costs every CTA a fence + counter round trip
+  // and the last one a serial tail -- 4.76 ms/step against 4.57 with the separate (PDL-overlapped) finalize launches: off
+  { const char* e = getenv("MAPNET_TC_FUSE_FIN"); fuse_fin = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 0); }
   { const char* e = getenv("MAPNET_TC_FUSE_BWD"); fuse_bwd = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   build_table();
   if (max_B == 0) return 0;      // spec-only handle: parameter table, no device memory
@@ -337,7 +351,8 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
     MN_TRY(launch_pack_weights<float>(d_wdescs, (int)convs.size(), params, (float*)w_krsc, (float*)w_dg, max_w_elems,
                                       precision == PREC_BF16_SIMT, st));
   // stem: im2col -> GEMM -> BN -> ReLU -> maxpool
-  MN_TRY(launch_stem_im2col<T>(x, (T*)A0, B, H, W, Hc, Wc, kStemK, st));
+  if (stem_s2d) MN_TRY(launch_stem_s2d(x, (bf16*)A0, B, H, W, Hc + 3, s2d_wsp(Wc), st));
+  else MN_TRY(launch_stem_im2col<T>(x, (T*)A0, B, H, W, Hc, Wc, kStemK, st));
   {
     const EpiFin f0 = fin_forward(convs[0].bn, (long long)B * Hc * Wc, params, bufs);
     MN_TRY(conv_fprop<T>(0, (const T*)A0, nullptr, (T*)y0, B, st, training != 0, &f0));

@@ -73,6 +73,7 @@ struct Net {
   // optional per-conv-launch timing (bench.py roofline): CUDA events around every conv call
   struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
   int profile_on;
+  int stem_s2d;                  // stem conv on an overlapped view of the space-to-depth image (env MAPNET_STEM_S2D)
   int stem_fuse;                 // stem BN backward reductions inside the pool backward (env MAPNET_STEM_FUSE)
   int fuse_fin;                  // BN finalize inside the last CTA of the accumulating conv (env MAPNET_TC_FUSE_FIN)
   int fuse_bwd;                  // BN backward reductions accumulated in the dgrad epilogue (env MAPNET_TC_FUSE_BWD)
