@@ -54,6 +54,8 @@ def lib():
     L.mapnet_adam_step_dev.restype = c_int
     L.mapnet_test_conv.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]
+    L.mapnet_test_stem.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.mapnet_test_stem.restype = c_int
     L.mapnet_launch_count.restype = ctypes.c_ulonglong
     L.mapnet_profile.argtypes = [c_void_p, c_int]
     L.mapnet_profile.restype = c_int
@@ -74,7 +76,7 @@ EXPORTED = ["mapnet_last_error", "mapnet_abi_version", "mapnet_trunk_create", "m
             "mapnet_param_count", "mapnet_param_info", "mapnet_params_numel", "mapnet_bufs_numel",
             "mapnet_forward", "mapnet_backward", "mapnet_loss_fwd_bwd", "mapnet_sqnorm", "mapnet_adam_step",
             "mapnet_test_conv", "mapnet_launch_count", "mapnet_profile", "mapnet_profile_read",
-            "mapnet_adam_step_dev", "mapnet_bench_conv"]
+            "mapnet_adam_step_dev", "mapnet_bench_conv", "mapnet_test_stem"]
 
 
 def check(rc, what):

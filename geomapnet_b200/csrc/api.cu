@@ -141,6 +141,46 @@ int mapnet_test_conv(int precision, int kind, int B, int Hi, int Wi, int Ci, int
   return r;
 }
 
+// the tensor-core stem alone: space-to-depth image -> packed weights -> fprop [-> wgrad -> .grad layout]
+int mapnet_test_stem(int B, int H, int W, const float* x_nchw, const float* w_oihw, void* y_out, const void* dy,
+                     float* dw_oihw, void* stream) {
+  MN_TRY(require_device());
+  MN_CHECK(B >= 1 && H >= 32 && W >= 32 && x_nchw && w_oihw && y_out, "test_stem: bad argument");
+  MN_CHECK(tc_overlapped_view_supported(), "test_stem: the driver rejects overlapped tensor maps");
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvGeom g; WeightDesc wd; memset(&wd, 0, sizeof(wd));
+  stem_s2d_geometry(H, W, 64, &g, &wd);
+  g.B = B; wd.p_off = 0; wd.k_off = 0;
+  const int Hs = g.Hi, Wsp = stem_s2d_wsp(g.Wo);
+  bf16 *S = nullptr, *wk = nullptr; float* dwk = nullptr; WeightDesc* d_wd = nullptr;
+  TcConvPlan *pf = nullptr, *pw = nullptr;
+  int r = 0;
+  auto body = [&]() -> int {
+    MN_CUDA(cudaMalloc(&S, (size_t)B * Hs * Wsp * 16 * sizeof(bf16)));
+    MN_CUDA(cudaMalloc(&wk, (size_t)64 * 256 * sizeof(bf16)));
+    MN_CUDA(cudaMalloc(&dwk, (size_t)64 * 256 * sizeof(float)));
+    MN_CUDA(cudaMalloc(&d_wd, sizeof(WeightDesc)));
+    MN_CUDA(cudaMemcpyAsync(d_wd, &wd, sizeof(wd), cudaMemcpyHostToDevice, st));
+    MN_CUDA(cudaMemsetAsync(dwk, 0, (size_t)64 * 256 * sizeof(float), st));
+    MN_TRY(launch_stem_s2d(x_nchw, S, B, H, W, Hs, Wsp, st));
+    MN_TRY(launch_pack_weights<bf16>(d_wd, 1, w_oihw, wk, nullptr, 64 * 256, 0, st));
+    MN_TRY(tc_plan_create(&pf, g, 0, wk));
+    MN_TRY(tc_conv_run(pf, S, nullptr, nullptr, y_out, st));
+    if (dy != nullptr && dw_oihw != nullptr) {
+      MN_TRY(tc_plan_create(&pw, g, 2, nullptr));
+      MN_TRY(tc_conv_run(pw, S, (const bf16*)dy, nullptr, dwk, st));
+      MN_TRY(launch_unpack_wgrads(d_wd, 1, dwk, dw_oihw, 64 * 256, st));
+    }
+    MN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  };
+  r = body();
+  if (pf) tc_plan_destroy(pf);
+  if (pw) tc_plan_destroy(pw);
+  cudaFree(S); cudaFree(wk); cudaFree(dwk); cudaFree(d_wd);
+  return r;
+}
+
 // micro-benchmark of one tcgen05 conv launch configuration (plan built once, CUDA-event timing)
 int mapnet_bench_conv(int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride, const void* in0,
                       const void* in1, const void* wmat, void* out, int iters, float* host_ms) {

@@ -76,8 +76,11 @@ k_small_gemm(const float* __restrict__ A, long long sam, long long sak, const fl
              const float* __restrict__ bias, float* __restrict__ aux, const float* __restrict__ mask,
              int kchunk) {
   pdl_prologue();
-  __shared__ float As[32][33];
-  __shared__ float Bs[32][33];
+  // 64-deep K tiles, the NEXT tile's 16 global loads per thread are in flight while the current one is
+  // multiplied: these GEMMs are a few MFLOP, their cost is the chain of load latencies
+  constexpr int KT = 64;
+  __shared__ float As[KT][33];
+  __shared__ float Bs[KT][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
@@ -85,21 +88,41 @@ k_small_gemm(const float* __restrict__ A, long long sam, long long sak, const fl
   const int kbeg = blockIdx.z * kchunk;
   const int kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
   const bool split = gridDim.z > 1;
-  for (int k0 = kbeg; k0 < kend; k0 += 32) {
-    for (int e = threadIdx.x; e < 1024; e += 256) {
+  float ra[KT * 32 / 256], rb[KT * 32 / 256];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < KT * 32 / 256; ++j) {
+      const int e = threadIdx.x + j * 256;
       // make the fastest-varying loader index follow the unit-stride dimension
       int r, kk;
-      if (sak == 1) { r = e >> 5; kk = e & 31; } else { kk = e >> 5; r = e & 31; }
+      if (sak == 1) { r = e / KT; kk = e % KT; } else { kk = e >> 5; r = e & 31; }
       const int m = m0 + r, k = k0 + kk;
-      As[kk][r] = (m < M && k < kend) ? A[(long long)m * sam + (long long)k * sak] : 0.f;
-      int rb, kb;
-      if (sbk == 1) { rb = e >> 5; kb = e & 31; } else { kb = e >> 5; rb = e & 31; }
-      const int n = n0 + rb, k2 = k0 + kb;
-      Bs[kb][rb] = (n < N && k2 < kend) ? Bm[(long long)n * sbn + (long long)k2 * sbk] : 0.f;
+      ra[j] = (m < M && k < kend) ? A[(long long)m * sam + (long long)k * sak] : 0.f;
+      int r2, kb;
+      if (sbk == 1) { r2 = e / KT; kb = e % KT; } else { kb = e >> 5; r2 = e & 31; }
+      const int n = n0 + r2, k2 = k0 + kb;
+      rb[j] = (n < N && k2 < kend) ? Bm[(long long)n * sbn + (long long)k2 * sbk] : 0.f;
     }
-    __syncthreads();
+  };
+  auto stash = [&]() {
 #pragma unroll
-    for (int kk = 0; kk < 32; ++kk) {
+    for (int j = 0; j < KT * 32 / 256; ++j) {
+      const int e = threadIdx.x + j * 256;
+      int r, kk;
+      if (sak == 1) { r = e / KT; kk = e % KT; } else { kk = e >> 5; r = e & 31; }
+      As[kk][r] = ra[j];
+      int r2, kb;
+      if (sbk == 1) { r2 = e / KT; kb = e % KT; } else { kb = e >> 5; r2 = e & 31; }
+      Bs[kb][r2] = rb[j];
+    }
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += KT) {
+    stash();
+    __syncthreads();
+    if (k0 + KT < kend) fetch(k0 + KT);
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
       const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
       const float b0 = Bs[kk][tx * 2], b1 = Bs[kk][tx * 2 + 1];
       acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
@@ -140,7 +163,7 @@ int launch_small_gemm(int epi, const float* A, long long sam, long long sak, con
     int splits = 148 / (int)(grid.x * grid.y);
     if (splits > K / 64) splits = K / 64;
     if (splits > 1) {
-      kchunk = ((K + splits - 1) / splits + 31) / 32 * 32;
+      kchunk = ((K + splits - 1) / splits + 63) / 64 * 64;
       grid.z = cdiv(K, kchunk);
       MN_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
     }

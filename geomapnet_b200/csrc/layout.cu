@@ -242,6 +242,18 @@ k_stem_s2d(const float* __restrict__ x, bf16* __restrict__ S, int B, int H, int 
   }
 }
 
+int stem_s2d_wsp(int wc) { return (wc + 3 + 3) / 4 * 4; }   // blocks per image row, rows 128 B aligned
+
+void stem_s2d_geometry(int H, int W, int Co, ConvGeom* g, WeightDesc* wd) {
+  const int hc = (H + 6 - 7) / 2 + 1, wc = (W + 6 - 7) / 2 + 1;
+  wd->Co = Co; wd->Ci_real = 3; wd->Ci = 64; wd->KH = 4; wd->KW = 1; wd->im2col_k = 256; wd->s2d = 1;
+  g->B = 0; g->Hi = hc + 3; g->Wi = wc; g->Ci = 64; g->Co = Co; g->KH = 4; g->KW = 1; g->stride = 1; g->pad = 0;
+  g->Ho = hc; g->Wo = wc;
+  g->in_pix_stride = 16 * 2;
+  g->in_row_stride = (long long)stem_s2d_wsp(wc) * 32;
+  g->in_img_stride = (long long)(hc + 3) * g->in_row_stride;
+}
+
 int launch_stem_s2d(const float* x_nchw, bf16* S, int B, int H, int W, int Hs, int Wsp, cudaStream_t st) {
   const long long n = (long long)B * Hs * Wsp;
   long long grid = (n + 255) / 256;

@@ -30,7 +30,6 @@ void set_last_error(const char* fmt, ...) {
 const char* get_last_error() { return g_err; }
 
 static const int kStages[4][3] = {{64, 3, 1}, {128, 4, 2}, {256, 6, 2}, {512, 3, 2}};
-static int s2d_wsp(int wc) { return (wc + 3 + 3) / 4 * 4; }   // blocks per row of the space-to-depth image (128 B aligned rows)
 static const int kStemK = 192;   // 7*7*3 = 147 padded to a multiple of 64 (tensor-core K block)
 
 static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
@@ -79,11 +78,7 @@ void Net::build_table() {
     c.wd.s2d = 0;
     if (stem && stem_s2d) {
       // 4 taps (filter rows of the space-to-depth image) x 64 contiguous elements (4 blocks x 16 channels)
-      const int hc = conv_out(Hi, 7, 2, 3), wc = conv_out(Wi, 7, 2, 3);
-      c.wd.Ci = 64; c.wd.KH = 4; c.wd.KW = 1; c.wd.im2col_k = 256; c.wd.s2d = 1;
-      c.g.Hi = hc + 3; c.g.Wi = wc; c.g.Ci = 64; c.g.Co = Co; c.g.KH = 4; c.g.KW = 1; c.g.stride = 1; c.g.pad = 0;
-      c.g.Ho = hc; c.g.Wo = wc;
-      c.g.in_pix_stride = 16 * 2; c.g.in_row_stride = (long long)s2d_wsp(wc) * 32; c.g.in_img_stride = (long long)(hc + 3) * c.g.in_row_stride;
+      stem_s2d_geometry(Hi, Wi, Co, &c.g, &c.wd);
     } else if (stem) {
       c.wd.Ci = kStemK; c.wd.KH = c.wd.KW = 1; c.wd.im2col_k = kStemK;
       c.g.Hi = conv_out(Hi, 7, 2, 3); c.g.Wi = conv_out(Wi, 7, 2, 3);   // GEMM view: 1x1 conv over the patch matrix
@@ -351,7 +346,7 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
     MN_TRY(launch_pack_weights<float>(d_wdescs, (int)convs.size(), params, (float*)w_krsc, (float*)w_dg, max_w_elems,
                                       precision == PREC_BF16_SIMT, st));
   // stem: im2col -> GEMM -> BN -> ReLU -> maxpool
-  if (stem_s2d) MN_TRY(launch_stem_s2d(x, (bf16*)A0, B, H, W, Hc + 3, s2d_wsp(Wc), st));
+  if (stem_s2d) MN_TRY(launch_stem_s2d(x, (bf16*)A0, B, H, W, Hc + 3, stem_s2d_wsp(Wc), st));
   else MN_TRY(launch_stem_im2col<T>(x, (T*)A0, B, H, W, Hc, Wc, kStemK, st));
   {
     const EpiFin f0 = fin_forward(convs[0].bn, (long long)B * Hc * Wc, params, bufs);

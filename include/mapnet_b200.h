@@ -108,6 +108,12 @@ int mapnet_profile_read(mapnet_trunk_t* h, double* host_ms3, double* host_flops3
 int mapnet_test_conv(int precision, int kind /*0 fprop 1 dgrad 2 wgrad*/, int B, int Hi, int Wi, int Ci, int Co,
                      int k, int stride, const void* in0, const void* in1, const void* wmat, void* out, void* stream);
 
+/* the tensor-core stem (7x7/s2/p3, 3 -> 64) alone, as the trunk runs it: space-to-depth image, packed weights,
+ * fprop into y_out (bf16 NHWC [B,Hc,Wc,64]) and, when dy / dw_oihw are given, the weight gradient in the
+ * .grad layout [64,3,7,7].  Replaces torchvision ResNet.conv1 (/root/reference/models/posenet.py:66). */
+int mapnet_test_stem(int B, int H, int W, const float* x_nchw, const float* w_oihw, void* y_out, const void* dy,
+                     float* dw_oihw, void* stream);
+
 /* micro-benchmark of one tensor-core conv configuration (tools/bench_conv.py): average ms per launch */
 int mapnet_bench_conv(int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride, const void* in0,
                       const void* in1, const void* wmat, void* out, int iters, float* host_ms);

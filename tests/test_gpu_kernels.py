@@ -75,6 +75,33 @@ def test_conv_engines(precision, geom):
     assert float((out.cpu() - ref).abs().max() / ref.abs().max()) < 5e-5
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64), (3, 97, 65), (4, 256, 256)])
+def test_tensor_core_stem_matches_conv2d(shape):
+    """The bf16 stem (space-to-depth image + overlapped TMA view, layout.cu / conv_tc.cu) against torch's
+    7x7/s2/p3 conv2d on the same bf16-rounded operands: output and weight gradient (the stem has no input
+    gradient).  Odd sizes exercise the zero halo of the space-to-depth image."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * (2.0 / 147) ** 0.5
+    xr = x.bfloat16().float(); wr = w.bfloat16().float().requires_grad_(True)
+    y = F.conv2d(xr, wr, None, 2, 3)
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    y.backward(dy)
+    Hc, Wc = y.shape[2], y.shape[3]
+    xd = x.cuda().contiguous(); wd = w.cuda().contiguous()
+    out = torch.empty(B, Hc, Wc, 64, dtype=torch.bfloat16, device="cuda")
+    dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    dw = torch.zeros(64, 3, 7, 7, dtype=torch.float32, device="cuda")
+    L = _lib.lib()
+    _lib.check(L.mapnet_test_stem(B, H, W, xd.data_ptr(), wd.data_ptr(), out.data_ptr(), dyn.data_ptr(), dw.data_ptr(),
+                                  _lib.stream_ptr()), "mapnet_test_stem")
+    torch.cuda.synchronize()
+    ref = y.detach().permute(0, 2, 3, 1)
+    assert float((out.float().cpu() - ref).abs().max() / ref.abs().max()) < 1.2e-2      # bf16 output rounding
+    assert float((dw.cpu() - wr.grad).abs().max() / wr.grad.abs().max()) < 5e-5
+
+
 CRIT_KEYS = ["posenet_n64t1", "posenet_n7t1", "mapnet_n32t3", "mapnet_n5t2", "online_n16t10",
              "online_n3t4", "online_gps_n16t10", "online_gps_n2t6"]
 

@@ -1,10 +1,5 @@
 mkdir -p gpurun_out
-echo "=== gpu tests (s2d stem)"; timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for sd in 1 0; do
-echo "=== bench STEM_S2D=$sd"; MAPNET_STEM_S2D=$sd timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench28_$sd.json 2> gpurun_out/bench28_$sd.err; tail -n 3 gpurun_out/bench28_$sd.err | cut -c1-300
-python - <<PY
-import json
-d=json.load(open('gpurun_out/bench28_$sd.json')); r=d['roofline']
-print('s2d$sd', d['value'], d['ms_per_step'], 'eager', d['config'].get('eager_ms_per_step'), 'e2e', d['e2e']['value'], d['gpu_launches'], r['conv_ms_per_step'], {k:round(v['tflops']) for k,v in r['per_class'].items()})
-PY
-done
+echo "=== stem unit test"; timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "stem" 2>&1 | tail -15
+echo "=== tc vs simt"; timeout 300 python -m pytest tests/test_gpu_step.py -m gpu -q -s -k "tensor_core_path_matches" 2>&1 | grep -E "tc-vs-simt|assert|passed|failed|Error" | cut -c1-600
+echo "=== tc vs simt, im2col stem"; MAPNET_STEM_S2D=0 timeout 300 python -m pytest tests/test_gpu_step.py -m gpu -q -s -k "tensor_core_path_matches" 2>&1 | grep -E "tc-vs-simt|assert|passed|failed|Error" | cut -c1-600
+echo "=== all gpu tests (no -x)"; timeout 700 python -m pytest tests -m gpu -q 2>&1 | tail -6
