@@ -141,6 +141,24 @@ int mapnet_test_conv(int precision, int kind, int B, int Hi, int Wi, int Ci, int
   return r;
 }
 
+// conv1 (3x3/s2) dgrad with the block's 1x1/s2 downsample dgrad folded in (tc_plan_add_shortcut)
+int mapnet_test_dgrad_shortcut(int B, int Hi, int Wi, int Ci, int Co, const void* dy1, const void* dy2,
+                               const void* w1_dg, const void* w2_dg, void* dx, void* stream) {
+  MN_TRY(require_device());
+  MN_CHECK(dy1 && dy2 && w1_dg && w2_dg && dx, "test_dgrad_shortcut: null argument");
+  ConvGeom g;
+  g.B = B; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Co = Co; g.KH = g.KW = 3; g.stride = 2; g.pad = 1;
+  g.Ho = (Hi + 2 - 3) / 2 + 1; g.Wo = (Wi + 2 - 3) / 2 + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  TcConvPlan* plan = nullptr;
+  MN_TRY(tc_plan_create(&plan, g, 1, (const bf16*)w1_dg));
+  int r = tc_plan_add_shortcut(plan, (const bf16*)w2_dg);
+  if (r == 0) r = tc_conv_run(plan, (const bf16*)dy1, (const bf16*)dy2, nullptr, dx, st);
+  if (r == 0) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) { set_last_error("test_dgrad_shortcut: %s", cudaGetErrorString(e)); r = 1; } }
+  tc_plan_destroy(plan);
+  return r;
+}
+
 // the tensor-core stem alone: space-to-depth image -> packed weights -> fprop [-> wgrad -> .grad layout]
 int mapnet_test_stem(int B, int H, int W, const float* x_nchw, const float* w_oihw, void* y_out, const void* dy,
                      float* dw_oihw, void* stream) {

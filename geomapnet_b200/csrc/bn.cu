@@ -6,6 +6,8 @@
 // Replaces the library calls behind torchvision BasicBlock / ResNet.forward
 // (cuDNN BN fwd-training/bwd, THCUNN threshold, TH add, SpatialDilatedMaxPooling;
 // SURVEY.md section 2c) that /root/reference/models/posenet.py:66 runs.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "bn_fin.cuh"
 
@@ -309,7 +311,9 @@ static int ew_grid(long long n) {
   long long g = (n + kEwThreads - 1) / kEwThreads;
   // few fat threads: the per-thread channel-parameter prologue is amortised over >= 4 vectors and
   // 148*4 blocks x 256 threads x 4 loads in flight cover the HBM latency-bandwidth product
-  const long long cap = 148LL * 4;
+  static int per_sm = 0;
+  if (per_sm == 0) { const char* e = getenv("MAPNET_EW_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1 || per_sm > 8) per_sm = 4; }
+  const long long cap = 148LL * per_sm;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 

@@ -104,18 +104,39 @@ bool tc_overlapped_view_supported() {
 // ---------------------------------------------------------------------------------
 // device parameter blocks
 // ---------------------------------------------------------------------------------
+// map: bits 0..1 = activation tensor map (A operand), bit 2 = the SECOND weight matrix (mapB2: the 1x1
+// downsample conv folded into a stride-2 dgrad, see tc_plan_add_shortcut)
 struct TapDesc { int dh, dw, map, kidx; };
 
+// One output class of a launch.  fprop and stride-1 dgrad have a single class; a stride-2 dgrad has
+// s*s parity classes -- output pixels (jh*os+oa, jw*os+ob) -- each with its own subset of the filter
+// taps.  All classes of a launch share the tile box and the tile grid (sized for the largest class).
+struct ClassDesc { int Hs, Ws, oa, ob, tap0, num_taps; };
+
 struct ConvParams {
-  // M space: (n, jh, jw) over [Nimg, Hs, Ws]; tile box TN x TH x TW = 128 pixels
-  int Nimg, Hs, Ws, TW, TH, TN, tiles_w, tiles_h, tiles_n, n_tiles_m, n_tiles_n;
+  // M space: (n, jh, jw) over [Nimg, Hs, Ws] of the tile's class; tile box TN x TH x TW = 128 pixels
+  int Nimg, TW, TH, TN, tiles_w, tiles_h, tiles_n, n_tiles_m, n_tiles_n;
+  int n_classes;
+  ClassDesc cls[4];
   // K space
-  int num_taps, cblocks, Cs;
-  TapDesc taps[9];
+  int cblocks, Cs;
+  TapDesc taps[10];
   // output tensor [Nimg, Hout, Wout, Cout]; pixel (n, jh*os+oa, jw*os+ob)
-  int Hout, Wout, Cout, os, oa, ob;
+  int Hout, Wout, Cout, os;
   int debug;     // micro-benchmark only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
 };
+
+// work item -> (class, N tile, first M tile of the group): classes are laid out one after the other
+// (heaviest first), inside a class the N tile varies fastest
+struct TileCoord { int cls, tn, group; };
+__device__ __forceinline__ TileCoord decode_tile(const int tile, const int per_class, const int n_tiles_n) {
+  TileCoord t;
+  t.cls = tile / per_class;
+  const int r = tile - t.cls * per_class;
+  t.group = r / n_tiles_n;
+  t.tn = r - t.group * n_tiles_n;
+  return t;
+}
 
 struct WgradChunk { int dh, dw, map, c0, tap; };   // one 64-channel slice of X at one filter tap
 
@@ -456,7 +477,8 @@ template <int BN, int CL>
 __global__ void __launch_bounds__(192, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-          const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
+          const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
+          const __grid_constant__ ConvParams P, const bf16* __restrict__ residual,
           bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E, const EpiFin Fin) {
   constexpr int STAGES = conv_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;        // 128 pixels x 64 ch bf16
@@ -494,25 +516,29 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   // same sequence, CTA r takes M tile group*CL + r (possibly past the end: a dummy tile whose
   // loads are zero-filled by TMA and whose epilogue stores nothing)
   const int n_groups = (P.n_tiles_m + CL - 1) / CL;
-  const int total_tiles = n_groups * P.n_tiles_n;
+  const int per_class = n_groups * P.n_tiles_n;
+  const int total_tiles = per_class * P.n_classes;
   const int first_tile = blockIdx.x / CL;
   const int tile_step = gridDim.x / CL;
-  const int kblocks = P.num_taps * P.cblocks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int tn = tile % P.n_tiles_n;
-        int tm = (tile / P.n_tiles_n) * CL + (int)crank;
+        const TileCoord tc = decode_tile(tile, per_class, P.n_tiles_n);
+        const ClassDesc cd = P.cls[tc.cls];
+        const int tn = tc.tn;
+        int tm = tc.group * CL + (int)crank;
         const int tw = tm % P.tiles_w; tm /= P.tiles_w;
         const int th = tm % P.tiles_h;
         const int tb = tm / P.tiles_h;
         const int jw0 = tw * P.TW, jh0 = th * P.TH, n0 = tb * P.TN;
-        for (int t = 0; t < P.num_taps; ++t) {
+        for (int t = cd.tap0; t < cd.tap0 + cd.num_taps; ++t) {
           const TapDesc tap = P.taps[t];
-          const CUtensorMap* mA = (tap.map == 0) ? &mapA0 : (tap.map == 1) ? &mapA1 : (tap.map == 2) ? &mapA2 : &mapA3;
+          const int am = tap.map & 3;
+          const CUtensorMap* mA = (am == 0) ? &mapA0 : (am == 1) ? &mapA1 : (am == 2) ? &mapA2 : &mapA3;
+          const CUtensorMap* mB = (tap.map & 4) ? &mapB2 : &mapB;
           for (int cb = 0; cb < P.cblocks; ++cb) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -520,10 +546,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
             tma_load_4d(sa, mA, full0 + 8 * stage, cb * 64, jw0 + tap.dw, jh0 + tap.dh, n0);
             if (CL == 1) {
-              tma_load_2d(sa + A_BYTES, &mapB, full0 + 8 * stage, tap.kidx * P.Cs + cb * 64, tn * BN);
+              tma_load_2d(sa + A_BYTES, mB, full0 + 8 * stage, tap.kidx * P.Cs + cb * 64, tn * BN);
             } else {
               constexpr int BROWS = BN / CL;      // this CTA's slice of the weight tile
-              tma_load_2d_mc(sa + A_BYTES + crank * (BROWS * 128), &mapB, full0 + 8 * stage,
+              tma_load_2d_mc(sa + A_BYTES + crank * (BROWS * 128), mB, full0 + 8 * stage,
                              tap.kidx * P.Cs + cb * 64, tn * BN + (int)crank * BROWS, CMASK);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -538,6 +564,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int kblocks = P.cls[tile / per_class].num_taps * P.cblocks;
       mbar_wait(tempty0 + 8 * as, aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
@@ -586,9 +613,12 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int etid = q * 32 + lane;
     auto flush_stats = [&](int tn_flush) { epi_flush<BN>(epi_stats, stats, P.Cout, tn_flush, E.yd != nullptr, etid); };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-      const int tn = tile % P.n_tiles_n;
+      const TileCoord tc = decode_tile(tile, per_class, P.n_tiles_n);
+      const ClassDesc cd = P.cls[tc.cls];
+      const int kblocks = cd.num_taps * P.cblocks;
+      const int tn = tc.tn;
       if (stats != nullptr && tn != st_tn) { if (st_tn >= 0) flush_stats(st_tn); st_tn = tn; }
-      int tm = (tile / P.n_tiles_n) * CL + (int)crank;
+      int tm = tc.group * CL + (int)crank;
       const int tw = tm % P.tiles_w; tm /= P.tiles_w;
       const int th = tm % P.tiles_h;
       const int tb = tm / P.tiles_h;
@@ -601,8 +631,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const int lh = (m / P.TW) % P.TH;
         const int ln = m / (P.TW * P.TH);
         const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
-        rvalid[i] = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
-        const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
+        rvalid[i] = (jw < cd.Ws) && (jh < cd.Hs) && (n < P.Nimg);
+        const long long pix = ((long long)n * P.Hout + (jh * P.os + cd.oa)) * P.Wout + (jw * P.os + cd.ob);
         rowoff[i] = (rvalid[i] ? pix * P.Cout : 0) + tn * BN;     // outside rows: clamped, loads stay in bounds
       }
       if (P.debug == 3) {           // micro-benchmark: no epilogue work at all
@@ -645,7 +675,8 @@ template <int BN>
 __global__ void __launch_bounds__(192, 1)
 k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-           const __grid_constant__ CUtensorMap mapB, const ConvParams P, const bf16* __restrict__ residual,
+           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
+           const __grid_constant__ ConvParams P, const bf16* __restrict__ residual,
            bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E, const EpiFin Fin) {
   constexpr int STAGES = conv2_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;
@@ -680,25 +711,29 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   pdl_prologue();      // nothing above touches global memory: setup overlaps the previous kernel's tail
 
   const int n_groups = (P.n_tiles_m + 1) / 2;
-  const int total_tiles = n_groups * P.n_tiles_n;
+  const int per_class = n_groups * P.n_tiles_n;
+  const int total_tiles = per_class * P.n_classes;
   const int first_tile = blockIdx.x / 2;
   const int tile_step = gridDim.x / 2;
-  const int kblocks = P.num_taps * P.cblocks;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int tn = tile % P.n_tiles_n;
-        int tm = (tile / P.n_tiles_n) * 2 + (int)crank;
+        const TileCoord tc = decode_tile(tile, per_class, P.n_tiles_n);
+        const ClassDesc cd = P.cls[tc.cls];
+        const int tn = tc.tn;
+        int tm = tc.group * 2 + (int)crank;
         const int tw = tm % P.tiles_w; tm /= P.tiles_w;
         const int th = tm % P.tiles_h;
         const int tb = tm / P.tiles_h;
         const int jw0 = tw * P.TW, jh0 = th * P.TH, n0 = tb * P.TN;
-        for (int t = 0; t < P.num_taps; ++t) {
+        for (int t = cd.tap0; t < cd.tap0 + cd.num_taps; ++t) {
           const TapDesc tap = P.taps[t];
-          const CUtensorMap* mA = (tap.map == 0) ? &mapA0 : (tap.map == 1) ? &mapA1 : (tap.map == 2) ? &mapA2 : &mapA3;
+          const int am = tap.map & 3;
+          const CUtensorMap* mA = (am == 0) ? &mapA0 : (am == 1) ? &mapA1 : (am == 2) ? &mapA2 : &mapA3;
+          const CUtensorMap* mB = (tap.map & 4) ? &mapB2 : &mapB;
           for (int cb = 0; cb < P.cblocks; ++cb) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -706,7 +741,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
             else mbar_arrive_cluster(lfull);
             tma_load_4d_2sm(sa, mA, lfull, cb * 64, jw0 + tap.dw, jh0 + tap.dh, n0);
-            tma_load_2d_2sm(sa + A_BYTES, &mapB, lfull, tap.kidx * P.Cs + cb * 64, tn * BN + (int)crank * (BN / 2));
+            tma_load_2d_2sm(sa + A_BYTES, mB, lfull, tap.kidx * P.Cs + cb * 64, tn * BN + (int)crank * (BN / 2));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -720,6 +755,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int kblocks = P.cls[tile / per_class].num_taps * P.cblocks;
         mbar_wait(tempty0 + 8 * as, aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -765,9 +801,12 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const int etid = q * 32 + lane;
     auto flush_stats = [&](int tn_flush) { epi_flush<BN>(epi_stats, stats, P.Cout, tn_flush, E.yd != nullptr, etid); };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-      const int tn = tile % P.n_tiles_n;
+      const TileCoord tc = decode_tile(tile, per_class, P.n_tiles_n);
+      const ClassDesc cd = P.cls[tc.cls];
+      const int kblocks = cd.num_taps * P.cblocks;
+      const int tn = tc.tn;
       if (stats != nullptr && tn != st_tn) { if (st_tn >= 0) flush_stats(st_tn); st_tn = tn; }
-      int tm = (tile / P.n_tiles_n) * 2 + (int)crank;
+      int tm = tc.group * 2 + (int)crank;
       const int tw = tm % P.tiles_w; tm /= P.tiles_w;
       const int th = tm % P.tiles_h;
       const int tb = tm / P.tiles_h;
@@ -780,8 +819,8 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const int lh = (m / P.TW) % P.TH;
         const int ln = m / (P.TW * P.TH);
         const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
-        rvalid[i] = (jw < P.Ws) && (jh < P.Hs) && (n < P.Nimg);
-        const long long pix = ((long long)n * P.Hout + (jh * P.os + P.oa)) * P.Wout + (jw * P.os + P.ob);
+        rvalid[i] = (jw < cd.Ws) && (jh < cd.Hs) && (n < P.Nimg);
+        const long long pix = ((long long)n * P.Hout + (jh * P.os + cd.oa)) * P.Wout + (jw * P.os + cd.ob);
         rowoff[i] = (rvalid[i] ? pix * P.Cout : 0) + tn * BN;     // outside rows: clamped, loads stay in bounds
       }
       epi_tile_dispatch<BN>(epi_mode, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, kblocks > 0, tfull0 + 8 * as,
@@ -1270,7 +1309,7 @@ k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ C
 // ---------------------------------------------------------------------------------
 struct ConvLaunch {
   ConvParams P;
-  CUtensorMap mapA[4], mapB;
+  CUtensorMap mapA[4], mapB, mapB2;
   int n_maps;
   // parity views: (a,b) of map i
   int pa[4], pb[4];
@@ -1280,6 +1319,7 @@ struct TcConvPlan {
   ConvGeom g;
   int kind;
   const bf16* wmat;
+  const bf16* wmat2;                    // dgrad weight matrix [Ci][Co2] of a folded 1x1/stride-2 shortcut conv, or null
   int BN, CL;
   bool two_cta;                         // cta_group::2 kernel (256 x BN pair tiles)
   bool halo;                            // halo-resident 3x3/s1 engine
@@ -1291,6 +1331,7 @@ struct TcConvPlan {
   WgradParams WP;
   CUtensorMap mapX[4], mapDY;
   int wpa[4], wpb[4], w_nmaps;
+  int shortcut_flops_k;                 // K of the folded shortcut (0: none), for the callers' FLOP accounting
   // cached pointers the maps were encoded for
   const void *c_in0, *c_in1;
   bool smem_attr_set;
@@ -1334,6 +1375,39 @@ static int use_2cta() {     // -1 auto (cost model), 0 never, 1 whenever the cha
 // warp ~600 cycles for N <= 128 and ~980 for N = 256 on one CTA, ~490 / ~1075 on a CTA pair;
 // TMA alone sustains ~55 B/cycle per CTA; a kernel needs waves x (k-blocks x max(...) + ~2000).
 struct TileChoice { int BN; bool two_cta; };
+// `ncls` classes of `mtiles` M tiles each, class c with kb[c] k-blocks per tile (a stride-2 dgrad launched as ONE
+// grid over its parity classes); work items are dealt round-robin to the persistent CTAs, heaviest class first
+static TileChoice choose_tiles_classes(int Cout, long long mtiles, int ncls, const int* kb) {
+  const int forced_bn = []() { const char* e = getenv("MAPNET_TC_BN"); return e ? atoi(e) : 0; }();
+  const int mode2 = use_2cta();
+  TileChoice best = {64, false};
+  double best_t = 1e30;
+  for (int two = 0; two <= 1; ++two) {
+    if (two && mode2 == 0) continue;
+    if (!two && mode2 == 1 && Cout % 128 == 0) continue;
+    for (int bn = 64; bn <= 256; bn *= 2) {
+      if (Cout % bn != 0) continue;
+      if (two && bn < 128) continue;
+      if (forced_bn && bn != forced_bn && Cout % forced_bn == 0 && !(two && forced_bn < 128)) continue;
+      const long long per_class = (two ? (mtiles + 1) / 2 : mtiles) * (Cout / bn);
+      const int slots = two ? 74 : 148;
+      const double bytes = 16384.0 + (two ? bn * 64.0 : bn * 128.0);
+      const double issue = two ? (bn <= 128 ? 490.0 : 1075.0) : (bn <= 64 ? 580.0 : (bn <= 128 ? 600.0 : 980.0));
+      const double per_kb = (bytes / 55.0 > issue) ? bytes / 55.0 : issue;
+      // slot j gets items j, j + slots, ...: the busiest slot bounds the launch
+      double t = 0.0;
+      const long long total = per_class * ncls;
+      for (int j = 0; j < slots && j < total; ++j) {
+        double tj = 0.0;
+        for (long long it = j; it < total; it += slots) tj += kb[it / per_class] * per_kb + 2000.0;
+        if (tj > t) t = tj;
+      }
+      if (t < best_t) { best_t = t; best.BN = bn; best.two_cta = (two != 0); }
+    }
+  }
+  return best;
+}
+
 static TileChoice choose_tiles(int Cout, long long Mpix, int kblocks) {
   const int forced_bn = []() { const char* e = getenv("MAPNET_TC_BN"); return e ? atoi(e) : 0; }();
   const int mode2 = use_2cta();
@@ -1371,7 +1445,8 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
            "tc conv: kernel %dx%d unsupported", g.KH, g.KW);
   MN_CHECK(g.in_pix_stride == 0 || (g.stride == 1 && kind != 1), "tc conv: strided input views only for stride-1 fprop / wgrad");
   TcConvPlan* p = new TcConvPlan();
-  p->g = g; p->kind = kind; p->wmat = wmat; p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false;
+  p->g = g; p->kind = kind; p->wmat = wmat; p->wmat2 = nullptr; p->shortcut_flops_k = 0;
+  p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false;
   p->CL = pick_cl();
   p->two_cta = false;
   p->halo = false;
@@ -1441,12 +1516,14 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     ConvLaunch L; memset(&L, 0, sizeof(L));
     ConvParams& P = L.P;
     { const char* e = getenv("MAPNET_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
-    P.Nimg = g.B; P.Hs = g.Ho; P.Ws = g.Wo;
+    P.Nimg = g.B;
+    P.n_classes = 1;
+    P.cls[0].Hs = g.Ho; P.cls[0].Ws = g.Wo; P.cls[0].oa = 0; P.cls[0].ob = 0; P.cls[0].tap0 = 0; P.cls[0].num_taps = KK;
     pick_box(g.Wo, g.Ho, 128, &P.TW, &P.TH, &P.TN);
     P.tiles_w = cdiv(g.Wo, P.TW); P.tiles_h = cdiv(g.Ho, P.TH); P.tiles_n = cdiv(g.B, P.TN);
     P.n_tiles_m = P.tiles_w * P.tiles_h * P.tiles_n; P.n_tiles_n = g.Co / p->BN;
-    P.num_taps = KK; P.cblocks = g.Ci / 64; P.Cs = g.Ci;
-    P.Hout = g.Ho; P.Wout = g.Wo; P.Cout = g.Co; P.os = 1; P.oa = 0; P.ob = 0;
+    P.cblocks = g.Ci / 64; P.Cs = g.Ci;
+    P.Hout = g.Ho; P.Wout = g.Wo; P.Cout = g.Co; P.os = 1;
     L.n_maps = 0;
     for (int kh = 0; kh < g.KH; ++kh)
       for (int kw = 0; kw < g.KW; ++kw) {
@@ -1465,34 +1542,84 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     p->launches.push_back(L);
   } else if (kind == 1) {
     // ---------------- dgrad: gather over dY [B,Ho,Wo,Co], output dX [B,Hi,Wi,Ci] ----------------
-    {
-      // stride-2 dgrad runs as s*s parity classes of ~M/4 pixels and <= KK taps each; size the tiles for one class
-      const TileChoice tc = choose_tiles(g.Ci, g.M_in() / (s * s), ((KK + s * s - 1) / (s * s)) * (g.Co / 64));
-      p->BN = tc.BN; p->two_cta = tc.two_cta;
-      if (tc.two_cta) p->CL = 2;
-    }
+    // A stride-s dgrad is s*s parity classes of output pixels (a, b) = (ih % s, iw % s), each reached by its own
+    // subset of the filter taps (3x3/s2: 4, 2, 2 and 1 taps; 1x1/s2: 1, 0, 0, 0).
+    struct ClassTaps { int a, b, n; TapDesc t[9]; };
+    ClassTaps ct[4]; int ncls = 0;
     for (int a = 0; a < s; ++a)
       for (int b = 0; b < s; ++b) {
-        ConvLaunch L; memset(&L, 0, sizeof(L));
-        ConvParams& P = L.P;
-        P.Nimg = g.B; P.Hs = cdiv(g.Hi - a, s); P.Ws = cdiv(g.Wi - b, s);
-        if (P.Hs <= 0 || P.Ws <= 0) continue;
-        pick_box(P.Ws, P.Hs, 128, &P.TW, &P.TH, &P.TN);
-        P.tiles_w = cdiv(P.Ws, P.TW); P.tiles_h = cdiv(P.Hs, P.TH); P.tiles_n = cdiv(g.B, P.TN);
-        P.n_tiles_m = P.tiles_w * P.tiles_h * P.tiles_n; P.n_tiles_n = g.Ci / p->BN;
-        P.cblocks = g.Co / 64; P.Cs = g.Co;
-        P.Hout = g.Hi; P.Wout = g.Wi; P.Cout = g.Ci; P.os = s; P.oa = a; P.ob = b;
-        P.num_taps = 0;
+        if (cdiv(g.Hi - a, s) <= 0 || cdiv(g.Wi - b, s) <= 0) continue;
+        ClassTaps& c = ct[ncls++];
+        c.a = a; c.b = b; c.n = 0;
         for (int kh = 0; kh < g.KH; ++kh)
           for (int kw = 0; kw < g.KW; ++kw) {
             const int eh = a + pad - kh, ew = b + pad - kw;
             if (posmod(eh, s) != 0 || posmod(ew, s) != 0) continue;
-            TapDesc& t = P.taps[P.num_taps++];
+            TapDesc& t = c.t[c.n++];
             t.dh = floordiv(eh, s); t.dw = floordiv(ew, s); t.map = 0; t.kidx = kh * g.KW + kw;
           }
+      }
+    int merge = 1;       // read per plan (not cached): the A/B parity test flips it between trunks
+    { const char* e = getenv("MAPNET_TC_DGRAD_MERGE"); if (e) merge = atoi(e); }
+    if (s == 1 || merge) {
+      // ONE launch over all classes, heaviest class first (the persistent CTAs take work items round-robin).
+      // Measured on B200 (profiles/r01b_launch_shares.csv): as four launches of 1..4 taps on 1/4 of the pixels
+      // the stride-2 dgrads of layer2.0/3.0/4.0 ran at 100-130 TFLOP/s -- each launch a single short wave.
+      for (int i = 1; i < ncls; ++i)              // stable insertion sort by tap count, descending
+        for (int j = i; j > 0 && ct[j].n > ct[j - 1].n; --j) { ClassTaps tmp = ct[j]; ct[j] = ct[j - 1]; ct[j - 1] = tmp; }
+      const int Hs0 = cdiv(g.Hi, s), Ws0 = cdiv(g.Wi, s);      // the largest class (a = b = 0)
+      ConvLaunch L; memset(&L, 0, sizeof(L));
+      ConvParams& P = L.P;
+      { const char* e = getenv("MAPNET_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
+      P.Nimg = g.B;
+      pick_box(Ws0, Hs0, 128, &P.TW, &P.TH, &P.TN);
+      P.tiles_w = cdiv(Ws0, P.TW); P.tiles_h = cdiv(Hs0, P.TH); P.tiles_n = cdiv(g.B, P.TN);
+      P.n_tiles_m = P.tiles_w * P.tiles_h * P.tiles_n;
+      int kbs[4];
+      for (int i = 0; i < ncls; ++i) kbs[i] = ct[i].n * (g.Co / 64);
+      {
+        const TileChoice tc = choose_tiles_classes(g.Ci, P.n_tiles_m, ncls, kbs);
+        p->BN = tc.BN; p->two_cta = tc.two_cta;
+        if (tc.two_cta) p->CL = 2;
+      }
+      P.n_tiles_n = g.Ci / p->BN;
+      P.cblocks = g.Co / 64; P.Cs = g.Co;
+      P.Hout = g.Hi; P.Wout = g.Wi; P.Cout = g.Ci; P.os = s;
+      P.n_classes = ncls;
+      int nt = 0;
+      for (int i = 0; i < ncls; ++i) {
+        ClassDesc& c = P.cls[i];
+        c.Hs = cdiv(g.Hi - ct[i].a, s); c.Ws = cdiv(g.Wi - ct[i].b, s); c.oa = ct[i].a; c.ob = ct[i].b;
+        c.tap0 = nt; c.num_taps = ct[i].n;
+        for (int k = 0; k < ct[i].n; ++k) P.taps[nt++] = ct[i].t[k];
+      }
+      L.n_maps = 1; L.pa[0] = L.pb[0] = 0;
+      p->launches.push_back(L);
+    } else {
+      {
+        // one launch per class: size the tiles for one class
+        const TileChoice tc = choose_tiles(g.Ci, g.M_in() / (s * s), ((KK + s * s - 1) / (s * s)) * (g.Co / 64));
+        p->BN = tc.BN; p->two_cta = tc.two_cta;
+        if (tc.two_cta) p->CL = 2;
+      }
+      for (int i = 0; i < ncls; ++i) {
+        ConvLaunch L; memset(&L, 0, sizeof(L));
+        ConvParams& P = L.P;
+        P.Nimg = g.B;
+        P.n_classes = 1;
+        ClassDesc& c = P.cls[0];
+        c.Hs = cdiv(g.Hi - ct[i].a, s); c.Ws = cdiv(g.Wi - ct[i].b, s); c.oa = ct[i].a; c.ob = ct[i].b;
+        c.tap0 = 0; c.num_taps = ct[i].n;
+        for (int k = 0; k < ct[i].n; ++k) P.taps[k] = ct[i].t[k];
+        pick_box(c.Ws, c.Hs, 128, &P.TW, &P.TH, &P.TN);
+        P.tiles_w = cdiv(c.Ws, P.TW); P.tiles_h = cdiv(c.Hs, P.TH); P.tiles_n = cdiv(g.B, P.TN);
+        P.n_tiles_m = P.tiles_w * P.tiles_h * P.tiles_n; P.n_tiles_n = g.Ci / p->BN;
+        P.cblocks = g.Co / 64; P.Cs = g.Co;
+        P.Hout = g.Hi; P.Wout = g.Wi; P.Cout = g.Ci; P.os = s;
         L.n_maps = 1; L.pa[0] = L.pb[0] = 0;
         p->launches.push_back(L);
       }
+    }
   } else {
     // ---------------- wgrad ----------------
     WgradParams& P = p->WP; memset(&P, 0, sizeof(P));
@@ -1537,6 +1664,28 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
 }
 
 void tc_plan_destroy(TcConvPlan* p) { delete p; }
+
+// Fold the dgrad of the block's 1x1 / stride-2 downsample conv into the (merged) dgrad of its 3x3 / stride-2 conv1:
+// both produce d(block input), the shortcut only reaches the pixel class (0, 0), where it is one more filter tap
+// that reads the OTHER incoming gradient (tc_conv_run's in1, shaped like in0) against the shortcut's own weight
+// matrix wmat2 = [Ci][Co].  Replaces 4 launches, a zero-filled full-size tensor and its re-read as a residual.
+int tc_plan_add_shortcut(TcConvPlan* p, const bf16* wmat2) {
+  MN_CHECK(p != nullptr && wmat2 != nullptr, "tc_plan_add_shortcut: null argument");
+  MN_CHECK(p->kind == 1 && !p->halo && p->g.stride == 2 && p->g.KH == 3 && p->launches.size() == 1,
+           "tc_plan_add_shortcut: needs a merged 3x3 stride-2 dgrad plan");
+  ConvParams& P = p->launches[0].P;
+  ClassDesc& c = P.cls[P.n_classes - 1];
+  MN_CHECK(c.oa == 0 && c.ob == 0 && c.tap0 + c.num_taps == 9 && p->wmat2 == nullptr,
+           "tc_plan_add_shortcut: unexpected class layout");
+  TapDesc& t = P.taps[9];
+  t.dh = 0; t.dw = 0; t.map = 1 | 4; t.kidx = 0;        // activation map 1 (= in1), second weight matrix
+  c.num_taps += 1;
+  p->wmat2 = wmat2;
+  p->shortcut_flops_k = p->g.Co;
+  p->c_in0 = p->c_in1 = nullptr;
+  return 0;
+}
+int tc_plan_launches(const TcConvPlan* p) { return p->halo ? 1 : (p->kind == 2 ? 1 : (int)p->launches.size()); }
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
@@ -1599,7 +1748,8 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     return 0;
   }
   if (p->kind == 0 || p->kind == 1) {
-    if (p->c_in0 != in0) {
+    MN_CHECK(p->wmat2 == nullptr || in1 != nullptr, "tc_conv_run: a dgrad plan with a folded shortcut needs the shortcut's gradient as in1");
+    if (p->c_in0 != in0 || (p->wmat2 != nullptr && p->c_in1 != in1)) {
       for (auto& L : p->launches) {
         if (p->kind == 0) {
           for (int i = 0; i < L.n_maps; ++i)
@@ -1608,13 +1758,19 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
         } else {
           MN_TRY(encode_view(&L.mapA[0], in0, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, L.P.TW, L.P.TH, L.P.TN));
           MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Co, g.Ci, p->BN / p->CL));
+          if (p->wmat2 != nullptr) {
+            MN_TRY(encode_view(&L.mapA[1], in1, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, L.P.TW, L.P.TH, L.P.TN));
+            MN_TRY(encode_w_map(&L.mapB2, p->wmat2, g.Co, g.Ci, p->BN / p->CL));
+            L.n_maps = 2;
+          }
         }
         for (int i = L.n_maps; i < 4; ++i) L.mapA[i] = L.mapA[0];
+        if (p->wmat2 == nullptr) L.mapB2 = L.mapB;
       }
-      p->c_in0 = in0;
+      p->c_in0 = in0; p->c_in1 = in1;
     }
     size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024;
-    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*, double*, EpiBwd, EpiFin) = nullptr;
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*, double*, EpiBwd, EpiFin) = nullptr;
     if (p->two_cta) {
       smem = (size_t)conv2_stages(p->BN) * (128 * 128 + (p->BN / 2) * 128) + 1024;
       kern = (p->BN == 256) ? k_tc_conv2<256> : k_tc_conv2<128>;
@@ -1628,13 +1784,13 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       p->smem_attr_set = true;
     }
     F.expected = 0;
-    for (auto& L : p->launches) {     // the sums of a stride-2 dgrad come from all its parity launches
-      const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n;
+    for (auto& L : p->launches) {     // the sums of a stride-2 dgrad come from all its parity classes / launches
+      const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n * L.P.n_classes;
       const int max_clusters = (p->CL == 4) ? 32 : nsm / p->CL;
       F.expected += (unsigned int)((groups < max_clusters ? groups : max_clusters) * p->CL);
     }
     for (auto& L : p->launches) {
-      const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n;
+      const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n * L.P.n_classes;
       const int max_clusters = (p->CL == 4) ? 32 : nsm / p->CL;
       const int nclusters = groups < max_clusters ? groups : max_clusters;
       cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
@@ -1645,7 +1801,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-      MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.P, residual, (bf16*)out, stats, E, F));
+      MN_CUDA(cudaLaunchKernelEx(&cfg, kern, L.mapA[0], L.mapA[1], L.mapA[2], L.mapA[3], L.mapB, L.mapB2, L.P, residual, (bf16*)out, stats, E, F));
       ++g_launch_count;
     }
     return 0;

@@ -54,7 +54,13 @@ struct TcConvPlan;   // opaque: tile shapes, tap tables and cached TMA tensor ma
 // kind 0 fprop (wmat = [Co][KH][KW][Ci]), 1 dgrad (wmat = [Ci][KH][KW][Co]), 2 wgrad (wmat unused)
 int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wmat);
 void tc_plan_destroy(TcConvPlan* p);
-// fprop: in0 = x, out = y (bf16);  dgrad: in0 = dy, out = dx (bf16);  wgrad: in0 = x, in1 = dy, out = fp32 dW (accumulated)
+// dgrad plans of a 3x3 / stride-2 conv only: fold the dgrad of the parallel 1x1 / stride-2 shortcut conv (same
+// input and output shapes; wmat2 = [Ci][Co]) into the same launch -- tc_conv_run then takes the shortcut's
+// incoming gradient as in1 and writes d(input) of BOTH convs
+int tc_plan_add_shortcut(TcConvPlan* p, const bf16* wmat2);
+int tc_plan_launches(const TcConvPlan* p);
+// fprop: in0 = x, out = y (bf16);  dgrad: in0 = dy [, in1 = the folded shortcut's dy], out = dx (bf16);
+// wgrad: in0 = x, in1 = dy, out = fp32 dW (accumulated)
 // stats != nullptr (fprop, no residual): per-channel sum / sum of squares of the stored output are
 // accumulated into the replica accumulators for the fused BatchNorm statistics
 // bwd != nullptr (dgrad only, with stats): the stored gradient is gated by the consumer BN's ReLU

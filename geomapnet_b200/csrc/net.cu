@@ -122,6 +122,7 @@ void Net::build_table() {
         convs[bl.convd].bn = add_bn(std::string(pre) + "downsample.1", planes);
       }
       bl.y1 = bl.h = bl.y2 = bl.yd = bl.out = nullptr;
+      bl.ds_fold = 0;          // set by ensure_tc_plans on the tensor-core path only
       blocks.push_back(bl);
       inpl = planes; h = bl.Ho; w = bl.Wo;
     }
@@ -150,6 +151,7 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   // and the last one a serial tail -- 4.76 ms/step against 4.57 with the separate (PDL-overlapped) finalize launches: off
   { const char* e = getenv("MAPNET_TC_FUSE_FIN"); fuse_fin = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 0); }
   { const char* e = getenv("MAPNET_TC_FUSE_BWD"); fuse_bwd = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
+  { const char* e = getenv("MAPNET_TC_DS_FOLD"); ds_fold = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   build_table();
   if (max_B == 0) return 0;      // spec-only handle: parameter table, no device memory
   const size_t es = elt();
@@ -254,15 +256,23 @@ int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStre
   return r;
 }
 template <typename T>
-int Net::conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd, const EpiFin* fin) {
+int Net::conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd, const EpiFin* fin,
+                    const T* dy_shortcut, int ci_shortcut) {
   ConvGeom g = convs[ci].g; g.B = B;
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
-  if (precision == PREC_BF16_TC)
-    r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, nullptr, (const bf16*)residual, dx, st, bwd ? bn_accum : nullptr, bwd, bwd ? fin : nullptr);
-  else r = launch_conv_simt_dgrad<T>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
-  prof_end(st, e0, 1, conv_flops(g, B, false));
+  double flops = conv_flops(g, B, false);
+  if (precision == PREC_BF16_TC) {
+    // dy_shortcut: the block's downsample-conv dgrad rides in the same launch (tc_plan_add_shortcut)
+    r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, (const bf16*)dy_shortcut, (const bf16*)residual, dx, st, bwd ? bn_accum : nullptr, bwd,
+                    bwd ? fin : nullptr);
+    if (dy_shortcut != nullptr) { ConvGeom gs = convs[ci_shortcut].g; gs.B = B; flops += conv_flops(gs, B, false); }
+  } else {
+    MN_CHECK(dy_shortcut == nullptr, "conv_dgrad: folded shortcut is a tensor-core path feature");
+    r = launch_conv_simt_dgrad<T>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
+  }
+  prof_end(st, e0, 1, flops);
   return r;
 }
 template <typename T>
@@ -292,6 +302,14 @@ int Net::ensure_tc_plans(int B) {
     MN_TRY(tc_plan_create(&tc_fprop[i], g, 0, wk));
     if (i > 0) MN_TRY(tc_plan_create(&tc_dgrad[i], g, 1, wd));
     MN_TRY(tc_plan_create(&tc_wgrad[i], g, 2, nullptr));
+  }
+  // stride-2 blocks: the 1x1 downsample dgrad becomes one more tap of conv1's (single-launch) dgrad
+  for (auto& bl : blocks) {
+    bl.ds_fold = 0;
+    if (!ds_fold || bl.convd < 0 || convs[bl.conv1].g.stride != 2 || convs[bl.conv1].g.KH != 3) continue;
+    if (tc_plan_launches(tc_dgrad[bl.conv1]) != 1) continue;       // MAPNET_TC_DGRAD_MERGE=0: per-class launches
+    MN_TRY(tc_plan_add_shortcut(tc_dgrad[bl.conv1], (const bf16*)w_dg + convs[bl.convd].wd.k_off));
+    bl.ds_fold = 1;
   }
   tc_B = B;
   return 0;
@@ -497,7 +515,10 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
       fb2 = fin_backward(convs[pb.conv2].bn, (pb.convd >= 0) ? convs[pb.convd].bn : -1, (long long)B * pb.Ho * pb.Wo, params, grads);
     }
     MN_TRY(conv_wgrad<T>(bl.conv1, zin, S1, B, st));
-    if (ds) {
+    if (ds && bl.ds_fold) {
+      MN_TRY(conv_wgrad<T>(bl.convd, zin, S2, B, st));
+      MN_TRY(conv_dgrad<T>(bl.conv1, S1, nullptr, S0, B, st, next_pre ? &e2 : nullptr, &fb2, S2, bl.convd));
+    } else if (ds) {
       MN_TRY(conv_wgrad<T>(bl.convd, zin, S2, B, st));
       MN_TRY(conv_dgrad<T>(bl.convd, S2, nullptr, S0, B, st));
       MN_TRY(conv_dgrad<T>(bl.conv1, S1, S0, S0, B, st, next_pre ? &e2 : nullptr, &fb2));

@@ -36,6 +36,7 @@ struct BlockL {
   int conv1, conv2, convd;       // indices into convs (convd = -1: identity)
   int Hi, Wi, Ho, Wo, Cin, Cout, stride;
   void *y1, *h, *y2, *yd, *out;  // activation buffers (T)
+  int ds_fold;                   // the downsample dgrad is folded into conv1's dgrad launch (tcgen05 path)
 };
 
 struct Net {
@@ -78,6 +79,7 @@ struct Net {
   int fuse_fin;                  // BN finalize inside the last CTA of the accumulating conv (env MAPNET_TC_FUSE_FIN)
   int fuse_bwd;                  // BN backward reductions accumulated in the dgrad epilogue (env MAPNET_TC_FUSE_BWD)
   int fuse_stats;                // BN statistics accumulated in the tcgen05 conv epilogue (env MAPNET_TC_FUSE_STATS)
+  int ds_fold;                   // fold each 1x1/s2 downsample dgrad into its block's conv1 dgrad (env MAPNET_TC_DS_FOLD)
   std::vector<ProfRec> prof;
   int prof_begin(cudaStream_t st, cudaEvent_t* e0);
   void prof_end(cudaStream_t st, cudaEvent_t e0, int cls, double flops);
@@ -101,7 +103,8 @@ struct Net {
                                        cudaStream_t st);
   template <typename T> int conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st,
                                        bool with_stats = false, const EpiFin* fin = nullptr);
-  template <typename T> int conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd = nullptr, const EpiFin* fin = nullptr);
+  template <typename T> int conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd = nullptr,
+                                       const EpiFin* fin = nullptr, const T* dy_shortcut = nullptr, int ci_shortcut = -1);
   EpiFin fin_forward(int bi, long long M, const float* params, float* bufs);
   EpiFin fin_backward(int bi, int bi_ds, long long M, const float* params, float* grads);
   template <typename T> int conv_wgrad(int ci, const T* x, const T* dy, int B, cudaStream_t st);

@@ -108,6 +108,12 @@ int mapnet_profile_read(mapnet_trunk_t* h, double* host_ms3, double* host_flops3
 int mapnet_test_conv(int precision, int kind /*0 fprop 1 dgrad 2 wgrad*/, int B, int Hi, int Wi, int Ci, int Co,
                      int k, int stride, const void* in0, const void* in1, const void* wmat, void* out, void* stream);
 
+/* the tensor-core dgrad of a downsampling BasicBlock's two input-side convs in ONE launch, as the trunk runs it:
+ * dx = dgrad(conv1 3x3/s2/p1; dy1, w1_dg [Ci][3][3][Co]) + dgrad(downsample 1x1/s2; dy2, w2_dg [Ci][Co]), all bf16 NHWC
+ * (torchvision BasicBlock.forward's two uses of the block input, /root/reference/models/posenet.py:66). */
+int mapnet_test_dgrad_shortcut(int B, int Hi, int Wi, int Ci, int Co, const void* dy1, const void* dy2,
+                               const void* w1_dg, const void* w2_dg, void* dx, void* stream);
+
 /* the tensor-core stem (7x7/s2/p3, 3 -> 64) alone, as the trunk runs it: space-to-depth image, packed weights,
  * fprop into y_out (bf16 NHWC [B,Hc,Wc,64]) and, when dy / dw_oihw are given, the weight gradient in the
  * .grad layout [64,3,7,7].  Replaces torchvision ResNet.conv1 (/root/reference/models/posenet.py:66). */

@@ -102,6 +102,48 @@ def test_tensor_core_stem_matches_conv2d(shape):
     assert float((dw.cpu() - wr.grad).abs().max() / wr.grad.abs().max()) < 5e-5
 
 
+# the three downsampling blocks of ResNet-34 at their real channel counts (small batch / maps), plus odd sizes
+SHORTCUT_CASES = [(2, 64, 64, 64, 128), (2, 32, 32, 128, 256), (2, 16, 16, 256, 512), (3, 17, 13, 128, 256),
+                  (2, 18, 22, 64, 128), (1, 9, 7, 256, 512), (9, 16, 16, 256, 512)]
+
+
+@pytest.mark.parametrize("geom", SHORTCUT_CASES)
+def test_merged_stride2_dgrad_with_folded_shortcut(geom):
+    """d(block input) of a downsampling BasicBlock in ONE tcgen05 launch: the four parity classes of the 3x3/s2
+    conv1 dgrad plus the 1x1/s2 downsample dgrad as an extra tap of class (0,0) (conv_tc.cu,
+    tc_plan_add_shortcut), against torch autograd through both convs on the same bf16-rounded operands."""
+    B, H, W, Ci, Co = geom
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, Ci, H, W, generator=g).bfloat16().float().requires_grad_(True)
+    w1 = (torch.randn(Co, Ci, 3, 3, generator=g) * (2.0 / (Ci * 9)) ** 0.5).bfloat16().float()
+    w2 = (torch.randn(Co, Ci, 1, 1, generator=g) * (2.0 / Ci) ** 0.5).bfloat16().float()
+    y1 = F.conv2d(x, w1, None, 2, 1)
+    y2 = F.conv2d(x, w2, None, 2, 0)
+    assert y1.shape == y2.shape
+    dy1 = torch.randn(y1.shape, generator=g).bfloat16().float()
+    dy2 = torch.randn(y2.shape, generator=g).bfloat16().float()
+    (y1 * dy1).sum().backward(retain_graph=True)
+    dx1 = x.grad.clone()
+    (y2 * dy2).sum().backward()
+    dx = x.grad                                                   # dx1 + shortcut part
+    d1 = dy1.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    d2 = dy2.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    w1_dg = w1.permute(1, 2, 3, 0).contiguous().bfloat16().cuda()           # [Ci][kh][kw][Co]
+    w2_dg = w2.permute(1, 2, 3, 0).contiguous().bfloat16().cuda()           # [Ci][1][1][Co]
+    out = torch.full((B, H, W, Ci), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L = _lib.lib()
+    _lib.check(L.mapnet_test_dgrad_shortcut(B, H, W, Ci, Co, d1.data_ptr(), d2.data_ptr(), w1_dg.data_ptr(),
+                                            w2_dg.data_ptr(), out.data_ptr(), _lib.stream_ptr()),
+               "mapnet_test_dgrad_shortcut")
+    torch.cuda.synchronize()
+    ref = dx.permute(0, 2, 3, 1)
+    got = out.float().cpu()
+    assert bool(torch.isfinite(got).all()), "some output pixel class was not written"
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1.2e-2         # bf16 output rounding
+    # the shortcut must really be in there: without it the error is O(1)
+    assert float((got - dx1.permute(0, 2, 3, 1)).abs().max() / ref.abs().max()) > 0.1
+
+
 CRIT_KEYS = ["posenet_n64t1", "posenet_n7t1", "mapnet_n32t3", "mapnet_n5t2", "online_n16t10",
              "online_n3t4", "online_gps_n16t10", "online_gps_n2t6"]
 

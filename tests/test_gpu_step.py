@@ -152,6 +152,43 @@ def test_dgrad_fused_bn_backward_matches_separate_reduction(name):
     assert errs[worst] < 5e-2, (worst, errs[worst])
 
 
+@pytest.mark.parametrize("name", ["posenet_b8_256", "posenet_ragged", "mapnet_tiny"])
+def test_merged_stride2_dgrad_matches_per_class_launches(name):
+    """MAPNET_TC_DGRAD_MERGE=1 / MAPNET_TC_DS_FOLD=1 (default): each stride-2 dgrad is ONE launch over its four
+    parity classes with the block's downsample dgrad folded in; =0/0: one launch per class, the downsample
+    dgrad written to a zero-filled tensor and added as a residual (the path validated before).  Same forward,
+    same masks: only the fp32 summation order (shortcut inside vs outside the accumulator) and therefore a
+    few bf16 roundings of d(block input) differ."""
+    from oracle import weights
+    g, cfg = load_golden(name)
+    st = weights.make_state(int(g["seed"]))
+    x, targ = weights.make_inputs(cfg, int(g["seed"]))
+    res = {}
+    keys = ("MAPNET_TC_DGRAD_MERGE", "MAPNET_TC_DS_FOLD")
+    old = {k: os.environ.get(k) for k in keys}
+    try:
+        for mode in ("1", "0"):
+            for k in keys:
+                os.environ[k] = mode                      # read when the trunk / its plans are created
+            model, net = make_product_model(st, cfg["kind"], "bf16")
+            crit = make_product_criterion(cfg["kind"])
+            model.train()
+            loss, pred, grads, _ = product_step(model, net, crit, x, targ, do_step=False)
+            res[mode] = (float(loss), {k: v.float().cpu() for k, v in grads.items()})
+    finally:
+        for k in keys:
+            if old[k] is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = old[k]
+    (la, ga), (lb, gb) = res["1"], res["0"]
+    assert abs(la - lb) <= 1e-5 * abs(lb), (la, lb)
+    errs = {k: float((ga[k] - gb[k]).norm() / (gb[k].norm() + 1e-20)) for k in gb}
+    worst = max(errs, key=errs.get)
+    print("merged-vs-per-class stride-2 dgrad", name, worst, errs[worst])
+    assert errs[worst] < 5e-2, (worst, errs[worst])
+
+
 def test_eval_mode_forward_matches_oracle():
     """model.eval(): BN running statistics, no state change (validation path,
     common/train.py:214-256)."""
