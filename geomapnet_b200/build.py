@@ -14,12 +14,18 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(CSRC, "libmapnet_b200.so")
-OBJ = os.path.join(CSRC, "_obj")
+# MAPNET_BUILD_EPI_WARPS=4|8: epilogue warps per CTA of the tcgen05 conv engines (conv_tc.cu, MN_EPI_WARPS).  The
+# non-default value builds a SECOND library (libmapnet_b200_e<N>.so, loaded with MAPNET_LIB_VARIANT=e<N>) so both
+# can be measured in one GPU session; the default is what the package loads.
+DEFAULT_EPI_WARPS = 4
+EPI_WARPS = int(os.environ.get("MAPNET_BUILD_EPI_WARPS", DEFAULT_EPI_WARPS))
+_SUFFIX = "" if EPI_WARPS == DEFAULT_EPI_WARPS else "_e%d" % EPI_WARPS
+OUT = os.path.join(CSRC, "libmapnet_b200%s.so" % _SUFFIX)
+OBJ = os.path.join(CSRC, "_obj" + _SUFFIX)
 SOURCES = ["api.cu", "net.cu", "bn.cu", "conv_simt.cu", "conv_tc.cu", "layout.cu", "head.cu", "loss.cu", "adam.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v", "-DMN_EPI_WARPS=%d" % EPI_WARPS]
 
 
 def _digest():

@@ -107,6 +107,7 @@ unsigned long long mapnet_launch_count(void) { return g_launch_count; }
 int mapnet_profile(mapnet_trunk_t* h, int enable) {
   MN_CHECK(h != nullptr, "profile: null handle");
   h->net.profile_on = enable ? 1 : 0;
+  if (enable) MN_TRY(h->net.prof_reserve(2048));      // no event creation inside the profiled steps
   return 0;
 }
 

@@ -192,6 +192,19 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&x)[32], int lane) 
 static constexpr int kEpiRowStride = 36;                 // floats per scratch row (32 + 4 pad)
 static constexpr int kEpiScratchFloats = 32 * kEpiRowStride;
 
+// Epilogue warps per CTA of the fprop / dgrad engines.  TMEM lane quarter q = warp % 4 is fixed by the hardware;
+// with 8 warps the two warps of a quarter split the 32-column chunks of the accumulator (even / odd chunks).
+// Most launches of the network are ONE wave of one tile per CTA, where the epilogue is not hidden behind the
+// next tile's MMAs but sits at the end of the kernel: halving it is worth one pipeline stage of shared memory.
+#ifndef MN_EPI_WARPS
+#define MN_EPI_WARPS 4
+#endif
+static constexpr int kEpiWarps = MN_EPI_WARPS;
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "MN_EPI_WARPS must be 4 or 8");
+static constexpr int kEpiSplit = kEpiWarps / 4;          // warps per TMEM lane quarter
+static constexpr int kEpiThreads = 32 * kEpiWarps;
+static constexpr int kConvThreads = 64 + kEpiThreads;    // warp 0 TMA producer, warp 1 MMA issuer, then the epilogue
+
 // Epilogue variants (template flags): the flags are launch-uniform, and specialising on them keeps every
 // variant's chunk body straight-line code (runtime flags cost ~3x: branches fence the scheduler and the
 // four epilogue warps are latency-, not throughput-bound).
@@ -345,32 +358,34 @@ __device__ __forceinline__ void epi_tile(const uint32_t tmem_addr, const bool ha
                                          const uint32_t tfull_phase, Release release, float* __restrict__ scr,
                                          float (*stw)[BN / 32][32], const long long (&rowoff)[4],
                                          const bool (&rvalid)[4], const bool do_store, const int tn,
-                                         const bf16* residual, bf16* out, const EpiBwd& E, const int lane) {
+                                         const bf16* residual, bf16* out, const EpiBwd& E, const int lane,
+                                         const int half) {
   bool rstore[4]; float rw[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { rstore[i] = rvalid[i] && do_store; rw[i] = rvalid[i] ? 1.f : 0.f; }
   // the first chunk's operand loads are in flight while the MMAs finish
+  // this warp's chunks: half, half + kEpiSplit, ...  (kEpiSplit == 1: all of them)
   EpiRegs G;
-  epi_issue_loads<F>(G, rowoff, 0, residual, E, lane);
+  epi_issue_loads<F>(G, rowoff, half * 32, residual, E, lane);
   mbar_wait(tfull_bar, tfull_phase);
   tc_fence_after();
   uint32_t v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = 0u;      // has_acc == false: no filter tap reaches this output class, D = 0
-  if (has_acc) tmem_ld32(tmem_addr, v);
+  if (has_acc) tmem_ld32(tmem_addr + half * 32, v);
 #pragma unroll 1
-  for (int cc = 0; cc < BN / 32; ++cc) {
-    if (cc > 0) epi_issue_loads<F>(G, rowoff, cc * 32, residual, E, lane);
+  for (int cc = half; cc < BN / 32; cc += kEpiSplit) {
+    if (cc > half) epi_issue_loads<F>(G, rowoff, cc * 32, residual, E, lane);
     if (has_acc) tmem_ld_wait();
-    if (cc == BN / 32 - 1) {
-      // all TMEM reads of this accumulator stage are complete: hand it back
+    if (cc + kEpiSplit >= BN / 32) {
+      // all of this warp's TMEM reads of this accumulator stage are complete: hand it back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) release();
     }
     epi_stage(v, scr, lane);
     // the next chunk's TMEM read overlaps this chunk's processing
-    if (has_acc && cc + 1 < BN / 32) tmem_ld32(tmem_addr + (cc + 1) * 32, v);
+    if (has_acc && cc + kEpiSplit < BN / 32) tmem_ld32(tmem_addr + (cc + kEpiSplit) * 32, v);
     epi_chunk<F>(scr, G, rowoff, rstore, rw, cc * 32, tn * BN + cc * 32, out, E, lane, stw[0][cc][lane],
                  stw[1][cc][lane], stw[2][cc][lane]);
   }
@@ -383,9 +398,9 @@ __device__ __forceinline__ void epi_tile_dispatch(const int mode, const uint32_t
                                                   float* __restrict__ scr, float (*stw)[BN / 32][32],
                                                   const long long (&rowoff)[4], const bool (&rvalid)[4],
                                                   const bool do_store, const int tn, const bf16* residual, bf16* out,
-                                                  const EpiBwd& E, const int lane) {
+                                                  const EpiBwd& E, const int lane, const int half) {
 #define MN_EPI_CASE(Fv) case (Fv): epi_tile<(Fv), BN>(tmem_addr, has_acc, tfull_bar, tfull_phase, release, scr, stw, rowoff, \
-                                                      rvalid, do_store, tn, residual, out, E, lane); break;
+                                                      rvalid, do_store, tn, residual, out, E, lane, half); break;
   switch (mode) {
     MN_EPI_CASE(0)
     MN_EPI_CASE(EPI_RES)
@@ -413,10 +428,10 @@ __device__ __forceinline__ int epi_mode_of(const bf16* residual, const double* s
   return m;
 }
 
-// ---- statistics flush + fused BatchNorm finalize (epilogue warps only: 128 threads, named barrier 1) ----
+// ---- statistics flush + fused BatchNorm finalize (epilogue warps only: kEpiThreads threads, named barrier 1) ----
 static constexpr int kConvReplicas = 8;        // accumulator replicas the conv engines spread their flushes over
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 // Combine the four epilogue warps' running column sums of N tile `tn` in shared memory and add them to this
 // CTA's accumulator replica: one fp64 atomic per (statistic, column) per CTA.
@@ -427,7 +442,7 @@ __device__ __forceinline__ void epi_flush(float (*all)[3][BN / 32][32], double* 
   double* acc = stats + (size_t)(blockIdx.x % kConvReplicas) * kStatStride;
   const int nstat = third ? 3 : 2;
 #pragma unroll 1
-  for (int e = etid; e < nstat * BN; e += 128) {
+  for (int e = etid; e < nstat * BN; e += kEpiThreads) {
     const int j = e / BN, rem = e - j * BN, i = rem >> 5, l = rem & 31;
     const float t = all[0][j][i][l] + all[1][j][i][l] + all[2][j][i][l] + all[3][j][i][l];
     all[0][j][i][l] = 0.f; all[1][j][i][l] = 0.f; all[2][j][i][l] = 0.f; all[3][j][i][l] = 0.f;
@@ -448,7 +463,7 @@ __device__ __forceinline__ void epi_finalize(const EpiFin& Fin, double* __restri
   __threadfence();
   const int nacc = (Fin.mode == 3) ? 3 : 2;
 #pragma unroll 1
-  for (int c = etid; c < C; c += 128) {
+  for (int c = etid; c < C; c += kEpiThreads) {
     double s[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int r = 0; r < kConvReplicas; ++r) {
@@ -464,7 +479,9 @@ __device__ __forceinline__ void epi_finalize(const EpiFin& Fin, double* __restri
 }
 
 // as many stages as fit in 227 KB: the engines are bound by bytes in flight x L2 latency
-static constexpr int conv_stages(int BN) { return BN <= 64 ? 8 : (BN <= 128 ? 6 : 4); }   // + 18 KB epilogue scratch
+static constexpr int conv_stages(int BN) {      // + 18 KB (4 epilogue warps) / 37 KB (8) of epilogue scratch
+  return kEpiWarps == 4 ? (BN <= 64 ? 8 : (BN <= 128 ? 6 : 4)) : (BN <= 64 ? 7 : (BN <= 128 ? 5 : 3));
+}
 static constexpr int wgrad_stages(int BN) { return BN <= 64 ? 9 : (BN <= 128 ? 6 : 4); }
 
 // ---------------------------------------------------------------------------------
@@ -474,7 +491,7 @@ static constexpr int wgrad_stages(int BN) { return BN <= 64 ? 9 : (BN <= 128 ? 6
 // M tiles of the same N tile and share the weight tile -- each loads 1/CL of it and TMA-
 // multicasts it to all (the engines are L2-bandwidth bound, this cuts the B traffic by CL).
 template <int BN, int CL>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
@@ -501,7 +518,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
@@ -595,9 +612,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     }
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
-    const int q = warp & 3;
-    __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
-    float* scr = epi_scratch[q];
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int ew = warp - 2;                // epilogue warp index, 0 .. kEpiWarps-1
+    const int half = ew >> 2;               // which of the quarter's chunk subsets (0 when kEpiWarps == 4)
+    // per-warp transpose scratch: dynamic shared memory behind the pipeline stages (static is capped at 48 KB)
+    float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) + ew * kEpiScratchFloats;
     const int epi_mode = epi_mode_of(residual, stats, E);
     int as = 0; uint32_t aphase = 0;
     // fused BatchNorm statistics (fprop only): lane L keeps the running column sums of column
@@ -608,9 +627,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     __shared__ float epi_stats[4][3][BN / 32][32];
     float (*stw)[BN / 32][32] = epi_stats[q];
 #pragma unroll 1
-    for (int i = 0; i < BN / 32; ++i) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
+    for (int i = half; i < BN / 32; i += kEpiSplit) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
     int st_tn = -1;
-    const int etid = q * 32 + lane;
+    const int etid = ew * 32 + lane;
     auto flush_stats = [&](int tn_flush) { epi_flush<BN>(epi_stats, stats, P.Cout, tn_flush, E.yd != nullptr, etid); };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile(tile, per_class, P.n_tiles_n);
@@ -646,7 +665,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       }
       epi_tile_dispatch<BN>(epi_mode, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, kblocks > 0, tfull0 + 8 * as,
                             aphase, [&]() { mbar_arrive(tempty0 + 8 * as); }, scr, stw, rowoff, rvalid, P.debug != 4, tn,
-                            residual, out, E, lane);
+                            residual, out, E, lane, half);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
@@ -669,10 +688,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 // the leader spans both CTAs' shared memory and TMEM.  Per-SM bytes per FLOP drop to what
 // a 256x256 GEMM tile needs -- the engines are bound by shared-memory ingest, not by math.
 // ---------------------------------------------------------------------------------
-static constexpr int conv2_stages(int BN) { return BN <= 128 ? 8 : 6; }
+static constexpr int conv2_stages(int BN) { return kEpiWarps == 4 ? (BN <= 128 ? 8 : 6) : (BN <= 128 ? 7 : 5); }
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
            const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
@@ -697,9 +716,9 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     // full: leader's arrive.expect_tx + peer's remote arrive; empty / tfull: one multicast commit;
-    // tempty: 4 epilogue warps of each CTA arrive on the LEADER's barrier
+    // tempty: the epilogue warps of each CTA arrive on the LEADER's barrier
     for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 2 * kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_base_smem), TMEM_COLS);
@@ -785,9 +804,11 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     }
   } else {
     // ===================== epilogue (both CTAs; own TMEM half) =====================
-    const int q = warp & 3;
-    __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
-    float* scr = epi_scratch[q];
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int ew = warp - 2;                // epilogue warp index, 0 .. kEpiWarps-1
+    const int half = ew >> 2;               // which of the quarter's chunk subsets (0 when kEpiWarps == 4)
+    // per-warp transpose scratch: dynamic shared memory behind the pipeline stages (static is capped at 48 KB)
+    float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) + ew * kEpiScratchFloats;
     const int epi_mode = epi_mode_of(residual, stats, E);
     int as = 0; uint32_t aphase = 0;
     // running column sums of this warp, [statistic][chunk][lane] (lane <-> column epi_stat_col(lane)); kept in
@@ -796,9 +817,9 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     __shared__ float epi_stats[4][3][BN / 32][32];
     float (*stw)[BN / 32][32] = epi_stats[q];
 #pragma unroll 1
-    for (int i = 0; i < BN / 32; ++i) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
+    for (int i = half; i < BN / 32; i += kEpiSplit) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
     int st_tn = -1;
-    const int etid = q * 32 + lane;
+    const int etid = ew * 32 + lane;
     auto flush_stats = [&](int tn_flush) { epi_flush<BN>(epi_stats, stats, P.Cout, tn_flush, E.yd != nullptr, etid); };
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile(tile, per_class, P.n_tiles_n);
@@ -825,7 +846,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       }
       epi_tile_dispatch<BN>(epi_mode, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, kblocks > 0, tfull0 + 8 * as,
                             aphase, [&]() { mbar_arrive_cluster(mapa(tempty0 + 8 * as, 0)); }, scr, stw, rowoff, rvalid, true, tn,
-                            residual, out, E, lane);
+                            residual, out, E, lane, half);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
@@ -862,11 +883,12 @@ struct HaloParams {
   int b_stationary;             // weights loaded once per CTA (9*cblocks tiles)
   int dq[9], kidx[9];           // per tap: shift in padded-linear space, K index of its weight slice
   int use_base_offset;
+  int scr_off;                  // byte offset (from the 1024-aligned base) of the epilogue warps' transpose scratch
   int debug;                    // micro-benchmark only: 1 = skip MMAs, 2 = skip TMA loads
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ HaloParams P, const bf16* __restrict__ residual, bf16* __restrict__ out,
                double* __restrict__ stats, const EpiBwd E, const EpiFin Fin) {
@@ -889,7 +911,7 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     prefetch_tmap(&mapA); prefetch_tmap(&mapB);
     for (int i = 0; i < MAXNP; ++i) { mbar_init(pfull0 + 8 * i, 1); mbar_init(pempty0 + 8 * i, 1); }
     for (int i = 0; i < MAXNB; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, kEpiWarps); }
     mbar_init(bstat, 1);
     fence_mbar_init();
   }
@@ -997,9 +1019,11 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;
-    __shared__ __align__(16) float epi_scratch[4][kEpiScratchFloats];
-    float* scr = epi_scratch[q];
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int ew = warp - 2;                // epilogue warp index, 0 .. kEpiWarps-1
+    const int half = ew >> 2;               // which of the quarter's chunk subsets (0 when kEpiWarps == 4)
+    // per-warp transpose scratch: dynamic shared memory behind the patch / weight rings (static is capped at 48 KB)
+    float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + P.scr_off) + ew * kEpiScratchFloats;
     const int epi_mode = epi_mode_of(residual, stats, E);
     int as = 0; uint32_t aphase = 0;
     // running column sums of this warp, [statistic][chunk][lane] (lane <-> column epi_stat_col(lane)); kept in
@@ -1008,9 +1032,9 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __shared__ float epi_stats[4][3][BN / 32][32];
     float (*stw)[BN / 32][32] = epi_stats[q];
 #pragma unroll 1
-    for (int i = 0; i < BN / 32; ++i) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
+    for (int i = half; i < BN / 32; i += kEpiSplit) { stw[0][i][lane] = 0.f; stw[1][i][lane] = 0.f; stw[2][i][lane] = 0.f; }
     int st_tn = -1;
-    const int etid = q * 32 + lane;
+    const int etid = ew * 32 + lane;
     auto flush_stats = [&](int tn_flush) { epi_flush<BN>(epi_stats, stats, P.Cout, tn_flush, E.yd != nullptr, etid); };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tn = tile % P.n_tiles_n;
@@ -1028,7 +1052,7 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       epi_tile_dispatch<BN>(epi_mode, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, true, tfull0 + 8 * as,
                             aphase, [&]() { mbar_arrive(tempty0 + 8 * as); }, scr, stw, rowoff, rvalid, true, tn,
-                            residual, out, E, lane);
+                            residual, out, E, lane, half);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (stats != nullptr && st_tn >= 0) flush_stats(st_tn);
@@ -1474,7 +1498,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
         const long long wbytes = 9LL * H.cblocks * bn * 128;
         // 227 KB per CTA minus the alignment slack and the kernel's static shared memory (epilogue scratch,
         // per-warp statistics, barriers)
-        const long long budget = 227LL * 1024 - 1024 - (4LL * kEpiScratchFloats * 4 + 1536LL * (bn / 32) + 512);
+        const long long budget = 227LL * 1024 - 1024 - ((long long)kEpiWarps * kEpiScratchFloats * 4 + 1536LL * (bn / 32) + 512);
         H.b_stationary = (Cn == bn && wbytes + 2LL * H.patch_bytes <= budget) ? 1 : 0;
         long long left = budget - (H.b_stationary ? wbytes : 0);
         if (H.b_stationary) { H.NP = (int)(left / H.patch_bytes); H.NB = 0; }
@@ -1499,7 +1523,8 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
               H.kidx[t] = t;
               H.dq[t] = (kind == 0) ? ((kh - 1) * H.P + (kw - 1)) : ((1 - kh) * H.P + (1 - kw));
             }
-          p->halo_smem = (size_t)H.NP * H.patch_bytes + (size_t)(H.b_stationary ? 9 * H.cblocks : H.NB) * bn * 128 + 1024;
+          H.scr_off = H.NP * H.patch_bytes + (H.b_stationary ? 9 * H.cblocks : H.NB) * bn * 128;
+          p->halo_smem = (size_t)H.scr_off + (size_t)kEpiWarps * kEpiScratchFloats * 4 + 1024;
           *out = p;
           return 0;
         }
@@ -1743,7 +1768,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     const int total = H.n_tiles_m * H.n_tiles_n;
     const int grid = total < nsm ? total : nsm;
     F.expected = (unsigned int)grid;
-    MN_LAUNCH(kern, grid, 192, p->halo_smem, st, p->hmapA, p->hmapB, H, residual, (bf16*)out, stats, E, F);
+    MN_LAUNCH(kern, grid, kConvThreads, p->halo_smem, st, p->hmapA, p->hmapB, H, residual, (bf16*)out, stats, E, F);
     MN_LAUNCH_CHECK();
     return 0;
   }
@@ -1769,10 +1794,11 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       }
       p->c_in0 = in0; p->c_in1 = in1;
     }
-    size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024;
+    const size_t scratch = (size_t)kEpiWarps * kEpiScratchFloats * 4;      // epilogue transpose scratch behind the stages
+    size_t smem = (size_t)conv_stages(p->BN) * (128 * 128 + p->BN * 128) + 1024 + scratch;
     void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvParams, const bf16*, bf16*, double*, EpiBwd, EpiFin) = nullptr;
     if (p->two_cta) {
-      smem = (size_t)conv2_stages(p->BN) * (128 * 128 + (p->BN / 2) * 128) + 1024;
+      smem = (size_t)conv2_stages(p->BN) * (128 * 128 + (p->BN / 2) * 128) + 1024 + scratch;
       kern = (p->BN == 256) ? k_tc_conv2<256> : k_tc_conv2<128>;
     }
 #define PICK(BNv, CLv) if (!p->two_cta && p->BN == BNv && p->CL == CLv) kern = k_tc_conv<BNv, CLv>;
@@ -1794,7 +1820,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       const int max_clusters = (p->CL == 4) ? 32 : nsm / p->CL;
       const int nclusters = groups < max_clusters ? groups : max_clusters;
       cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(nclusters * p->CL); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cfg.gridDim = dim3(nclusters * p->CL); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
       cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = p->CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

@@ -141,7 +141,7 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_CHECK(max_B >= 0 && H >= 32 && W >= 32, "create: need max_B>=0 and H,W>=32 (got %d,%d,%d)", max_B, H, W);
   MN_CHECK(precision >= 0 && precision <= 2, "create: bad precision %d", precision);
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
-  last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0;
+  last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0; prof_pool_used = 0;
   { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   { const char* e = getenv("MAPNET_STEM_S2D");
     stem_s2d = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1) && (max_B == 0 || tc_overlapped_view_supported()); }
@@ -207,19 +207,40 @@ void Net::destroy() {
   tc_fprop.clear(); tc_dgrad.clear(); tc_wgrad.clear();
   for (void* p : allocs) cudaFree(p);
   allocs.clear();
+  for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
+  prof_pool.clear();
 }
 
 // ---- conv dispatch -------------------------------------------------------------
+// events come from a pool that is only ever grown: creating two events per conv launch inside the profiled
+// step made the host the bottleneck and the idle gaps landed inside the brackets
+int Net::prof_event(cudaEvent_t* e) {
+  if (prof_pool_used == prof_pool.size()) {
+    cudaEvent_t ev;
+    MN_CUDA(cudaEventCreate(&ev));
+    prof_pool.push_back(ev);
+  }
+  *e = prof_pool[prof_pool_used++];
+  return 0;
+}
+int Net::prof_reserve(int n_events) {
+  while ((int)prof_pool.size() < n_events) {
+    cudaEvent_t ev;
+    MN_CUDA(cudaEventCreate(&ev));
+    prof_pool.push_back(ev);
+  }
+  return 0;
+}
 int Net::prof_begin(cudaStream_t st, cudaEvent_t* e0) {
   if (!profile_on) return 0;
-  MN_CUDA(cudaEventCreate(e0));
+  MN_TRY(prof_event(e0));
   MN_CUDA(cudaEventRecord(*e0, st));
   return 0;
 }
 void Net::prof_end(cudaStream_t st, cudaEvent_t e0, int cls, double flops) {
   if (!profile_on) return;
   ProfRec r; r.e0 = e0; r.cls = cls; r.flops = flops;
-  cudaEventCreate(&r.e1);
+  if (prof_event(&r.e1) != 0) return;
   cudaEventRecord(r.e1, st);
   prof.push_back(r);
 }
@@ -230,9 +251,9 @@ int Net::prof_read(double* ms3, double* flops3, int* launches3) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
     ms3[r.cls] += ms; flops3[r.cls] += r.flops; launches3[r.cls] += 1;
-    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
   }
   prof.clear();
+  prof_pool_used = 0;
   return 0;
 }
 

@@ -81,6 +81,9 @@ struct Net {
   int fuse_stats;                // BN statistics accumulated in the tcgen05 conv epilogue (env MAPNET_TC_FUSE_STATS)
   int ds_fold;                   // fold each 1x1/s2 downsample dgrad into its block's conv1 dgrad (env MAPNET_TC_DS_FOLD)
   std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_pool; size_t prof_pool_used;
+  int prof_event(cudaEvent_t* e);
+  int prof_reserve(int n_events);
   int prof_begin(cudaStream_t st, cudaEvent_t* e0);
   void prof_end(cudaStream_t st, cudaEvent_t e0, int cls, double flops);
   int prof_read(double* ms3, double* flops3, int* launches3);   // classes: 0 fprop, 1 dgrad, 2 wgrad
