@@ -211,18 +211,40 @@ int mapnet_bench_conv(int kind, int B, int Hi, int Wi, int Ci, int Co, int k, in
   MN_TRY(tc_plan_create(&plan, g, kind, (const bf16*)wmat));
   cudaStream_t st = 0;
   int r = 0;
-  for (int i = 0; i < 3 && r == 0; ++i) r = tc_conv_run(plan, (const bf16*)in0, (const bf16*)in1, nullptr, out, st);
+  // MAPNET_BENCH_EPI=1: the epilogue variants the training step really runs -- fprop with the fused BatchNorm
+  // statistics, dgrad with the ReLU gate + BatchNorm-backward sums (gate tensor and Y = the input operand's
+  // sibling buffers; the values are irrelevant for timing); =2 additionally isolates each launch with an event
+  // record (what bench.py's per-conv brackets do: no programmatic overlap with the neighbours)
+  static int epi = -1;
+  if (epi < 0) { const char* e = getenv("MAPNET_BENCH_EPI"); epi = e ? atoi(e) : 0; }
+  double* stats = nullptr;
+  EpiBwd E; memset(&E, 0, sizeof(E));
+  const bf16* res = nullptr;
+  if (epi && kind != 2) {
+    if (cudaMalloc((void**)&stats, 32 * 3 * 512 * sizeof(double)) != cudaSuccess) { set_last_error("bench_conv: cudaMalloc"); tc_plan_destroy(plan); return 1; }
+    cudaMemset(stats, 0, 32 * 3 * 512 * sizeof(double));
+    if (kind == 1) { E.y = (const bf16*)out; E.zmask = (const bf16*)out; res = (const bf16*)out; }   // shaped like the output
+  }
+  cudaEvent_t iso;
+  cudaEventCreate(&iso);
+  auto run = [&]() {
+    int rc = tc_conv_run(plan, (const bf16*)in0, (const bf16*)in1, res, out, st, stats, (kind == 1 && stats) ? &E : nullptr);
+    if (epi == 2) cudaEventRecord(iso, st);
+    return rc;
+  };
+  for (int i = 0; i < 3 && r == 0; ++i) r = run();
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, st);
-  for (int i = 0; i < iters && r == 0; ++i) r = tc_conv_run(plan, (const bf16*)in0, (const bf16*)in1, nullptr, out, st);
+  for (int i = 0; i < iters && r == 0; ++i) r = run();
   cudaEventRecord(e1, st);
   cudaError_t e = cudaEventSynchronize(e1);
   if (r == 0 && e != cudaSuccess) { set_last_error("bench_conv: %s", cudaGetErrorString(e)); r = 1; }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   if (host_ms) *host_ms = ms / (iters > 0 ? iters : 1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(iso);
+  if (stats) cudaFree(stats);
   tc_plan_destroy(plan);
   return r;
 }

@@ -31,10 +31,16 @@ STEP_CONFIGS = {
     "online_tiny":      dict(kind="online", N=2, T=6, H=64, W=64, lr=1e-5, wd=0.0, clip=5.0),
     "online_gps_tiny":  dict(kind="online_gps", N=2, T=6, H=64, W=64, lr=1e-5, wd=0.0, clip=5.0),
     "posenet_b8_256":   dict(kind="posenet", N=8, H=256, W=256),
+    # the shape real 7Scenes frames (640x480) reach the net with after Resize(256), no crop
+    # (scripts/train.py:119-128): odd width, feature maps 128x171 ... 8x11
+    "posenet_7scenes_b4": dict(kind="posenet", N=4, H=256, W=341),
 }
 FULL_CONFIGS = {
     "posenet_b64_256":  dict(kind="posenet", N=64, H=256, W=256),            # BASELINE configs[1]
     "mapnet_n32t3_256": dict(kind="mapnet", N=32, T=3, H=256, W=256),        # BASELINE configs[2]
+    # BASELINE configs[4] per-GPU shape: MapNet++ steps=5 through MFOnline (2T = 10 frames), bs16 = 160 frames,
+    # MapNetOnlineCriterion, lr 1e-5, wd 0, max_grad_norm 5, filter_nans (mapnet++_7Scenes.ini:15-20)
+    "online_n16t10_256": dict(kind="online", N=16, T=10, H=256, W=256, lr=1e-5, wd=0.0, clip=5.0),
 }
 
 

@@ -53,8 +53,11 @@ def _run(name, precision, tol):
             json.dump(rep, f, indent=1, default=str)
 
 
-TINY = ["posenet_tiny", "posenet_ragged", "mapnet_tiny", "online_tiny", "online_gps_tiny", "posenet_b8_256"]
-FULL = ["posenet_b64_256", "mapnet_n32t3_256"]
+# posenet_7scenes_b4: 256x341, the shape real 7Scenes frames have after Resize(256) (odd width: feature maps
+# 128x171 -> 64x86 -> 32x43 -> 16x22 -> 8x11); online_n16t10_256: BASELINE configs[4] per-GPU shape (160 frames)
+TINY = ["posenet_tiny", "posenet_ragged", "mapnet_tiny", "online_tiny", "online_gps_tiny", "posenet_b8_256",
+        "posenet_7scenes_b4"]
+FULL = ["posenet_b64_256", "mapnet_n32t3_256", "online_n16t10_256"]
 
 
 @pytest.mark.parametrize("name", TINY)
@@ -72,7 +75,8 @@ def test_step_bf16_tensor_core(name):
     _run(name, "bf16", TOL_BF16)
 
 
-@pytest.mark.parametrize("name", ["posenet_tiny", "posenet_ragged", "mapnet_tiny", "online_tiny", "online_gps_tiny"])
+@pytest.mark.parametrize("name", ["posenet_tiny", "posenet_ragged", "mapnet_tiny", "online_tiny", "online_gps_tiny",
+                                  "posenet_7scenes_b4"])
 def test_step_bf16_tensor_core_tiny_shapes(name):
     """tiny / ragged shapes (BatchNorm over as few as 16 samples, 2x2 feature maps, odd
     widths) exercise every TMA edge case; they are too ill-conditioned for a tight bf16
@@ -81,7 +85,7 @@ def test_step_bf16_tensor_core_tiny_shapes(name):
     _run(name, "bf16", dict(loss=1e-1, pred=5e-1, grad=1e9, grad_head=1e9, post=1e-2, sgrad=1e9))
 
 
-@pytest.mark.parametrize("name", ["posenet_b8_256", "posenet_ragged"])
+@pytest.mark.parametrize("name", ["posenet_b8_256", "posenet_ragged", "posenet_7scenes_b4"])
 def test_tensor_core_path_matches_cuda_core_path_on_bf16(name):
     """Same bf16 storage / operands, two independent engines: tcgen05 (precision bf16) vs
     CUDA-core fp32 FMA (precision bf16_simt).  Only accumulation order differs."""
@@ -97,7 +101,7 @@ def test_tensor_core_path_matches_cuda_core_path_on_bf16(name):
         loss, pred, grads, _ = product_step(model, net, crit, x, targ, do_step=False)
         res[prec] = (float(loss), pred.cpu(), {k: v.cpu() for k, v in grads.items()})
     la, pa, ga = res["bf16"]; lb, pb, gb = res["bf16_simt"]
-    tight = name != "posenet_ragged"
+    tight = name == "posenet_b8_256"      # the bounds below were calibrated on this config only
     el = abs(la - lb) / abs(lb)
     ep = float((pa - pb).abs().max() / pb.abs().max())
     eg = {k: float((ga[k] - gb[k]).norm() / gb[k].norm()) for k in
@@ -152,7 +156,7 @@ def test_dgrad_fused_bn_backward_matches_separate_reduction(name):
     assert errs[worst] < 5e-2, (worst, errs[worst])
 
 
-@pytest.mark.parametrize("name", ["posenet_b8_256", "posenet_ragged", "mapnet_tiny"])
+@pytest.mark.parametrize("name", ["posenet_b8_256", "posenet_ragged", "mapnet_tiny", "posenet_7scenes_b4"])
 def test_merged_stride2_dgrad_matches_per_class_launches(name):
     """MAPNET_TC_DGRAD_MERGE=1 / MAPNET_TC_DS_FOLD=1 (default): each stride-2 dgrad is ONE launch over its four
     parity classes with the block's downsample dgrad folded in; =0/0: one launch per class, the downsample

@@ -20,7 +20,8 @@ def _golden(golden_dir, name):
     return g, ast.literal_eval(str(g["cfg"]))
 
 
-@pytest.mark.parametrize("name", ["posenet_tiny", "posenet_ragged", "mapnet_tiny", "online_tiny", "online_gps_tiny"])
+@pytest.mark.parametrize("name", ["posenet_tiny", "posenet_ragged", "mapnet_tiny", "online_tiny", "online_gps_tiny",
+                                  "posenet_7scenes_b4"])
 def test_oracle_step_matches_reference_golden(golden_dir, name):
     g, cfg = _golden(golden_dir, name)
     st = weights.make_state(int(g["seed"]))

@@ -1,0 +1,92 @@
+"""Summarise an `ncu --set full` report into profiles/ (run HERE, on the report gpurun brought back).
+
+    python tools/ncu_summary.py gpurun_out/conv_full.ncu-rep r01d
+
+writes profiles/<tag>_ncu_full_summary.csv (one row per captured launch: duration, tensor-pipe activity, DRAM
+bytes and rate, L2 throughput, registers) and profiles/ncu_traffic.json (dram read + write bytes per launch of the
+dominant conv kernel = the launch list's biggest total among the captured kernels), which bench.py reports as
+`roofline.traffic`.
+"""
+import csv
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WANT = [  # (column label, substrings that must all appear in the ncu metric name)
+    ("dur_ns", ["gpu__time_duration.sum"]),
+    ("tensor_pipe_pct_active", ["sm__pipe_tensor", "pct_of_peak_sustained_active"]),
+    ("tensor_pipe_pct_elapsed", ["sm__pipe_tensor", "pct_of_peak_sustained_elapsed"]),
+    ("dram_read_bytes", ["dram__bytes_read.sum"]),
+    ("dram_write_bytes", ["dram__bytes_write.sum"]),
+    ("dram_pct", ["dram__throughput.avg.pct_of_peak_sustained_elapsed"]),
+    ("l2_pct", ["lts__throughput.avg.pct_of_peak_sustained_elapsed"]),
+    ("sm_pct", ["sm__throughput.avg.pct_of_peak_sustained_elapsed"]),
+    ("regs", ["launch__registers_per_thread"]),
+    ("smem_dyn", ["launch__shared_mem_per_block_dynamic"]),
+    ("grid", ["launch__grid_size"]),
+]
+
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}
+
+
+def main():
+    rep, tag = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr_i = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr, units, data = rows[hdr_i], rows[hdr_i + 1], rows[hdr_i + 2:]
+    col = {}
+    for label, subs in WANT:
+        cands = [j for j, h in enumerate(hdr) if all(s in h for s in subs)]
+        if cands:
+            # prefer the exact / shortest metric name
+            col[label] = min(cands, key=lambda j: len(hdr[j]))
+    kn = hdr.index("Kernel Name")
+    out_rows, per_kernel = [], {}
+    for r in data:
+        if len(r) <= kn:
+            continue
+        name = re.sub(r"^(void )?mapnet::", "", r[kn])
+        name = re.sub(r"\(.*$", "", name)
+        rec = {"kernel": name}
+        for label, j in col.items():
+            try:
+                v = float(r[j].replace(",", ""))
+            except ValueError:
+                v = None
+            if v is not None and label in ("dur_ns", "dram_read_bytes", "dram_write_bytes"):
+                v *= UNIT.get(units[j], 1.0)
+            rec[label] = v
+        out_rows.append(rec)
+        k = per_kernel.setdefault(name, {"n": 0, "dur": 0.0, "bytes": 0.0})
+        k["n"] += 1
+        k["dur"] += rec.get("dur_ns") or 0.0
+        k["bytes"] += (rec.get("dram_read_bytes") or 0.0) + (rec.get("dram_write_bytes") or 0.0)
+    labels = ["kernel"] + [l for l, _ in WANT if l in col]
+    path = os.path.join(ROOT, "profiles", "%s_ncu_full_summary.csv" % tag)
+    with open(path, "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on; one row per captured launch; metric columns: "
+                + "; ".join("%s=%s" % (l, hdr[col[l]]) for l in labels[1:]) + "\n")
+        w = csv.writer(f)
+        w.writerow(labels)
+        for rec in out_rows:
+            w.writerow([rec.get(l) for l in labels])
+    print("wrote", path, len(out_rows), "launches")
+    conv = {k: v for k, v in per_kernel.items() if k.startswith("k_tc_")}
+    if conv:
+        top = max(conv, key=lambda k: conv[k]["dur"])
+        t = conv[top]
+        traffic = {"kernel": top, "launches_captured": t["n"], "dram_bytes_per_launch": t["bytes"] / t["n"],
+                   "avg_duration_us": t["dur"] / t["n"] / 1e3, "source": os.path.basename(path)}
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
+        print("ncu_traffic.json:", traffic)
+
+
+if __name__ == "__main__":
+    main()
