@@ -31,10 +31,16 @@ class FusedAdam(optim.Optimizer):
 
     # -- contiguous runs --------------------------------------------------------
     def _plan(self, gi, params):
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
-        cached = self._runs.get(gi)
-        if cached is not None and cached[0] == key:
-            return cached[1]
+        """Contiguous runs of the group's parameters (one launch each) with their moment buffers.
+
+        The plan is keyed on the RUN STRUCTURE -- which parameters sit in which run, i.e. parameter addresses and the
+        relative placement of their gradients -- not on absolute gradient addresses: a free-standing parameter (the
+        criterion's sax / saq / srx / srq) gets a freshly allocated .grad from autograd every step, and the launch
+        takes the gradient pointer of the day anyway.  Keyed on absolute gradient addresses the plan was rebuilt on
+        every such step; harmless eagerly (moments and step are carried over) but not while a CUDA graph is being
+        captured: the rebuild's allocations, zero fills, moment copies and the step-counter fill were captured with
+        the step and replayed each time, resetting those parameters' Adam state on every replay
+        (tests/test_gpu_graph.py: criterion scalars 0.38 lr off after 4 replays)."""
         order = sorted(params, key=lambda p: p.data_ptr())
         runs, cur = [], None
         for p in order:
@@ -48,6 +54,15 @@ class FusedAdam(optim.Optimizer):
                     continue
             cur = {"params": [p]}
             runs.append(cur)
+        key = tuple(tuple(q.data_ptr() for q in r["params"]) for r in runs)
+        cached = self._runs.get(gi)
+        if cached is not None and cached[0] == key:
+            # still valid only while the state's moments ARE the run buffers (load_state_dict replaces them)
+            def bound(r):
+                ea = self.state[r["params"][0]].get("exp_avg")
+                return ea is not None and ea.data_ptr() == r["m"].data_ptr()
+            if all(bound(r) for r in cached[1]):
+                return cached[1]
         for r in runs:
             first, last = r["params"][0], r["params"][-1]
             r["n"] = (last.data_ptr() + last.numel() * 4 - first.data_ptr()) // 4

@@ -142,3 +142,42 @@ def test_optimizer_wrapper_surface(built):
     p[0].grad = torch.zeros(3)
     with pytest.raises(RuntimeError):
         o.learner.step()             # CPU tensors: no CPU path
+
+
+def test_fused_adam_plan_is_keyed_on_run_structure(built):
+    """FusedAdam._plan (host logic, no kernels): the run structure and the moment buffers must survive a change of
+    the ABSOLUTE gradient addresses of free-standing parameters (autograd hands the criterion scalars a fresh .grad
+    every step) -- a rebuild during CUDA-graph capture would be replayed with the step and reset their Adam state --
+    and must be rebuilt, keeping the moments, when load_state_dict replaces the state tensors."""
+    from geomapnet_b200.common.optimizer import FusedAdam
+    flat = torch.zeros(64 + 64 + 8)
+    gflat = torch.zeros_like(flat)
+    a = torch.nn.Parameter(flat[0:60].view(6, 10)); b = torch.nn.Parameter(flat[64:72])     # 4-float gap: one run
+    s1 = torch.nn.Parameter(torch.zeros(1)); s2 = torch.nn.Parameter(torch.zeros(1))
+    a.grad = gflat[0:60].view(6, 10); b.grad = gflat[64:72]
+    s1.grad = torch.ones(1); s2.grad = torch.ones(1)
+    opt = FusedAdam([{"params": [a, b]}, {"params": [s1, s2]}], lr=1e-3)
+    r0 = opt._plan(0, [a, b]); r1 = opt._plan(1, [s1, s2])
+    assert len(r0) == 1 and r0[0]["n"] == 72 and [p is q for p, q in zip(r0[0]["params"], (a, b))] == [True, True]
+    assert len(r1) == 2 and all(r["n"] == 1 for r in r1)
+    m_ptrs = [r["m"].data_ptr() for r in r1]
+    opt.state[s1]["exp_avg"].fill_(0.25)                       # pretend a step happened
+    keep = [s1.grad, s2.grad]                                   # keep the old tensors alive: new addresses guaranteed
+    s1.grad = torch.full((1,), 2.0); s2.grad = torch.full((1,), 3.0)
+    assert s1.grad.data_ptr() != keep[0].data_ptr()
+    r1b = opt._plan(1, [s1, s2])
+    assert r1b is r1 and [r["m"].data_ptr() for r in r1b] == m_ptrs
+    assert opt._plan(0, [a, b]) is r0
+    # a different gradient LAYOUT of a multi-parameter run does change the structure (b's grad no longer follows a's)
+    b.grad = torch.zeros(8)
+    r0b = opt._plan(0, [a, b])
+    assert r0b is not r0 and len(r0b) == 2
+    # load_state_dict replaces the state tensors: rebuilt, moments carried over
+    import copy
+    sd = copy.deepcopy(opt.state_dict())                        # what torch.load of a checkpoint hands over
+    opt.load_state_dict(sd)
+    assert opt.state[s1]["exp_avg"].data_ptr() not in m_ptrs
+    r1c = opt._plan(1, [s1, s2])
+    assert r1c is not r1
+    assert float(opt.state[s1]["exp_avg"]) == 0.25
+    assert opt.state[s1]["exp_avg"].data_ptr() in [r["m"].data_ptr() for r in r1c]
