@@ -1,6 +1,7 @@
 """Summarise an `ncu --set full` report into profiles/ (run HERE, on the report gpurun brought back).
 
-    python tools/ncu_summary.py gpurun_out/conv_full.ncu-rep r01d
+    python tools/ncu_summary.py gpurun_out/conv_full.ncu-rep r02a
+    python tools/ncu_summary.py --csv gpurun_out/conv_full_fwd_raw.csv gpurun_out/conv_full_bwd_raw.csv r02a
 
 writes profiles/<tag>_ncu_full_summary.csv (one row per captured launch: duration, tensor-pipe activity, DRAM
 bytes and rate, L2 throughput, registers) and profiles/ncu_traffic.json (dram read + write bytes per launch of the
@@ -35,8 +36,18 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 
 
 
 def main():
-    rep, tag = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    args = sys.argv[1:]
+    if args and args[0] == "--csv":          # one or more `ncu -i x.ncu-rep --page raw --csv` exports made on the GPU box
+        tag = args[-1]
+        raw = ""
+        for i, f in enumerate(args[1:-1]):
+            txt = open(f).read()
+            if i > 0:                        # drop the repeated header + units rows
+                txt = "\n".join(txt.splitlines()[2:]) + "\n"
+            raw += txt
+    else:
+        rep, tag = args[0], args[1]
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr_i = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr, units, data = rows[hdr_i], rows[hdr_i + 1], rows[hdr_i + 2:]

@@ -1,26 +1,29 @@
-# Final validation call of the round: full -m gpu suite, smoke(), bench lines, one ncu --set full capture of the
-# conv engines, conv microbench with the step's epilogue variants.
-# Usage:  gpurun --timeout 420 -- 'bash tools/run_gpu_batch.sh'
+# Round-end validation call: full -m gpu suite, smoke(), the bench lines, the ncu launch list and ONE ncu --set full
+# capture of the conv engines.  The .ncu-rep files stay on the box (gpurun brings back at most 64 MiB -- two reports
+# of 16 launches were 73 MB and the whole gpurun_out/ of that call was dropped): they are exported to CSV there and
+# only the CSV travels; summarise it here with  python tools/ncu_summary.py --csv gpurun_out/conv_full_raw.csv <tag>.
+# Usage:  gpurun --timeout 480 -- 'bash tools/run_gpu_batch.sh'
 mkdir -p gpurun_out
 T0=$(date +%s)
 el() { echo "[t+$(( $(date +%s) - T0 ))s] $*"; }
 el "=== all gpu tests (no -x)"
-timeout 240 python -m pytest tests -m gpu -q -s --durations=6 2>&1 | grep -vE "^\s*$|^tests/.*UserWarning|losses.append|Consider using|Docs:" | tail -45 | cut -c1-600
+timeout 240 python -m pytest tests -m gpu -q -s --durations=6 2>&1 | grep -E "graph-vs-eager|merged-vs|tc-vs-simt|fused-vs|passed|failed|FAILED|Error|^E " | cut -c1-600
 el "=== smoke"
 timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -4
 el "=== bench default (posenet_bs64) with cpu baseline"
-timeout 200 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "rc=$?"; cut -c1-300 gpurun_out/bench_final.json
+timeout 200 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "rc=$?"; cat gpurun_out/bench_final.json
 el "=== bench mapnet_n32t3 / mapnetpp_n16t10"
-timeout 100 python bench.py --no-cpu-baseline --workload mapnet_n32t3 > gpurun_out/bench_mapnet.json 2> gpurun_out/bench_mapnet.err; echo "rc=$?"; cut -c1-200 gpurun_out/bench_mapnet.json
-timeout 100 python bench.py --no-cpu-baseline --workload mapnetpp_n16t10 > gpurun_out/bench_mapnetpp.json 2> gpurun_out/bench_mapnetpp.err; echo "rc=$?"; cut -c1-200 gpurun_out/bench_mapnetpp.json
-el "=== ncu --set full, conv engines (second eager step: stem + layer1/2 fprop, then a backward slice)"
-timeout 150 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -s 107 -c 16 -f -o gpurun_out/conv_full_fwd \
-  python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_fwd.log 2>&1; echo "rc=$?"
-timeout 150 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -s 150 -c 16 -f -o gpurun_out/conv_full_bwd \
-  python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_bwd.log 2>&1; echo "rc=$?"
-ls -la gpurun_out/*.ncu-rep
-el "=== conv microbench: plain / step epilogues / step epilogues + isolated launches"
-timeout 60 python tools/bench_conv.py 64 2>&1 | tail -6
-MAPNET_BENCH_EPI=1 timeout 60 python tools/bench_conv.py 64 2>&1 | tail -6
-MAPNET_BENCH_EPI=2 timeout 60 python tools/bench_conv.py 64 2>&1 | tail -6
+timeout 100 python bench.py --no-cpu-baseline --workload mapnet_n32t3 | tee gpurun_out/bench_mapnet.json
+timeout 100 python bench.py --no-cpu-baseline --workload mapnetpp_n16t10 | tee gpurun_out/bench_mapnetpp.json
+el "=== ncu launch list"
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 1100 -c 330 --csv --log-file gpurun_out/launches_raw.csv \
+  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/launches_bench.log 2>&1; echo "rc=$?"
+el "=== ncu --set full, conv engines (second eager step: 12 forward launches, 12 backward launches)"
+for part in "fwd 107" "bwd 150"; do
+  set -- $part
+  timeout 150 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -s $2 -c 12 -f -o /tmp/conv_full_$1 \
+    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_$1.log 2>&1; echo "rc=$?"
+  ncu -i /tmp/conv_full_$1.ncu-rep --page raw --csv > gpurun_out/conv_full_$1_raw.csv 2>/dev/null
+done
+ls -la gpurun_out/*.csv; du -sh gpurun_out
 el "=== done"
