@@ -400,7 +400,9 @@ def run_b200(args, cfg, rank, local_rank, world):
     # The profiled steps run eagerly with a CUDA-event pair around every conv launch.  Two unprofiled
     # steps are enqueued first WITHOUT a sync, so the device is busy while the host runs ahead and the
     # profiled launches are already queued when the device reaches them: no host-side gap lands
-    # inside a bracket (what remains is the event-record cost and the lost PDL overlap, ~1 us each).
+    # inside a bracket.  What remains is the isolation itself: a bracketed launch cannot overlap its prologue /
+    # pipeline fill / tail with its neighbours as it does in the CUDA-graph step, +5-7 us per launch
+    # (profiles/r01d_conv_microbench.txt, block 3 vs block 2) -- `achieved` is therefore a LOWER bound.
     for i in range(2):
         step(*dev_batches[i % nb])
     if rank == 0:
@@ -425,8 +427,11 @@ def run_b200(args, cfg, rank, local_rank, world):
                 if args.precision == "bf16" else "k_conv_simt (fp32 CUDA-core strict path)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "%s (MEASURED_PEAKS.json bf16_tflops_sustained)" % peaks["src"],
-                "traffic": _ncu_traffic(), "conv_ms_per_step": tot_ms / psteps, "conv_launches_per_step": tot_n // psteps,
+                "traffic": (_ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_detail": _ncu_traffic(),
+                "conv_ms_per_step": tot_ms / psteps, "conv_launches_per_step": tot_n // psteps,
                 "conv_share_of_step": (tot_ms / psteps) / ms_step, "per_class": per_class,
+                "note": "event-bracketed launches run isolated (no programmatic overlap with their neighbours): "
+                        "achieved / frac are lower bounds of what the same kernels do inside the CUDA-graph step",
                 "step_frac_of_conv_flop_roofline": (value / world) * O.train_flops_per_image(cfg["H"], cfg["W"]) / (peak * 1e12)}
 
     # ---------------- cpu baseline: oracle port on the host cores (rank 0, N=1 only) -------------
