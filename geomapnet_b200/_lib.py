@@ -61,6 +61,8 @@ def lib():
     L.mapnet_test_dgrad_shortcut.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]
     L.mapnet_test_dgrad_shortcut.restype = c_int
+    L.mapnet_test_plan_describe.argtypes = [c_int] * 9 + [c_char_p, c_int]
+    L.mapnet_test_plan_describe.restype = c_int
     L.mapnet_launch_count.restype = ctypes.c_ulonglong
     L.mapnet_profile.argtypes = [c_void_p, c_int]
     L.mapnet_profile.restype = c_int
@@ -82,7 +84,7 @@ EXPORTED = ["mapnet_last_error", "mapnet_abi_version", "mapnet_trunk_create", "m
             "mapnet_forward", "mapnet_backward", "mapnet_loss_fwd_bwd", "mapnet_sqnorm", "mapnet_adam_step",
             "mapnet_test_conv", "mapnet_launch_count", "mapnet_profile", "mapnet_profile_read",
             "mapnet_adam_step_dev", "mapnet_bench_conv", "mapnet_test_stem",
-            "mapnet_test_dgrad_shortcut"]
+            "mapnet_test_dgrad_shortcut", "mapnet_test_plan_describe"]
 
 
 def check(rc, what):

@@ -142,6 +142,22 @@ int mapnet_test_conv(int precision, int kind, int B, int Hi, int Wi, int Ci, int
   return r;
 }
 
+// JSON description of the plan the tensor-core engines would use for this conv (no device needed)
+int mapnet_test_plan_describe(int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride, int with_shortcut,
+                              char* buf, int cap) {
+  ConvGeom g;
+  g.B = B; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Co = Co; g.KH = g.KW = k; g.stride = stride; g.pad = (k - 1) / 2;
+  g.Ho = (Hi + 2 * g.pad - k) / stride + 1; g.Wo = (Wi + 2 * g.pad - k) / stride + 1;
+  TcConvPlan* plan = nullptr;
+  static const bf16 dummy[8] = {};
+  MN_TRY(tc_plan_create(&plan, g, kind, dummy));
+  int r = 0;
+  if (with_shortcut) r = tc_plan_add_shortcut(plan, dummy);
+  if (r == 0) r = tc_plan_describe(plan, buf, cap);
+  tc_plan_destroy(plan);
+  return r;
+}
+
 // conv1 (3x3/s2) dgrad with the block's 1x1/s2 downsample dgrad folded in (tc_plan_add_shortcut)
 int mapnet_test_dgrad_shortcut(int B, int Hi, int Wi, int Ci, int Co, const void* dy1, const void* dy2,
                                const void* w1_dg, const void* w2_dg, void* dx, void* stream) {

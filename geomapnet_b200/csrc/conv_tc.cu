@@ -20,6 +20,7 @@
 //       with fp32 red.global.add into the flat wgrad buffer.
 #include <cudaTypedefs.h>
 
+#include <stdarg.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -1710,6 +1711,71 @@ int tc_plan_add_shortcut(TcConvPlan* p, const bf16* wmat2) {
   p->c_in0 = p->c_in1 = nullptr;
   return 0;
 }
+// Host-only description of a plan as JSON (tests/test_tc_plan.py emulates it on the CPU: the tap / parity-class /
+// tile arithmetic is host logic and is checked without a GPU against torch's convolutions).
+int tc_plan_describe(const TcConvPlan* p, char* buf, int cap) {
+  MN_CHECK(p != nullptr && buf != nullptr && cap > 0, "tc_plan_describe: bad argument");
+  int n = 0;
+  bool ovf = false;
+  auto put = [&](const char* fmt, ...) {
+    if (ovf) return;
+    va_list ap;
+    va_start(ap, fmt);
+    const int w = vsnprintf(buf + n, (size_t)(cap - n), fmt, ap);
+    va_end(ap);
+    if (w < 0 || w >= cap - n) ovf = true; else n += w;
+  };
+  put("{\"kind\":%d,\"halo\":%d,\"BN\":%d,\"two_cta\":%d,\"CL\":%d,\"shortcut\":%d", p->kind, p->halo ? 1 : 0, p->BN,
+      p->two_cta ? 1 : 0, p->CL, p->wmat2 != nullptr ? 1 : 0);
+  if (p->halo) {
+    const HaloParams& H = p->HP;
+    put(",\"halo_params\":{\"Nimg\":%d,\"H\":%d,\"W\":%d,\"P\":%d,\"tiles_per_img\":%d,\"n_tiles_m\":%d,\"n_tiles_n\":%d,"
+        "\"cblocks\":%d,\"Cs\":%d,\"Cout\":%d,\"R\":%d,\"NP\":%d,\"NB\":%d,\"b_stationary\":%d,\"smem\":%lld,\"dq\":[",
+        H.Nimg, H.H, H.W, H.P, H.tiles_per_img, H.n_tiles_m, H.n_tiles_n, H.cblocks, H.Cs, H.Cout, H.R, H.NP, H.NB,
+        H.b_stationary, (long long)p->halo_smem);
+    for (int t = 0; t < 9; ++t) put("%s%d", t ? "," : "", H.dq[t]);
+    put("],\"kidx\":[");
+    for (int t = 0; t < 9; ++t) put("%s%d", t ? "," : "", H.kidx[t]);
+    put("]}");
+  } else if (p->kind == 2) {
+    const WgradParams& P = p->WP;
+    put(",\"wgrad\":{\"TW\":%d,\"TH\":%d,\"TN\":%d,\"tiles_w\":%d,\"tiles_h\":%d,\"tiles_n\":%d,\"n_pix_tiles\":%d,"
+        "\"n_chunks\":%d,\"n_mtiles\":%d,\"n_ntiles\":%d,\"BN\":%d,\"splits\":%d,\"tiles_per_split\":%d,\"Ci\":%d,\"Co\":%d,"
+        "\"KK\":%d,\"maps\":[",
+        P.TW, P.TH, P.TN, P.tiles_w, P.tiles_h, P.tiles_n, P.n_pix_tiles, P.n_chunks, P.n_mtiles, P.n_ntiles, P.BN,
+        P.splits, P.tiles_per_split, P.Ci, P.Co, P.KK);
+    for (int i = 0; i < p->w_nmaps; ++i) put("%s[%d,%d]", i ? "," : "", p->wpa[i], p->wpb[i]);
+    put("],\"chunks\":[");
+    for (int i = 0; i < P.n_chunks; ++i)
+      put("%s[%d,%d,%d,%d,%d]", i ? "," : "", P.chunks[i].dh, P.chunks[i].dw, P.chunks[i].map, P.chunks[i].c0, P.chunks[i].tap);
+    put("]}");
+  } else {
+    put(",\"launches\":[");
+    for (size_t li = 0; li < p->launches.size(); ++li) {
+      const ConvLaunch& L = p->launches[li];
+      const ConvParams& P = L.P;
+      put("%s{\"TW\":%d,\"TH\":%d,\"TN\":%d,\"tiles_w\":%d,\"tiles_h\":%d,\"tiles_n\":%d,\"n_tiles_m\":%d,\"n_tiles_n\":%d,"
+          "\"cblocks\":%d,\"Cs\":%d,\"Hout\":%d,\"Wout\":%d,\"Cout\":%d,\"os\":%d,\"Nimg\":%d,\"maps\":[",
+          li ? "," : "", P.TW, P.TH, P.TN, P.tiles_w, P.tiles_h, P.tiles_n, P.n_tiles_m, P.n_tiles_n, P.cblocks, P.Cs,
+          P.Hout, P.Wout, P.Cout, P.os, P.Nimg);
+      for (int i = 0; i < L.n_maps; ++i) put("%s[%d,%d]", i ? "," : "", L.pa[i], L.pb[i]);
+      put("],\"classes\":[");
+      for (int c = 0; c < P.n_classes; ++c) {
+        const ClassDesc& cd = P.cls[c];
+        put("%s{\"Hs\":%d,\"Ws\":%d,\"oa\":%d,\"ob\":%d,\"taps\":[", c ? "," : "", cd.Hs, cd.Ws, cd.oa, cd.ob);
+        for (int t = cd.tap0; t < cd.tap0 + cd.num_taps; ++t)
+          put("%s[%d,%d,%d,%d]", t > cd.tap0 ? "," : "", P.taps[t].dh, P.taps[t].dw, P.taps[t].map, P.taps[t].kidx);
+        put("]}");
+      }
+      put("]}");
+    }
+    put("]");
+  }
+  put("}");
+  MN_CHECK(!ovf, "tc_plan_describe: buffer of %d bytes is too small", cap);
+  return 0;
+}
+
 int tc_plan_launches(const TcConvPlan* p) { return p->halo ? 1 : (p->kind == 2 ? 1 : (int)p->launches.size()); }
 
 template <typename K>

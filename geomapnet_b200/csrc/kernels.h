@@ -59,6 +59,7 @@ void tc_plan_destroy(TcConvPlan* p);
 // incoming gradient as in1 and writes d(input) of BOTH convs
 int tc_plan_add_shortcut(TcConvPlan* p, const bf16* wmat2);
 int tc_plan_launches(const TcConvPlan* p);
+int tc_plan_describe(const TcConvPlan* p, char* buf, int cap);      // JSON, host-only (CPU tests of the plan arithmetic)
 // fprop: in0 = x, out = y (bf16);  dgrad: in0 = dy [, in1 = the folded shortcut's dy], out = dx (bf16);
 // wgrad: in0 = x, in1 = dy, out = fp32 dW (accumulated)
 // stats != nullptr (fprop, no residual): per-channel sum / sum of squares of the stored output are

@@ -108,6 +108,11 @@ int mapnet_profile_read(mapnet_trunk_t* h, double* host_ms3, double* host_flops3
 int mapnet_test_conv(int precision, int kind /*0 fprop 1 dgrad 2 wgrad*/, int B, int Hi, int Wi, int Ci, int Co,
                      int k, int stride, const void* in0, const void* in1, const void* wmat, void* out, void* stream);
 
+/* host-only: the tile / parity-class / filter-tap plan of the tensor-core engines for one conv, as JSON
+ * (tests/test_tc_plan.py replays it on the CPU against torch's convolutions; kind 0 fprop, 1 dgrad, 2 wgrad) */
+int mapnet_test_plan_describe(int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride, int with_shortcut,
+                              char* buf, int cap);
+
 /* the tensor-core dgrad of a downsampling BasicBlock's two input-side convs in ONE launch, as the trunk runs it:
  * dx = dgrad(conv1 3x3/s2/p1; dy1, w1_dg [Ci][3][3][Co]) + dgrad(downsample 1x1/s2; dy2, w2_dg [Ci][Co]), all bf16 NHWC
  * (torchvision BasicBlock.forward's two uses of the block input, /root/reference/models/posenet.py:66). */
