@@ -61,6 +61,14 @@ def lib():
     L.mapnet_test_dgrad_shortcut.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]
     L.mapnet_test_dgrad_shortcut.restype = c_int
+    L.mapnet_preprocess_create.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, c_int]
+    L.mapnet_preprocess_output_size.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
+    L.mapnet_preprocess_run.argtypes = [c_void_p, c_void_p, c_int, POINTER(c_float), POINTER(c_float), c_void_p, c_void_p,
+                                        c_void_p]
+    L.mapnet_preprocess_destroy.argtypes = [c_void_p]
+    for name in ("mapnet_preprocess_create", "mapnet_preprocess_output_size", "mapnet_preprocess_run",
+                 "mapnet_preprocess_destroy"):
+        getattr(L, name).restype = c_int
     L.mapnet_test_plan_describe.argtypes = [c_int] * 9 + [c_char_p, c_int]
     L.mapnet_test_plan_describe.restype = c_int
     L.mapnet_launch_count.restype = ctypes.c_ulonglong
@@ -84,7 +92,8 @@ EXPORTED = ["mapnet_last_error", "mapnet_abi_version", "mapnet_trunk_create", "m
             "mapnet_forward", "mapnet_backward", "mapnet_loss_fwd_bwd", "mapnet_sqnorm", "mapnet_adam_step",
             "mapnet_test_conv", "mapnet_launch_count", "mapnet_profile", "mapnet_profile_read",
             "mapnet_adam_step_dev", "mapnet_bench_conv", "mapnet_test_stem",
-            "mapnet_test_dgrad_shortcut", "mapnet_test_plan_describe"]
+            "mapnet_test_dgrad_shortcut", "mapnet_test_plan_describe", "mapnet_preprocess_create",
+            "mapnet_preprocess_output_size", "mapnet_preprocess_run", "mapnet_preprocess_destroy"]
 
 
 def check(rc, what):
