@@ -8,6 +8,8 @@ T0=$(date +%s)
 el() { echo "[t+$(( $(date +%s) - T0 ))s] $*"; }
 el "=== all gpu tests (no -x)"
 timeout 240 python -m pytest tests -m gpu -q -s --durations=6 2>&1 | grep -E "graph-vs-eager|merged-vs|tc-vs-simt|fused-vs|passed|failed|FAILED|Error|^E " | cut -c1-600
+el "=== staged kernels (first GPU run of the f2 input pipeline; opt-in test)"
+MAPNET_STAGED_TESTS=1 timeout 120 python -m pytest tests/test_gpu_preprocess.py -m gpu -q 2>&1 | tail -5 | cut -c1-400
 el "=== smoke"
 timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -4
 el "=== bench default (posenet_bs64) with cpu baseline"
