@@ -53,3 +53,24 @@ def test_roofline_helpers_and_clock_reduction():
     s.rows.append((now + 100.0, ["210", "1965", "90.0", "Active", "Not Active", "Not Active", "Not Active"]))   # outside the window
     out = s.summary(now, now + 0.5)
     assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"] and out["samples"] == 5
+
+
+def test_ncu_summary_tool_on_a_sample_report(tmp_path):
+    """tools/ncu_summary.py (turns an `ncu --set full` report into profiles/<tag>_ncu_full_summary.csv and the
+    roofline.traffic source) against one of the reports Nsight Compute ships as samples."""
+    import glob
+    reps = sorted(glob.glob("/opt/nvidia/nsight-compute/*/extras/samples/instructionMix/sobelFloat.ncu-rep"))
+    import shutil
+    if not reps or shutil.which("ncu") is None:
+        pytest.skip("no Nsight Compute sample report / ncu on this machine")
+    env = dict(os.environ, NCU_SUMMARY_OUT=str(tmp_path), NCU_SUMMARY_PREFIX="void Sobel")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), reps[0], "t"], capture_output=True,
+                       text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = open(tmp_path / "t_ncu_full_summary.csv").read().splitlines()
+    assert lines[0].startswith("#") and lines[1].startswith("kernel,dur_ns,")
+    cols = lines[1].split(",")
+    row = dict(zip(cols, lines[2].split(",")))
+    assert float(row["dur_ns"]) > 1000 and float(row["dram_read_bytes"]) > 1e5 and "tensor_pipe_pct_active" in cols
+    t = json.load(open(tmp_path / "ncu_traffic.json"))
+    assert t["dram_bytes_per_launch"] > 1e5 and t["launches_captured"] >= 1

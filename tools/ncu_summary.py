@@ -17,6 +17,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT_DIR = os.environ.get("NCU_SUMMARY_OUT", os.path.join(ROOT, "profiles"))      # tests write elsewhere
 
 WANT = [  # (column label, substrings that must all appear in the ncu metric name)
     ("dur_ns", ["gpu__time_duration.sum"]),
@@ -79,7 +80,7 @@ def main():
         k["dur"] += rec.get("dur_ns") or 0.0
         k["bytes"] += (rec.get("dram_read_bytes") or 0.0) + (rec.get("dram_write_bytes") or 0.0)
     labels = ["kernel"] + [l for l, _ in WANT if l in col]
-    path = os.path.join(ROOT, "profiles", "%s_ncu_full_summary.csv" % tag)
+    path = os.path.join(OUT_DIR, "%s_ncu_full_summary.csv" % tag)
     with open(path, "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on; one row per captured launch; metric columns: "
                 + "; ".join("%s=%s" % (l, hdr[col[l]]) for l in labels[1:]) + "\n")
@@ -88,13 +89,13 @@ def main():
         for rec in out_rows:
             w.writerow([rec.get(l) for l in labels])
     print("wrote", path, len(out_rows), "launches")
-    conv = {k: v for k, v in per_kernel.items() if k.startswith("k_tc_")}
+    conv = {k: v for k, v in per_kernel.items() if k.startswith(os.environ.get("NCU_SUMMARY_PREFIX", "k_tc_"))}
     if conv:
         top = max(conv, key=lambda k: conv[k]["dur"])
         t = conv[top]
         traffic = {"kernel": top, "launches_captured": t["n"], "dram_bytes_per_launch": t["bytes"] / t["n"],
                    "avg_duration_us": t["dur"] / t["n"] / 1e3, "source": os.path.basename(path)}
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
+        with open(os.path.join(OUT_DIR, "ncu_traffic.json"), "w") as f:
             json.dump(traffic, f, indent=1)
         print("ncu_traffic.json:", traffic)
 
