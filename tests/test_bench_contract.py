@@ -74,3 +74,20 @@ def test_ncu_summary_tool_on_a_sample_report(tmp_path):
     assert float(row["dur_ns"]) > 1000 and float(row["dram_read_bytes"]) > 1e5 and "tensor_pipe_pct_active" in cols
     t = json.load(open(tmp_path / "ncu_traffic.json"))
     assert t["dram_bytes_per_launch"] > 1e5 and t["launches_captured"] >= 1
+
+
+def test_ncu_stall_summary_tool_on_a_sample_report(tmp_path):
+    import glob
+    import shutil
+    reps = sorted(glob.glob("/opt/nvidia/nsight-compute/*/extras/samples/instructionMix/sobelFloat.ncu-rep"))
+    if not reps or shutil.which("ncu") is None:
+        pytest.skip("no Nsight Compute sample report / ncu on this machine")
+    src = subprocess.run(["ncu", "-i", reps[0], "--page", "source", "--csv"], capture_output=True, text=True, timeout=300)
+    assert src.returncode == 0
+    (tmp_path / "s.csv").write_text(src.stdout)
+    env = dict(os.environ, NCU_SUMMARY_OUT=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_stalls.py"), str(tmp_path / "s.csv"), "t", "top=5"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stderr[-1500:]
+    txt = open(tmp_path / "t_ncu_stalls.txt").read()
+    assert "Sobel" in txt and "long_sb" in txt and txt.count("%") > 10

@@ -27,5 +27,9 @@ for part in "fwd 107" "bwd 150"; do
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_$1.log 2>&1; echo "rc=$?"
   ncu -i /tmp/conv_full_$1.ncu-rep --page raw --csv > gpurun_out/conv_full_$1_raw.csv 2>/dev/null
 done
+# source-level stall samples of a short slice (3 launches: one report per direction would be tens of MB of CSV)
+timeout 120 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -s 120 -c 3 -f -o /tmp/conv_src \
+  python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_src.log 2>&1; echo "rc=$?"
+ncu -i /tmp/conv_src.ncu-rep --page source --csv > gpurun_out/conv_source.csv 2>/dev/null    # -> python tools/ncu_stalls.py
 ls -la gpurun_out/*.csv; du -sh gpurun_out
 el "=== done"
