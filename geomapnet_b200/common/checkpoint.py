@@ -27,35 +27,32 @@ import torch
 __all__ = ["load_state_dict", "save_checkpoint", "load_checkpoint", "checkpoint_filename"]
 
 
-def load_state_dict(model, state_dict):
-    """common/train.py:22-53.  Returns the (re-keyed) state dict that was loaded."""
-    model_names = [n for n, _ in model.named_parameters()]
-    state_names = [n for n in state_dict.keys()]
-    if not model_names or not state_names:
-        raise KeyError("load_state_dict: empty model or state dict")
-    # find prefix for the model and state dicts from the first param name
-    if model_names[0].find(state_names[0]) >= 0:
-        model_prefix = model_names[0].replace(state_names[0], "")
-        state_prefix = None
-    elif state_names[0].find(model_names[0]) >= 0:
-        state_prefix = state_names[0].replace(model_names[0], "")
-        model_prefix = None
-    else:
-        raise KeyError("Could not find the correct prefixes between %s and %s" % (model_names[0], state_names[0]))
+def _prefix_fix(model_first, state_first):
+    """(add, strip): what turns a state-dict key into the model's key.  The two FIRST parameter names must be equal
+    up to a leading module prefix on one side (``mapnet.`` / ``module.``); anything else is a KeyError."""
+    if model_first.endswith(state_first):
+        return model_first[:len(model_first) - len(state_first)], ""
+    if state_first.endswith(model_first):
+        return "", state_first[:len(state_first) - len(model_first)]
+    raise KeyError("Could not find the correct prefixes between %s and %s" % (model_first, state_first))
 
-    new_state_dict = OrderedDict()
-    for k, v in state_dict.items():
-        if state_prefix is None:
-            k = model_prefix + k
-        else:
-            k = k.replace(state_prefix, "")
-        new_state_dict[k] = v
-    # what nn.BatchNorm2d._load_from_state_dict does for checkpoints older than its version 2
+
+def load_state_dict(model, state_dict):
+    """Prefix-tolerant load (behaviour of /root/reference/common/train.py:22-53).  Returns the re-keyed dict."""
+    model_first = next((n for n, _ in model.named_parameters()), None)
+    state_first = next(iter(state_dict.keys()), None)
+    if model_first is None or state_first is None:
+        raise KeyError("load_state_dict: empty model or state dict")
+    add, strip = _prefix_fix(model_first, state_first)
+    rekeyed = OrderedDict((add + (k[len(strip):] if strip and k.startswith(strip) else k), v)
+                          for k, v in state_dict.items())
+    # checkpoints written before BatchNorm tracked its batch count (torch < 0.4.1) carry no num_batches_tracked
+    # entries; nn.BatchNorm2d fills them with zeros on load, the product's plain BN containers get the same here
     for k, v in model.state_dict().items():
-        if k.endswith(".num_batches_tracked") and k not in new_state_dict:
-            new_state_dict[k] = torch.zeros_like(v)
-    model.load_state_dict(new_state_dict)
-    return new_state_dict
+        if k.endswith(".num_batches_tracked"):
+            rekeyed.setdefault(k, torch.zeros_like(v))
+    model.load_state_dict(rekeyed)
+    return rekeyed
 
 
 def checkpoint_filename(logdir, epoch):

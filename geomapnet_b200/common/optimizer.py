@@ -9,6 +9,7 @@ buffer) instead of ~10 pointwise launches x 114 tensors
 torch.optim.Adam's structure (step, exp_avg, exp_avg_sq per parameter) so
 common/train.py:167-176,202 (checkpoint resume) keeps working.
 """
+import bisect
 import ctypes
 
 import torch
@@ -47,7 +48,12 @@ class FusedAdam(optim.Optimizer):
             if cur is not None:
                 last = cur["params"][-1]
                 gap = (p.data_ptr() - (last.data_ptr() + last.numel() * 4)) // 4
-                same = (p.device == last.device and 0 <= gap < _PAD and
+                # a gap is swept by the kernels: only tolerated inside ONE storage on both sides (the flat
+                # PoseNet buffers, whose padding the package zero-fills) -- never caching-allocator slack
+                # between separately allocated tensors, which may hold stale NaN / Inf
+                one_storage = (p.untyped_storage().data_ptr() == last.untyped_storage().data_ptr() and
+                               p.grad.untyped_storage().data_ptr() == last.grad.untyped_storage().data_ptr())
+                same = (p.device == last.device and (gap == 0 or (0 < gap < _PAD and one_storage)) and
                         (p.data_ptr() - last.data_ptr()) == (p.grad.data_ptr() - last.grad.data_ptr()))
                 if same:
                     cur["params"].append(p)
@@ -88,9 +94,12 @@ class FusedAdam(optim.Optimizer):
         return runs
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=1.0, max_grad_norm=0.0):
+    def step(self, closure=None, grad_scale=1.0, max_grad_norm=0.0, clip_groups=(0,)):
         """grad_scale multiplies every gradient first (1/world_size after a sum-allreduce);
-        max_grad_norm > 0 applies clip_grad_norm_ over ALL groups' gradients (fused)."""
+        max_grad_norm > 0 applies clip_grad_norm_ (fused) to the param groups listed in `clip_groups` --
+        the norm is taken over those groups only and only they are scaled.  Default: group 0, the model
+        (common/train.py:357-358 clips model.parameters(); the criterion's sax/saq/srx/srq groups of
+        scripts/train.py:104-110 are neither counted nor scaled).  clip_groups=None: every group."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -104,7 +113,7 @@ class FusedAdam(optim.Optimizer):
             for p in params:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
                     raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients (no CPU path)")
-            groups.append((group, self._plan(gi, params)))
+            groups.append((group, self._plan(gi, params), clip_groups is None or gi in clip_groups))
         if not groups:
             return loss
         dev = groups[0][1][0]["params"][0].device
@@ -117,14 +126,16 @@ class FusedAdam(optim.Optimizer):
                 total = self._scratch[1024:1025]
                 total.zero_()
                 part = self._scratch[1025:1026]
-                for group, runs in groups:
+                for group, runs, clipped in groups:
+                    if not clipped:
+                        continue
                     for r in runs:
                         g0 = r["params"][0].grad
                         _lib.check(L.mapnet_sqnorm(g0.data_ptr(), r["n"], self._scratch.data_ptr(),
                                                    part.data_ptr(), st), "mapnet_sqnorm")
                         total += part
                 sq_ptr = total.data_ptr()
-            for group, runs in groups:
+            for group, runs, clipped in groups:
                 b1, b2 = group["betas"]
                 for r in runs:
                     p0 = r["params"][0]
@@ -136,7 +147,7 @@ class FusedAdam(optim.Optimizer):
                         p0.data_ptr(), p0.grad.data_ptr(), r["m"].data_ptr(), r["v"].data_ptr(), r["n"],
                         float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                         float(group["weight_decay"]), r["step_dev"].data_ptr(), float(grad_scale),
-                        ctypes.c_void_p(sq_ptr) if sq_ptr else None, float(max_grad_norm or 0.0), st),
+                        ctypes.c_void_p(sq_ptr) if (sq_ptr and clipped) else None, float(max_grad_norm or 0.0), st),
                         "mapnet_adam_step_dev")
         return loss
 
@@ -152,35 +163,35 @@ class FusedAdam(optim.Optimizer):
 
 
 class Optimizer:
-    """Wrapper around the learner + learning-rate schedule (common/optimizer.py:8-47)."""
+    """Learner + learning-rate schedule behind the reference's wrapper surface
+    (``Optimizer(params, method, base_lr, weight_decay, **kwargs)``, ``.learner``, ``.adjust_lr(epoch)``,
+    ``.mult_lr(f)`` -- what /root/reference/common/train.py:128,281,359 and scripts/train.py:112 use).
+    'adam' is the fused flat-buffer Adam above; 'sgd' / 'rmsprop' go to torch.optim unchanged.  Only SGD has a
+    schedule: the rate drops by ``lr_decay`` at every epoch listed in ``lr_stepvalues``."""
+
+    _LEARNERS = {"sgd": optim.SGD, "adam": FusedAdam, "rmsprop": optim.RMSprop}
 
     def __init__(self, params, method, base_lr, weight_decay, **kwargs):
-        self.method = method
-        self.base_lr = base_lr
-        if self.method == 'sgd':
-            self.lr_decay = kwargs.pop('lr_decay')
-            self.lr_stepvalues = sorted(kwargs.pop('lr_stepvalues'))
-            self.learner = optim.SGD(params, lr=self.base_lr, weight_decay=weight_decay, **kwargs)
-        elif self.method == 'adam':
-            self.learner = FusedAdam(params, lr=self.base_lr, weight_decay=weight_decay, **kwargs)
-        elif self.method == 'rmsprop':
-            self.learner = optim.RMSprop(params, lr=self.base_lr, weight_decay=weight_decay, **kwargs)
-        else:
+        if method not in self._LEARNERS:
             raise NotImplementedError(method)
+        self.method, self.base_lr = method, base_lr
+        if method == "sgd":
+            self.lr_decay = kwargs.pop("lr_decay")
+            self.lr_stepvalues = sorted(kwargs.pop("lr_stepvalues"))
+        self.learner = self._LEARNERS[method](params, lr=base_lr, weight_decay=weight_decay, **kwargs)
+
+    def _each_group(self, fn):
+        for group in self.learner.param_groups:
+            group["lr"] = fn(group["lr"])
 
     def adjust_lr(self, epoch):
-        if self.method != 'sgd':
+        """Rate for `epoch`; written into every param group when there is a schedule (SGD)."""
+        if self.method != "sgd":
             return self.base_lr
-        decay_factor = 1
-        for s in self.lr_stepvalues:
-            if epoch < s:
-                break
-            decay_factor *= self.lr_decay
-        lr = self.base_lr * decay_factor
-        for param_group in self.learner.param_groups:
-            param_group['lr'] = lr
+        drops = bisect.bisect_right(self.lr_stepvalues, epoch)      # step values already reached
+        lr = self.base_lr * self.lr_decay ** drops
+        self._each_group(lambda _: lr)
         return lr
 
     def mult_lr(self, f):
-        for param_group in self.learner.param_groups:
-            param_group['lr'] *= f
+        self._each_group(lambda lr: lr * f)

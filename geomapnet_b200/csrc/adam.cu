@@ -9,16 +9,20 @@
 namespace mapnet {
 
 __global__ void __launch_bounds__(256)
-k_sqnorm_partial(const float* __restrict__ g, long long n, float* __restrict__ partials) {
+k_sqnorm_partial(const float* __restrict__ g, long long n, float* __restrict__ partials, int vec) {
   pdl_prologue();
   double acc = 0.0;
-  const long long n4 = n >> 2;
+  if (!vec) {      // gradient buffer not 16-byte aligned: scalar grid-stride loop
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      acc += (double)g[i] * g[i];
+  }
+  const long long n4 = vec ? (n >> 2) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(g)[i];
     acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0)
+  if (vec && blockIdx.x == 0 && threadIdx.x == 0)
     for (long long i = n4 << 2; i < n; ++i) acc += (double)g[i] * g[i];
   __shared__ double red[8];
   acc = warp_sum_d(acc);
@@ -41,7 +45,8 @@ __global__ void k_sqnorm_final(const float* __restrict__ partials, int nblk, flo
 
 int launch_sqnorm(const float* g, long long n, float* partials, float* out_sq, cudaStream_t st) {
   const int nblk = 296;
-  MN_LAUNCH(k_sqnorm_partial, nblk, 256, 0, st, g, n, partials);
+  const int vec = (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  MN_LAUNCH(k_sqnorm_partial, nblk, 256, 0, st, g, n, partials, vec);
   MN_LAUNCH_CHECK();
   MN_LAUNCH(k_sqnorm_final, 1, 32, 0, st, partials, nblk, out_sq, 0);
   MN_LAUNCH_CHECK();
@@ -57,7 +62,7 @@ __global__ void k_inc_i32(int* c) {
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
        long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-       float gscale, const float* __restrict__ sqnorm, float max_norm, const int* __restrict__ step_dev) {
+       float gscale, const float* __restrict__ sqnorm, float max_norm, const int* __restrict__ step_dev, int vec) {
   pdl_prologue();
   if (step_dev != nullptr) {
     // CUDA-graph friendly: the step count lives on the device (bias corrections cannot be
@@ -75,6 +80,15 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
     coef *= c;
   }
   const float step = lr / bc1;
+  if (!vec) {      // some buffer is not 16-byte aligned (free-standing parameters): scalar grid-stride loop
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      float gr = g[i] * coef + wd * p[i];
+      m[i] = m[i] + (1.f - b1) * (gr - m[i]);
+      v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
+      p[i] = p[i] - step * (m[i] / (sqrtf(v[i]) / bc2_sqrt + eps));
+    }
+    return;
+  }
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -115,7 +129,9 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
     MN_LAUNCH(k_inc_i32, 1, 1, 0, st, step_dev);
     MN_LAUNCH_CHECK();
   }
-  MN_LAUNCH(k_adam, (int)grid, 256, 0, st, p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), gscale, sqnorm_or_null, max_norm, step_dev);
+  const int vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                    reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  MN_LAUNCH(k_adam, (int)grid, 256, 0, st, p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), gscale, sqnorm_or_null, max_norm, step_dev, vec);
   MN_LAUNCH_CHECK();
   return 0;
 }
