@@ -488,7 +488,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="posenet_bs64", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt", "tc_split"])
     ap.add_argument("--droprate", type=float, default=0.5)       # every reference .ini uses 0.5
     ap.add_argument("--ref-frames", type=int, default=32, help="frames per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

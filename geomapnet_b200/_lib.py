@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _VARIANT = os.environ.get("MAPNET_LIB_VARIANT", "")
 LIB_PATH = os.path.join(_HERE, "csrc", "libmapnet_b200%s.so" % (("_" + _VARIANT) if _VARIANT else ""))
 
-PREC = {"fp32": 0, "bf16": 1, "bf16_simt": 2}
+PREC = {"fp32": 0, "bf16": 1, "bf16_simt": 2, "tc_split": 3}
 LOSS_MODE = {"posenet": 0, "mapnet": 1, "online": 2, "online_gps": 3}
 
 _lib = None

@@ -133,6 +133,36 @@ int mapnet_test_conv(int precision, int kind, int B, int Hi, int Wi, int Ci, int
     if (kind == 1) return launch_conv_simt_dgrad<bf16>(g, (const bf16*)in0, (const float*)wmat, nullptr, (bf16*)out, st);
     return launch_conv_simt_wgrad<bf16>(g, (const bf16*)in0, (const bf16*)in1, (float*)out, st);
   }
+  if (precision == PREC_TC_SPLIT) {
+    // strict tensor-core mode: fp32 NHWC tensors and fp32 K-major weight matrices in (as for PREC_FP32), fp32 out;
+    // the operands are cut into fp16 hi / lo planes here (the training step's element-wise kernels write that form)
+    g.split = 1; g.fmt_z = 0; g.fmt_g = 0;
+    const long long n_in = (long long)B * Hi * Wi * Ci, n_out = (long long)B * g.Ho * g.Wo * Co;
+    const int KK = k * k;
+    void *s0 = nullptr, *s1 = nullptr, *sw = nullptr;
+    TcConvPlan* plan = nullptr;
+    auto body = [&]() -> int {
+      const long long n0 = (kind == 1) ? n_out : n_in;
+      MN_CUDA(cudaMalloc(&s0, (size_t)n0 * 4));
+      MN_TRY(launch_split_tensor((const float*)in0, s0, n0, 0, st));
+      if (kind == 2) {
+        MN_CUDA(cudaMalloc(&s1, (size_t)n_out * 4));
+        MN_TRY(launch_split_tensor((const float*)in1, s1, n_out, 0, st));
+      } else {
+        MN_CUDA(cudaMalloc(&sw, (size_t)Co * KK * Ci * 8));
+        if (kind == 0) MN_TRY(launch_split_weight_matrix((const float*)wmat, sw, Co, KK, Ci, 0, st));
+        else MN_TRY(launch_split_weight_matrix((const float*)wmat, sw, Ci, KK, Co, 0, st));
+      }
+      MN_TRY(tc_plan_create(&plan, g, kind, (const bf16*)sw));
+      MN_TRY(tc_conv_run(plan, (const bf16*)s0, (const bf16*)s1, nullptr, out, st));
+      MN_CUDA(cudaStreamSynchronize(st));
+      return 0;
+    };
+    const int r = body();
+    if (plan) tc_plan_destroy(plan);
+    cudaFree(s0); cudaFree(s1); cudaFree(sw);
+    return r;
+  }
   MN_CHECK(precision == PREC_BF16_TC, "test_conv: bad precision");
   TcConvPlan* plan = nullptr;
   MN_TRY(tc_plan_create(&plan, g, kind, (const bf16*)wmat));

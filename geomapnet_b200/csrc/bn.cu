@@ -36,9 +36,9 @@ __device__ __forceinline__ void ld8(const float* __restrict__ p, float* o) {
 }
 
 
-template <typename T, int MODE>
+template <typename T, typename TZ, int MODE>
 __global__ void __launch_bounds__(kEwThreads)
-k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __restrict__ y,
+k_channel_sums(const T* __restrict__ a, const TZ* __restrict__ zmask, const T* __restrict__ y,
                const T* __restrict__ yd, long long M, int C, double* __restrict__ accum,
                unsigned int* __restrict__ counter, BnFin f) {
   pdl_prologue();
@@ -65,7 +65,7 @@ k_channel_sums(const T* __restrict__ a, const T* __restrict__ zmask, const T* __
     } else {
       Vec8<T> g, yy; g.load(a + off); yy.load(y + off);
       if (zmask != nullptr) {
-        Vec8<T> z; z.load(zmask + off);
+        Vec8<TZ> z; z.load(zmask + off);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g.v[i] = (z.v[i] > 0.f) ? g.v[i] : 0.f;
       } else if (ymask) {
@@ -132,17 +132,17 @@ static int sums_grid(long long M, int C) {
   return (int)(want < cap ? want : cap);
 }
 
-template <typename T>
-static int launch_sums(int mode, const T* a, const T* zmask, const T* y, const T* yd, long long M, int C,
+template <typename T, typename TZ>
+static int launch_sums(int mode, const T* a, const TZ* zmask, const T* y, const T* yd, long long M, int C,
                        double* accum, unsigned int* counter, const BnFin& f, cudaStream_t st) {
   MN_CHECK(C % 8 == 0 && C >= 8 && (kEwThreads % (C >> 3)) == 0 && C <= 512, "channel_sums: unsupported C=%d", C);
   const int grid = sums_grid(M, C);
   const int rows_par = kEwThreads / (C >> 3);
   const int nacc = (mode == 2) ? 3 : 2;
   const size_t smem = (size_t)rows_par * nacc * C * sizeof(float);
-  if (mode == 0) MN_LAUNCH((k_channel_sums<T, 0>), grid, kEwThreads, smem, st, a, nullptr, nullptr, nullptr, M, C, accum, counter, f);
-  else if (mode == 1) MN_LAUNCH((k_channel_sums<T, 1>), grid, kEwThreads, smem, st, a, zmask, y, nullptr, M, C, accum, counter, f);
-  else MN_LAUNCH((k_channel_sums<T, 2>), grid, kEwThreads, smem, st, a, zmask, y, yd, M, C, accum, counter, f);
+  if (mode == 0) MN_LAUNCH((k_channel_sums<T, TZ, 0>), grid, kEwThreads, smem, st, a, nullptr, nullptr, nullptr, M, C, accum, counter, f);
+  else if (mode == 1) MN_LAUNCH((k_channel_sums<T, TZ, 1>), grid, kEwThreads, smem, st, a, zmask, y, nullptr, M, C, accum, counter, f);
+  else MN_LAUNCH((k_channel_sums<T, TZ, 2>), grid, kEwThreads, smem, st, a, zmask, y, yd, M, C, accum, counter, f);
   MN_LAUNCH_CHECK();
   return 0;
 }
@@ -248,13 +248,13 @@ int launch_bn_stats(const T* y, long long M, int C, const float* gamma, const fl
   BnFin f; memset(&f, 0, sizeof(f));
   f.gamma = gamma; f.beta = beta; f.run_mean = run_mean; f.run_var = run_var; f.mean = mean_out;
   f.invstd = invstd_out; f.scale = scale; f.shift = shift; f.training = 1;
-  return launch_sums<T>(0, y, nullptr, nullptr, nullptr, M, C, accum, counter, f, st);
+  return launch_sums<T, T>(0, y, nullptr, nullptr, nullptr, M, C, accum, counter, f, st);
 }
 template int launch_bn_stats<float>(const float*, long long, int, const float*, const float*, float*, float*, float*, float*, float*, float*, int, double*, unsigned int*, cudaStream_t);
 template int launch_bn_stats<bf16>(const bf16*, long long, int, const float*, const float*, float*, float*, float*, float*, float*, float*, int, double*, unsigned int*, cudaStream_t);
 
-template <typename T>
-int launch_bn_bwd_reduce(const T* dout, const T* zmask, const T* y, const T* yd, long long M, int C,
+template <typename T, typename TZ>
+int launch_bn_bwd_reduce(const T* dout, const TZ* zmask, const T* y, const T* yd, long long M, int C,
                          const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
                          float* coef, const float* gamma2, const float* mean2, const float* invstd2,
                          float* dgamma2, float* dbeta2, float* coef2, double* accum, unsigned int* counter,
@@ -264,19 +264,23 @@ int launch_bn_bwd_reduce(const T* dout, const T* zmask, const T* y, const T* yd,
   f.gamma = gamma; f.mean = const_cast<float*>(mean); f.invstd = const_cast<float*>(invstd);
   f.dgamma = dgamma; f.dbeta = dbeta; f.coef = coef;
   f.gamma2 = gamma2; f.mean2 = mean2; f.invstd2 = invstd2; f.dgamma2 = dgamma2; f.dbeta2 = dbeta2; f.coef2 = coef2;
-  return launch_sums<T>(yd != nullptr ? 2 : 1, dout, zmask, y, yd, M, C, accum, counter, f, st);
+  return launch_sums<T, TZ>(yd != nullptr ? 2 : 1, dout, zmask, y, yd, M, C, accum, counter, f, st);
 }
-template int launch_bn_bwd_reduce<float>(const float*, const float*, const float*, const float*, long long, int, const float*, const float*, const float*, float*, float*, float*, const float*, const float*, const float*, float*, float*, float*, double*, unsigned int*, cudaStream_t, const float*, const float*);
-template int launch_bn_bwd_reduce<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, long long, int, const float*, const float*, const float*, float*, float*, float*, const float*, const float*, const float*, float*, float*, float*, double*, unsigned int*, cudaStream_t, const float*, const float*);
+#define MN_INST_BWD_REDUCE(TA, TZ) template int launch_bn_bwd_reduce<TA, TZ>(const TA*, const TZ*, const TA*, const TA*, long long, int, const float*, const float*, const float*, float*, float*, float*, const float*, const float*, const float*, float*, float*, float*, double*, unsigned int*, cudaStream_t, const float*, const float*);
+MN_INST_BWD_REDUCE(float, float)
+MN_INST_BWD_REDUCE(bf16, bf16)
+MN_INST_BWD_REDUCE(float, hsplit)
 
 // ---------------------------------------------------------------------------
 // forward apply:  z = relu?( scale*y + shift  [+ zres | + scale2*y2 + shift2] )
 // ---------------------------------------------------------------------------
-template <typename T, int RES>  // RES 0 none, 1 identity tensor, 2 second BN (downsample branch)
+// y (and the downsample branch's conv output) are conv outputs (T); the identity residual and the result are
+// forward conv operands (TZ)
+template <typename T, typename TZ, int RES>  // RES 0 none, 1 identity tensor, 2 second BN (downsample branch)
 __global__ void __launch_bounds__(kEwThreads)
 k_bn_apply(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-           const T* __restrict__ res, const float* __restrict__ scale2, const float* __restrict__ shift2,
-           T* __restrict__ z, long long nvec, int C, int relu) {
+           const void* __restrict__ res, const float* __restrict__ scale2, const float* __restrict__ shift2,
+           TZ* __restrict__ z, long long nvec, int C, int relu) {
   pdl_prologue();
   const int cv = C >> 3;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,15 +296,15 @@ k_bn_apply(const T* __restrict__ y, const float* __restrict__ scale, const float
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = v.v[k] * sc[k] + sh[k];
     if (RES == 1) {
-      Vec8<T> r; r.load(res + i * 8);
+      Vec8<TZ> r; r.load(reinterpret_cast<const TZ*>(res) + i * 8);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] += r.v[k];
     } else if (RES == 2) {
-      Vec8<T> r; r.load(res + i * 8);
+      Vec8<T> r; r.load(reinterpret_cast<const T*>(res) + i * 8);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] += r.v[k] * sc2[k] + sh2[k];
     }
-    Vec8<T> w;
+    Vec8<TZ> w;
 #pragma unroll
     for (int k = 0; k < 8; ++k) w.v[k] = relu ? fmaxf(o[k], 0.f) : o[k];
     w.store(z + i * 8);
@@ -318,29 +322,31 @@ static int ew_grid(long long n) {
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
-template <typename T>
-int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_mode, const T* res,
-                    const float* scale2, const float* shift2, T* z, long long M, int C, int relu,
+template <typename T, typename TZ>
+int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_mode, const void* res,
+                    const float* scale2, const float* shift2, TZ* z, long long M, int C, int relu,
                     cudaStream_t st) {
   const long long nvec = M * (C >> 3);
   const int grid = ew_grid(nvec);
-  if (res_mode == 0) MN_LAUNCH((k_bn_apply<T, 0>), grid, kEwThreads, 0, st, y, scale, shift, nullptr, nullptr, nullptr, z, nvec, C, relu);
-  else if (res_mode == 1) MN_LAUNCH((k_bn_apply<T, 1>), grid, kEwThreads, 0, st, y, scale, shift, res, nullptr, nullptr, z, nvec, C, relu);
-  else MN_LAUNCH((k_bn_apply<T, 2>), grid, kEwThreads, 0, st, y, scale, shift, res, scale2, shift2, z, nvec, C, relu);
+  if (res_mode == 0) MN_LAUNCH((k_bn_apply<T, TZ, 0>), grid, kEwThreads, 0, st, y, scale, shift, nullptr, nullptr, nullptr, z, nvec, C, relu);
+  else if (res_mode == 1) MN_LAUNCH((k_bn_apply<T, TZ, 1>), grid, kEwThreads, 0, st, y, scale, shift, res, nullptr, nullptr, z, nvec, C, relu);
+  else MN_LAUNCH((k_bn_apply<T, TZ, 2>), grid, kEwThreads, 0, st, y, scale, shift, res, scale2, shift2, z, nvec, C, relu);
   MN_LAUNCH_CHECK();
   return 0;
 }
-template int launch_bn_apply<float>(const float*, const float*, const float*, int, const float*, const float*, const float*, float*, long long, int, int, cudaStream_t);
-template int launch_bn_apply<bf16>(const bf16*, const float*, const float*, int, const bf16*, const float*, const float*, bf16*, long long, int, int, cudaStream_t);
+#define MN_INST_BN_APPLY(TA, TZ) template int launch_bn_apply<TA, TZ>(const TA*, const float*, const float*, int, const void*, const float*, const float*, TZ*, long long, int, int, cudaStream_t);
+MN_INST_BN_APPLY(float, float)
+MN_INST_BN_APPLY(bf16, bf16)
+MN_INST_BN_APPLY(float, hsplit)
 
 // ---------------------------------------------------------------------------
 // stem: z0 = maxpool3x3s2p1( relu( scale*y0 + shift ) ), argmax position kept
 // (first maximum in window scan order wins, as torch's max_pool2d does)
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename TZ>
 __global__ void __launch_bounds__(kEwThreads)
 k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-            T* __restrict__ z, uint8_t* __restrict__ amax, int B, int H, int W, int Ho, int Wo, int C) {
+            TZ* __restrict__ z, uint8_t* __restrict__ amax, int B, int H, int W, int Ho, int Wo, int C) {
   pdl_prologue();
   const int cv = C >> 3;
   const long long nvec = (long long)B * Ho * Wo * cv;
@@ -372,7 +378,7 @@ k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const floa
         }
       }
     }
-    Vec8<T> o;
+    Vec8<TZ> o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = best[k];
     o.store(z + i * 8);
@@ -383,16 +389,18 @@ k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const floa
   }
 }
 
-template <typename T>
-int launch_stem_pool(const T* y, const float* scale, const float* shift, T* z, uint8_t* amax, int B, int H,
+template <typename T, typename TZ>
+int launch_stem_pool(const T* y, const float* scale, const float* shift, TZ* z, uint8_t* amax, int B, int H,
                      int W, int Ho, int Wo, int C, cudaStream_t st) {
   const long long nvec = (long long)B * Ho * Wo * (C >> 3);
-  MN_LAUNCH(k_stem_pool<T>, ew_grid(nvec), kEwThreads, 0, st, y, scale, shift, z, amax, B, H, W, Ho, Wo, C);
+  MN_LAUNCH((k_stem_pool<T, TZ>), ew_grid(nvec), kEwThreads, 0, st, y, scale, shift, z, amax, B, H, W, Ho, Wo, C);
   MN_LAUNCH_CHECK();
   return 0;
 }
-template int launch_stem_pool<float>(const float*, const float*, const float*, float*, uint8_t*, int, int, int, int, int, int, cudaStream_t);
-template int launch_stem_pool<bf16>(const bf16*, const float*, const float*, bf16*, uint8_t*, int, int, int, int, int, int, cudaStream_t);
+#define MN_INST_STEM_POOL(TA, TZ) template int launch_stem_pool<TA, TZ>(const TA*, const float*, const float*, TZ*, uint8_t*, int, int, int, int, int, int, cudaStream_t);
+MN_INST_STEM_POOL(float, float)
+MN_INST_STEM_POOL(bf16, bf16)
+MN_INST_STEM_POOL(float, hsplit)
 
 // stem backward through max-pool and ReLU:  g0[b,ih,iw,c] = [a0>0] * sum_{windows whose argmax is (ih,iw)} dz
 template <typename T>
@@ -562,12 +570,14 @@ template int launch_stem_pool_bwd<float>(const float*, const uint8_t*, const flo
 template int launch_stem_pool_bwd<bf16>(const bf16*, const uint8_t*, const bf16*, const float*, const float*, bf16*, int, int, int, int, int, int, cudaStream_t, double*);
 
 // backward apply: dy = A*g + B*y + C  [, dyd = Ad*g + Bd*yd + Cd] [, gout = g]
-template <typename T, int DS, int GOUT>
+// dout / y / yd / gout: fp32-math tensors (T); zmask: a forward conv operand (TZ); dy / dyd: backward conv operands (TG)
+template <typename T, typename TZ, typename TG, int DS, int GOUT>
 __global__ void __launch_bounds__(kEwThreads)
-k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T* __restrict__ y,
-               const float* __restrict__ coef, T* __restrict__ dy, const T* __restrict__ yd,
-               const float* __restrict__ coefd, T* __restrict__ dyd, T* __restrict__ gout, long long nvec,
-               int C, const float* __restrict__ mscale, const float* __restrict__ mshift) {
+k_bn_bwd_apply(const T* __restrict__ dout, const TZ* __restrict__ zmask, const T* __restrict__ y,
+               const float* __restrict__ coef, TG* __restrict__ dy, const T* __restrict__ yd,
+               const float* __restrict__ coefd, TG* __restrict__ dyd, T* __restrict__ gout, long long nvec,
+               int C, const float* __restrict__ mscale, const float* __restrict__ mshift,
+               const float* __restrict__ gscale) {
   pdl_prologue();
   const int cv = C >> 3;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -577,24 +587,29 @@ k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T*
   if (ymask) { ld8(mscale + c0, msc); ld8(mshift + c0, msh); }
   ld8(coef + c0, cA); ld8(coef + C + c0, cB); ld8(coef + 2 * C + c0, cC);
   if (DS) { ld8(coefd + c0, dA); ld8(coefd + C + c0, dB); ld8(coefd + 2 * C + c0, dC); }
+  if (gscale != nullptr) {                     // the stored conv operands carry the step's power-of-two scale
+    const float S = __ldg(gscale);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { cA[k] *= S; cB[k] *= S; cC[k] *= S; if (DS) { dA[k] *= S; dB[k] *= S; dC[k] *= S; } }
+  }
 #pragma unroll 4
   for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     Vec8<T> g, yy; g.load(dout + i * 8); yy.load(y + i * 8);
     if (zmask != nullptr) {
-      Vec8<T> z; z.load(zmask + i * 8);
+      Vec8<TZ> z; z.load(zmask + i * 8);
 #pragma unroll
       for (int k = 0; k < 8; ++k) g.v[k] = (z.v[k] > 0.f) ? g.v[k] : 0.f;
     } else if (ymask) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) g.v[k] = (yy.v[k] * msc[k] + msh[k] > 0.f) ? g.v[k] : 0.f;
     }
-    Vec8<T> o;
+    Vec8<TG> o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = cA[k] * g.v[k] + cB[k] * yy.v[k] + cC[k];
     o.store(dy + i * 8);
     if (DS) {
       Vec8<T> y2; y2.load(yd + i * 8);
-      Vec8<T> o2;
+      Vec8<TG> o2;
 #pragma unroll
       for (int k = 0; k < 8; ++k) o2.v[k] = dA[k] * g.v[k] + dB[k] * y2.v[k] + dC[k];
       o2.store(dyd + i * 8);
@@ -603,21 +618,24 @@ k_bn_bwd_apply(const T* __restrict__ dout, const T* __restrict__ zmask, const T*
   }
 }
 
-template <typename T>
-int launch_bn_bwd_apply(const T* dout, const T* zmask, const T* y, const float* coef, T* dy, const T* yd,
-                        const float* coefd, T* dyd, T* gout, long long M, int C, cudaStream_t st,
-                        const float* mscale, const float* mshift) {
+template <typename T, typename TZ, typename TG>
+int launch_bn_bwd_apply(const T* dout, const TZ* zmask, const T* y, const float* coef, TG* dy, const T* yd,
+                        const float* coefd, TG* dyd, T* gout, long long M, int C, cudaStream_t st,
+                        const float* mscale, const float* mshift, const float* gscale) {
   const long long nvec = M * (C >> 3);
   const int grid = ew_grid(nvec);
   const bool ds = (yd != nullptr), go = (gout != nullptr);
-  if (ds && !go) MN_LAUNCH((k_bn_bwd_apply<T, 1, 0>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
-  else if (!ds && go) MN_LAUNCH((k_bn_bwd_apply<T, 0, 1>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
-  else if (!ds && !go) MN_LAUNCH((k_bn_bwd_apply<T, 0, 0>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
-  else MN_LAUNCH((k_bn_bwd_apply<T, 1, 1>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift);
+  if (ds && !go) MN_LAUNCH((k_bn_bwd_apply<T, TZ, TG, 1, 0>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift, gscale);
+  else if (!ds && go) MN_LAUNCH((k_bn_bwd_apply<T, TZ, TG, 0, 1>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift, gscale);
+  else if (!ds && !go) MN_LAUNCH((k_bn_bwd_apply<T, TZ, TG, 0, 0>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift, gscale);
+  else MN_LAUNCH((k_bn_bwd_apply<T, TZ, TG, 1, 1>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift, gscale);
   MN_LAUNCH_CHECK();
   return 0;
 }
-template int launch_bn_bwd_apply<float>(const float*, const float*, const float*, const float*, float*, const float*, const float*, float*, float*, long long, int, cudaStream_t, const float*, const float*);
-template int launch_bn_bwd_apply<bf16>(const bf16*, const bf16*, const bf16*, const float*, bf16*, const bf16*, const float*, bf16*, bf16*, long long, int, cudaStream_t, const float*, const float*);
+#define MN_INST_BWD_APPLY(TA, TZ, TG) template int launch_bn_bwd_apply<TA, TZ, TG>(const TA*, const TZ*, const TA*, const float*, TG*, const TA*, const float*, TG*, TA*, long long, int, cudaStream_t, const float*, const float*, const float*);
+MN_INST_BWD_APPLY(float, float, float)
+MN_INST_BWD_APPLY(bf16, bf16, bf16)
+MN_INST_BWD_APPLY(float, hsplit, hsplit)
+MN_INST_BWD_APPLY(float, hsplit, bsplit)
 
 }  // namespace mapnet

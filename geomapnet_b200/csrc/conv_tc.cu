@@ -121,10 +121,12 @@ struct ConvParams {
   ClassDesc cls[4];
   // K space
   int cblocks, Cs;
-  TapDesc taps[10];
+  TapDesc taps[20];        // strict (split-operand) mode: every filter tap appears twice (hi and lo weight planes)
   // output tensor [Nimg, Hout, Wout, Cout]; pixel (n, jh*os+oa, jw*os+ob)
   int Hout, Wout, Cout, os;
   int debug;     // micro-benchmark only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
+  int fmt_a, fmt_b;        // UMMA operand element formats: 0 = fp16, 1 = bf16
+  int out32;               // strict mode: output (and residual) are fp32 tensors
 };
 
 // work item -> (class, N tile, first M tile of the group): classes are laid out one after the other
@@ -140,17 +142,30 @@ __device__ __forceinline__ TileCoord decode_tile(const int tile, const int per_c
 }
 
 struct WgradChunk { int dh, dw, map, c0, tap; };   // one 64-channel slice of X at one filter tap
+struct WgradTap { int dh, dw, map; };
 
 struct WgradParams {
   int Nimg, Ho, Wo, TW, TH, TN, tiles_w, tiles_h, tiles_n, n_pix_tiles;
-  int n_chunks;            // total X chunks = taps * Ci/64
+  int n_chunks;            // total X chunks = taps * cpt
+  int cpt;                 // 64-element chunks per tap: Ci/64 (strict mode: 2*Ci/64 chunks of the split planes)
   int n_mtiles;            // ceil(n_chunks / 2)
-  int n_ntiles, BN;        // Co tiles of BN columns
+  int n_ntiles, BN;        // Co tiles of BN columns (strict mode: columns of the split planes, 2*Co in all)
   int splits, tiles_per_split;
-  int Ci, Co, KK;          // dW layout [Co][KK][Ci]
+  int Ci, Co, KK;          // dW layout [Co][KK][Ci] (real channels)
   int debug;               // micro-benchmark only: 3 = skip the atomic epilogue
-  WgradChunk chunks[72];
+  int split;               // strict mode: X and dY are split 16-bit planes, the four hi/lo products are summed
+  int fmt_a, fmt_b;        // UMMA operand element formats: 0 = fp16, 1 = bf16
+  const float* oscale;     // device scalar multiplied into the accumulators before the atomics, or null
+  WgradTap taps[16];
 };
+// chunk c = (tap c / cpt, 64-element block c % cpt)
+__device__ __forceinline__ WgradChunk wgrad_chunk(const WgradParams& P, int c) {
+  WgradChunk ch;
+  ch.tap = c / P.cpt;
+  ch.c0 = (c - ch.tap * P.cpt) * 64;
+  ch.dh = P.taps[ch.tap].dh; ch.dw = P.taps[ch.tap].dw; ch.map = P.taps[ch.tap].map;
+  return ch;
+}
 
 // BN statistic accumulators: kStatReplicas x [2][<=512] doubles (same buffer bn.cu uses)
 static const int kStatReplicas = 32;
@@ -215,6 +230,7 @@ enum : int {
   EPI_BWD = 4,      // dgrad: gate + (sum g, sum g*y); gate = mscale*y+mshift > 0 unless EPI_ZMASK
   EPI_ZMASK = 8,    // gate = zmask > 0
   EPI_YD = 16,      // third sum over the downsample-branch BN input
+  EPI_OUT32 = 32,   // strict mode: fp32 output and residual (combines with EPI_RES / EPI_STATS only)
 };
 
 struct EpiRegs { uint4 r[4], y[4], z[4], d[4]; };
@@ -254,7 +270,11 @@ __device__ __forceinline__ void epi_issue_loads(EpiRegs& G, const long long (&ro
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long long off = rowoff[i] + po;
-    if (F & EPI_RES) G.r[i] = *reinterpret_cast<const uint4*>(residual + off);   // may alias `out`: plain load
+    if ((F & EPI_RES) && (F & EPI_OUT32)) {       // fp32 residual: 8 floats, second half in the (otherwise unused) y slot
+      const float* rp = reinterpret_cast<const float*>(residual) + off;
+      G.r[i] = *reinterpret_cast<const uint4*>(rp);
+      G.y[i] = *reinterpret_cast<const uint4*>(rp + 4);
+    } else if (F & EPI_RES) G.r[i] = *reinterpret_cast<const uint4*>(residual + off);   // may alias `out`: plain load
     if (F & EPI_BWD) G.y[i] = __ldg(reinterpret_cast<const uint4*>(E.y + off));
     if (F & EPI_ZMASK) G.z[i] = __ldg(reinterpret_cast<const uint4*>(E.zmask + off));
     if (F & EPI_YD) G.d[i] = __ldg(reinterpret_cast<const uint4*>(E.yd + off));
@@ -294,11 +314,20 @@ __device__ __forceinline__ void epi_chunk(float* __restrict__ scr, const EpiRegs
   float c0[8], c1[8], c2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { c0[k] = 0.f; c1[k] = 0.f; c2[k] = 0.f; }
+  float osc = 1.f;
+  if (F & EPI_OUT32) { if (E.oscale != nullptr) osc = __ldg(E.oscale); }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float f[8] = {lo[i].x, lo[i].y, lo[i].z, lo[i].w, hi[i].x, hi[i].y, hi[i].z, hi[i].w};
     float yv[8];
-    if (F & EPI_RES) {
+    if (F & EPI_OUT32) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] *= osc;
+    }
+    if ((F & EPI_RES) && (F & EPI_OUT32)) {
+      const float4 r0 = *reinterpret_cast<const float4*>(&G.r[i]), r1 = *reinterpret_cast<const float4*>(&G.y[i]);
+      f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+    } else if (F & EPI_RES) {
       float r[8];
       unpack8(G.r[i], r);
 #pragma unroll
@@ -317,14 +346,25 @@ __device__ __forceinline__ void epi_chunk(float* __restrict__ scr, const EpiRegs
       }
     }
     uint4 o;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+    if (F & EPI_OUT32) {
+      if (rstore[i]) {
+        float* op = reinterpret_cast<float*>(out) + rowoff[i] + coff + 8 * p;
+        *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      }
+    } else {
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-    if (rstore[i]) *reinterpret_cast<uint4*>(out + rowoff[i] + coff + 8 * p) = o;
+      for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+      if (rstore[i]) *reinterpret_cast<uint4*>(out + rowoff[i] + coff + 8 * p) = o;
+    }
     if (F & (EPI_STATS | EPI_BWD)) {
       // the values AS STORED; rw = 1 for rows inside the tensor, 0 outside
       float x[8];
-      unpack8(o, x);
+      if (F & EPI_OUT32) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = f[k];
+      } else unpack8(o, x);
 #pragma unroll
       for (int k = 0; k < 8; ++k) x[k] *= rw[i];
       if (F & EPI_BWD) {
@@ -412,13 +452,17 @@ __device__ __forceinline__ void epi_tile_dispatch(const int mode, const uint32_t
     MN_EPI_CASE(EPI_BWD | EPI_ZMASK | EPI_RES)
     MN_EPI_CASE(EPI_BWD | EPI_ZMASK | EPI_YD)
     MN_EPI_CASE(EPI_BWD | EPI_ZMASK | EPI_RES | EPI_YD)
+    MN_EPI_CASE(EPI_OUT32)
+    MN_EPI_CASE(EPI_OUT32 | EPI_RES)
+    MN_EPI_CASE(EPI_OUT32 | EPI_STATS)
     default: __trap();
   }
 #undef MN_EPI_CASE
 }
 
-__device__ __forceinline__ int epi_mode_of(const bf16* residual, const double* stats, const EpiBwd& E) {
+__device__ __forceinline__ int epi_mode_of(const bf16* residual, const double* stats, const EpiBwd& E, const int out32) {
   int m = (residual != nullptr) ? EPI_RES : 0;
+  if (out32) m |= EPI_OUT32;
   if (E.y != nullptr) {
     m |= EPI_BWD;
     if (E.zmask != nullptr) m |= EPI_ZMASK;
@@ -577,7 +621,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t IDESC = make_idesc_fmt(128, BN, 0, 0, (uint32_t)P.fmt_a, (uint32_t)P.fmt_b);
     constexpr uint64_t DESC_BASE = make_smem_desc_base(16, 1024);
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
@@ -618,7 +662,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int half = ew >> 2;               // which of the quarter's chunk subsets (0 when kEpiWarps == 4)
     // per-warp transpose scratch: dynamic shared memory behind the pipeline stages (static is capped at 48 KB)
     float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) + ew * kEpiScratchFloats;
-    const int epi_mode = epi_mode_of(residual, stats, E);
+    const int epi_mode = epi_mode_of(residual, stats, E, P.out32);
     int as = 0; uint32_t aphase = 0;
     // fused BatchNorm statistics (fprop only): lane L keeps the running column sums of column
     // cc*32+L over all rows this warp has stored, flushed with fp64 atomics per N tile
@@ -770,7 +814,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      constexpr uint32_t IDESC = make_idesc_bf16(256, BN, 0, 0);
+      const uint32_t IDESC = make_idesc_fmt(256, BN, 0, 0, (uint32_t)P.fmt_a, (uint32_t)P.fmt_b);
       constexpr uint64_t DESC_BASE = make_smem_desc_base(16, 1024);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
@@ -810,7 +854,7 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const int half = ew >> 2;               // which of the quarter's chunk subsets (0 when kEpiWarps == 4)
     // per-warp transpose scratch: dynamic shared memory behind the pipeline stages (static is capped at 48 KB)
     float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) + ew * kEpiScratchFloats;
-    const int epi_mode = epi_mode_of(residual, stats, E);
+    const int epi_mode = epi_mode_of(residual, stats, E, P.out32);
     int as = 0; uint32_t aphase = 0;
     // running column sums of this warp, [statistic][chunk][lane] (lane <-> column epi_stat_col(lane)); kept in
     // shared memory so that the chunk loop can stay ROLLED: unrolled, the epilogue alone was > 100 KB of
@@ -1025,7 +1069,7 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int half = ew >> 2;               // which of the quarter's chunk subsets (0 when kEpiWarps == 4)
     // per-warp transpose scratch: dynamic shared memory behind the patch / weight rings (static is capped at 48 KB)
     float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + P.scr_off) + ew * kEpiScratchFloats;
-    const int epi_mode = epi_mode_of(residual, stats, E);
+    const int epi_mode = epi_mode_of(residual, stats, E, 0);
     int as = 0; uint32_t aphase = 0;
     // running column sums of this warp, [statistic][chunk][lane] (lane <-> column epi_stat_col(lane)); kept in
     // shared memory so that the chunk loop can stay ROLLED: unrolled, the epilogue alone was > 100 KB of
@@ -1066,6 +1110,44 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------
+// wgrad epilogue: lane = accumulator row (one input channel of chunk `ch`), v = 32 consecutive output columns
+// starting at column col0.  fp32 red.global.add into dW[co][tap][ci].
+// Strict mode: rows and columns index the split planes -- row r of a 64-element chunk is channel
+// (r/16)*8 + r%8 of plane (r/8)%2, columns likewise -- and the four hi/lo products of one (co, ci) pair land in
+// four accumulator cells: the two planes of a column pair (i, i+8) are added in registers, the two planes of a
+// row pair (lane, lane^8) with one shuffle, and the lanes of plane 0 issue a quarter of the atomics.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void wgrad_store(const WgradParams& P, float* __restrict__ dw, const uint32_t (&v)[32],
+                                            const bool valid, const WgradChunk& ch, const int ci_l, const int col0,
+                                            const int lane) {
+  if (!P.split) {
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int co = col0 + i;
+        if (co < P.Co)
+          atomicAdd(dw + ((long long)co * P.KK + ch.tap) * P.Ci + ch.c0 + ci_l, __uint_as_float(v[i]));
+      }
+    }
+    return;
+  }
+  const float osc = (P.oscale != nullptr) ? __ldg(P.oscale) : 1.f;
+  // real input channel of this row: chunk offset c0 (in split elements) -> c0/2 real channels
+  const int ci = (ch.c0 >> 1) + ((ci_l >> 4) << 3) + (ci_l & 7);
+  const bool plane0 = (ci_l & 8) == 0;
+#pragma unroll
+  for (int g = 0; g < 2; ++g)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float s = __uint_as_float(v[16 * g + k]) + __uint_as_float(v[16 * g + 8 + k]);
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      const int co = ((col0 + 16 * g) >> 1) + k;
+      if (valid && plane0 && co < P.Co)
+        atomicAdd(dw + ((long long)co * P.KK + ch.tap) * P.Ci + ci, s * osc);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -1121,8 +1203,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      const WgradChunk ch0 = P.chunks[c_lo];
-      const WgradChunk ch1 = P.chunks[(n_valid_chunks == 2) ? c_lo + 1 : c_lo];
+      const WgradChunk ch0 = wgrad_chunk(P, c_lo);
+      const WgradChunk ch1 = wgrad_chunk(P, (n_valid_chunks == 2) ? c_lo + 1 : c_lo);
       const CUtensorMap* m0 = (ch0.map == 0) ? &mapX0 : (ch0.map == 1) ? &mapX1 : (ch0.map == 2) ? &mapX2 : &mapX3;
       const CUtensorMap* m1 = (ch1.map == 0) ? &mapX0 : (ch1.map == 1) ? &mapX1 : (ch1.map == 2) ? &mapX2 : &mapX3;
       for (int t = t_beg; t < t_end; ++t) {
@@ -1143,7 +1225,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 1, 1);
+    const uint32_t IDESC = make_idesc_fmt(128, BN, 1, 1, (uint32_t)P.fmt_a, (uint32_t)P.fmt_b);
     // MN-major, 128B swizzle: LBO = stride between 64-element MN chunks, SBO = 8-pixel group stride
     constexpr uint64_t DESC_BASE = make_smem_desc_base(CHUNK_BYTES, 1024);
     int stage = 0; uint32_t phase = 0;
@@ -1169,7 +1251,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
     const int m = q * 32 + lane;
     const int j = m >> 6, ci_l = m & 63;
     const bool valid = j < n_valid_chunks;
-    const WgradChunk ch = P.chunks[valid ? c_lo + j : c_lo];
+    const WgradChunk ch = wgrad_chunk(P, valid ? c_lo + j : c_lo);
     mbar_wait(tfull, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -1177,14 +1259,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CU
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
       tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int co = nt * BN + cc * 32 + i;
-          if (co < P.Co)
-            atomicAdd(dw + ((long long)co * P.KK + ch.tap) * P.Ci + ch.c0 + ci_l, __uint_as_float(v[i]));
-        }
-      }
+      wgrad_store(P, dw, v, valid, ch, ci_l, nt * BN + cc * 32, lane);
     }
   }
   tc_fence_before();
@@ -1252,8 +1327,8 @@ k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ C
       int stage = 0; uint32_t phase = 0;
       const int ca = (n_valid >= 1) ? c_lo : 0;
       const int cb2 = (n_valid == 2) ? c_lo + 1 : ca;
-      const WgradChunk ch0 = P.chunks[ca];
-      const WgradChunk ch1 = P.chunks[cb2];
+      const WgradChunk ch0 = wgrad_chunk(P, ca);
+      const WgradChunk ch1 = wgrad_chunk(P, cb2);
       const CUtensorMap* m0 = (ch0.map == 0) ? &mapX0 : (ch0.map == 1) ? &mapX1 : (ch0.map == 2) ? &mapX2 : &mapX3;
       const CUtensorMap* m1 = (ch1.map == 0) ? &mapX0 : (ch1.map == 1) ? &mapX1 : (ch1.map == 2) ? &mapX2 : &mapX3;
       for (int t = t_beg; t < t_end; ++t) {
@@ -1278,7 +1353,7 @@ k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ C
     }
   } else if (warp == 1) {
     if (leader) {
-      constexpr uint32_t IDESC = make_idesc_bf16(256, BN, 1, 1);
+      const uint32_t IDESC = make_idesc_fmt(256, BN, 1, 1, (uint32_t)P.fmt_a, (uint32_t)P.fmt_b);
       constexpr uint64_t DESC_BASE = make_smem_desc_base(CHUNK_BYTES, 1024);
       int stage = 0; uint32_t phase = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
@@ -1304,7 +1379,7 @@ k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ C
     const int m = q * 32 + lane;
     const int j = m >> 6, ci_l = m & 63;
     const bool valid = j < n_valid;
-    const WgradChunk ch = P.chunks[valid ? c_lo + j : 0];
+    const WgradChunk ch = wgrad_chunk(P, valid ? c_lo + j : 0);
     mbar_wait(tfull, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -1312,14 +1387,7 @@ k_tc_wgrad2(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ C
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
       tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int co = nt * BN + cc * 32 + i;
-          if (co < P.Co)
-            atomicAdd(dw + ((long long)co * P.KK + ch.tap) * P.Ci + ch.c0 + ci_l, __uint_as_float(v[i]));
-        }
-      }
+      wgrad_store(P, dw, v, valid, ch, ci_l, nt * BN + cc * 32, lane);
     }
   }
   tc_fence_before();
@@ -1360,6 +1428,7 @@ struct TcConvPlan {
   // cached pointers the maps were encoded for
   const void *c_in0, *c_in1;
   bool smem_attr_set;
+  const float* out_scale;               // strict mode dgrad / wgrad: device scalar applied to the accumulators, or null
 };
 
 static void pick_box(int Wd, int Hd, int pixels, int* TW, int* TH, int* TN) {
@@ -1471,16 +1540,19 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   MN_CHECK(g.in_pix_stride == 0 || (g.stride == 1 && kind != 1), "tc conv: strided input views only for stride-1 fprop / wgrad");
   TcConvPlan* p = new TcConvPlan();
   p->g = g; p->kind = kind; p->wmat = wmat; p->wmat2 = nullptr; p->shortcut_flops_k = 0;
-  p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false;
+  p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false; p->out_scale = nullptr;
   p->CL = pick_cl();
   p->two_cta = false;
   p->halo = false;
   const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
+  // strict mode: the engines see 2*C 16-bit channels per pixel and every filter tap twice (hi / lo weight planes)
+  const int SP = g.split ? 2 : 1;
+  MN_CHECK(!g.split || (KK <= 9 && g.in_pix_stride == 0), "tc conv: strict mode supports dense inputs and up to 9 taps");
   {
     static int halo_mode = -1, halo_bo = -1;
     if (halo_mode < 0) { const char* e = getenv("MAPNET_TC_HALO"); halo_mode = e ? atoi(e) : 1; }
     if (halo_bo < 0) { const char* e = getenv("MAPNET_TC_HALO_BASEOFF"); halo_bo = e ? atoi(e) : 0; }   // measured: swizzle follows absolute smem address bits, base_offset must stay 0
-    if (halo_mode && (kind == 0 || kind == 1) && g.KH == 3 && s == 1 && g.Wi + 2 <= 256) {
+    if (halo_mode && !g.split && (kind == 0 || kind == 1) && g.KH == 3 && s == 1 && g.Wi + 2 <= 256) {
       // fprop: gather x [B,H,W,Ci] -> y [.,Co]; dgrad: gather dy [B,H,W,Co] -> dx [.,Ci] (same spatial dims)
       const int Cs = (kind == 0) ? g.Ci : g.Co, Cn = (kind == 0) ? g.Co : g.Ci;
       HaloParams& H = p->HP; memset(&H, 0, sizeof(H));
@@ -1535,26 +1607,28 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   if (kind == 0) {
     // ---------------- fprop ----------------
     {
-      const TileChoice tc = choose_tiles(g.Co, g.M_out(), KK * (g.Ci / 64));
+      const TileChoice tc = choose_tiles(g.Co, g.M_out(), SP * KK * (SP * g.Ci / 64));
       p->BN = tc.BN; p->two_cta = tc.two_cta;
       if (tc.two_cta) p->CL = 2;
     }
     ConvLaunch L; memset(&L, 0, sizeof(L));
     ConvParams& P = L.P;
     { const char* e = getenv("MAPNET_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
+    P.fmt_a = P.fmt_b = g.split ? g.fmt_z : 1; P.out32 = g.split;
     P.Nimg = g.B;
     P.n_classes = 1;
-    P.cls[0].Hs = g.Ho; P.cls[0].Ws = g.Wo; P.cls[0].oa = 0; P.cls[0].ob = 0; P.cls[0].tap0 = 0; P.cls[0].num_taps = KK;
+    P.cls[0].Hs = g.Ho; P.cls[0].Ws = g.Wo; P.cls[0].oa = 0; P.cls[0].ob = 0; P.cls[0].tap0 = 0; P.cls[0].num_taps = SP * KK;
     pick_box(g.Wo, g.Ho, 128, &P.TW, &P.TH, &P.TN);
     P.tiles_w = cdiv(g.Wo, P.TW); P.tiles_h = cdiv(g.Ho, P.TH); P.tiles_n = cdiv(g.B, P.TN);
     P.n_tiles_m = P.tiles_w * P.tiles_h * P.tiles_n; P.n_tiles_n = g.Co / p->BN;
-    P.cblocks = g.Ci / 64; P.Cs = g.Ci;
+    P.cblocks = SP * g.Ci / 64; P.Cs = SP * g.Ci;
     P.Hout = g.Ho; P.Wout = g.Wo; P.Cout = g.Co; P.os = 1;
     L.n_maps = 0;
+    for (int pass = 0; pass < SP; ++pass)
     for (int kh = 0; kh < g.KH; ++kh)
       for (int kw = 0; kw < g.KW; ++kw) {
-        TapDesc& t = P.taps[kh * g.KW + kw];
-        t.kidx = kh * g.KW + kw;
+        TapDesc& t = P.taps[pass * KK + kh * g.KW + kw];
+        t.kidx = pass * KK + kh * g.KW + kw;
         if (s == 1) { t.dh = kh - pad; t.dw = kw - pad; t.map = 0; L.pa[0] = L.pb[0] = 0; if (L.n_maps < 1) L.n_maps = 1; }
         else {
           const int a = posmod(kh - pad, 2), b = posmod(kw - pad, 2);
@@ -1570,7 +1644,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     // ---------------- dgrad: gather over dY [B,Ho,Wo,Co], output dX [B,Hi,Wi,Ci] ----------------
     // A stride-s dgrad is s*s parity classes of output pixels (a, b) = (ih % s, iw % s), each reached by its own
     // subset of the filter taps (3x3/s2: 4, 2, 2 and 1 taps; 1x1/s2: 1, 0, 0, 0).
-    struct ClassTaps { int a, b, n; TapDesc t[9]; };
+    struct ClassTaps { int a, b, n; TapDesc t[18]; };
     ClassTaps ct[4]; int ncls = 0;
     for (int a = 0; a < s; ++a)
       for (int b = 0; b < s; ++b) {
@@ -1584,6 +1658,10 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
             TapDesc& t = c.t[c.n++];
             t.dh = floordiv(eh, s); t.dw = floordiv(ew, s); t.map = 0; t.kidx = kh * g.KW + kw;
           }
+        if (g.split) {                      // the same taps again against the lo weight planes
+          const int n1 = c.n;
+          for (int k = 0; k < n1; ++k) { c.t[c.n] = c.t[k]; c.t[c.n].kidx += KK; ++c.n; }
+        }
       }
     int merge = 1;       // read per plan (not cached): the A/B parity test flips it between trunks
     { const char* e = getenv("MAPNET_TC_DGRAD_MERGE"); if (e) merge = atoi(e); }
@@ -1597,19 +1675,20 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
       ConvLaunch L; memset(&L, 0, sizeof(L));
       ConvParams& P = L.P;
       { const char* e = getenv("MAPNET_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
+      P.fmt_a = P.fmt_b = g.split ? g.fmt_g : 1; P.out32 = g.split;
       P.Nimg = g.B;
       pick_box(Ws0, Hs0, 128, &P.TW, &P.TH, &P.TN);
       P.tiles_w = cdiv(Ws0, P.TW); P.tiles_h = cdiv(Hs0, P.TH); P.tiles_n = cdiv(g.B, P.TN);
       P.n_tiles_m = P.tiles_w * P.tiles_h * P.tiles_n;
       int kbs[4];
-      for (int i = 0; i < ncls; ++i) kbs[i] = ct[i].n * (g.Co / 64);
+      for (int i = 0; i < ncls; ++i) kbs[i] = ct[i].n * (SP * g.Co / 64);
       {
         const TileChoice tc = choose_tiles_classes(g.Ci, P.n_tiles_m, ncls, kbs);
         p->BN = tc.BN; p->two_cta = tc.two_cta;
         if (tc.two_cta) p->CL = 2;
       }
       P.n_tiles_n = g.Ci / p->BN;
-      P.cblocks = g.Co / 64; P.Cs = g.Co;
+      P.cblocks = SP * g.Co / 64; P.Cs = SP * g.Co;
       P.Hout = g.Hi; P.Wout = g.Wi; P.Cout = g.Ci; P.os = s;
       P.n_classes = ncls;
       int nt = 0;
@@ -1624,13 +1703,14 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     } else {
       {
         // one launch per class: size the tiles for one class
-        const TileChoice tc = choose_tiles(g.Ci, g.M_in() / (s * s), ((KK + s * s - 1) / (s * s)) * (g.Co / 64));
+        const TileChoice tc = choose_tiles(g.Ci, g.M_in() / (s * s), SP * ((KK + s * s - 1) / (s * s)) * (SP * g.Co / 64));
         p->BN = tc.BN; p->two_cta = tc.two_cta;
         if (tc.two_cta) p->CL = 2;
       }
       for (int i = 0; i < ncls; ++i) {
         ConvLaunch L; memset(&L, 0, sizeof(L));
         ConvParams& P = L.P;
+        P.fmt_a = P.fmt_b = g.split ? g.fmt_g : 1; P.out32 = g.split;
         P.Nimg = g.B;
         P.n_classes = 1;
         ClassDesc& c = P.cls[0];
@@ -1640,7 +1720,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
         pick_box(c.Ws, c.Hs, 128, &P.TW, &P.TH, &P.TN);
         P.tiles_w = cdiv(c.Ws, P.TW); P.tiles_h = cdiv(c.Hs, P.TH); P.tiles_n = cdiv(g.B, P.TN);
         P.n_tiles_m = P.tiles_w * P.tiles_h * P.tiles_n; P.n_tiles_n = g.Ci / p->BN;
-        P.cblocks = g.Co / 64; P.Cs = g.Co;
+        P.cblocks = SP * g.Co / 64; P.Cs = SP * g.Co;
         P.Hout = g.Hi; P.Wout = g.Wi; P.Cout = g.Ci; P.os = s;
         L.n_maps = 1; L.pa[0] = L.pb[0] = 0;
         p->launches.push_back(L);
@@ -1650,35 +1730,35 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
     // ---------------- wgrad ----------------
     WgradParams& P = p->WP; memset(&P, 0, sizeof(P));
     { const char* e = getenv("MAPNET_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
-    p->BN = (g.Co % 256 == 0) ? 256 : ((g.Co % 128 == 0) ? 128 : 64);
+    const int CoS = SP * g.Co, CiS = SP * g.Ci;      // GEMM N / M extents in 16-bit operand elements
+    p->BN = (CoS % 256 == 0) ? 256 : ((CoS % 128 == 0) ? 128 : 64);
     MN_CHECK(p->BN == 64 || p->BN == 128 || p->BN == 256, "tc wgrad: Co=%d unsupported", g.Co);
+    P.split = g.split; P.fmt_a = g.split ? g.fmt_z : 1; P.fmt_b = g.split ? g.fmt_g : 1;
     P.BN = p->BN; P.Nimg = g.B; P.Ho = g.Ho; P.Wo = g.Wo; P.Ci = g.Ci; P.Co = g.Co; P.KK = KK;
     pick_box(g.Wo, g.Ho, 64, &P.TW, &P.TH, &P.TN);
     P.tiles_w = cdiv(g.Wo, P.TW); P.tiles_h = cdiv(g.Ho, P.TH); P.tiles_n = cdiv(g.B, P.TN);
     P.n_pix_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
-    P.n_chunks = KK * (g.Ci / 64);
-    MN_CHECK(P.n_chunks <= 72, "tc wgrad: too many chunks");
-    p->two_cta = (use_2cta() != 0) && (g.Co % 128 == 0);
-    if (p->two_cta) p->BN = (g.Co % 256 == 0) ? 256 : 128;
+    P.cpt = CiS / 64;
+    P.n_chunks = KK * P.cpt;
+    MN_CHECK(KK <= 16, "tc wgrad: too many filter taps");
+    p->two_cta = (use_2cta() != 0) && (CoS % 128 == 0);
+    if (p->two_cta) p->BN = (CoS % 256 == 0) ? 256 : 128;
     P.BN = p->BN;
-    P.n_mtiles = cdiv(P.n_chunks, p->two_cta ? 4 : 2); P.n_ntiles = g.Co / p->BN;
+    P.n_mtiles = cdiv(P.n_chunks, p->two_cta ? 4 : 2); P.n_ntiles = CoS / p->BN;
     p->w_nmaps = 0;
-    int ci = 0;
     for (int kh = 0; kh < g.KH; ++kh)
-      for (int kw = 0; kw < g.KW; ++kw)
-        for (int cb = 0; cb < g.Ci / 64; ++cb) {
-          WgradChunk& c = P.chunks[ci++];
-          c.tap = kh * g.KW + kw; c.c0 = cb * 64;
-          if (s == 1) { c.dh = kh - pad; c.dw = kw - pad; c.map = 0; p->wpa[0] = p->wpb[0] = 0; if (p->w_nmaps < 1) p->w_nmaps = 1; }
-          else {
-            const int a = posmod(kh - pad, 2), b = posmod(kw - pad, 2);
-            c.dh = floordiv(kh - pad, 2); c.dw = floordiv(kw - pad, 2);
-            int mi = -1;
-            for (int i = 0; i < p->w_nmaps; ++i) if (p->wpa[i] == a && p->wpb[i] == b) mi = i;
-            if (mi < 0) { mi = p->w_nmaps++; p->wpa[mi] = a; p->wpb[mi] = b; }
-            c.map = mi;
-          }
+      for (int kw = 0; kw < g.KW; ++kw) {
+        WgradTap& c = P.taps[kh * g.KW + kw];
+        if (s == 1) { c.dh = kh - pad; c.dw = kw - pad; c.map = 0; p->wpa[0] = p->wpb[0] = 0; if (p->w_nmaps < 1) p->w_nmaps = 1; }
+        else {
+          const int a = posmod(kh - pad, 2), b = posmod(kw - pad, 2);
+          c.dh = floordiv(kh - pad, 2); c.dw = floordiv(kw - pad, 2);
+          int mi = -1;
+          for (int i = 0; i < p->w_nmaps; ++i) if (p->wpa[i] == a && p->wpb[i] == b) mi = i;
+          if (mi < 0) { mi = p->w_nmaps++; p->wpa[mi] = a; p->wpb[mi] = b; }
+          c.map = mi;
         }
+      }
     const int units = P.n_mtiles * P.n_ntiles;
     int splits = (p->two_cta ? 74 * 2 : 148 * 2) / units; if (splits < 1) splits = 1;
     if (splits > P.n_pix_tiles) splits = P.n_pix_tiles;
@@ -1690,6 +1770,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
 }
 
 void tc_plan_destroy(TcConvPlan* p) { delete p; }
+void tc_plan_set_out_scale(TcConvPlan* p, const float* inv_scale) { if (p != nullptr) p->out_scale = inv_scale; }
 
 // Fold the dgrad of the block's 1x1 / stride-2 downsample conv into the (merged) dgrad of its 3x3 / stride-2 conv1:
 // both produce d(block input), the shortcut only reaches the pixel class (0, 0), where it is one more filter tap
@@ -1697,8 +1778,8 @@ void tc_plan_destroy(TcConvPlan* p) { delete p; }
 // matrix wmat2 = [Ci][Co].  Replaces 4 launches, a zero-filled full-size tensor and its re-read as a residual.
 int tc_plan_add_shortcut(TcConvPlan* p, const bf16* wmat2) {
   MN_CHECK(p != nullptr && wmat2 != nullptr, "tc_plan_add_shortcut: null argument");
-  MN_CHECK(p->kind == 1 && !p->halo && p->g.stride == 2 && p->g.KH == 3 && p->launches.size() == 1,
-           "tc_plan_add_shortcut: needs a merged 3x3 stride-2 dgrad plan");
+  MN_CHECK(p->kind == 1 && !p->halo && !p->g.split && p->g.stride == 2 && p->g.KH == 3 && p->launches.size() == 1,
+           "tc_plan_add_shortcut: needs a merged 3x3 stride-2 dgrad plan (bf16 mode)");
   ConvParams& P = p->launches[0].P;
   ClassDesc& c = P.cls[P.n_classes - 1];
   MN_CHECK(c.oa == 0 && c.ob == 0 && c.tap0 + c.num_taps == 9 && p->wmat2 == nullptr,
@@ -1746,8 +1827,10 @@ int tc_plan_describe(const TcConvPlan* p, char* buf, int cap) {
         P.splits, P.tiles_per_split, P.Ci, P.Co, P.KK);
     for (int i = 0; i < p->w_nmaps; ++i) put("%s[%d,%d]", i ? "," : "", p->wpa[i], p->wpb[i]);
     put("],\"chunks\":[");
-    for (int i = 0; i < P.n_chunks; ++i)
-      put("%s[%d,%d,%d,%d,%d]", i ? "," : "", P.chunks[i].dh, P.chunks[i].dw, P.chunks[i].map, P.chunks[i].c0, P.chunks[i].tap);
+    for (int i = 0; i < P.n_chunks; ++i) {
+      const int tap = i / P.cpt, c0 = (i - tap * P.cpt) * 64;
+      put("%s[%d,%d,%d,%d,%d]", i ? "," : "", P.taps[tap].dh, P.taps[tap].dw, P.taps[tap].map, c0, tap);
+    }
     put("]}");
   } else {
     put(",\"launches\":[");
@@ -1814,7 +1897,10 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
   } else {
     MN_CHECK(stats == nullptr || residual == nullptr, "tc_conv_run: fprop statistics with a fused residual are not built");
   }
+  MN_CHECK(!p->g.split || bwd == nullptr, "tc_conv_run: the fused BatchNorm-backward epilogue is a bf16-mode feature");
+  E.oscale = p->out_scale;
   const ConvGeom& g = p->g;
+  const int SP = g.split ? 2 : 1;
   int nsm = 148;
   if (p->halo) {
     HaloParams& H = p->HP;
@@ -1844,11 +1930,11 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       for (auto& L : p->launches) {
         if (p->kind == 0) {
           for (int i = 0; i < L.n_maps; ++i)
-            MN_TRY(encode_view(&L.mapA[i], in0, g.B, g.Hi, g.Wi, g.Ci, g.stride, L.pa[i], L.pb[i], L.P.TW, L.P.TH, L.P.TN, &g));
-          MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Ci, g.Co, p->BN / p->CL));
+            MN_TRY(encode_view(&L.mapA[i], in0, g.B, g.Hi, g.Wi, SP * g.Ci, g.stride, L.pa[i], L.pb[i], L.P.TW, L.P.TH, L.P.TN, &g));
+          MN_TRY(encode_w_map(&L.mapB, p->wmat, SP * g.KH * g.KW * SP * g.Ci, g.Co, p->BN / p->CL));
         } else {
-          MN_TRY(encode_view(&L.mapA[0], in0, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, L.P.TW, L.P.TH, L.P.TN));
-          MN_TRY(encode_w_map(&L.mapB, p->wmat, g.KH * g.KW * g.Co, g.Ci, p->BN / p->CL));
+          MN_TRY(encode_view(&L.mapA[0], in0, g.B, g.Ho, g.Wo, SP * g.Co, 1, 0, 0, L.P.TW, L.P.TH, L.P.TN));
+          MN_TRY(encode_w_map(&L.mapB, p->wmat, SP * g.KH * g.KW * SP * g.Co, g.Ci, p->BN / p->CL));
           if (p->wmat2 != nullptr) {
             MN_TRY(encode_view(&L.mapA[1], in1, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, L.P.TW, L.P.TH, L.P.TN));
             MN_TRY(encode_w_map(&L.mapB2, p->wmat2, g.Co, g.Ci, p->BN / p->CL));
@@ -1900,11 +1986,12 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
   }
   // wgrad: in0 = x [B,Hi,Wi,Ci], in1 = dy [B,Ho,Wo,Co]
   WgradParams& P = p->WP;
+  P.oscale = p->out_scale;
   if (p->c_in0 != in0 || p->c_in1 != in1) {
     for (int i = 0; i < p->w_nmaps; ++i)
-      MN_TRY(encode_view(&p->mapX[i], in0, g.B, g.Hi, g.Wi, g.Ci, g.stride, p->wpa[i], p->wpb[i], P.TW, P.TH, P.TN, &g));
+      MN_TRY(encode_view(&p->mapX[i], in0, g.B, g.Hi, g.Wi, SP * g.Ci, g.stride, p->wpa[i], p->wpb[i], P.TW, P.TH, P.TN, &g));
     for (int i = p->w_nmaps; i < 4; ++i) p->mapX[i] = p->mapX[0];
-    MN_TRY(encode_view(&p->mapDY, in1, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, P.TW, P.TH, P.TN));
+    MN_TRY(encode_view(&p->mapDY, in1, g.B, g.Ho, g.Wo, SP * g.Co, 1, 0, 0, P.TW, P.TH, P.TN));
     p->c_in0 = in0; p->c_in1 = in1;
   }
   static int occ = -1;

@@ -37,6 +37,7 @@ int launch_gap(const T* z, float* feat, int B, int HW, int C, cudaStream_t st) {
 }
 template int launch_gap<float>(const float*, float*, int, int, int, cudaStream_t);
 template int launch_gap<bf16>(const bf16*, float*, int, int, int, cudaStream_t);
+template int launch_gap<hsplit>(const hsplit*, float*, int, int, int, cudaStream_t);
 
 template <typename T>
 __global__ void k_gap_bwd(const float* __restrict__ dfeat, T* __restrict__ dz, int B, int HW, int C) {
@@ -64,6 +65,39 @@ int launch_gap_bwd(const float* dfeat, T* dz, int B, int HW, int C, cudaStream_t
 }
 template int launch_gap_bwd<float>(const float*, float*, int, int, int, cudaStream_t);
 template int launch_gap_bwd<bf16>(const float*, bf16*, int, int, int, cudaStream_t);
+
+// ---- strict mode: this step's power-of-two gradient scale -------------------------------------
+// The backward conv operands are fp16 hi/lo planes (abs. error max(2^-22 |x|, 2^-25)): S = 2^(8 - ceil(log2 max|d pred|))
+// puts max|d pred| at 2^8.  Measured on the CPU oracle (tools/experiments/grad_ranges.py): the gradient tensors of all
+// 36 convs have max|.| within 0.2x .. 1x of max|d pred| scale and rms within 14x of each other, four orders of magnitude
+// inside the window [2^-8 (rms), 65504 (max)] this leaves on either side.
+__global__ void k_grad_scale(const float* __restrict__ g, int n, float* __restrict__ scale2) {
+  pdl_prologue();
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float a = fabsf(g[i]); m = (a > m || a != a) ? a : m; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, m, o); m = (t > m || t != t) ? t : m; }
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = (red[w] > m || red[w] != red[w]) ? red[w] : m;
+    float S = 1.f;
+    if (m > 0.f && m < 3.0e38f) {            // finite and non-zero (NaN fails both comparisons)
+      int e;
+      frexpf(m, &e);                          // m = f * 2^e, f in [0.5, 1)  =>  m <= 2^e
+      int k = 8 - e;
+      k = k > 100 ? 100 : (k < -100 ? -100 : k);
+      S = ldexpf(1.f, k);
+    }
+    scale2[0] = S; scale2[1] = 1.f / S;
+  }
+}
+int launch_grad_scale(const float* g, int n, float* scale2, cudaStream_t st) {
+  MN_LAUNCH(k_grad_scale, 1, 256, 0, st, g, n, scale2);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
 
 // ---- small strided fp32 GEMM:  C[m*ldc+n] = epi( sum_k A[m*sam+k*sak] * B[n*sbn+k*sbk] ) ----
 // EPI 0: + bias[n] (bias may be null)

@@ -11,6 +11,10 @@ struct ConvGeom {
   // (0 = dense).  The stem uses an overlapped view of its space-to-depth image: a "pixel" is 64
   // consecutive elements and consecutive pixels start 16 elements apart (layout.cu, k_stem_s2d).
   long long in_pix_stride = 0, in_row_stride = 0, in_img_stride = 0;
+  // tensor-core path, strict mode: activations / gradients are split 16-bit operand planes (common.cuh: hsplit /
+  // bsplit, 2*C 16-bit "channels" per pixel), the weight matrices hold hi and lo planes as 2*KH*KW taps (layout.cu),
+  // outputs are fp32.  fmt_z / fmt_g: element format of the forward / backward operands (0 = fp16, 1 = bf16).
+  int split = 0, fmt_z = 1, fmt_g = 1;
   __host__ __device__ long long M_out() const { return (long long)B * Ho * Wo; }
   __host__ __device__ long long M_in() const { return (long long)B * Hi * Wi; }
   __host__ __device__ int Kdim() const { return KH * KW * Ci; }
@@ -21,25 +25,27 @@ template <typename T>
 int launch_bn_stats(const T* y, long long M, int C, const float* gamma, const float* beta, float* run_mean,
                     float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift, int training,
                     double* accum, unsigned int* counter, cudaStream_t st);
-template <typename T>
-int launch_bn_bwd_reduce(const T* dout, const T* zmask, const T* y, const T* yd, long long M, int C,
+template <typename T, typename TZ>
+int launch_bn_bwd_reduce(const T* dout, const TZ* zmask, const T* y, const T* yd, long long M, int C,
                          const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
                          float* coef, const float* gamma2, const float* mean2, const float* invstd2,
                          float* dgamma2, float* dbeta2, float* coef2, double* accum, unsigned int* counter,
                          cudaStream_t st, const float* mscale = nullptr, const float* mshift = nullptr);
-template <typename T>
-int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_mode, const T* res,
-                    const float* scale2, const float* shift2, T* z, long long M, int C, int relu, cudaStream_t st);
-template <typename T>
-int launch_stem_pool(const T* y, const float* scale, const float* shift, T* z, uint8_t* amax, int B, int H,
+// res: res_mode 1 -> const TZ* (identity branch), 2 -> const T* (downsample branch conv output)
+template <typename T, typename TZ>
+int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_mode, const void* res,
+                    const float* scale2, const float* shift2, TZ* z, long long M, int C, int relu, cudaStream_t st);
+template <typename T, typename TZ>
+int launch_stem_pool(const T* y, const float* scale, const float* shift, TZ* z, uint8_t* amax, int B, int H,
                      int W, int Ho, int Wo, int C, cudaStream_t st);
 template <typename T>
 int launch_stem_pool_bwd(const T* dz, const uint8_t* amax, const T* y, const float* scale, const float* shift,
                          T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st, double* accum = nullptr);
-template <typename T>
-int launch_bn_bwd_apply(const T* dout, const T* zmask, const T* y, const float* coef, T* dy, const T* yd,
-                        const float* coefd, T* dyd, T* gout, long long M, int C, cudaStream_t st,
-                        const float* mscale = nullptr, const float* mshift = nullptr);
+template <typename T, typename TZ, typename TG>
+int launch_bn_bwd_apply(const T* dout, const TZ* zmask, const T* y, const float* coef, TG* dy, const T* yd,
+                        const float* coefd, TG* dyd, T* gout, long long M, int C, cudaStream_t st,
+                        const float* mscale = nullptr, const float* mshift = nullptr, const float* gscale = nullptr);
+// gscale != nullptr (strict mode): dy / dyd are stored multiplied by the device scalar gscale[0] (a power of two)
 
 // ---- conv_simt.cu: fp32 CUDA-core implicit GEMM (strict-parity path) -----------
 template <typename T>
@@ -59,6 +65,9 @@ void tc_plan_destroy(TcConvPlan* p);
 // incoming gradient as in1 and writes d(input) of BOTH convs
 int tc_plan_add_shortcut(TcConvPlan* p, const bf16* wmat2);
 int tc_plan_launches(const TcConvPlan* p);
+// dgrad / wgrad plans: multiply the accumulators by the device scalar *inv_scale before they are added to the residual /
+// the wgrad buffer (strict mode: the gradient operand planes carry a per-step power-of-two scale)
+void tc_plan_set_out_scale(TcConvPlan* p, const float* inv_scale);
 int tc_plan_describe(const TcConvPlan* p, char* buf, int cap);      // JSON, host-only (CPU tests of the plan arithmetic)
 // fprop: in0 = x, out = y (bf16);  dgrad: in0 = dy [, in1 = the folded shortcut's dy], out = dx (bf16);
 // wgrad: in0 = x, in1 = dy, out = fp32 dW (accumulated)
@@ -73,6 +82,7 @@ struct EpiBwd {
   const bf16* yd;       // downsample-branch BN input (third sum), or null
   const float* mscale;  // gate recomputed from y when zmask is null
   const float* mshift;
+  const float* oscale;  // strict mode (fp32 output): device scalar multiplied into the accumulators, or null (set by the plan)
 };
 // fin != nullptr (with stats): the last CTA to flush its sums also finalizes them (bn_fin.cuh) -- forward:
 // mean / invstd / scale / shift / running statistics; backward: d gamma, d beta, dy coefficients
@@ -103,6 +113,11 @@ struct WeightDesc {   // one conv's weight in the flat parameter buffer and in t
 template <typename TW>
 int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* params, TW* w_krsc, TW* w_dg,
                         int max_elems, int round_bf16, cudaStream_t st);
+// strict tensor-core mode: hi / lo operand planes of the weights (layout.cu); fmt 0 = fp16, 1 = bf16
+int launch_pack_weights_split(const WeightDesc* d_descs, int nconv, const float* params, float* w_krsc_f32, float* w_dg_f32,
+                              void* w_krsc2, void* w_dg2, int max_elems, int fmt_f, int fmt_g, cudaStream_t st);
+int launch_split_tensor(const float* in, void* out, long long n, int fmt, cudaStream_t st);
+int launch_split_weight_matrix(const float* w, void* out, long long rows, int KK, int C, int fmt, cudaStream_t st);
 int launch_unpack_wgrads(const WeightDesc* d_descs, int nconv, const float* dw_krsc, float* grads,
                          int max_elems, cudaStream_t st);
 // space-to-depth image of the stem input: S[b][bh][bw][16] bf16, channel (pr*2+pc)*3+c of block (bh,bw)
@@ -124,6 +139,8 @@ int launch_small_gemm(int epi, const float* A, long long sam, long long sak, con
                       const float* mask, cudaStream_t st);
 int launch_colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
 int launch_dpred_filter(const float* in, float* out, int n, int filter, cudaStream_t st);
+// scale[0] = S = 2^(8 - ceil(log2 max|g|)) (1 when max|g| is 0 or not finite), scale[1] = 1/S
+int launch_grad_scale(const float* g, int n, float* scale2, cudaStream_t st);
 int launch_dropout_mask(float* mask, long long n, float p, unsigned long long seed, unsigned long long offset,
                         unsigned long long* ctr_dev, unsigned long long ctr_stride, cudaStream_t st);
 int launch_head_dh(const float* dpred, const float* wx, const float* wq, const float* mask, const float* fcpre,

@@ -106,6 +106,128 @@ int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* param
 template int launch_pack_weights<float>(const WeightDesc*, int, const float*, float*, float*, int, int, cudaStream_t);
 template int launch_pack_weights<bf16>(const WeightDesc*, int, const float*, bf16*, bf16*, int, int, cudaStream_t);
 
+// ---------------------------------------------------------------------------------
+// Strict tensor-core mode (split 16-bit operand planes, common.cuh): weights as hi + lo planes in the
+// activations' K order.  A conv with KK filter taps becomes 2*KK "taps" of 2*Ci 16-bit channels:
+//   tap  t        holds hi(w) in BOTH plane slots of every 8-channel group,
+//   tap  KK + t   holds lo(w) in both,
+// so an activation row [xh xl] (the same 8-interleaved K order) against the two taps gives
+// xh*wh + xl*wh + xh*wl + xl*wl = (xh + xl) * (wh + wl): every hi/lo cross product, fp32-accumulated in TMEM.
+//   w_krsc2[co][2*KK][2*Ci]   (fprop; element format fmt_f: 0 fp16, 1 bf16)
+//   w_dg2  [ci][2*KK][2*Co]   (dgrad; element format fmt_g)
+// The stem's patch-matrix row (im2col_k, or 256 for the space-to-depth stem) is treated as ONE tap of that many channels.
+// Element offsets into the packed buffers are 4 x the bf16 ones (WeightDesc::k_off * 4).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void split16(float v, int fmt, uint16_t& hi, uint16_t& lo) {
+  if (fmt == 0) {
+    __half h, l; split_f16(v, h, l);
+    hi = __half_as_ushort(h); lo = __half_as_ushort(l);
+  } else {
+    bf16 h, l; split_bf16(v, h, l);
+    hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
+  }
+}
+// position of (channel c, plane p) inside a pixel's 2*C split channels
+__device__ __forceinline__ int split_k(int c, int p) { return ((c >> 3) << 4) + (p << 3) + (c & 7); }
+
+// input: the fp32 K-major matrices launch_pack_weights<float> produces ([rows][KK][C]; rows = Co, C = Ci for
+// fprop / wgrad, rows = Ci, C = Co for dgrad); one thread converts 8 channels: coalesced 32-byte loads and stores
+__global__ void __launch_bounds__(256)
+k_split_weight_rows(const WeightDesc* __restrict__ descs, const float* __restrict__ w_krsc, const float* __restrict__ w_dg,
+                    uint16_t* __restrict__ w_krsc2, uint16_t* __restrict__ w_dg2, int fmt_f, int fmt_g) {
+  pdl_prologue();
+  const WeightDesc d = descs[blockIdx.y];
+  const bool dg = blockIdx.z != 0;
+  if (dg && (d.im2col_k > 0 || w_dg2 == nullptr)) return;          // the stem has no dgrad
+  const int KK = (d.im2col_k > 0) ? 1 : d.KH * d.KW;
+  const int C = (d.im2col_k > 0) ? d.im2col_k : (dg ? d.Co : d.Ci);
+  const int rows = dg ? d.Ci : d.Co;
+  const float* src = (dg ? w_dg : w_krsc) + d.k_off;
+  uint16_t* dst = (dg ? w_dg2 : w_krsc2) + 4 * d.k_off;
+  const int fmt = dg ? fmt_g : fmt_f;
+  const int cv = C >> 3;
+  const long long nvec = (long long)rows * KK * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const long long rt = i / cv;
+    const int t = (int)(rt % KK);
+    const long long r = rt / KK;
+    Vec8<float> v; v.load(src + i * 8);
+    uint4 H, L;
+    uint16_t* h = reinterpret_cast<uint16_t*>(&H);
+    uint16_t* l = reinterpret_cast<uint16_t*>(&L);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) split16(v.v[k], fmt, h[k], l[k]);
+    uint4* o0 = reinterpret_cast<uint4*>(dst + ((r * 2 * KK + t) * 2 * C + c8 * 16));
+    uint4* o1 = reinterpret_cast<uint4*>(dst + ((r * 2 * KK + KK + t) * 2 * C + c8 * 16));
+    o0[0] = H; o0[1] = H; o1[0] = L; o1[1] = L;
+  }
+}
+
+// w_krsc_f32 / w_dg_f32: scratch for the fp32 K-major matrices (wk_total floats each)
+int launch_pack_weights_split(const WeightDesc* d_descs, int nconv, const float* params, float* w_krsc_f32, float* w_dg_f32,
+                              void* w_krsc2, void* w_dg2, int max_elems, int fmt_f, int fmt_g, cudaStream_t st) {
+  MN_TRY(launch_pack_weights<float>(d_descs, nconv, params, w_krsc_f32, w_dg2 != nullptr ? w_dg_f32 : nullptr, max_elems, 0, st));
+  dim3 grid(64, nconv, w_dg2 != nullptr ? 2 : 1);
+  MN_LAUNCH(k_split_weight_rows, grid, 256, 0, st, d_descs, (const float*)w_krsc_f32, (const float*)w_dg_f32,
+            (uint16_t*)w_krsc2, (uint16_t*)w_dg2, fmt_f, fmt_g);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
+// one fp32 K-major matrix [rows][KK][C] -> [rows][2*KK][2*C] hi / lo planes (test entry points)
+__global__ void __launch_bounds__(256)
+k_split_weight_matrix(const float* __restrict__ src, uint16_t* __restrict__ dst, long long rows, int KK, int C, int fmt) {
+  pdl_prologue();
+  const int cv = C >> 3;
+  const long long nvec = rows * KK * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const long long rt = i / cv;
+    const int t = (int)(rt % KK);
+    const long long r = rt / KK;
+    Vec8<float> v; v.load(src + i * 8);
+    uint4 H, L;
+    uint16_t* h = reinterpret_cast<uint16_t*>(&H);
+    uint16_t* l = reinterpret_cast<uint16_t*>(&L);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) split16(v.v[k], fmt, h[k], l[k]);
+    uint4* o0 = reinterpret_cast<uint4*>(dst + ((r * 2 * KK + t) * 2 * C + c8 * 16));
+    uint4* o1 = reinterpret_cast<uint4*>(dst + ((r * 2 * KK + KK + t) * 2 * C + c8 * 16));
+    o0[0] = H; o0[1] = H; o1[0] = L; o1[1] = L;
+  }
+}
+int launch_split_weight_matrix(const float* w, void* out, long long rows, int KK, int C, int fmt, cudaStream_t st) {
+  MN_CHECK(C % 8 == 0, "split_weight_matrix: C must be a multiple of 8");
+  MN_LAUNCH(k_split_weight_matrix, 256, 256, 0, st, w, (uint16_t*)out, rows, KK, C, fmt);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
+// fp32 tensor -> split operand planes (test entry points; the training step's element-wise kernels write the
+// split form directly)
+template <typename TS>
+__global__ void __launch_bounds__(256) k_split_tensor(const float* __restrict__ in, TS* __restrict__ out, long long nvec) {
+  pdl_prologue();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    Vec8<float> v; v.load(in + i * 8);
+    Vec8<TS> o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = v.v[k];
+    o.store(out + i * 8);
+  }
+}
+int launch_split_tensor(const float* in, void* out, long long n, int fmt, cudaStream_t st) {
+  MN_CHECK(n % 8 == 0, "split_tensor: element count must be a multiple of 8");
+  const long long nvec = n / 8;
+  long long grid = (nvec + 255) / 256; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
+  if (fmt == 0) MN_LAUNCH(k_split_tensor<hsplit>, (int)grid, 256, 0, st, in, (hsplit*)out, nvec);
+  else MN_LAUNCH(k_split_tensor<bsplit>, (int)grid, 256, 0, st, in, (bsplit*)out, nvec);
+  MN_LAUNCH_CHECK();
+  return 0;
+}
+
+
 __global__ void __launch_bounds__(256)
 k_unpack_wgrads(const WeightDesc* __restrict__ descs, const float* __restrict__ dw, float* __restrict__ grads) {
   pdl_prologue();
@@ -201,6 +323,7 @@ int launch_stem_im2col(const float* x_nchw, T* A, int B, int H, int W, int Ho, i
 }
 template int launch_stem_im2col<float>(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 template int launch_stem_im2col<bf16>(const float*, bf16*, int, int, int, int, int, int, cudaStream_t);
+template int launch_stem_im2col<hsplit>(const float*, hsplit*, int, int, int, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------------
 // stem, tensor-core path: space-to-depth instead of a materialised im2col matrix.

@@ -10,6 +10,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace mapnet {
 
 // ---- error string ------------------------------------------------------------
@@ -139,7 +141,11 @@ void Net::build_table() {
 int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   max_B = max_B_; H = H_; W = W_; feat_dim = feat_dim_; precision = precision_;
   MN_CHECK(max_B >= 0 && H >= 32 && W >= 32, "create: need max_B>=0 and H,W>=32 (got %d,%d,%d)", max_B, H, W);
-  MN_CHECK(precision >= 0 && precision <= 2, "create: bad precision %d", precision);
+  MN_CHECK(precision >= 0 && precision <= 3, "create: bad precision %d", precision);
+  // strict tensor-core mode: forward operands are fp16 hi/lo planes; the backward operands' format is a build-time
+  // experiment switch (MAPNET_SPLIT_GRAD_FMT: 0 = fp16 planes, 1 = bf16 planes -- fp32 exponent range, 16 significant bits)
+  split_fmt_z = 0;
+  { const char* e = getenv("MAPNET_SPLIT_GRAD_FMT"); split_fmt_g = (e ? atoi(e) : 1) ? 1 : 0; }
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0; prof_pool_used = 0;
   { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
@@ -167,9 +173,14 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
     MN_TRY(alloc(&bl.y1, n)); MN_TRY(alloc(&bl.h, n)); MN_TRY(alloc(&bl.y2, n)); MN_TRY(alloc(&bl.out, n));
     if (bl.convd >= 0) MN_TRY(alloc(&bl.yd, n));
   }
-  const size_t wes = (precision == PREC_BF16_TC) ? 2 : 4;
+  const size_t wes = (precision == PREC_BF16_TC) ? 2 : (precision == PREC_TC_SPLIT ? 8 : 4);
   MN_TRY(alloc(&w_krsc, (size_t)wk_total * wes));
   MN_TRY(alloc(&w_dg, (size_t)wk_total * wes));
+  w_krsc_f32 = w_dg_f32 = nullptr;
+  if (precision == PREC_TC_SPLIT) {      // fp32 K-major matrices the hi / lo planes are cut from
+    MN_TRY(alloc((void**)&w_krsc_f32, (size_t)wk_total * 4));
+    MN_TRY(alloc((void**)&w_dg_f32, (size_t)wk_total * 4));
+  }
   MN_TRY(alloc((void**)&dw_krsc, (size_t)wk_total * 4));
   std::vector<WeightDesc> wd;
   for (auto& c : convs) wd.push_back(c.wd);
@@ -196,6 +207,8 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_TRY(alloc((void**)&sq_partials, 1024 * 4));
   MN_TRY(alloc((void**)&sq_out, 16));
   MN_TRY(alloc((void**)&drop_ctr, 16));
+  MN_TRY(alloc((void**)&gscale, 16));
+  { const float one[2] = {1.f, 1.f}; MN_CUDA(cudaMemcpy(gscale, one, sizeof(one), cudaMemcpyHostToDevice)); }
   MN_CUDA(cudaMemset(drop_ctr, 0, 16));
   return 0;
 }
@@ -263,53 +276,62 @@ static double conv_flops(const ConvGeom& g, int B, bool stem) {
   return 2.0 * (double)B * g.Ho * g.Wo * g.Co * k;
 }
 
-template <typename T>
-int Net::conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st, bool with_stats, const EpiFin* fin) {
+// The CUDA-core engine works on one element type; it is only reachable in the modes whose A / Z / G types coincide.
+template <typename P> struct SimtConv {
+  static constexpr bool ok = std::is_same<typename P::A, typename P::Z>::value && std::is_same<typename P::A, typename P::G>::value;
+};
+
+template <typename P>
+int Net::conv_fprop(int ci, const typename P::Z* x, const typename P::A* residual, typename P::A* y, int B, cudaStream_t st,
+                    bool with_stats, const EpiFin* fin) {
   ConvGeom g = convs[ci].g; g.B = B;
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
-  if (precision == PREC_BF16_TC)
+  if (tc())
     r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st, (with_stats && fuse_stats) ? bn_accum : nullptr,
                     nullptr, (with_stats && fuse_stats) ? fin : nullptr);
-  else r = launch_conv_simt_fprop<T>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
+  else if constexpr (SimtConv<P>::ok)
+    r = launch_conv_simt_fprop<typename P::A>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
+  else { set_last_error("conv_fprop: no CUDA-core engine for split operands"); r = 2; }
   prof_end(st, e0, 0, conv_flops(g, B, ci == 0));
   return r;
 }
-template <typename T>
-int Net::conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd, const EpiFin* fin,
-                    const T* dy_shortcut, int ci_shortcut) {
+template <typename P>
+int Net::conv_dgrad(int ci, const typename P::G* dy, const typename P::A* residual, typename P::A* dx, int B, cudaStream_t st,
+                    const EpiBwd* bwd, const EpiFin* fin, const typename P::G* dy_shortcut, int ci_shortcut) {
   ConvGeom g = convs[ci].g; g.B = B;
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
   double flops = conv_flops(g, B, false);
-  if (precision == PREC_BF16_TC) {
+  if (tc()) {
     // dy_shortcut: the block's downsample-conv dgrad rides in the same launch (tc_plan_add_shortcut)
     r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, (const bf16*)dy_shortcut, (const bf16*)residual, dx, st, bwd ? bn_accum : nullptr, bwd,
                     bwd ? fin : nullptr);
     if (dy_shortcut != nullptr) { ConvGeom gs = convs[ci_shortcut].g; gs.B = B; flops += conv_flops(gs, B, false); }
-  } else {
+  } else if constexpr (SimtConv<P>::ok) {
     MN_CHECK(dy_shortcut == nullptr, "conv_dgrad: folded shortcut is a tensor-core path feature");
-    r = launch_conv_simt_dgrad<T>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
-  }
+    r = launch_conv_simt_dgrad<typename P::A>(g, dy, (const float*)w_dg + convs[ci].wd.k_off, residual, dx, st);
+  } else { set_last_error("conv_dgrad: no CUDA-core engine for split operands"); r = 2; }
   prof_end(st, e0, 1, flops);
   return r;
 }
-template <typename T>
-int Net::conv_wgrad(int ci, const T* x, const T* dy, int B, cudaStream_t st) {
+template <typename P>
+int Net::conv_wgrad(int ci, const typename P::Z* x, const typename P::G* dy, int B, cudaStream_t st) {
   ConvGeom g = convs[ci].g; g.B = B;
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
-  if (precision == PREC_BF16_TC) r = tc_conv_run(tc_wgrad[ci], (const bf16*)x, (const bf16*)dy, nullptr, dw_krsc + convs[ci].wd.k_off, st);
-  else r = launch_conv_simt_wgrad<T>(g, x, dy, dw_krsc + convs[ci].wd.k_off, st);
+  if (tc()) r = tc_conv_run(tc_wgrad[ci], (const bf16*)x, (const bf16*)dy, nullptr, dw_krsc + convs[ci].wd.k_off, st);
+  else if constexpr (SimtConv<P>::ok) r = launch_conv_simt_wgrad<typename P::A>(g, x, dy, dw_krsc + convs[ci].wd.k_off, st);
+  else { set_last_error("conv_wgrad: no CUDA-core engine for split operands"); r = 2; }
   prof_end(st, e0, 2, conv_flops(g, B, ci == 0));
   return r;
 }
 
 int Net::ensure_tc_plans(int B) {
-  if (precision != PREC_BF16_TC || tc_B == B) return 0;
+  if (!tc() || tc_B == B) return 0;
   for (auto* p : tc_fprop) tc_plan_destroy(p);
   for (auto* p : tc_dgrad) tc_plan_destroy(p);
   for (auto* p : tc_wgrad) tc_plan_destroy(p);
@@ -318,11 +340,17 @@ int Net::ensure_tc_plans(int B) {
   tc_wgrad.assign(convs.size(), nullptr);
   for (size_t i = 0; i < convs.size(); ++i) {
     ConvGeom g = convs[i].g; g.B = B;
-    const bf16* wk = (const bf16*)w_krsc + convs[i].wd.k_off;
-    const bf16* wd = (const bf16*)w_dg + convs[i].wd.k_off;
+    const bool sp = precision == PREC_TC_SPLIT;
+    if (sp) { g.split = 1; g.fmt_z = split_fmt_z; g.fmt_g = split_fmt_g; }
+    const bf16* wk = (const bf16*)w_krsc + (sp ? 4 : 1) * convs[i].wd.k_off;     // split planes: 4 x the 16-bit elements
+    const bf16* wd = (const bf16*)w_dg + (sp ? 4 : 1) * convs[i].wd.k_off;
     MN_TRY(tc_plan_create(&tc_fprop[i], g, 0, wk));
     if (i > 0) MN_TRY(tc_plan_create(&tc_dgrad[i], g, 1, wd));
     MN_TRY(tc_plan_create(&tc_wgrad[i], g, 2, nullptr));
+    if (sp && split_fmt_g == 0) {       // fp16 gradient planes carry the step's power-of-two scale: divide it out
+      if (i > 0) tc_plan_set_out_scale(tc_dgrad[i], gscale + 1);
+      tc_plan_set_out_scale(tc_wgrad[i], gscale + 1);
+    }
   }
   // stride-2 blocks: the 1x1 downsample dgrad becomes one more tap of conv1's (single-launch) dgrad
   for (auto& bl : blocks) {
@@ -336,9 +364,10 @@ int Net::ensure_tc_plans(int B) {
   return 0;
 }
 
-template <typename T>
-int Net::bn_forward(int bi, const T* y, long long M, const float* params, float* bufs, int training,
+template <typename P>
+int Net::bn_forward(int bi, const typename P::A* y, long long M, const float* params, float* bufs, int training,
                     cudaStream_t st) {
+  typedef typename P::A T;
   BNL& b = bns[bi];
   if (fuse_stats && training && fuse_fin) return 0;   // the conv's last CTA finalized the statistics
   if (fuse_stats && training)   // sums were accumulated by the conv epilogue
@@ -374,53 +403,58 @@ EpiFin Net::fin_backward(int bi, int bi_ds, long long M, const float* params, fl
 }
 
 // ---- forward -------------------------------------------------------------------
-template <typename T>
+template <typename P>
 int Net::forward_t(const float* x, const float* params, float* bufs, int B, int training, float droprate,
                    unsigned long long seed, unsigned long long step, float* pred, cudaStream_t st) {
+  typedef typename P::A T;        // conv outputs
+  typedef typename P::Z TZ;       // forward conv operands
   MN_TRY(ensure_tc_plans(B));
   // operand copies of the master weights (they change every optimizer step)
   if (precision == PREC_BF16_TC)
     MN_TRY(launch_pack_weights<bf16>(d_wdescs, (int)convs.size(), params, (bf16*)w_krsc, (bf16*)w_dg, max_w_elems, 0, st));
+  else if (precision == PREC_TC_SPLIT)
+    MN_TRY(launch_pack_weights_split(d_wdescs, (int)convs.size(), params, w_krsc_f32, w_dg_f32, w_krsc, w_dg, max_w_elems,
+                                     split_fmt_z, split_fmt_g, st));
   else
     MN_TRY(launch_pack_weights<float>(d_wdescs, (int)convs.size(), params, (float*)w_krsc, (float*)w_dg, max_w_elems,
                                       precision == PREC_BF16_SIMT, st));
   // stem: im2col -> GEMM -> BN -> ReLU -> maxpool
   if (stem_s2d) MN_TRY(launch_stem_s2d(x, (bf16*)A0, B, H, W, Hc + 3, stem_s2d_wsp(Wc), st));
-  else MN_TRY(launch_stem_im2col<T>(x, (T*)A0, B, H, W, Hc, Wc, kStemK, st));
+  else MN_TRY(launch_stem_im2col<TZ>(x, (TZ*)A0, B, H, W, Hc, Wc, kStemK, st));
   {
     const EpiFin f0 = fin_forward(convs[0].bn, (long long)B * Hc * Wc, params, bufs);
-    MN_TRY(conv_fprop<T>(0, (const T*)A0, nullptr, (T*)y0, B, st, training != 0, &f0));
+    MN_TRY(conv_fprop<P>(0, (const TZ*)A0, nullptr, (T*)y0, B, st, training != 0, &f0));
   }
-  MN_TRY(bn_forward<T>(convs[0].bn, (const T*)y0, (long long)B * Hc * Wc, params, bufs, training, st));
+  MN_TRY(bn_forward<P>(convs[0].bn, (const T*)y0, (long long)B * Hc * Wc, params, bufs, training, st));
   {
     BNL& b = bns[convs[0].bn];
-    MN_TRY(launch_stem_pool<T>((const T*)y0, b.scale, b.shift, (T*)z0, amax0, B, Hc, Wc, Hp, Wp, 64, st));
+    MN_TRY((launch_stem_pool<T, TZ>((const T*)y0, b.scale, b.shift, (TZ*)z0, amax0, B, Hc, Wc, Hp, Wp, 64, st)));
   }
-  const T* zin = (const T*)z0;
+  const TZ* zin = (const TZ*)z0;
   for (auto& bl : blocks) {
     const long long Mo = (long long)B * bl.Ho * bl.Wo;
     BNL& b1 = bns[convs[bl.conv1].bn];
     BNL& b2 = bns[convs[bl.conv2].bn];
     const EpiFin f1 = fin_forward(convs[bl.conv1].bn, Mo, params, bufs);
     const EpiFin f2 = fin_forward(convs[bl.conv2].bn, Mo, params, bufs);
-    MN_TRY(conv_fprop<T>(bl.conv1, zin, nullptr, (T*)bl.y1, B, st, training != 0, &f1));
-    MN_TRY(bn_forward<T>(convs[bl.conv1].bn, (const T*)bl.y1, Mo, params, bufs, training, st));
-    MN_TRY(launch_bn_apply<T>((const T*)bl.y1, b1.scale, b1.shift, 0, nullptr, nullptr, nullptr, (T*)bl.h, Mo, bl.Cout, 1, st));
-    MN_TRY(conv_fprop<T>(bl.conv2, (const T*)bl.h, nullptr, (T*)bl.y2, B, st, training != 0, &f2));
-    MN_TRY(bn_forward<T>(convs[bl.conv2].bn, (const T*)bl.y2, Mo, params, bufs, training, st));
+    MN_TRY(conv_fprop<P>(bl.conv1, zin, nullptr, (T*)bl.y1, B, st, training != 0, &f1));
+    MN_TRY(bn_forward<P>(convs[bl.conv1].bn, (const T*)bl.y1, Mo, params, bufs, training, st));
+    MN_TRY((launch_bn_apply<T, TZ>((const T*)bl.y1, b1.scale, b1.shift, 0, nullptr, nullptr, nullptr, (TZ*)bl.h, Mo, bl.Cout, 1, st)));
+    MN_TRY(conv_fprop<P>(bl.conv2, (const TZ*)bl.h, nullptr, (T*)bl.y2, B, st, training != 0, &f2));
+    MN_TRY(bn_forward<P>(convs[bl.conv2].bn, (const T*)bl.y2, Mo, params, bufs, training, st));
     if (bl.convd >= 0) {
       BNL& bd = bns[convs[bl.convd].bn];
       const EpiFin fd = fin_forward(convs[bl.convd].bn, Mo, params, bufs);
-      MN_TRY(conv_fprop<T>(bl.convd, zin, nullptr, (T*)bl.yd, B, st, training != 0, &fd));
-      MN_TRY(bn_forward<T>(convs[bl.convd].bn, (const T*)bl.yd, Mo, params, bufs, training, st));
-      MN_TRY(launch_bn_apply<T>((const T*)bl.y2, b2.scale, b2.shift, 2, (const T*)bl.yd, bd.scale, bd.shift, (T*)bl.out, Mo, bl.Cout, 1, st));
+      MN_TRY(conv_fprop<P>(bl.convd, zin, nullptr, (T*)bl.yd, B, st, training != 0, &fd));
+      MN_TRY(bn_forward<P>(convs[bl.convd].bn, (const T*)bl.yd, Mo, params, bufs, training, st));
+      MN_TRY((launch_bn_apply<T, TZ>((const T*)bl.y2, b2.scale, b2.shift, 2, bl.yd, bd.scale, bd.shift, (TZ*)bl.out, Mo, bl.Cout, 1, st)));
     } else {
-      MN_TRY(launch_bn_apply<T>((const T*)bl.y2, b2.scale, b2.shift, 1, zin, nullptr, nullptr, (T*)bl.out, Mo, bl.Cout, 1, st));
+      MN_TRY((launch_bn_apply<T, TZ>((const T*)bl.y2, b2.scale, b2.shift, 1, zin, nullptr, nullptr, (TZ*)bl.out, Mo, bl.Cout, 1, st)));
     }
-    zin = (const T*)bl.out;
+    zin = (const TZ*)bl.out;
   }
   // head
-  MN_TRY(launch_gap<T>(zin, feat, B, Hf * Wf, 512, st));
+  MN_TRY(launch_gap<TZ>(zin, feat, B, Hf * Wf, 512, st));
   const float* mk = nullptr;
   if (droprate > 0.f) {
     const unsigned long long stride = (unsigned long long)max_B * feat_dim;
@@ -438,16 +472,24 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
 }
 
 // ---- backward ------------------------------------------------------------------
-template <typename T>
+template <typename P>
 int Net::backward_t(const float* dpred, const float* params, float* grads, int filter_nans, cudaStream_t st) {
+  typedef typename P::A T;        // conv outputs, gradients w.r.t. block outputs (fp32 math tensors)
+  typedef typename P::Z TZ;       // forward conv operands
+  typedef typename P::G TG;       // backward conv operands (gradients w.r.t. conv outputs)
   MN_CHECK(last_B > 0 && last_training, "backward: no training-mode forward precedes this call");
   const int B = last_B;
   const int F = feat_dim;
   MN_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)wk_total * 4, st));
-  T* S0 = (T*)scratch[0]; T* S1 = (T*)scratch[1]; T* S2 = (T*)scratch[2]; T* S3 = (T*)scratch[3]; T* S4 = (T*)scratch[4];
+  // S0: d(block output), S3: gated gradient of the identity branch, S4: d h -- T;  S1 / S2: d(conv output) -- TG
+  T* S0 = (T*)scratch[0]; TG* S1 = (TG*)scratch[1]; TG* S2 = (TG*)scratch[2]; T* S3 = (T*)scratch[3]; T* S4 = (T*)scratch[4];
 
   // ---- head (models/posenet.py:67-73 backward, NaN filter :28-34) ----
   MN_TRY(launch_dpred_filter(dpred, dpredf, B * 6, filter_nans, st));
+  // strict mode: the backward conv operands are fp16 planes; ONE power-of-two scale per step (from max|d pred|)
+  // places every gradient tensor inside fp16's window, the consuming conv epilogues divide it out again
+  const float* gs = nullptr;
+  if (precision == PREC_TC_SPLIT && split_fmt_g == 0) { MN_TRY(launch_grad_scale(dpredf, B * 6, gscale, st)); gs = gscale; }
   // dW_xyz[c][j] = sum_b dpred[b][c] * hdrop[b][j]
   MN_TRY(launch_small_gemm(0, dpredf, 1, 6, hdrop, 1, F, grads + xyz_w, F, 3, F, B, nullptr, nullptr, nullptr, st));
   MN_TRY(launch_small_gemm(0, dpredf + 3, 1, 6, hdrop, 1, F, grads + wpqr_w, F, 3, F, B, nullptr, nullptr, nullptr, st));
@@ -467,7 +509,7 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
   bool pre = false;
   for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
     BlockL& bl = blocks[bi];
-    const T* zin = (bi == 0) ? (const T*)z0 : (const T*)blocks[bi - 1].out;
+    const TZ* zin = (bi == 0) ? (const TZ*)z0 : (const TZ*)blocks[bi - 1].out;
     const long long Mo = (long long)B * bl.Ho * bl.Wo;
     const int C = bl.Cout;
     BNL& b1 = bns[convs[bl.conv1].bn];
@@ -482,47 +524,47 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
           MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
                                               params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef,
                                               bn_accum, st));
-        MN_TRY(launch_bn_bwd_apply<T>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st));
+        MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st, nullptr, nullptr, gs)));
       } else {
-        MN_TRY(launch_bn_bwd_reduce<T>(S0, (const T*)bl.out, (const T*)bl.y2, (const T*)bl.yd, Mo, C,
+        MN_TRY((launch_bn_bwd_reduce<T, TZ>(S0, (const TZ*)bl.out, (const T*)bl.y2, (const T*)bl.yd, Mo, C,
                                        params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
                                        params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef,
-                                       bn_accum, bn_counter, st));
-        MN_TRY(launch_bn_bwd_apply<T>(S0, (const T*)bl.out, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st));
+                                       bn_accum, bn_counter, st)));
+        MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S0, (const TZ*)bl.out, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st, nullptr, nullptr, gs)));
       }
     } else if (pre) {
       if (!fuse_fin)
         MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
-      MN_TRY(launch_bn_bwd_apply<T>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st));
+      MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st, nullptr, nullptr, gs)));
       gres = S0;              // already gated; conv1's dgrad adds it in place
     } else {
-      MN_TRY(launch_bn_bwd_reduce<T>(S0, (const T*)bl.out, (const T*)bl.y2, nullptr, Mo, C,
+      MN_TRY((launch_bn_bwd_reduce<T, TZ>(S0, (const TZ*)bl.out, (const T*)bl.y2, nullptr, Mo, C,
                                      params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
-                                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st));
-      MN_TRY(launch_bn_bwd_apply<T>(S0, (const T*)bl.out, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, S3, Mo, C, st));
+                                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st)));
+      MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S0, (const TZ*)bl.out, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, S3, Mo, C, st, nullptr, nullptr, gs)));
     }
     // conv2
-    MN_TRY(conv_wgrad<T>(bl.conv2, (const T*)bl.h, S1, B, st));
+    MN_TRY(conv_wgrad<P>(bl.conv2, (const TZ*)bl.h, S1, B, st));
     // h = relu(bn1(y1)) has no residual: its ReLU mask is recomputed from y1 (scale*y+shift > 0),
     // one tensor read less in both backward passes
     if (fuse_bwd) {
       EpiBwd e1; memset(&e1, 0, sizeof(e1));
       e1.y = (const bf16*)bl.y1; e1.mscale = b1.scale; e1.mshift = b1.shift;
       const EpiFin fb1 = fin_backward(convs[bl.conv1].bn, -1, Mo, params, grads);
-      MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st, &e1, &fb1));
+      MN_TRY(conv_dgrad<P>(bl.conv2, S1, nullptr, S4, B, st, &e1, &fb1));
       if (!fuse_fin)
         MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
-      MN_TRY(launch_bn_bwd_apply<T>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st));
+      MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st, nullptr, nullptr, gs)));
     } else {
-      MN_TRY(conv_dgrad<T>(bl.conv2, S1, nullptr, S4, B, st));
-      MN_TRY(launch_bn_bwd_reduce<T>(S4, nullptr, (const T*)bl.y1, nullptr, Mo, C,
+      MN_TRY(conv_dgrad<P>(bl.conv2, S1, nullptr, S4, B, st));
+      MN_TRY((launch_bn_bwd_reduce<T, TZ>(S4, nullptr, (const T*)bl.y1, nullptr, Mo, C,
                                      params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
                                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st,
-                                     b1.scale, b1.shift));
-      MN_TRY(launch_bn_bwd_apply<T>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st,
-                                    b1.scale, b1.shift));
+                                     b1.scale, b1.shift)));
+      MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st,
+                                    b1.scale, b1.shift, gs)));
     }
     // conv1 (+ downsample conv): d zin; with fuse_bwd it is gated by the previous block's output ReLU
     // and carries that block's BN2 (+ downsample BN) reductions
@@ -535,16 +577,16 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
       e2.yd = (pb.convd >= 0) ? (const bf16*)pb.yd : nullptr;
       fb2 = fin_backward(convs[pb.conv2].bn, (pb.convd >= 0) ? convs[pb.convd].bn : -1, (long long)B * pb.Ho * pb.Wo, params, grads);
     }
-    MN_TRY(conv_wgrad<T>(bl.conv1, zin, S1, B, st));
+    MN_TRY(conv_wgrad<P>(bl.conv1, zin, S1, B, st));
     if (ds && bl.ds_fold) {
-      MN_TRY(conv_wgrad<T>(bl.convd, zin, S2, B, st));
-      MN_TRY(conv_dgrad<T>(bl.conv1, S1, nullptr, S0, B, st, next_pre ? &e2 : nullptr, &fb2, S2, bl.convd));
+      MN_TRY(conv_wgrad<P>(bl.convd, zin, S2, B, st));
+      MN_TRY(conv_dgrad<P>(bl.conv1, S1, nullptr, S0, B, st, next_pre ? &e2 : nullptr, &fb2, S2, bl.convd));
     } else if (ds) {
-      MN_TRY(conv_wgrad<T>(bl.convd, zin, S2, B, st));
-      MN_TRY(conv_dgrad<T>(bl.convd, S2, nullptr, S0, B, st));
-      MN_TRY(conv_dgrad<T>(bl.conv1, S1, S0, S0, B, st, next_pre ? &e2 : nullptr, &fb2));
+      MN_TRY(conv_wgrad<P>(bl.convd, zin, S2, B, st));
+      MN_TRY(conv_dgrad<P>(bl.convd, S2, nullptr, S0, B, st));
+      MN_TRY(conv_dgrad<P>(bl.conv1, S1, S0, S0, B, st, next_pre ? &e2 : nullptr, &fb2));
     } else {
-      MN_TRY(conv_dgrad<T>(bl.conv1, S1, gres, S0, B, st, next_pre ? &e2 : nullptr, &fb2));
+      MN_TRY(conv_dgrad<P>(bl.conv1, S1, gres, S0, B, st, next_pre ? &e2 : nullptr, &fb2));
     }
     pre = next_pre;
   }
@@ -554,17 +596,17 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     const long long M0 = (long long)B * Hc * Wc;
     if (stem_fuse) {
       // the pool/ReLU backward accumulates the stem BN's (sum g, sum g*y) while it has g and y in registers
-      MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S1, B, Hc, Wc, Hp, Wp, 64, st, bn_accum));
+      MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S4, B, Hc, Wc, Hp, Wp, 64, st, bn_accum));
       MN_TRY(launch_bn_bwd_finalize_accum(M0, 64, params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef,
                                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
     } else {
-      MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S1, B, Hc, Wc, Hp, Wp, 64, st));
-      MN_TRY(launch_bn_bwd_reduce<T>(S1, nullptr, (const T*)y0, nullptr, M0, 64,
+      MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S4, B, Hc, Wc, Hp, Wp, 64, st));
+      MN_TRY((launch_bn_bwd_reduce<T, TZ>(S4, (const TZ*)nullptr, (const T*)y0, nullptr, M0, 64,
                                      params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef,
-                                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st));
+                                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st)));
     }
-    MN_TRY(launch_bn_bwd_apply<T>(S1, nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st));
-    MN_TRY(conv_wgrad<T>(0, (const T*)A0, S2, B, st));
+    MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, (const TZ*)nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st, nullptr, nullptr, gs)));
+    MN_TRY(conv_wgrad<P>(0, (const TZ*)A0, S2, B, st));
   }
   MN_TRY(launch_unpack_wgrads(d_wdescs, (int)convs.size(), dw_krsc, grads, max_w_elems, st));
   return 0;
@@ -575,14 +617,18 @@ int Net::forward(const float* x, const float* params, float* bufs, int B, int tr
   MN_CHECK(B >= 1 && B <= max_B, "forward: batch %d outside [1, max_B=%d]", B, max_B);
   MN_CHECK(x && params && bufs && pred, "forward: null pointer argument");
   MN_CHECK(droprate >= 0.f && droprate < 1.f, "forward: droprate %f outside [0,1)", droprate);
-  if (precision == PREC_FP32) return forward_t<float>(x, params, bufs, B, training, droprate, seed, step, pred, st);
-  return forward_t<bf16>(x, params, bufs, B, training, droprate, seed, step, pred, st);
+  if (precision == PREC_FP32) return forward_t<TypesF32>(x, params, bufs, B, training, droprate, seed, step, pred, st);
+  if (precision == PREC_TC_SPLIT) return forward_t<TypesSplitHH>(x, params, bufs, B, training, droprate, seed, step, pred, st);
+  return forward_t<TypesBF16>(x, params, bufs, B, training, droprate, seed, step, pred, st);
 }
 
 int Net::backward(const float* dpred, const float* params, float* grads, int filter_nans, cudaStream_t st) {
   MN_CHECK(dpred && params && grads, "backward: null pointer argument");
-  if (precision == PREC_FP32) return backward_t<float>(dpred, params, grads, filter_nans, st);
-  return backward_t<bf16>(dpred, params, grads, filter_nans, st);
+  if (precision == PREC_FP32) return backward_t<TypesF32>(dpred, params, grads, filter_nans, st);
+  if (precision == PREC_TC_SPLIT)
+    return split_fmt_g == 0 ? backward_t<TypesSplitHH>(dpred, params, grads, filter_nans, st)
+                            : backward_t<TypesSplitHB>(dpred, params, grads, filter_nans, st);
+  return backward_t<TypesBF16>(dpred, params, grads, filter_nans, st);
 }
 
 }  // namespace mapnet

@@ -9,7 +9,9 @@
 
 namespace mapnet {
 
-enum Precision { PREC_FP32 = 0, PREC_BF16_TC = 1, PREC_BF16_SIMT = 2 };
+// PREC_TC_SPLIT: strict tensor-core mode -- fp32-stored conv outputs, conv operands as split fp16 hi/lo planes (22
+// significant bits), every product formed by 4 tcgen05 MMAs (hi*hi + hi*lo + lo*hi + lo*lo), fp32 accumulation in TMEM
+enum Precision { PREC_FP32 = 0, PREC_BF16_TC = 1, PREC_BF16_SIMT = 2, PREC_TC_SPLIT = 3 };
 
 struct ParamEntry {
   std::string name;
@@ -58,6 +60,9 @@ struct Net {
   void *A0, *y0, *z0; uint8_t* amax0;
   void* scratch[5]; long long scratch_elems;
   void *w_krsc, *w_dg; float* dw_krsc; WeightDesc* d_wdescs;
+  float *w_krsc_f32, *w_dg_f32;  // strict mode: fp32 K-major matrices the hi / lo weight planes are cut from
+  int split_fmt_z, split_fmt_g;  // strict mode: element format of the forward / backward operand planes (0 fp16, 1 bf16)
+  float* gscale;                 // strict mode, device: {S, 1/S} -- this step's power-of-two gradient scale
   double* bn_accum; unsigned int* bn_counter;
   float *feat, *fcpre, *hdrop, *mask, *dh, *dfeat, *dpredf;
   float* bn_small;               // backing store of the BN small arrays
@@ -88,7 +93,8 @@ struct Net {
   void prof_end(cudaStream_t st, cudaEvent_t e0, int cls, double flops);
   int prof_read(double* ms3, double* flops3, int* launches3);   // classes: 0 fprop, 1 dgrad, 2 wgrad
 
-  size_t elt() const { return precision == PREC_FP32 ? 4 : 2; }
+  size_t elt() const { return (precision == PREC_FP32 || precision == PREC_TC_SPLIT) ? 4 : 2; }
+  bool tc() const { return precision == PREC_BF16_TC || precision == PREC_TC_SPLIT; }
 
   int init(int max_B, int H, int W, int feat_dim, int precision);
   void destroy();
@@ -99,19 +105,21 @@ struct Net {
  private:
   int alloc(void** p, size_t bytes);
   void build_table();
-  template <typename T> int forward_t(const float* x, const float* params, float* bufs, int B, int training,
+  // P: element-type bundle of the precision mode (common.cuh: TypesF32 / TypesBF16 / TypesSplitHH / TypesSplitHB)
+  template <typename P> int forward_t(const float* x, const float* params, float* bufs, int B, int training,
                                       float droprate, unsigned long long seed, unsigned long long step,
                                       float* pred, cudaStream_t st);
-  template <typename T> int backward_t(const float* dpred, const float* params, float* grads, int filter_nans,
+  template <typename P> int backward_t(const float* dpred, const float* params, float* grads, int filter_nans,
                                        cudaStream_t st);
-  template <typename T> int conv_fprop(int ci, const T* x, const T* residual, T* y, int B, cudaStream_t st,
-                                       bool with_stats = false, const EpiFin* fin = nullptr);
-  template <typename T> int conv_dgrad(int ci, const T* dy, const T* residual, T* dx, int B, cudaStream_t st, const EpiBwd* bwd = nullptr,
-                                       const EpiFin* fin = nullptr, const T* dy_shortcut = nullptr, int ci_shortcut = -1);
+  template <typename P> int conv_fprop(int ci, const typename P::Z* x, const typename P::A* residual, typename P::A* y, int B,
+                                       cudaStream_t st, bool with_stats = false, const EpiFin* fin = nullptr);
+  template <typename P> int conv_dgrad(int ci, const typename P::G* dy, const typename P::A* residual, typename P::A* dx, int B,
+                                       cudaStream_t st, const EpiBwd* bwd = nullptr, const EpiFin* fin = nullptr,
+                                       const typename P::G* dy_shortcut = nullptr, int ci_shortcut = -1);
   EpiFin fin_forward(int bi, long long M, const float* params, float* bufs);
   EpiFin fin_backward(int bi, int bi_ds, long long M, const float* params, float* grads);
-  template <typename T> int conv_wgrad(int ci, const T* x, const T* dy, int B, cudaStream_t st);
-  template <typename T> int bn_forward(int bi, const T* y, long long M, const float* params, float* bufs,
+  template <typename P> int conv_wgrad(int ci, const typename P::Z* x, const typename P::G* dy, int B, cudaStream_t st);
+  template <typename P> int bn_forward(int bi, const typename P::A* y, long long M, const float* params, float* bufs,
                                        int training, cudaStream_t st);
   int ensure_tc_plans(int B);
 };

@@ -212,5 +212,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
          (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// same with explicit operand element formats (0 = fp16, 1 = bf16; both fp32-accumulated)
+__host__ __device__ constexpr uint32_t make_idesc_fmt(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major,
+                                                      uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
+}
+
 }  // namespace ptx
 }  // namespace mapnet

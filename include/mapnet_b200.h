@@ -39,6 +39,8 @@ typedef struct mapnet_trunk mapnet_trunk_t;
 #define MAPNET_PREC_FP32 0      /* fp32 CUDA-core implicit GEMM: strict 1e-4 parity mode            */
 #define MAPNET_PREC_BF16 1      /* tcgen05 tensor-core implicit GEMM, bf16 operands, fp32 accumulate */
 #define MAPNET_PREC_BF16_SIMT 2 /* bf16 storage + CUDA-core fp32 math: cross-check of mode 1         */
+#define MAPNET_PREC_TC_SPLIT 3  /* tcgen05 strict mode: fp32 conv outputs, conv operands as split fp16 hi/lo planes,\
+                                   4 MMAs per product, fp32 accumulate -- meets the 1e-4 parity bar on tensor cores */
 
 /* criterion modes (common/criterion.py) */
 #define MAPNET_LOSS_POSENET 0    /* PoseNetCriterion      pred [N,6],    targ [N,6]        */

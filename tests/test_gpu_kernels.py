@@ -19,12 +19,12 @@ def _conv_case(precision, B, H, W, Ci, Co, k, stride, seed=0):
     x = torch.randn(B, Ci, H, W, generator=g)
     w = torch.randn(Co, Ci, k, k, generator=g) * (2.0 / (Ci * k * k)) ** 0.5
     pad = (k - 1) // 2
-    if precision != "fp32":
+    if precision not in ("fp32", "tc_split"):
         x = x.bfloat16().float(); w = w.bfloat16().float()
     xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True)
     y = F.conv2d(xr, wr, None, stride, pad)
     dy = torch.randn(y.shape, generator=g)
-    if precision != "fp32":
+    if precision not in ("fp32", "tc_split"):
         dy = dy.bfloat16().float()
     y.backward(dy)
     return x, w, dy, y.detach(), xr.grad, wr.grad
@@ -46,18 +46,21 @@ CASES = [(2, 16, 16, 64, 64, 3, 1), (2, 16, 16, 64, 128, 3, 2), (2, 16, 16, 64, 
          (2, 16, 16, 128, 256, 1, 2), (3, 17, 13, 128, 256, 3, 2)]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16_simt", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16_simt", "bf16", "tc_split"])
 @pytest.mark.parametrize("geom", CASES)
 def test_conv_engines(precision, geom):
+    """tc_split (strict tensor-core mode): UNROUNDED fp32 operands in, fp32 out -- the entry point cuts them into
+    fp16 hi/lo planes (22 significant bits) and the tcgen05 engines form all four hi/lo products; the bound is the
+    fp32 CUDA-core engine's."""
     B, H, W, Ci, Co, k, stride = geom
     x, w, dy, y, dx, dw = _conv_case(precision, *geom)
-    act = torch.float32 if precision == "fp32" else torch.bfloat16
+    act = torch.float32 if precision in ("fp32", "tc_split") else torch.bfloat16
     wt = torch.bfloat16 if precision == "bf16" else torch.float32
     xn = x.permute(0, 2, 3, 1).contiguous().to(act).cuda()
     dyn = dy.permute(0, 2, 3, 1).contiguous().to(act).cuda()
     w_krsc = w.permute(0, 2, 3, 1).contiguous().to(wt).cuda()          # [Co][kh][kw][Ci]
     w_dg = w.permute(1, 2, 3, 0).contiguous().to(wt).cuda()            # [Ci][kh][kw][Co]
-    tol = 2e-5 if precision == "fp32" else 1.2e-2     # bf16 output rounding: 2^-8 relative
+    tol = 2e-5 if precision in ("fp32", "tc_split") else 1.2e-2     # bf16 output rounding: 2^-8 relative
     # fprop
     out = torch.empty(y.permute(0, 2, 3, 1).shape, dtype=act, device="cuda")
     _run_conv(precision, 0, xn, None, w_krsc, out, geom)

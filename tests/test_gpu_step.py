@@ -70,6 +70,18 @@ def test_step_fp32_strict_full_size(name):
     _run(name, "fp32", TOL_FP32)
 
 
+@pytest.mark.parametrize("name", TINY)
+def test_step_tc_split_strict(name):
+    """The north-star bar ON the tensor cores: precision="tc_split" (tcgen05, fp16 hi/lo operand planes, 4 MMAs per
+    product, fp32 accumulate / storage) against the reference goldens at the fp32 tolerances."""
+    _run(name, "tc_split", TOL_FP32)
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_step_tc_split_strict_full_size(name):
+    _run(name, "tc_split", TOL_FP32)
+
+
 @pytest.mark.parametrize("name", ["posenet_b8_256"] + FULL)
 def test_step_bf16_tensor_core(name):
     _run(name, "bf16", TOL_BF16)

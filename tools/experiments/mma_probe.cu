@@ -92,8 +92,8 @@ int main() {
   Case cases[] = {
       {"1 bf16 x bf16", 1, 1, 1, 0, 1.f, 1.f},
       {"2 fp16 x fp16", 0, 0, 1, 0, 1.f, 1.f},
-      {"3 fp16 x bf16 (mixed)", 0, 1, 1, 0, 1.f, 1.f},
-      {"3b bf16 x fp16 (mixed)", 1, 0, 1, 0, 1.f, 1.f},
+      // {"3 fp16 x bf16 (mixed)", 0, 1, ...}: measured on B200 -> "an illegal instruction was encountered": A and B of a
+      // kind::f16 MMA must have the same element format
       {"4 fp16 subnormal A (|a| ~ 1e-6)", 0, 0, 1, 0, 1e-6f, 1.f},
       {"4b fp16 subnormal A and B products (1e-6 x 1e-2)", 0, 0, 1, 0, 1e-6f, 1e-2f},
       {"5 scale-input-d 2^-11 (D = AB_k0 + 2^-11 AB + AB_k1..3)", 0, 0, 1, 1, 1.f, 1.f},
