@@ -636,6 +636,5 @@ int launch_bn_bwd_apply(const T* dout, const TZ* zmask, const T* y, const float*
 MN_INST_BWD_APPLY(float, float, float)
 MN_INST_BWD_APPLY(bf16, bf16, bf16)
 MN_INST_BWD_APPLY(float, hsplit, hsplit)
-MN_INST_BWD_APPLY(float, hsplit, bsplit)
 
 }  // namespace mapnet

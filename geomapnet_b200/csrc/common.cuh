@@ -122,24 +122,19 @@ template <> struct Vec8<bf16> {
 };
 
 // ---- split 16-bit operand planes (strict tensor-core mode) --------------------------------
-// A value x is stored as hi + lo with hi = rn16(x), lo = rn16(x - hi): two fp16 (hsplit: 22 significant
-// bits, |x| <= 65504) or two bf16 (bsplit: 16 significant bits, fp32 range) numbers.  Storage layout per 8
+// A value x is stored as hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits, |x| <= 65504
+// (saturating), absolute error max(2^-22 |x|, 2^-25).  Storage layout per 8
 // consecutive channels: 8 x hi (16 B) then 8 x lo (16 B) -- one logical element is 4 bytes, so the NHWC
 // indexing of the element-wise kernels (pointer + 8*i) is unchanged, and the conv engines see a 16-bit tensor
 // with 2C "channels" whose K order is (c/8, plane, c%8); the packed weight matrices use the same K order
 // (layout.cu), so every hi/lo cross product is formed by ordinary tcgen05 MMAs.  Only Vec8 access is defined.
 struct hsplit { uint32_t raw; };
-struct bsplit { uint32_t raw; };
 
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   float c = fminf(fmaxf(v, -65504.f), 65504.f);        // saturate instead of overflowing to inf
   c = (v != v) ? v : c;                                 // NaN stays NaN
   hi = __float2half_rn(c);
   lo = __float2half_rn(c - __half2float(hi));
-}
-__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
 template <> struct Vec8<hsplit> {
@@ -165,37 +160,12 @@ template <> struct Vec8<hsplit> {
     *(reinterpret_cast<uint4*>(p) + 1) = b;
   }
 };
-template <> struct Vec8<bsplit> {
-  float v[8];
-  __device__ __forceinline__ void load(const bsplit* p) {
-    const uint4 a = *reinterpret_cast<const uint4*>(p);
-    const uint4 b = *(reinterpret_cast<const uint4*>(p) + 1);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* l = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 fh = __bfloat1622float2(h[i]), fl = __bfloat1622float2(l[i]);
-      v[2 * i] = fh.x + fl.x; v[2 * i + 1] = fh.y + fl.y;
-    }
-  }
-  __device__ __forceinline__ void store(bsplit* p) const {
-    uint4 a, b;
-    bf16* h = reinterpret_cast<bf16*>(&a);
-    bf16* l = reinterpret_cast<bf16*>(&b);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
-    *reinterpret_cast<uint4*>(p) = a;
-    *(reinterpret_cast<uint4*>(p) + 1) = b;
-  }
-};
-
 // Element types of one precision mode: A = conv outputs and everything derived by fp32 math from them
 // (what BatchNorm reads, gradients w.r.t. block outputs), Z = forward conv operands (post-BN/ReLU activations,
 // the stem operand), G = backward conv operands (gradients w.r.t. conv outputs).
 struct TypesF32 { typedef float A; typedef float Z; typedef float G; };
 struct TypesBF16 { typedef bf16 A; typedef bf16 Z; typedef bf16 G; };
 struct TypesSplitHH { typedef float A; typedef hsplit Z; typedef hsplit G; };
-struct TypesSplitHB { typedef float A; typedef hsplit Z; typedef bsplit G; };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

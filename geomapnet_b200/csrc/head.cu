@@ -224,18 +224,46 @@ int launch_colsum(const float* A, int lda, int M, int N, float* out, cudaStream_
   return 0;
 }
 
-// dpred copy with the NaN filter of models/posenet.py:28-34 applied to the
-// rotation half (the gradient entering fc_wpqr).
-__global__ void k_dpred_filter(const float* __restrict__ in, float* __restrict__ out, int n, int filter) {
+// The NaN filter of models/posenet.py:28-34: a backward hook on fc_wpqr that zeroes the NaN entries of that
+// Linear's THREE input gradients (bias, input, weight).  A NaN in d pred[b, 3+j] (qlog's backward at a zero
+// rotation) makes, in the reference,
+//   d W_wpqr[j, :] = sum_b dpred[b,3+j] * h[b,:]  NaN in the whole row j   -> zeroed: row j gets NO gradient this step,
+//   d b_wpqr[j]                                    NaN                      -> 0,
+//   d h[b, :]     = sum_j dpred[b,3+j] * W[j,:]    NaN for the whole sample -> zeroed: sample b's rotation half
+//                                                                              sends nothing into the trunk,
+// while the translation half (fc_xyz) is untouched.  Reproduced here by two filtered copies of d pred:
+//   out_w: column j of the rotation half zeroed when ANY sample has a NaN there   (weight / bias gradients)
+//   out_h: the rotation half of row b zeroed when ANY of its three entries is NaN (gradient into the trunk)
+// One block (n = 6 B is a few hundred elements).
+__global__ void __launch_bounds__(256)
+k_dpred_filter(const float* __restrict__ in, float* __restrict__ out_w, float* __restrict__ out_h, int B, int filter) {
   pdl_prologue();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float v = in[i];
-  if (filter && (i % 6) >= 3 && v != v) v = 0.f;
-  out[i] = v;
+  __shared__ int col_nan[3];
+  if (threadIdx.x < 3) col_nan[threadIdx.x] = 0;
+  __syncthreads();
+  if (filter)
+    for (int i = threadIdx.x; i < B * 3; i += blockDim.x) {
+      const int b = i / 3, j = i - b * 3;
+      const float v = in[b * 6 + 3 + j];
+      if (v != v) col_nan[j] = 1;        // benign race: every writer stores 1
+    }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = in[b * 6 + k];
+    const bool row_nan = filter && ((v[3] != v[3]) || (v[4] != v[4]) || (v[5] != v[5]));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { out_w[b * 6 + k] = v[k]; out_h[b * 6 + k] = v[k]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      out_w[b * 6 + 3 + j] = (filter && col_nan[j]) ? 0.f : v[3 + j];
+      out_h[b * 6 + 3 + j] = row_nan ? 0.f : v[3 + j];
+    }
+  }
 }
-int launch_dpred_filter(const float* in, float* out, int n, int filter, cudaStream_t st) {
-  MN_LAUNCH(k_dpred_filter, cdiv(n, 128), 128, 0, st, in, out, n, filter);
+int launch_dpred_filter(const float* in, float* out_w, float* out_h, int B, int filter, cudaStream_t st) {
+  MN_LAUNCH(k_dpred_filter, 1, 256, 0, st, in, out_w, out_h, B, filter);
   MN_LAUNCH_CHECK();
   return 0;
 }

@@ -11,8 +11,8 @@ struct ConvGeom {
   // (0 = dense).  The stem uses an overlapped view of its space-to-depth image: a "pixel" is 64
   // consecutive elements and consecutive pixels start 16 elements apart (layout.cu, k_stem_s2d).
   long long in_pix_stride = 0, in_row_stride = 0, in_img_stride = 0;
-  // tensor-core path, strict mode: activations / gradients are split 16-bit operand planes (common.cuh: hsplit /
-  // bsplit, 2*C 16-bit "channels" per pixel), the weight matrices hold hi and lo planes as 2*KH*KW taps (layout.cu),
+  // tensor-core path, strict mode: activations / gradients are split 16-bit operand planes (common.cuh: hsplit,
+  // 2*C 16-bit "channels" per pixel), the weight matrices hold hi and lo planes as 2*KH*KW taps (layout.cu),
   // outputs are fp32.  fmt_z / fmt_g: element format of the forward / backward operands (0 = fp16, 1 = bf16).
   int split = 0, fmt_z = 1, fmt_g = 1;
   __host__ __device__ long long M_out() const { return (long long)B * Ho * Wo; }
@@ -138,7 +138,9 @@ int launch_small_gemm(int epi, const float* A, long long sam, long long sak, con
                       long long sbk, float* C, int ldc, int M, int N, int K, const float* bias, float* aux,
                       const float* mask, cudaStream_t st);
 int launch_colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
-int launch_dpred_filter(const float* in, float* out, int n, int filter, cudaStream_t st);
+// two NaN-filtered copies of d pred [B,6] (models/posenet.py:28-34 hook semantics, head.cu): out_w for the head's weight /
+// bias gradients, out_h for the gradient into the trunk; filter == 0: plain copies
+int launch_dpred_filter(const float* in, float* out_w, float* out_h, int B, int filter, cudaStream_t st);
 // scale[0] = S = 2^(8 - ceil(log2 max|g|)) (1 when max|g| is 0 or not finite), scale[1] = 1/S
 int launch_grad_scale(const float* g, int n, float* scale2, cudaStream_t st);
 int launch_dropout_mask(float* mask, long long n, float p, unsigned long long seed, unsigned long long offset,

@@ -119,13 +119,9 @@ template int launch_pack_weights<bf16>(const WeightDesc*, int, const float*, bf1
 // Element offsets into the packed buffers are 4 x the bf16 ones (WeightDesc::k_off * 4).
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void split16(float v, int fmt, uint16_t& hi, uint16_t& lo) {
-  if (fmt == 0) {
-    __half h, l; split_f16(v, h, l);
-    hi = __half_as_ushort(h); lo = __half_as_ushort(l);
-  } else {
-    bf16 h, l; split_bf16(v, h, l);
-    hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
-  }
+  (void)fmt;                 // only fp16 planes are built (0); the parameter documents the operand format
+  __half h, l; split_f16(v, h, l);
+  hi = __half_as_ushort(h); lo = __half_as_ushort(l);
 }
 // position of (channel c, plane p) inside a pixel's 2*C split channels
 __device__ __forceinline__ int split_k(int c, int p) { return ((c >> 3) << 4) + (p << 3) + (c & 7); }
@@ -221,8 +217,8 @@ int launch_split_tensor(const float* in, void* out, long long n, int fmt, cudaSt
   MN_CHECK(n % 8 == 0, "split_tensor: element count must be a multiple of 8");
   const long long nvec = n / 8;
   long long grid = (nvec + 255) / 256; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
-  if (fmt == 0) MN_LAUNCH(k_split_tensor<hsplit>, (int)grid, 256, 0, st, in, (hsplit*)out, nvec);
-  else MN_LAUNCH(k_split_tensor<bsplit>, (int)grid, 256, 0, st, in, (bsplit*)out, nvec);
+  MN_CHECK(fmt == 0, "split_tensor: only fp16 planes are built");
+  MN_LAUNCH(k_split_tensor<hsplit>, (int)grid, 256, 0, st, in, (hsplit*)out, nvec);
   MN_LAUNCH_CHECK();
   return 0;
 }

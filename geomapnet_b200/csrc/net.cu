@@ -142,10 +142,10 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   max_B = max_B_; H = H_; W = W_; feat_dim = feat_dim_; precision = precision_;
   MN_CHECK(max_B >= 0 && H >= 32 && W >= 32, "create: need max_B>=0 and H,W>=32 (got %d,%d,%d)", max_B, H, W);
   MN_CHECK(precision >= 0 && precision <= 3, "create: bad precision %d", precision);
-  // strict tensor-core mode: forward operands are fp16 hi/lo planes; the backward operands' format is a build-time
-  // experiment switch (MAPNET_SPLIT_GRAD_FMT: 0 = fp16 planes, 1 = bf16 planes -- fp32 exponent range, 16 significant bits)
-  split_fmt_z = 0;
-  { const char* e = getenv("MAPNET_SPLIT_GRAD_FMT"); split_fmt_g = (e ? atoi(e) : 1) ? 1 : 0; }
+  // strict tensor-core mode: forward AND backward conv operands are fp16 hi/lo planes.  (bf16 planes for the gradients
+  // would need no scaling, but wgrad multiplies activations by gradients and tcgen05.mma kind::f16 rejects mixed operand
+  // formats -- measured on B200: "illegal instruction", tools/experiments/mma_probe.cu.)
+  split_fmt_z = 0; split_fmt_g = 0;
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0; prof_pool_used = 0;
   { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
@@ -203,7 +203,7 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_TRY(alloc((void**)&mask, (size_t)Bm * feat_dim * 4));
   MN_TRY(alloc((void**)&dh, (size_t)Bm * feat_dim * 4));
   MN_TRY(alloc((void**)&dfeat, (size_t)Bm * 512 * 4));
-  MN_TRY(alloc((void**)&dpredf, (size_t)Bm * 6 * 4));
+  MN_TRY(alloc((void**)&dpredf, (size_t)Bm * 6 * 4 * 2));      // two NaN-filtered copies of d pred (head.cu)
   MN_TRY(alloc((void**)&sq_partials, 1024 * 4));
   MN_TRY(alloc((void**)&sq_out, 16));
   MN_TRY(alloc((void**)&drop_ctr, 16));
@@ -485,17 +485,18 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
   T* S0 = (T*)scratch[0]; TG* S1 = (TG*)scratch[1]; TG* S2 = (TG*)scratch[2]; T* S3 = (T*)scratch[3]; T* S4 = (T*)scratch[4];
 
   // ---- head (models/posenet.py:67-73 backward, NaN filter :28-34) ----
-  MN_TRY(launch_dpred_filter(dpred, dpredf, B * 6, filter_nans, st));
+  float* dpredh = dpredf + (size_t)max_B * 6;         // second filtered copy (gradient into the trunk)
+  MN_TRY(launch_dpred_filter(dpred, dpredf, dpredh, B, filter_nans, st));
   // strict mode: the backward conv operands are fp16 planes; ONE power-of-two scale per step (from max|d pred|)
   // places every gradient tensor inside fp16's window, the consuming conv epilogues divide it out again
   const float* gs = nullptr;
-  if (precision == PREC_TC_SPLIT && split_fmt_g == 0) { MN_TRY(launch_grad_scale(dpredf, B * 6, gscale, st)); gs = gscale; }
+  if (precision == PREC_TC_SPLIT && split_fmt_g == 0) { MN_TRY(launch_grad_scale(dpredh, B * 6, gscale, st)); gs = gscale; }
   // dW_xyz[c][j] = sum_b dpred[b][c] * hdrop[b][j]
   MN_TRY(launch_small_gemm(0, dpredf, 1, 6, hdrop, 1, F, grads + xyz_w, F, 3, F, B, nullptr, nullptr, nullptr, st));
   MN_TRY(launch_small_gemm(0, dpredf + 3, 1, 6, hdrop, 1, F, grads + wpqr_w, F, 3, F, B, nullptr, nullptr, nullptr, st));
   MN_TRY(launch_colsum(dpredf, 6, B, 3, grads + xyz_b, st));
   MN_TRY(launch_colsum(dpredf + 3, 6, B, 3, grads + wpqr_b, st));
-  MN_TRY(launch_head_dh(dpredf, params + xyz_w, params + wpqr_w, last_has_mask ? mask : nullptr, fcpre, dh, B, F, st));
+  MN_TRY(launch_head_dh(dpredh, params + xyz_w, params + wpqr_w, last_has_mask ? mask : nullptr, fcpre, dh, B, F, st));
   // dW_fc[o][i] = sum_b dh[b][o] * feat[b][i];  db_fc = colsum(dh);  dfeat = dh @ W_fc
   MN_TRY(launch_small_gemm(0, dh, 1, F, feat, 1, 512, grads + fc_w, 512, F, 512, B, nullptr, nullptr, nullptr, st));
   MN_TRY(launch_colsum(dh, F, B, F, grads + fc_b, st));
@@ -625,9 +626,7 @@ int Net::forward(const float* x, const float* params, float* bufs, int B, int tr
 int Net::backward(const float* dpred, const float* params, float* grads, int filter_nans, cudaStream_t st) {
   MN_CHECK(dpred && params && grads, "backward: null pointer argument");
   if (precision == PREC_FP32) return backward_t<TypesF32>(dpred, params, grads, filter_nans, st);
-  if (precision == PREC_TC_SPLIT)
-    return split_fmt_g == 0 ? backward_t<TypesSplitHH>(dpred, params, grads, filter_nans, st)
-                            : backward_t<TypesSplitHB>(dpred, params, grads, filter_nans, st);
+  if (precision == PREC_TC_SPLIT) return backward_t<TypesSplitHH>(dpred, params, grads, filter_nans, st);
   return backward_t<TypesBF16>(dpred, params, grads, filter_nans, st);
 }
 

@@ -54,6 +54,20 @@ def _crit(ns, kind):
     return ns.MapNetOnlineCriterion(gps_mode=(kind == "online_gps"), **kw)
 
 
+# Gradient tensors kept ELEMENT-WISE (a per-tensor norm cannot see a gradient written in the wrong layout): one per
+# stage of the backward pass -- the stem, the first block, a downsample conv, the last conv, the first fc.  Tensors
+# larger than FULL_CAP elements are sampled with a fixed stride (deterministic; the rule is stored with the data).
+FULL_GRAD_NAMES = ["feature_extractor.conv1.weight", "feature_extractor.layer1.0.conv1.weight",
+                   "feature_extractor.layer2.0.downsample.0.weight", "feature_extractor.layer3.0.conv1.weight",
+                   "feature_extractor.layer4.2.conv2.weight", "feature_extractor.fc.weight", "fc_wpqr.weight",
+                   "feature_extractor.layer1.0.bn1.weight", "feature_extractor.layer4.2.bn2.bias"]
+FULL_CAP = 40000
+
+
+def sample_stride(numel):
+    return max(1, numel // FULL_CAP)
+
+
 def tensor_stats(t):
     t = t.detach().double().flatten()
     head = torch.zeros(8, dtype=torch.float64)
@@ -96,14 +110,48 @@ def run_step_config(name, cfg, seed=7):
         grad_head=np.stack(ghead),
         post_names=np.array(pnames), post_sum=np.array(psum), post_norm=np.array(pnorm),
         post_head=np.stack(phead),
+        grad_full_names=np.array(FULL_GRAD_NAMES),
         sgrad_names=np.array(list(cgrads.keys())),
         sgrads=np.array([float(v) if v is not None else np.nan for v in cgrads.values()]),
         post_svals=np.array([float(p.detach()) for _, p in crit.named_parameters()]),
     )
+    by_name = dict(zip(names, grads.values()))
+    for i, n in enumerate(FULL_GRAD_NAMES):
+        t = by_name[n].detach().flatten()
+        out["grad_full_%d" % i] = t[::sample_stride(t.numel())].numpy().copy()
     if x.numel() <= 4 * 6 * 3 * 64 * 64:
         out["x"] = x.numpy()
     np.savez_compressed(os.path.join(GOLD, "step_%s.npz" % name), **out)
     print("golden step_%s: loss=%.6f  ref time %.2fs" % (name, loss, dt), flush=True)
+
+
+# (emulation mode, config): fixtures of the ORACLE (not of the reference) run with the product's rounding points,
+# see mapnet_oracle.py `emulate`.  They separate "the narrow format is coarse" from "the kernel is wrong": the bf16
+# product is ~4e-2 off the fp32 reference on the pose, but must sit much closer to the oracle that rounds where it does.
+EMU_CONFIGS = [("bf16", "posenet_b8_256"), ("bf16", "posenet_b64_256"), ("bf16", "mapnet_n32t3_256"),
+               ("bf16", "online_n16t10_256"), ("f16x2", "posenet_b8_256"), ("f16x2", "posenet_b64_256")]
+
+
+def run_emulated(emulate, name, seed=7):
+    from . import mapnet_oracle as O
+    cfg = dict(STEP_CONFIGS, **FULL_CONFIGS)[name]
+    st = weights.make_state(seed)
+    x, targ = weights.make_inputs(cfg, seed)
+    kind = cfg["kind"]
+    t0 = time.time()
+    r = O.train_step(kind, st, x, targ, SVALS, lr=cfg.get("lr", 1e-4), weight_decay=cfg.get("wd", 5e-4),
+                     max_grad_norm=cfg.get("clip", 0.0), emulate=emulate, do_step=False,
+                     filter_nans=kind.startswith("online"))
+    names = list(r["grads"].keys())
+    out = dict(name=name, emulate=emulate, seed=seed, cfg=repr(cfg), oracle_seconds=time.time() - t0,
+               x_checksum=float(x.double().sum()), loss=np.float64(float(r["loss"])), pred=r["pred"].numpy(),
+               grad_names=np.array(names), grad_norm=np.array([float(r["grads"][k].double().norm()) for k in names]),
+               grad_full_names=np.array(FULL_GRAD_NAMES))
+    for i, n in enumerate(FULL_GRAD_NAMES):
+        t = r["grads"][n].detach().flatten()
+        out["grad_full_%d" % i] = t[::sample_stride(t.numel())].numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, "emu_%s_%s.npz" % (emulate, name)), **out)
+    print("oracle fixture emu_%s_%s: loss=%.6f  (%.1fs)" % (emulate, name, float(r["loss"]), out["oracle_seconds"]), flush=True)
 
 
 def run_pose_math(seed=7):
@@ -191,11 +239,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the BASELINE full-size configs (minutes)")
     ap.add_argument("--only", default=None)
+    ap.add_argument("--emulated", action="store_true", help="only the oracle-with-product-rounding fixtures (emu_*.npz)")
     a = ap.parse_args()
     if not ref_loader.available():
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if a.emulated:
+        for emulate, name in EMU_CONFIGS:
+            run_emulated(emulate, name)
+        return
     if a.only is None:
         run_keys()
         run_pose_math()

@@ -15,7 +15,9 @@ GPU box.  Pinned against the reference itself by tests/test_oracle_pinning.py
 Floating point: fp32 by default (what the reference computes in); pass float64
 tensors for a higher-precision arbiter.  ``emulate="bf16"`` reproduces the
 rounding points of the product's bf16 tensor-core path (operands of every conv
-rounded to bf16, stored activations rounded to bf16, fp32 accumulation/BN math).
+rounded to bf16, stored activations AND stored gradients rounded to bf16, fp32
+accumulation/BN math); ``emulate="f16x2"`` those of the strict tensor-core mode
+(conv operands = fp16 hi + lo planes, 22 significant bits; everything else fp32).
 """
 import math
 from collections import OrderedDict
@@ -194,18 +196,74 @@ BN_EPS = 1e-5       # torch.nn.BatchNorm2d default, used by torchvision resnet
 BN_MOMENTUM = 0.1
 
 
+def _round_bf16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def _round_f16x2(t):
+    """hi + lo with hi = fp16(t), lo = fp16(t - hi): the 22 significant bits the strict tensor-core mode's operand
+    planes carry (geomapnet_b200/csrc/common.cuh: hsplit; saturating at the fp16 range)."""
+    c = t.clamp(-65504.0, 65504.0)
+    hi = c.to(torch.float16).to(t.dtype)
+    return hi + (c - hi).to(torch.float16).to(t.dtype)
+
+
+class _RoundBoth(torch.autograd.Function):
+    """A tensor the product STORES in a narrow format: rounded on the way forward, and the gradient that flows back
+    through this point (the product stores that one too) rounded the same way."""
+
+    @staticmethod
+    def forward(ctx, t, fn):
+        ctx.fn = fn
+        return fn(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.fn(g), None
+
+
+class _RoundFwd(torch.autograd.Function):
+    """An operand copy (packed weights): rounded forward, gradient untouched (wgrad accumulates in fp32)."""
+
+    @staticmethod
+    def forward(ctx, t, fn):
+        return fn(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 def _rb(t, emulate):
-    """round-trip through bf16 when emulating the tensor-core path"""
+    """storage rounding point of an activation / conv output (and of the gradient w.r.t. it)"""
     if emulate == "bf16":
-        return t.to(torch.bfloat16).to(t.dtype)
+        return _RoundBoth.apply(t, _round_bf16)
     return t
 
 
 def _conv(x, w, stride, pad, emulate):
+    if emulate == "f16x2":
+        # strict tensor-core mode (precision tc_split): conv operands -- activations, weights and, in the backward
+        # pass, the gradient w.r.t. the conv output -- carry 22 significant bits; all four hi/lo products are
+        # formed and accumulated in fp32; conv outputs and everything element-wise stay fp32.
+        y = F.conv2d(_RoundFwd.apply(x, _round_f16x2), _RoundFwd.apply(w, _round_f16x2), None, stride, pad)
+        return _GradRound.apply(y)
     # operands rounded to bf16 (x already is when it is a stored activation);
     # products exact in fp32, fp32 accumulate -- what tcgen05 kind::f16 does.
-    y = F.conv2d(_rb(x, emulate), _rb(w, emulate), None, stride, pad)
+    y = F.conv2d(_rb(x, emulate), _RoundFwd.apply(w, _round_bf16) if emulate == "bf16" else w, None, stride, pad)
     return _rb(y, emulate)      # conv output is stored (bf16) before BN reads it
+
+
+class _GradRound(torch.autograd.Function):
+    """identity forward; the gradient w.r.t. a conv output is a backward conv OPERAND in the strict mode"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _round_f16x2(g)
 
 
 def _bn(y, st, prefix, training, bufs_out):
@@ -256,8 +314,25 @@ def trunk_forward(st, x, training=True, emulate=None, bufs_out=None, taps=None):
     return F.linear(feat, st[fe + "fc.weight"], st[fe + "fc.bias"])
 
 
+class _LinearNanFiltered(torch.autograd.Function):
+    """fc_wpqr with the backward hook of models/posenet.py:28-34,50-51: `filter_hook` clones every entry of the
+    Linear's grad_input -- the gradients w.r.t. bias, input and weight -- and sets their NaN entries to zero.
+    (Pinned against the reference module itself by tests/test_oracle_pinning.py with a NaN-producing gradient.)"""
+
+    @staticmethod
+    def forward(ctx, f, w, b):
+        ctx.save_for_backward(f, w)
+        return F.linear(f, w, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        f, w = ctx.saved_tensors
+        gf, gw, gb = g @ w, g.t() @ f, g.sum(0)
+        return tuple(torch.where(torch.isnan(t), torch.zeros_like(t), t) for t in (gf, gw, gb))
+
+
 def posenet_forward(st, x, training=True, drop_mask=None, emulate=None, bufs_out=None,
-                    taps=None):
+                    taps=None, filter_nans=False):
     """models/posenet.py:65-73.  drop_mask: None (droprate 0, the :68 guard) or a
     [B,feat_dim] tensor already scaled by 1/(1-p) (injected dropout mask)."""
     f = trunk_forward(st, x, training, emulate, bufs_out, taps)
@@ -265,7 +340,10 @@ def posenet_forward(st, x, training=True, drop_mask=None, emulate=None, bufs_out
     if drop_mask is not None:
         f = f * drop_mask
     xyz = F.linear(f, st["fc_xyz.weight"], st["fc_xyz.bias"])
-    wpqr = F.linear(f, st["fc_wpqr.weight"], st["fc_wpqr.bias"])
+    if filter_nans:
+        wpqr = _LinearNanFiltered.apply(f, st["fc_wpqr.weight"], st["fc_wpqr.bias"])
+    else:
+        wpqr = F.linear(f, st["fc_wpqr.weight"], st["fc_wpqr.bias"])
     return torch.cat((xyz, wpqr), 1)
 
 
@@ -322,11 +400,7 @@ def train_step(kind, st, x, targ, svals, learn=(True, True), lr=1e-4, weight_dec
     bufs_out = {}
     mkind = "posenet" if kind == "posenet" else "mapnet"
     pred = model_forward(mkind, full, x, training=True, drop_mask=drop_mask, emulate=emulate,
-                         bufs_out=bufs_out)
-    if filter_nans:
-        # models/posenet.py:28-34,50-51: NaNs in the gradient entering fc_wpqr are
-        # zeroed (hook on fc_wpqr); restated as a filter on d loss/d pred[..., 3:].
-        pred = _NanFilter.apply(pred)
+                         bufs_out=bufs_out, filter_nans=filter_nans)
     loss = criterion(kind, pred, targ, S)
     loss.backward()
     grads = OrderedDict((k, v.grad.detach().clone()) for k, v in P.items())
@@ -405,19 +479,6 @@ class OracleTrainer(object):
         for k, v in bufs_out.items():
             self.full[k] = v
         return float(loss.item())                                         # train.py:361
-
-
-class _NanFilter(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, pred):
-        return pred.view_as(pred)
-
-    @staticmethod
-    def backward(ctx, g):
-        g = g.clone()
-        q = g[..., 3:]
-        q[q != q] = 0
-        return g
 
 
 # --------------------------------------------------------------------------

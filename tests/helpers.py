@@ -84,6 +84,22 @@ def compare_with_golden(g, loss, pred, grads, sgrads, net, crit, tol, report=Non
     errs["grad_norm"] = gn
     errs["grad_norm_worst"] = worst
     errs["grad_head_vs_rms"] = gh
+    # element-wise comparison of the named gradient tensors (strided sample of the large ones): relative L2 error
+    gf, gf_worst, per = 0.0, None, {}
+    if "grad_full_names" in g.files:
+        for i, name in enumerate(g["grad_full_names"]):
+            ref = g["grad_full_%d" % i].astype(np.float64)
+            t = grads[str(name)].double().cpu().flatten().numpy()
+            stride = max(1, t.size // 40000)            # oracle/make_goldens.py: sample_stride
+            t = t[::stride]
+            assert t.shape == ref.shape, (str(name), t.shape, ref.shape)
+            e = float(np.linalg.norm(t - ref) / (np.linalg.norm(ref) + 1e-30))
+            per[str(name)] = e
+            if e > gf:
+                gf, gf_worst = e, str(name)
+    errs["grad_full"] = gf
+    errs["grad_full_worst"] = gf_worst
+    errs["grad_full_per_tensor"] = per
     sd = net.state_dict()
     pn = 0.0
     for i, name in enumerate(g["post_names"]):
@@ -102,6 +118,7 @@ def compare_with_golden(g, loss, pred, grads, sgrads, net, crit, tol, report=Non
     assert errs["pred"] <= tol["pred"], errs
     assert errs["grad_norm"] <= tol["grad"], errs
     assert errs["grad_head_vs_rms"] <= tol["grad_head"], errs
+    assert errs["grad_full"] <= tol.get("grad_full", 1e9), errs
     assert errs["post_norm"] <= tol["post"], errs
     assert errs["sgrad"] <= tol["sgrad"], errs
     return errs

@@ -60,22 +60,28 @@ def test_conv_engines(precision, geom):
     dyn = dy.permute(0, 2, 3, 1).contiguous().to(act).cuda()
     w_krsc = w.permute(0, 2, 3, 1).contiguous().to(wt).cuda()          # [Co][kh][kw][Ci]
     w_dg = w.permute(1, 2, 3, 0).contiguous().to(wt).cuda()            # [Ci][kh][kw][Co]
-    tol = 2e-5 if precision in ("fp32", "tc_split") else 1.2e-2     # bf16 output rounding: 2^-8 relative
+    # bf16: output rounding 2^-8 relative.  tc_split: fp32 outputs; what is left is the tensor core's fp32 accumulation
+    # (measured on B200, tools/experiments/mma_probe.cu: error grows linearly with K -- 1.2e-6 of sum|terms| at
+    # K = 4096 against 2e-8 at K = 64 -- i.e. the accumulator is truncated, not rounded, at every MMA)
+    tol = {"fp32": 2e-5, "tc_split": 1e-4}.get(precision, 1.2e-2)
+    errs = []
     # fprop
     out = torch.empty(y.permute(0, 2, 3, 1).shape, dtype=act, device="cuda")
     _run_conv(precision, 0, xn, None, w_krsc, out, geom)
     ref = y.permute(0, 2, 3, 1)
-    assert float((out.float().cpu() - ref).abs().max() / ref.abs().max()) < tol
+    errs.append(float((out.float().cpu() - ref).abs().max() / ref.abs().max()))
     # dgrad
     out = torch.empty(xn.shape, dtype=act, device="cuda")
     _run_conv(precision, 1, dyn, None, w_dg, out, geom)
     ref = dx.permute(0, 2, 3, 1)
-    assert float((out.float().cpu() - ref).abs().max() / ref.abs().max()) < tol
+    errs.append(float((out.float().cpu() - ref).abs().max() / ref.abs().max()))
     # wgrad (fp32 accumulators, accumulated into a zeroed buffer)
     out = torch.zeros(w_krsc.shape, dtype=torch.float32, device="cuda")
     _run_conv(precision, 2, xn, dyn, None, out, geom)
     ref = dw.permute(0, 2, 3, 1)
-    assert float((out.cpu() - ref).abs().max() / ref.abs().max()) < 5e-5
+    errs.append(float((out.cpu() - ref).abs().max() / ref.abs().max()))
+    print("conv-engine", precision, geom, "fprop %.2e dgrad %.2e wgrad %.2e" % tuple(errs))
+    assert errs[0] < tol and errs[1] < tol and errs[2] < max(5e-5, tol if precision == "tc_split" else 0.0), errs
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 64), (3, 97, 65), (4, 256, 256)])

@@ -99,3 +99,36 @@ def test_oracle_matches_live_reference(kind, cfg):
     for k, v in grads.items():
         k2 = k.replace("mapnet.", "", 1)
         assert float((v - r["grads"][k2]).norm()) <= 1e-5 * float(v.norm()) + 1e-12, k
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_oracle_nan_filter_matches_live_reference_hook():
+    """models/posenet.py:28-34,50-51 with a NaN-producing gradient: degenerate state (fc_wpqr = 0 -> every predicted
+    rotation is the identity -> qlog's backward gives NaN, the case the hook exists for) through the reference
+    MapNet + MapNetOnlineCriterion with filter_nans=True, against the oracle.  The hook zeroes NaNs of the Linear's
+    bias / input / weight gradients: whole weight rows and whole samples drop out, not single entries."""
+    ns = ref_loader.load()
+    st = weights.make_state(3)
+    st["fc_wpqr.weight"] = torch.zeros_like(st["fc_wpqr.weight"])
+    st["fc_wpqr.bias"] = torch.zeros_like(st["fc_wpqr.bias"])
+    cfg = dict(kind="online", N=2, T=4, H=64, W=64)
+    x, targ = weights.make_inputs(cfg, 3)
+    model = ref_loader.build_reference_model(st, "mapnet", filter_nans=True)
+    model.train()
+    crit = ns.MapNetOnlineCriterion(sax=0.0, saq=-3.0, srx=0.0, srq=-3.0, learn_beta=True, learn_gamma=True)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        loss, out, grads, cg = ref_loader.reference_step(model, crit, x, targ, do_step=False)
+    r = O.train_step("online", st, x, targ, SV, filter_nans=True, do_step=False)
+    # the unfiltered gradient really is NaN in the rotation half
+    r_nofilter = O.train_step("online", st, x, targ, SV, filter_nans=False, do_step=False)
+    assert bool(torch.isnan(r_nofilter["grads"]["fc_wpqr.weight"]).any())
+    n_zero_rows = 0
+    for k, v in grads.items():
+        k2 = k.replace("mapnet.", "", 1)
+        assert bool(torch.isfinite(v).all()) and bool(torch.isfinite(r["grads"][k2]).all()), k
+        assert float((v - r["grads"][k2]).norm()) <= 1e-5 * float(v.norm()) + 1e-12, k
+    for j in range(3):
+        n_zero_rows += int(bool((grads["mapnet.fc_wpqr.weight"][j] == 0).all()))
+    assert n_zero_rows >= 1, "the degenerate input was meant to wipe at least one fc_wpqr row"
