@@ -46,6 +46,10 @@ def lib():
     L.mapnet_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_uint64,
                                  c_uint64, c_void_p, c_void_p]
     L.mapnet_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.mapnet_backward_part.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.mapnet_backward_part.restype = c_int
+    L.mapnet_grad_part_range.argtypes = [c_void_p, c_int, POINTER(c_int64), POINTER(c_int64)]
+    L.mapnet_grad_part_range.restype = c_int
     L.mapnet_loss_fwd_bwd.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]
     L.mapnet_sqnorm.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
@@ -93,7 +97,8 @@ EXPORTED = ["mapnet_last_error", "mapnet_abi_version", "mapnet_trunk_create", "m
             "mapnet_test_conv", "mapnet_launch_count", "mapnet_profile", "mapnet_profile_read",
             "mapnet_adam_step_dev", "mapnet_bench_conv", "mapnet_test_stem",
             "mapnet_test_dgrad_shortcut", "mapnet_test_plan_describe", "mapnet_preprocess_create",
-            "mapnet_preprocess_output_size", "mapnet_preprocess_run", "mapnet_preprocess_destroy"]
+            "mapnet_preprocess_output_size", "mapnet_preprocess_run", "mapnet_preprocess_destroy",
+            "mapnet_backward_part", "mapnet_grad_part_range"]
 
 
 def check(rc, what):
@@ -128,6 +133,15 @@ class Trunk(object):
                                       ctypes.byref(off)), "mapnet_param_info")
             out.append((name.value.decode(), kind.value, tuple(shape[k] for k in range(ndim.value)), off.value))
         return out, L.mapnet_params_numel(self.h), L.mapnet_bufs_numel(self.h)
+
+    def grad_part_ranges(self):
+        """[(lo, hi)] float ranges of the flat gradient buffer completed by backward parts 0, 1, 2."""
+        out = []
+        lo, hi = c_int64(), c_int64()
+        for part in range(3):
+            check(lib().mapnet_grad_part_range(self.h, part, ctypes.byref(lo), ctypes.byref(hi)), "mapnet_grad_part_range")
+            out.append((lo.value, hi.value))
+        return out
 
     def close(self):
         if self.h:

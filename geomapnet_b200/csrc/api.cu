@@ -69,7 +69,22 @@ int mapnet_forward(mapnet_trunk_t* h, const float* x, const float* params_flat, 
 int mapnet_backward(mapnet_trunk_t* h, const float* dpred, const float* params_flat, float* grads_flat,
                     int filter_nans, void* stream) {
   MN_CHECK(h != nullptr, "backward: null handle");
-  return h->net.backward(dpred, params_flat, grads_flat, filter_nans, (cudaStream_t)stream);
+  return h->net.backward(dpred, params_flat, grads_flat, filter_nans, -1, (cudaStream_t)stream);
+}
+
+int mapnet_backward_part(mapnet_trunk_t* h, int part, const float* dpred, const float* params_flat, float* grads_flat,
+                         int filter_nans, void* stream) {
+  MN_CHECK(h != nullptr, "backward_part: null handle");
+  MN_CHECK(part >= 0 && part <= 2, "backward_part: part %d outside [0, 2]", part);
+  return h->net.backward(dpred, params_flat, grads_flat, filter_nans, part, (cudaStream_t)stream);
+}
+
+int mapnet_grad_part_range(mapnet_trunk_t* h, int part, int64_t* host_lo, int64_t* host_hi) {
+  MN_CHECK(h != nullptr && host_lo && host_hi && part >= 0 && part <= 2, "grad_part_range: bad argument");
+  long long lo = 0, hi = 0;
+  h->net.part_range(part, &lo, &hi);
+  *host_lo = lo; *host_hi = hi;
+  return 0;
 }
 
 int mapnet_loss_fwd_bwd(int mode, const float* pred, const float* targ, int N, int T_pred, int T_targ,
@@ -227,7 +242,7 @@ int mapnet_test_stem(int B, int H, int W, const float* x_nchw, const float* w_oi
     MN_CUDA(cudaMalloc(&d_wd, sizeof(WeightDesc)));
     MN_CUDA(cudaMemcpyAsync(d_wd, &wd, sizeof(wd), cudaMemcpyHostToDevice, st));
     MN_CUDA(cudaMemsetAsync(dwk, 0, (size_t)64 * 256 * sizeof(float), st));
-    MN_TRY(launch_stem_s2d(x_nchw, S, B, H, W, Hs, Wsp, st));
+    MN_TRY(launch_stem_s2d<bf16>(x_nchw, S, B, H, W, Hs, Wsp, st));
     MN_TRY(launch_pack_weights<bf16>(d_wd, 1, w_oihw, wk, nullptr, 64 * 256, 0, st));
     MN_TRY(tc_plan_create(&pf, g, 0, wk));
     MN_TRY(tc_conv_run(pf, S, nullptr, nullptr, y_out, st));

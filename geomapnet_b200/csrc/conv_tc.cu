@@ -1547,7 +1547,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
   // strict mode: the engines see 2*C 16-bit channels per pixel and every filter tap twice (hi / lo weight planes)
   const int SP = g.split ? 2 : 1;
-  MN_CHECK(!g.split || (KK <= 9 && g.in_pix_stride == 0), "tc conv: strict mode supports dense inputs and up to 9 taps");
+  MN_CHECK(!g.split || KK <= 9, "tc conv: strict mode supports up to 9 filter taps");
   {
     static int halo_mode = -1, halo_bo = -1;
     if (halo_mode < 0) { const char* e = getenv("MAPNET_TC_HALO"); halo_mode = e ? atoi(e) : 1; }

@@ -122,10 +122,11 @@ int launch_unpack_wgrads(const WeightDesc* d_descs, int nconv, const float* dw_k
                          int max_elems, cudaStream_t st);
 // space-to-depth image of the stem input: S[b][bh][bw][16] bf16, channel (pr*2+pc)*3+c of block (bh,bw)
 // = x[b][c][2*bh+pr-4][2*bw+pc-4] (0 outside the image, channels 12..15 = 0), row pitch Wsp blocks
-int launch_stem_s2d(const float* x_nchw, bf16* S, int B, int H, int W, int Hs, int Wsp, cudaStream_t st);
+template <typename TZ>
+int launch_stem_s2d(const float* x_nchw, TZ* S, int B, int H, int W, int Hs, int Wsp, cudaStream_t st);
 // geometry of the stem as the engines see it on that image (B left 0): 4 taps x 64 elements, overlapped view
 int stem_s2d_wsp(int wc);
-void stem_s2d_geometry(int H, int W, int Co, ConvGeom* g, WeightDesc* wd);
+void stem_s2d_geometry(int H, int W, int Co, ConvGeom* g, WeightDesc* wd, int elt_bytes = 2);
 template <typename T>
 int launch_stem_im2col(const float* x_nchw, T* A, int B, int H, int W, int Ho, int Wo, int Kpad, cudaStream_t st);
 

@@ -329,8 +329,9 @@ template int launch_stem_im2col<hsplit>(const float*, hsplit*, int, int, int, in
 // operand is an overlapped TMA view of S (pixel stride 16 elements, extent 64): a 4-tap conv with
 // "Cin" = 64 that the generic engines run unchanged.  35 MB written and read instead of 403 MB.
 // ---------------------------------------------------------------------------------
+template <typename TZ>
 __global__ void __launch_bounds__(256)
-k_stem_s2d(const float* __restrict__ x, bf16* __restrict__ S, int B, int H, int W, int Hs, int Wsp) {
+k_stem_s2d(const float* __restrict__ x, TZ* __restrict__ S, int B, int H, int W, int Hs, int Wsp) {
   pdl_prologue();
   const long long n = (long long)B * Hs * Wsp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -352,34 +353,37 @@ k_stem_s2d(const float* __restrict__ x, bf16* __restrict__ S, int B, int H, int 
         for (int c = 0; c < 3; ++c) v[(pr * 2 + pc) * 3 + c] = __ldg(x + (((long long)b * 3 + c) * H + ih) * W + iw);
       }
     }
-    uint4 o[2];
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+    Vec8<TZ> o0, o1;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-    uint4* dst = reinterpret_cast<uint4*>(S + i * 16);
-    dst[0] = o[0]; dst[1] = o[1];
+    for (int k = 0; k < 8; ++k) { o0.v[k] = v[k]; o1.v[k] = v[8 + k]; }
+    o0.store(S + i * 16);
+    o1.store(S + i * 16 + 8);
   }
 }
 
 int stem_s2d_wsp(int wc) { return (wc + 3 + 3) / 4 * 4; }   // blocks per image row, rows 128 B aligned
 
-void stem_s2d_geometry(int H, int W, int Co, ConvGeom* g, WeightDesc* wd) {
+// elt_bytes: bytes per stored element (2: bf16; 4: split fp16 planes, where a block of 16 channels is 32 16-bit elements)
+void stem_s2d_geometry(int H, int W, int Co, ConvGeom* g, WeightDesc* wd, int elt_bytes) {
   const int hc = (H + 6 - 7) / 2 + 1, wc = (W + 6 - 7) / 2 + 1;
   wd->Co = Co; wd->Ci_real = 3; wd->Ci = 64; wd->KH = 4; wd->KW = 1; wd->im2col_k = 256; wd->s2d = 1;
   g->B = 0; g->Hi = hc + 3; g->Wi = wc; g->Ci = 64; g->Co = Co; g->KH = 4; g->KW = 1; g->stride = 1; g->pad = 0;
   g->Ho = hc; g->Wo = wc;
-  g->in_pix_stride = 16 * 2;
-  g->in_row_stride = (long long)stem_s2d_wsp(wc) * 32;
+  g->in_pix_stride = 16 * elt_bytes;
+  g->in_row_stride = (long long)stem_s2d_wsp(wc) * 16 * elt_bytes;
   g->in_img_stride = (long long)(hc + 3) * g->in_row_stride;
 }
 
-int launch_stem_s2d(const float* x_nchw, bf16* S, int B, int H, int W, int Hs, int Wsp, cudaStream_t st) {
+template <typename TZ>
+int launch_stem_s2d(const float* x_nchw, TZ* S, int B, int H, int W, int Hs, int Wsp, cudaStream_t st) {
   const long long n = (long long)B * Hs * Wsp;
   long long grid = (n + 255) / 256;
   if (grid > 148LL * 8) grid = 148LL * 8;
-  MN_LAUNCH(k_stem_s2d, (int)grid, 256, 0, st, x_nchw, S, B, H, W, Hs, Wsp);
+  MN_LAUNCH(k_stem_s2d<TZ>, (int)grid, 256, 0, st, x_nchw, S, B, H, W, Hs, Wsp);
   MN_LAUNCH_CHECK();
   return 0;
 }
+template int launch_stem_s2d<bf16>(const float*, bf16*, int, int, int, int, int, cudaStream_t);
+template int launch_stem_s2d<hsplit>(const float*, hsplit*, int, int, int, int, int, cudaStream_t);
 
 }  // namespace mapnet

@@ -80,7 +80,7 @@ void Net::build_table() {
     c.wd.s2d = 0;
     if (stem && stem_s2d) {
       // 4 taps (filter rows of the space-to-depth image) x 64 contiguous elements (4 blocks x 16 channels)
-      stem_s2d_geometry(Hi, Wi, Co, &c.g, &c.wd);
+      stem_s2d_geometry(Hi, Wi, Co, &c.g, &c.wd, (int)elt());
     } else if (stem) {
       c.wd.Ci = kStemK; c.wd.KH = c.wd.KW = 1; c.wd.im2col_k = kStemK;
       c.g.Hi = conv_out(Hi, 7, 2, 3); c.g.Wi = conv_out(Wi, 7, 2, 3);   // GEMM view: 1x1 conv over the patch matrix
@@ -148,9 +148,10 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   split_fmt_z = 0; split_fmt_g = 0;
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0; prof_pool_used = 0;
-  { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
+  bwd_pre = false; bwd_next_part = 0;
+  { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = tc() && (e ? atoi(e) != 0 : 1); }
   { const char* e = getenv("MAPNET_STEM_S2D");
-    stem_s2d = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1) && (max_B == 0 || tc_overlapped_view_supported()); }
+    stem_s2d = tc() && (e ? atoi(e) != 0 : 1) && (max_B == 0 || tc_overlapped_view_supported()); }
   Hc = conv_out(H, 7, 2, 3); Wc = conv_out(W, 7, 2, 3);        // (build_table sets them again)
   { const char* e = getenv("MAPNET_STEM_FUSE"); stem_fuse = (e ? atoi(e) != 0 : 1) && (Hc % 2 == 0) && (Wc % 2 == 0); }
   // measured on B200 (posenet_bs64): finalizing inside the conv's last CTA costs every CTA a fence + counter round trip
@@ -419,7 +420,10 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
     MN_TRY(launch_pack_weights<float>(d_wdescs, (int)convs.size(), params, (float*)w_krsc, (float*)w_dg, max_w_elems,
                                       precision == PREC_BF16_SIMT, st));
   // stem: im2col -> GEMM -> BN -> ReLU -> maxpool
-  if (stem_s2d) MN_TRY(launch_stem_s2d(x, (bf16*)A0, B, H, W, Hc + 3, stem_s2d_wsp(Wc), st));
+  if (stem_s2d) {
+    if constexpr (std::is_same<TZ, float>::value) { MN_CHECK(false, "forward: the space-to-depth stem is a tensor-core path feature"); }
+    else MN_TRY(launch_stem_s2d<TZ>(x, (TZ*)A0, B, H, W, Hc + 3, stem_s2d_wsp(Wc), st));
+  }
   else MN_TRY(launch_stem_im2col<TZ>(x, (TZ*)A0, B, H, W, Hc, Wc, kStemK, st));
   {
     const EpiFin f0 = fin_forward(convs[0].bn, (long long)B * Hc * Wc, params, bufs);
@@ -468,29 +472,51 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
   MN_TRY(launch_small_gemm(0, hdrop, feat_dim, 1, params + xyz_w, feat_dim, 1, pred, 6, B, 3, feat_dim, params + xyz_b, nullptr, nullptr, st));
   MN_TRY(launch_small_gemm(0, hdrop, feat_dim, 1, params + wpqr_w, feat_dim, 1, pred + 3, 6, B, 3, feat_dim, params + wpqr_b, nullptr, nullptr, st));
   last_B = B; last_training = training; last_has_mask = (mk != nullptr);
+  bwd_next_part = 0;
   return 0;
 }
 
 // ---- backward ------------------------------------------------------------------
+// The backward pass runs in up to three PARTS so that a data-parallel caller can start the allreduce of a part's
+// gradients while the next part computes (geomapnet_b200/ddp.py): part 0 = head + layer4 (64 % of the parameters,
+// final after 20 % of the backward FLOPs), part 1 = layer3, part 2 = layer2, layer1, stem.  part < 0: everything.
+int Net::part_of_block(int bi) const { return blocks[bi].Cout >= 512 ? 0 : (blocks[bi].Cout >= 256 ? 1 : 2); }
+void Net::part_range(int part, long long* lo, long long* hi) const {
+  // float offsets into the flat parameter / gradient buffer; the table is in forward order, parts are contiguous
+  long long first[3] = {n_params, n_params, 0};
+  for (size_t bi = 0; bi < blocks.size(); ++bi) {
+    const int p = part_of_block((int)bi);
+    const long long off = convs[blocks[bi].conv1].wd.p_off;
+    if (p < 2 && off < first[p]) first[p] = off;
+  }
+  if (part == 0) { *lo = first[0]; *hi = n_params; }
+  else if (part == 1) { *lo = first[1]; *hi = first[0]; }
+  else { *lo = 0; *hi = first[1]; }
+}
+
 template <typename P>
-int Net::backward_t(const float* dpred, const float* params, float* grads, int filter_nans, cudaStream_t st) {
+int Net::backward_t(const float* dpred, const float* params, float* grads, int filter_nans, int part, cudaStream_t st) {
   typedef typename P::A T;        // conv outputs, gradients w.r.t. block outputs (fp32 math tensors)
   typedef typename P::Z TZ;       // forward conv operands
   typedef typename P::G TG;       // backward conv operands (gradients w.r.t. conv outputs)
   MN_CHECK(last_B > 0 && last_training, "backward: no training-mode forward precedes this call");
   const int B = last_B;
   const int F = feat_dim;
-  MN_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)wk_total * 4, st));
+  MN_CHECK(part <= 0 || bwd_next_part == part, "backward: part %d called out of order (next is %d)", part, bwd_next_part);
+  bwd_next_part = (part < 0 || part == 2) ? 0 : part + 1;
+  const bool do_head = part <= 0, do_stem = part < 0 || part == 2;
+  if (do_head) MN_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)wk_total * 4, st));
   // S0: d(block output), S3: gated gradient of the identity branch, S4: d h -- T;  S1 / S2: d(conv output) -- TG
   T* S0 = (T*)scratch[0]; TG* S1 = (TG*)scratch[1]; TG* S2 = (TG*)scratch[2]; T* S3 = (T*)scratch[3]; T* S4 = (T*)scratch[4];
 
   // ---- head (models/posenet.py:67-73 backward, NaN filter :28-34) ----
   float* dpredh = dpredf + (size_t)max_B * 6;         // second filtered copy (gradient into the trunk)
-  MN_TRY(launch_dpred_filter(dpred, dpredf, dpredh, B, filter_nans, st));
   // strict mode: the backward conv operands are fp16 planes; ONE power-of-two scale per step (from max|d pred|)
   // places every gradient tensor inside fp16's window, the consuming conv epilogues divide it out again
-  const float* gs = nullptr;
-  if (precision == PREC_TC_SPLIT && split_fmt_g == 0) { MN_TRY(launch_grad_scale(dpredh, B * 6, gscale, st)); gs = gscale; }
+  const float* gs = (precision == PREC_TC_SPLIT && split_fmt_g == 0) ? gscale : nullptr;
+  if (do_head) {
+  MN_TRY(launch_dpred_filter(dpred, dpredf, dpredh, B, filter_nans, st));
+  if (gs != nullptr) MN_TRY(launch_grad_scale(dpredh, B * 6, gscale, st));
   // dW_xyz[c][j] = sum_b dpred[b][c] * hdrop[b][j]
   MN_TRY(launch_small_gemm(0, dpredf, 1, 6, hdrop, 1, F, grads + xyz_w, F, 3, F, B, nullptr, nullptr, nullptr, st));
   MN_TRY(launch_small_gemm(0, dpredf + 3, 1, 6, hdrop, 1, F, grads + wpqr_w, F, 3, F, B, nullptr, nullptr, nullptr, st));
@@ -502,14 +528,20 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
   MN_TRY(launch_colsum(dh, F, B, F, grads + fc_b, st));
   MN_TRY(launch_small_gemm(0, dh, F, 1, params + fc_w, 1, 512, dfeat, 512, B, 512, F, nullptr, nullptr, nullptr, st));
   MN_TRY(launch_gap_bwd<T>(dfeat, S0, B, Hf * Wf, 512, st));
+  bwd_pre = false;
+  }
 
   // ---- residual blocks, last to first ----
   // fuse_bwd (tcgen05 path): the dgrad that PRODUCES a BatchNorm's incoming gradient gates it with that
   // BN's ReLU and accumulates its backward reductions in the epilogue (conv_tc.cu, EpiBwd), so only a tiny
   // finalize and the apply pass remain.  `pre` = S0 arrives gated with the BN2 sums of this block pending.
-  bool pre = false;
+  bool pre = bwd_pre;
+  int conv_lo = (int)convs.size(), conv_hi = -1;       // convs whose weight gradients this call completes
   for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
+    if (part >= 0 && part_of_block(bi) != part) continue;
     BlockL& bl = blocks[bi];
+    conv_lo = bl.conv1 < conv_lo ? bl.conv1 : conv_lo;
+    { const int last = bl.convd >= 0 ? bl.convd : bl.conv2; conv_hi = last > conv_hi ? last : conv_hi; }
     const TZ* zin = (bi == 0) ? (const TZ*)z0 : (const TZ*)blocks[bi - 1].out;
     const long long Mo = (long long)B * bl.Ho * bl.Wo;
     const int C = bl.Cout;
@@ -591,8 +623,10 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     }
     pre = next_pre;
   }
+  bwd_pre = pre;
   // ---- stem: maxpool -> ReLU -> BN -> conv (no input gradient: nothing consumes it) ----
-  {
+  if (do_stem) {
+    conv_lo = 0; if (conv_hi < 0) conv_hi = 0;
     BNL& b0 = bns[convs[0].bn];
     const long long M0 = (long long)B * Hc * Wc;
     if (stem_fuse) {
@@ -609,7 +643,8 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, (const TZ*)nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st, nullptr, nullptr, gs)));
     MN_TRY(conv_wgrad<P>(0, (const TZ*)A0, S2, B, st));
   }
-  MN_TRY(launch_unpack_wgrads(d_wdescs, (int)convs.size(), dw_krsc, grads, max_w_elems, st));
+  if (conv_hi >= conv_lo)
+    MN_TRY(launch_unpack_wgrads(d_wdescs + conv_lo, conv_hi - conv_lo + 1, dw_krsc, grads, max_w_elems, st));
   return 0;
 }
 
@@ -623,11 +658,12 @@ int Net::forward(const float* x, const float* params, float* bufs, int B, int tr
   return forward_t<TypesBF16>(x, params, bufs, B, training, droprate, seed, step, pred, st);
 }
 
-int Net::backward(const float* dpred, const float* params, float* grads, int filter_nans, cudaStream_t st) {
+int Net::backward(const float* dpred, const float* params, float* grads, int filter_nans, int part, cudaStream_t st) {
   MN_CHECK(dpred && params && grads, "backward: null pointer argument");
-  if (precision == PREC_FP32) return backward_t<TypesF32>(dpred, params, grads, filter_nans, st);
-  if (precision == PREC_TC_SPLIT) return backward_t<TypesSplitHH>(dpred, params, grads, filter_nans, st);
-  return backward_t<TypesBF16>(dpred, params, grads, filter_nans, st);
+  MN_CHECK(part >= -1 && part <= 2, "backward: part %d outside [-1, 2]", part);
+  if (precision == PREC_FP32) return backward_t<TypesF32>(dpred, params, grads, filter_nans, part, st);
+  if (precision == PREC_TC_SPLIT) return backward_t<TypesSplitHH>(dpred, params, grads, filter_nans, part, st);
+  return backward_t<TypesBF16>(dpred, params, grads, filter_nans, part, st);
 }
 
 }  // namespace mapnet

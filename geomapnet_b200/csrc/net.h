@@ -100,7 +100,11 @@ struct Net {
   void destroy();
   int forward(const float* x, const float* params, float* bufs, int B, int training, float droprate,
               unsigned long long seed, unsigned long long step, float* pred, cudaStream_t st);
-  int backward(const float* dpred, const float* params, float* grads, int filter_nans, cudaStream_t st);
+  // part: -1 = the whole backward pass; 0, 1, 2 = its three parts, called in that order (net.cu: part_of_block)
+  int backward(const float* dpred, const float* params, float* grads, int filter_nans, int part, cudaStream_t st);
+  int part_of_block(int bi) const;
+  void part_range(int part, long long* lo, long long* hi) const;
+  bool bwd_pre; int bwd_next_part;      // state carried between the parts of one backward pass
 
  private:
   int alloc(void** p, size_t bytes);
@@ -110,7 +114,7 @@ struct Net {
                                       float droprate, unsigned long long seed, unsigned long long step,
                                       float* pred, cudaStream_t st);
   template <typename P> int backward_t(const float* dpred, const float* params, float* grads, int filter_nans,
-                                       cudaStream_t st);
+                                       int part, cudaStream_t st);
   template <typename P> int conv_fprop(int ci, const typename P::Z* x, const typename P::A* residual, typename P::A* y, int B,
                                        cudaStream_t st, bool with_stats = false, const EpiFin* fin = nullptr);
   template <typename P> int conv_dgrad(int ci, const typename P::G* dy, const typename P::A* residual, typename P::A* dx, int B,

@@ -1,5 +1,6 @@
-"""Plain data parallel over the GPUs of one box: one process per GPU, ONE
-allreduce of the flat gradient buffer per step (NCCL over NVLink 5 / NVSwitch).
+"""Plain data parallel over the GPUs of one box: one process per GPU, the flat
+gradient buffer sum-reduced over NCCL (NVLink 5 / NVSwitch) -- in three slices
+that overlap the rest of the backward pass.
 
 The reference is single-GPU (common/train.py:193-196); this is the multi-GPU
 row of SURVEY.md section 8e.  Tuples (the N dimension of [N,T,3,H,W]) are sharded
@@ -8,6 +9,14 @@ couples frames inside a tuple (common/criterion.py:94-105).  BatchNorm
 statistics stay per-rank (no SyncBN), as when running the reference at the
 local batch size.  Equal local batches => mean of local L1 means == global L1
 mean, so averaged gradients equal the single-process gradient.
+
+Overlap: the backward pass finishes the gradients back to front.  The library
+runs it in three parts (mapnet_backward_part: head + layer4 = 64 % of the
+89.4 MB after ~20 % of the backward FLOPs, then layer3, then the rest) and
+calls back after each one; the callback enqueues that slice's allreduce on a
+side stream behind an event, so only the last 5 MB slice (and a 16-byte reduce
+of the criterion scalars) is exposed.  Measured in round 1 with ONE blocking
+allreduce after the backward: +0.42 ms per 4.1 ms step at 8 GPUs (SCALE_r01).
 
 All functions work on any device/backend (gloo on CPU in the tests).
 """
@@ -27,27 +36,21 @@ def shard_tuples(x, rank, world):
 
 
 def allreduce_flat_(flat_grad, extra_grads=(), group=None, average=False):
-    """ONE sum-allreduce over ``flat_grad`` with the (tiny) ``extra_grads`` tensors
-    (criterion scalars sax/saq/srx/srq) riding in its last padding slots.
-    In-place; returns the world size.  With average=False the caller folds 1/world
-    into the optimizer step (FusedAdam grad_scale)."""
+    """Sum-allreduce of ``flat_grad`` plus the (tiny) ``extra_grads`` tensors (criterion scalars
+    sax/saq/srx/srq), in place; returns the world size.  The extras travel as ONE packed tensor in a second,
+    16-byte collective (they are produced by a different autograd node than the flat buffer, so they cannot be
+    assumed to sit in it).  With average=False the caller folds 1/world into the optimizer step
+    (FusedAdam grad_scale)."""
     world = dist.get_world_size(group)
-    extras = [g for g in extra_grads if g is not None]
-    k = sum(g.numel() for g in extras)
-    if k > 0:
-        tail = flat_grad[flat_grad.numel() - k:]
-        saved = tail.clone()
-        off = 0
-        for g in extras:
-            tail[off:off + g.numel()] = g.reshape(-1).to(tail.dtype)
-            off += g.numel()
     dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
-    if k > 0:
+    extras = [g for g in extra_grads if g is not None]
+    if extras:
+        packed = torch.cat([g.reshape(-1).to(flat_grad.dtype) for g in extras])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
         off = 0
         for g in extras:
-            g.copy_(tail[off:off + g.numel()].view_as(g))
+            g.copy_(packed[off:off + g.numel()].view_as(g))
             off += g.numel()
-        tail.copy_(saved * world)   # padding slots: restore what the sum would have held
     if average:
         flat_grad.mul_(1.0 / world)
         for g in extras:
@@ -58,19 +61,31 @@ def allreduce_flat_(flat_grad, extra_grads=(), group=None, average=False):
 class FlatDataParallel(object):
     """Wraps a geomapnet_b200 PoseNet/MapNet (+ criterion) for data-parallel steps.
 
-        dp = FlatDataParallel(model, criterion)       # broadcasts rank 0's weights
-        loss = criterion(model(x_local), targ_local); loss.backward()
-        scale = dp.allreduce_grads()                  # one NCCL allreduce; returns 1/world
+        dp = FlatDataParallel(model, criterion)       # then dp.broadcast_parameters() once
+        loss = criterion(model(x_local), targ_local); loss.backward()   # slices are reduced WHILE this runs
+        scale = dp.allreduce_grads()                  # joins the side stream (+ the scalars); returns 1/world
         optimizer.learner.step(grad_scale=scale)
+
+    overlap=False: one blocking allreduce of the whole buffer inside allreduce_grads() (the round-1 behaviour).
     """
 
-    def __init__(self, model, criterion=None, group=None, broadcast=True):
+    def __init__(self, model, criterion=None, group=None, broadcast=True, overlap=True):
         self.model = model
         self.posenet = model.mapnet if hasattr(model, "mapnet") else model
         self.criterion = criterion
         self.group = group
         self.world = dist.get_world_size(group)
         self._broadcast_pending = broadcast
+        self.overlap = bool(overlap)
+        self._side = None
+        self._parts_done = 0
+        self._reduced_buf = None
+        if self.overlap:
+            self.posenet._grad_part_hook = self._on_part
+
+    def close(self):
+        if getattr(self.posenet, "_grad_part_hook", None) == self._on_part:
+            self.posenet._grad_part_hook = None
 
     def broadcast_parameters(self):
         flat, _ = self.posenet.flat_parameters()
@@ -81,14 +96,66 @@ class FlatDataParallel(object):
                 dist.broadcast(p.data, src=0, group=self.group)
         self._broadcast_pending = False
 
+    # -- overlap machinery -----------------------------------------------------------------------------------
+    def _side_stream(self, device):
+        if device.type != "cuda":
+            return None
+        if self._side is None or self._side.device != device:
+            self._side = torch.cuda.Stream(device)
+        return self._side
+
+    def _on_part(self, part, grad_slice):
+        """Called by PoseNet._run_backward right after backward part `part` was enqueued: its slice of the flat
+        gradient buffer is final once the compute stream reaches this point."""
+        if self._broadcast_pending:
+            raise RuntimeError("call broadcast_parameters() once after the model is on its device")
+        side = self._side_stream(grad_slice.device)
+        if side is None:                         # CPU tensors (gloo tests): no streams, reduce in place now
+            dist.all_reduce(grad_slice, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            side.wait_stream(torch.cuda.current_stream(grad_slice.device))
+            with torch.cuda.stream(side):
+                dist.all_reduce(grad_slice, op=dist.ReduceOp.SUM, group=self.group)
+        self._parts_done = part + 1
+
+    def _criterion_grads(self):
+        if self.criterion is None:
+            return []
+        return [p.grad for p in self.criterion.parameters() if p.requires_grad and p.grad is not None]
+
     def allreduce_grads(self):
         if self._broadcast_pending:
             raise RuntimeError("call broadcast_parameters() once after the model is on its device")
         _, gflat = self.posenet.flat_parameters()
         if gflat is None:
             raise RuntimeError("no gradient buffer: run backward() first")
-        extras = []
-        if self.criterion is not None:
-            extras = [p.grad for p in self.criterion.parameters() if p.requires_grad and p.grad is not None]
-        allreduce_flat_(gflat, extras, group=self.group, average=False)
+        # the buffer this reduces must be the one the optimizer reads through p.grad (gradient accumulation or
+        # zero_grad(set_to_none=False) make autograd accumulate into a DIFFERENT tensor than the last backward wrote)
+        g0 = self.posenet._param_list[0].grad
+        if g0 is None or not (gflat.data_ptr() <= g0.data_ptr() < gflat.data_ptr() + gflat.numel() * gflat.element_size()):
+            raise RuntimeError("FlatDataParallel: parameter .grad does not alias the flat gradient buffer of the last "
+                               "backward (gradient accumulation is not supported: call zero_grad() -- set_to_none=True -- "
+                               "before every backward)")
+        extras = self._criterion_grads()
+        if self.overlap and self._parts_done == 3:
+            self._parts_done = 0
+            side = self._side_stream(gflat.device)
+            if extras:
+                packed = torch.cat([g.reshape(-1).float() for g in extras])
+                if side is not None:
+                    side.wait_stream(torch.cuda.current_stream(gflat.device))
+                    with torch.cuda.stream(side):
+                        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+                else:
+                    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+            if side is not None:
+                torch.cuda.current_stream(gflat.device).wait_stream(side)
+            if extras:
+                off = 0
+                for g in extras:
+                    g.copy_(packed[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+        else:
+            self._parts_done = 0
+            allreduce_flat_(gflat, extras, group=self.group, average=False)
         return 1.0 / self.world

@@ -124,6 +124,7 @@ class PoseNet(nn.Module):
         self._seed = int(seed) if seed is not None else int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
         self._last_shape = None
         self._graph_rng = False      # True: dropout counter lives on the device (CUDA-graph capture)
+        self._grad_part_hook = None  # callable(part, flat_grad_slice) set by ddp.FlatDataParallel (overlapped allreduce)
 
     # ------------------------------------------------------------------ tree
     def _build_tree(self):
@@ -272,10 +273,22 @@ class PoseNet(nn.Module):
                 break
         gbuf = self._gflat[sel]
         self._gsel = sel
+        hook = self._grad_part_hook
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().mapnet_backward(trunk.h, dpred.data_ptr(), self._flat.data_ptr(),
-                                                  gbuf.data_ptr(), 1 if self.filter_nans else 0,
-                                                  _lib.stream_ptr()), "mapnet_backward")
+            if hook is None:
+                _lib.check(_lib.lib().mapnet_backward(trunk.h, dpred.data_ptr(), self._flat.data_ptr(),
+                                                      gbuf.data_ptr(), 1 if self.filter_nans else 0,
+                                                      _lib.stream_ptr()), "mapnet_backward")
+            else:
+                # data parallel: the pass runs in three parts; after each one the hook may start reducing that part's
+                # (final) slice of the flat gradient buffer on another stream while the next part computes
+                ranges = trunk.grad_part_ranges()
+                for part in range(3):
+                    _lib.check(_lib.lib().mapnet_backward_part(trunk.h, part, dpred.data_ptr(), self._flat.data_ptr(),
+                                                               gbuf.data_ptr(), 1 if self.filter_nans else 0,
+                                                               _lib.stream_ptr()), "mapnet_backward_part")
+                    lo, hi = ranges[part]
+                    hook(part, gbuf[lo:hi])
         self.last_grad_flat = gbuf
         out = []
         for name, kind, shape, off in self._table:

@@ -74,9 +74,20 @@ int mapnet_forward(mapnet_trunk_t* h, const float* x, const float* params_flat, 
 
 /* ---- backward of the last training forward: dpred [B,6] -> every parameter gradient,
  * written (not accumulated) into grads_flat at the offsets of params_flat.
- * filter_nans: zero NaNs in dpred[:,3:] first (models/posenet.py:28-34 hook). */
+ * filter_nans: the NaN filter of the models/posenet.py:28-34 hook on fc_wpqr (NaN entries of that Linear's bias /
+ * input / weight gradients become 0: a NaN in dpred[b,3+j] wipes row j of d W_wpqr and sample b's rotation
+ * half of the gradient into the trunk). */
 int mapnet_backward(mapnet_trunk_t* h, const float* dpred, const float* params_flat, float* grads_flat,
                     int filter_nans, void* stream);
+
+/* The same backward pass in three parts, called in order 0, 1, 2 with the same arguments: after part k returns
+ * (asynchronously, on `stream`) the gradients in grads_flat[lo_k, hi_k) (mapnet_grad_part_range) are final, so a
+ * data-parallel caller can enqueue their allreduce on another stream while the next part computes.
+ * Part 0 = head + layer4 (64 % of the parameters after ~20 % of the backward FLOPs), 1 = layer3, 2 = layer2, layer1, stem.
+ * (The reference is single-GPU, common/train.py:193-196; this is the overlap hook of SURVEY.md section 8e.) */
+int mapnet_backward_part(mapnet_trunk_t* h, int part, const float* dpred, const float* params_flat, float* grads_flat,
+                         int filter_nans, void* stream);
+int mapnet_grad_part_range(mapnet_trunk_t* h, int part, int64_t* host_lo, int64_t* host_hi);
 
 /* ---- fused criterion forward+backward.  s4 = device (sax,saq,srx,srq).
  * Outputs: loss[1], dpred (same shape as pred), ds4[4] = d loss / d s4. */

@@ -1,5 +1,5 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: tuple sharding and the
-single flat-gradient allreduce with the criterion scalars riding in the padding."""
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: tuple sharding, the flat-gradient allreduce (one blocking
+call, or three slices reduced from the backward-part hook) and the packed reduce of the criterion scalars."""
 import os
 import socket
 import sys
@@ -24,6 +24,10 @@ class _FakeNet(object):
         self._bufs = torch.randn(128, generator=g)
         self.g = torch.randn(1024 + 64, generator=g)
         self.g[1024:] = 0
+        p = torch.nn.Parameter(self._flat[:16])
+        p.grad = self.g[:16]                     # .grad aliases the flat gradient buffer, as in PoseNet
+        self._param_list = [p]
+        self._grad_part_hook = None
 
     def flat_parameters(self):
         return self._flat, self.g
@@ -42,8 +46,13 @@ def _worker(rank, world, port, q):
     crit.sax = torch.nn.Parameter(torch.tensor([float(rank)])); crit.saq = torch.nn.Parameter(torch.tensor([1.0]))
     crit.sax.grad = torch.tensor([1.0 + rank]); crit.saq.grad = torch.tensor([10.0 * (rank + 1)])
     g_before = net.g.clone()
-    dp = FlatDataParallel(net, crit)
+    dp = FlatDataParallel(net, crit, overlap=(os.environ.get("TEST_DDP_OVERLAP") == "1"))
     dp.broadcast_parameters()
+    if dp.overlap:
+        # what PoseNet._run_backward does: three parts, back to front, each followed by the hook
+        assert net._grad_part_hook is not None
+        for part, (lo, hi) in enumerate([(700, 1088), (300, 700), (0, 300)]):
+            net._grad_part_hook(part, net.g[lo:hi])
     scale = dp.allreduce_grads()
     gathered = [torch.zeros_like(g_before) for _ in range(world)]
     dist.all_gather(gathered, g_before)
@@ -55,11 +64,23 @@ def _worker(rank, world, port, q):
     # parameters were broadcast from rank 0
     ref = _FakeNet(0)
     ok = ok and torch.equal(net._flat, ref._flat) and float(crit.sax) == 0.0
+    # a .grad that does not alias the reduced buffer (gradient accumulation) is refused, not silently mis-reduced
+    net._param_list[0].grad = torch.zeros(16)
+    try:
+        dp.allreduce_grads()
+        ok = False
+    except RuntimeError:
+        pass
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
 
-def test_flat_allreduce_world2_gloo():
+import pytest
+
+
+@pytest.mark.parametrize("overlap", ["0", "1"])
+def test_flat_allreduce_world2_gloo(overlap, monkeypatch):
+    monkeypatch.setenv("TEST_DDP_OVERLAP", overlap)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
