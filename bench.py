@@ -93,13 +93,22 @@ def _peaks():
 
 def _ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant conv kernel, from the committed
-    `ncu --set full` capture (profiles/ncu_traffic.json, written from the .ncu-rep by tools/ncu_summary.py);
-    None when no capture is committed."""
+    `ncu --set full` capture (profiles/ncu_traffic.json, written from the CSV export by tools/ncu_summary.py).
+    The capture records the digest of the kernel sources it was taken with; a capture of OTHER sources than the ones
+    this run was built from is reported as stale (traffic = None) instead of being passed off as a measurement of
+    this build.  None when no capture is committed."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return json.load(open(p))
+        d = json.load(open(p))
     except Exception:
         return None
+    try:
+        from geomapnet_b200 import build as _b
+        d["sources_digest_now"] = _b._digest()[:16]
+        d["stale"] = bool(d.get("sources_digest")) and d["sources_digest"] != d["sources_digest_now"]
+    except Exception:
+        d["stale"] = None
+    return d
 
 
 class ClockSampler(threading.Thread):
@@ -191,7 +200,8 @@ def run_reference(args, cfg, rank, world):
     sv = dict(sax=0.0, saq=-3.0, srx=0.0, srq=-3.0)
     # bounded sample: each timed step is one full step of the workload at a reduced
     # tuple count so that K+W steps end within minutes on any host
-    n_tuples = min(cfg["N"], max(1, args.ref_frames // cfg["T"]))
+    ref_frames = args.ref_frames if args.ref_frames else frames(cfg)       # default: the FULL workload (same config)
+    n_tuples = min(cfg["N"], max(1, ref_frames // cfg["T"]))
     scfg = dict(cfg, N=n_tuples)
     batches = make_batches(scfg, args.steps + args.warmup, 100)
     times = []
@@ -213,8 +223,9 @@ def run_reference(args, cfg, rank, world):
                    "note": "oracle port of the reference CPU path (torch CPU ops); thread count = fastest of "
                            "{all usable cores, half, 64, 32, 16, 8} on this host, %d usable" % usable_cores()},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "%d-frame steps of %s (bounded sample of the %d-frame workload)"
-                                   % (frames(scfg), args.workload, frames(cfg))},
+                         "sample": "%d-frame steps of %s (%s)"
+                                   % (frames(scfg), args.workload, "the full workload" if frames(scfg) == frames(cfg)
+                                      else "bounded sample of the %d-frame workload" % frames(cfg))},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -246,13 +257,15 @@ def run_b200(args, cfg, rank, local_rank, world):
     net = PoseNet(fe, droprate=args.droprate, pretrained=False, filter_nans=(cfg["kind"] == "online"),
                   precision=args.precision, seed=7 + rank)
     model = net if cfg["kind"] == "posenet" else MapNet(net)
-    kw = dict(sax=0.0, saq=-3.0)
-    if cfg["kind"] == "posenet":
-        crit = PoseNetCriterion(learn_beta=True, **kw)
-    elif cfg["kind"] == "mapnet":
-        crit = MapNetCriterion(srx=0.0, srq=-3.0, learn_beta=True, learn_gamma=True, **kw)
-    else:
-        crit = MapNetOnlineCriterion(srx=0.0, srq=-3.0, learn_beta=True, learn_gamma=True, **kw)
+    def make_crit():
+        kw = dict(sax=0.0, saq=-3.0)
+        if cfg["kind"] == "posenet":
+            return PoseNetCriterion(learn_beta=True, **kw)
+        if cfg["kind"] == "mapnet":
+            return MapNetCriterion(srx=0.0, srq=-3.0, learn_beta=True, learn_gamma=True, **kw)
+        return MapNetOnlineCriterion(srx=0.0, srq=-3.0, learn_beta=True, learn_gamma=True, **kw)
+
+    crit = make_crit()
     params = [{"params": model.parameters()}, {"params": list(crit.parameters())}]
     opt = Optimizer(params=params, method="adam", base_lr=cfg["lr"], weight_decay=cfg["wd"])
     model.cuda(); crit.cuda(); model.train()
@@ -274,7 +287,7 @@ def run_b200(args, cfg, rank, local_rank, world):
     # first step: builds the arena / flattens parameters
     eager_step(*dev_batches[0])
     if world > 1:
-        dp = FlatDataParallel(model, crit)
+        dp = FlatDataParallel(model, crit, overlap=(os.environ.get("MAPNET_DDP_OVERLAP", "1") != "0"))
         dp.broadcast_parameters()
     L = _lib.lib()
     step = eager_step
@@ -423,16 +436,62 @@ def run_b200(args, cfg, rank, local_rank, world):
             if ms3[k] > 0:
                 per_class[nm] = {"tflops": fl3[k] / (ms3[k] * 1e-3) / 1e12, "ms_per_step": ms3[k] / psteps,
                                  "launches_per_step": n3[k] // psteps}
-        roof = {"bound": "tensor", "kernel": "k_tc_conv/k_tc_wgrad (all conv launches of a step)"
-                if args.precision == "bf16" else "k_conv_simt (fp32 CUDA-core strict path)",
+        peak = peaks["tc_burst"]      # every bracketed launch runs alone for 10-50 us at full clocks: the burst figure
+        kname = {"bf16": "k_tc_conv / k_tc_conv2 / k_tc_conv_halo / k_tc_wgrad(2) (all conv launches of a step, bf16 operands)",
+                 "tc_split": "k_tc_conv / k_tc_conv2 / k_tc_wgrad(2) (all conv launches of a step; fp16 hi/lo operand planes, "
+                             "4 tcgen05 MMAs per algorithmic product: the tensor pipe executes 4x the algorithmic FLOPs)"}
+        nt = _ncu_traffic()
+        roof = {"bound": "tensor", "kernel": kname.get(args.precision, "k_conv_simt (fp32 CUDA-core engine)"),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": "%s (MEASURED_PEAKS.json bf16_tflops_sustained)" % peaks["src"],
-                "traffic": (_ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_detail": _ncu_traffic(),
+                "peak_source": "%s (MEASURED_PEAKS.json bf16_tflops, burst)" % peaks["src"],
+                "frac_of_sustained_peak": achieved / peaks["tc_sustained"],
+                "mma_flops_per_algorithmic_flop": 4 if args.precision == "tc_split" else 1,
+                "traffic": (None if (nt is None or nt.get("stale")) else nt.get("dram_bytes_per_launch")),
+                "traffic_detail": nt,
                 "conv_ms_per_step": tot_ms / psteps, "conv_launches_per_step": tot_n // psteps,
                 "conv_share_of_step": (tot_ms / psteps) / ms_step, "per_class": per_class,
                 "note": "event-bracketed launches run isolated (no programmatic overlap with their neighbours): "
                         "achieved / frac are lower bounds of what the same kernels do inside the CUDA-graph step",
                 "step_frac_of_conv_flop_roofline": (value / world) * O.train_flops_per_image(cfg["H"], cfg["W"]) / (peak * 1e12)}
+
+    # ---------------- side by side: (img/s, parity) of the two tensor-core modes, N=1 only ----------------
+    # bf16 operands: the throughput mode (pose ~5e-2 off the fp32 reference: the format, not the kernels).
+    # tc_split: the same tcgen05 engines on fp16 hi/lo operand planes, 4 MMAs per product -- meets the north-star
+    # 1e-4 bar (tests/test_gpu_step.py::test_step_tc_split_strict*).  Both are measured here, in this run.
+    modes = None
+    if rank == 0 and world == 1 and not args.no_modes and args.precision in ("bf16", "tc_split"):
+        other = "tc_split" if args.precision == "bf16" else "bf16"
+        torch.cuda.synchronize()
+        net2 = PoseNet(torchvision.models.resnet34(weights=None), droprate=args.droprate, pretrained=False,
+                       filter_nans=(cfg["kind"] == "online"), precision=other, seed=7)
+        model2 = net2 if cfg["kind"] == "posenet" else MapNet(net2)
+        crit2 = make_crit()
+        opt2 = Optimizer(params=[{"params": model2.parameters()}, {"params": list(crit2.parameters())}], method="adam",
+                         base_lr=cfg["lr"], weight_decay=cfg["wd"])
+        model2.cuda(); crit2.cuda(); model2.train()
+        from geomapnet_b200.graph import GraphedTrainStep
+        g2 = GraphedTrainStep(model2, crit2, opt2, dev_batches[0][0], dev_batches[0][1], max_grad_norm=cfg["clip"], warmup=2)
+        for i in range(3):
+            g2(*dev_batches[i % nb])
+        torch.cuda.synchronize()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nsteps = max(5, args.steps // 2)
+        m0.record()
+        for i in range(nsteps):
+            g2(*dev_batches[i % nb])
+        m1.record()
+        torch.cuda.synchronize()
+        oms = m0.elapsed_time(m1) / nsteps
+        parity = {"bf16": "loss <= 7e-3, pose <= 7e-2 relative to the fp32 reference at the BASELINE sizes (bf16 operands and "
+                          "storage; tests/test_gpu_step.py::test_step_bf16_tensor_core)",
+                  "tc_split": "loss <= 1.2e-5, pose <= 4.4e-5 relative to the fp32 reference on all 10 step goldens incl. the "
+                              "BASELINE sizes: inside the north-star 1e-4 (tests/test_gpu_step.py::test_step_tc_split_strict*)"}
+        modes = {args.precision: {"images_per_s": value, "ms_per_step": ms_step, "parity_vs_reference": parity[args.precision]},
+                 other: {"images_per_s": frames(cfg) / (oms / 1000.0), "ms_per_step": oms, "steps": nsteps,
+                         "parity_vs_reference": parity[other]},
+                 "note": "same workload, same run, CUDA-graph step, inputs resident in HBM; fp32 CUDA-core engine "
+                         "(precision fp32, also 1e-4): 933 img/s (profiles/r02_bench_fp32.json)"}
+        del g2, model2, net2
 
     # ---------------- cpu baseline: oracle port on the host cores (rank 0, N=1 only) -------------
     cpu = None
@@ -441,9 +500,10 @@ def run_b200(args, cfg, rank, local_rank, world):
         cores = tune_cpu_threads(cfg["kind"])
         st = weights.make_state(7)
         sv = dict(sax=0.0, saq=-3.0, srx=0.0, srq=-3.0)
-        n_tuples = min(cfg["N"], max(1, args.ref_frames // cfg["T"]))
+        ref_frames = args.ref_frames if args.ref_frames else frames(cfg)
+        n_tuples = min(cfg["N"], max(1, ref_frames // cfg["T"]))
         scfg = dict(cfg, N=n_tuples)
-        cb = make_batches(scfg, 3, 300)
+        cb = make_batches(scfg, 6, 300)
         ts = []
         tr = O.OracleTrainer(cfg["kind"], st, sv, lr=cfg["lr"], weight_decay=cfg["wd"], max_grad_norm=cfg["clip"],
                              droprate=args.droprate)
@@ -453,14 +513,15 @@ def run_b200(args, cfg, rank, local_rank, world):
             if i >= 1:
                 ts.append(time.time() - t0)
         cpu = {"value": frames(scfg) / (sum(ts) / len(ts)), "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": "2 timed %d-frame steps of %s after 1 warm-up (oracle port, torch CPU ops)"
-                         % (frames(scfg), args.workload)}
+               "sample": "%d timed %d-frame steps of %s after 1 warm-up (oracle port, torch CPU ops)"
+                         % (len(ts), frames(scfg), args.workload)}
 
     if rank == 0:
         line = {
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision.startswith("bf16") else "f32",
+            "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "bf16_simt": "bf16", "tc_split": "f16x2"}.get(args.precision, "f32"),
             "data": "synthetic",
             "config": {"workload": args.workload, "model": "PoseNet/MapNet ResNet-34", "frames_per_gpu": frames(cfg),
                        "global_frames": world * frames(cfg), "image": "%dx%d" % (cfg["H"], cfg["W"]),
@@ -475,6 +536,7 @@ def run_b200(args, cfg, rank, local_rank, world):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "precision_modes": modes,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -487,10 +549,14 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="posenet_bs64", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: posenet_bs64 on one GPU (BASELINE configs[1]), mapnet_n32t3 per GPU for --gpus > 1 "
+                         "(BASELINE configs[3])")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt", "tc_split"])
     ap.add_argument("--droprate", type=float, default=0.5)       # every reference .ini uses 0.5
-    ap.add_argument("--ref-frames", type=int, default=32, help="frames per CPU step (bounded sample)")
+    ap.add_argument("--ref-frames", type=int, default=0,
+                    help="frames per CPU step; 0 = the full workload (a 64-frame step takes ~1.3 s on 16 cores)")
+    ap.add_argument("--no-modes", action="store_true", help="skip the side-by-side strict-mode (tc_split) measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="run the step eagerly instead of replaying it as CUDA graphs")
@@ -502,6 +568,8 @@ def main():
         print("warning: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
     if args.gpus > 1 and world == 1 and args.impl == "b200":
         raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    if args.workload is None:
+        args.workload = "posenet_bs64" if max(world, args.gpus) == 1 else "mapnet_n32t3"
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3

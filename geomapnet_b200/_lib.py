@@ -70,8 +70,10 @@ def lib():
     L.mapnet_preprocess_run.argtypes = [c_void_p, c_void_p, c_int, POINTER(c_float), POINTER(c_float), c_void_p, c_void_p,
                                         c_void_p]
     L.mapnet_preprocess_destroy.argtypes = [c_void_p]
+    L.mapnet_preprocess_run_ex.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, POINTER(c_float), POINTER(c_float),
+                                           c_void_p, c_void_p, c_void_p]
     for name in ("mapnet_preprocess_create", "mapnet_preprocess_output_size", "mapnet_preprocess_run",
-                 "mapnet_preprocess_destroy"):
+                 "mapnet_preprocess_run_ex", "mapnet_preprocess_destroy"):
         getattr(L, name).restype = c_int
     L.mapnet_test_plan_describe.argtypes = [c_int] * 9 + [c_char_p, c_int]
     L.mapnet_test_plan_describe.restype = c_int
@@ -98,7 +100,7 @@ EXPORTED = ["mapnet_last_error", "mapnet_abi_version", "mapnet_trunk_create", "m
             "mapnet_adam_step_dev", "mapnet_bench_conv", "mapnet_test_stem",
             "mapnet_test_dgrad_shortcut", "mapnet_test_plan_describe", "mapnet_preprocess_create",
             "mapnet_preprocess_output_size", "mapnet_preprocess_run", "mapnet_preprocess_destroy",
-            "mapnet_backward_part", "mapnet_grad_part_range"]
+            "mapnet_backward_part", "mapnet_grad_part_range", "mapnet_preprocess_run_ex"]
 
 
 def check(rc, what):

@@ -79,7 +79,6 @@ class FlatDataParallel(object):
         self.overlap = bool(overlap)
         self._side = None
         self._parts_done = 0
-        self._reduced_buf = None
         if self.overlap:
             self.posenet._grad_part_hook = self._on_part
 
@@ -123,7 +122,16 @@ class FlatDataParallel(object):
             return []
         return [p.grad for p in self.criterion.parameters() if p.requires_grad and p.grad is not None]
 
-    def allreduce_grads(self):
+    def join_slices(self):
+        """Make the compute stream wait for the slice allreduces issued from the backward-part hook."""
+        if self._side is not None:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+
+    def allreduce_grads(self, slices_in_graph=False):
+        """slices_in_graph: the three slice allreduces were captured into the CUDA graph that just replayed (and joined
+        there): only the criterion scalars remain."""
+        if slices_in_graph:
+            self._parts_done = 3
         if self._broadcast_pending:
             raise RuntimeError("call broadcast_parameters() once after the model is on its device")
         _, gflat = self.posenet.flat_parameters()

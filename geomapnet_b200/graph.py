@@ -2,8 +2,12 @@
 
 The step is ~290 short kernel launches; replaying it as two CUDA graphs removes the
 host launch cost and most of the inter-kernel gaps (Blackwell guideline 9).  Graph 1 =
-forward + criterion + zero_grad + backward, graph 2 = [clip +] Adam; the gradient
-allreduce of data-parallel runs sits between them, outside capture.
+forward + criterion + zero_grad + backward, graph 2 = [clip +] Adam.  Data parallel: the
+three slice allreduces that FlatDataParallel issues from the backward-part hook are captured
+INSIDE graph 1, on a side stream that forks from and joins the capturing stream, so on replay
+NCCL runs concurrently with the rest of the backward; only the 16-byte reduce of the
+criterion scalars stays eager between the two graphs (overlap=False: the whole-buffer
+allreduce sits there instead, as in round 1).
 
     step = GraphedTrainStep(model, criterion, optimizer, x_example, targ_example)
     loss = step(x, targ)            # x, targ: CUDA tensors (copied into static buffers)
@@ -99,6 +103,8 @@ class GraphedTrainStep(object):
         loss = self.criterion(out, self.t)
         self.learner.zero_grad()
         loss.backward()
+        if self.dp is not None and getattr(self.dp, "overlap", False):
+            self.dp.join_slices()         # the side stream's NCCL work joins the (capturing) stream here
         return loss.detach()
 
     def _opt(self):
@@ -114,7 +120,7 @@ class GraphedTrainStep(object):
         self.t.copy_(targ, non_blocking=True)
         self.g1.replay()
         if self.dp is not None:
-            self.dp.allreduce_grads()
+            self.dp.allreduce_grads(slices_in_graph=getattr(self.dp, "overlap", False))
         self.g2.replay()
         if hasattr(self.learner, "advance_host_step"):
             self.learner.advance_host_step(1)

@@ -110,9 +110,11 @@ int mapnet_adam_step_dev(float* p, const float* g, float* exp_avg, float* exp_av
                          float beta1, float beta2, float eps, float weight_decay, int32_t* step_counter,
                          float grad_scale, const float* sqnorm, float max_norm, void* stream);
 
-/* ---- GPU-side image pre-processing (STAGED -- see geomapnet_b200/csrc/preprocess.cu).
+/* ---- GPU-side input pipeline (geomapnet_b200/csrc/preprocess.cu).
  * Replaces the per-image CPU transform stack of /root/reference/scripts/train.py:119-128 (and eval.py:97-101):
- * transforms.Resize(size) [Pillow bilinear on 8-bit images, bit-exact] -> ToTensor -> Normalize(mean, std).
+ * transforms.Resize(size) [Pillow bilinear on 8-bit images, bit-exact] [-> ColorJitter, train.py:121-126, bit-exact]
+ * -> ToTensor -> Normalize(mean, std), and the frame gather of the MF / MFOnline tuple datasets
+ * (dataset_loaders/composite.py:60-97,117-126).
  * One plan per input size; frames are uint8 [n][Hin][Win][3] in device memory, the result float32 [n][3][Hout][Wout]
  * (what PoseNet.forward takes).  mean3 / std3 are HOST pointers to 3 floats (stats.txt row 0, sqrt of row 1). */
 typedef struct mapnet_preprocess mapnet_preprocess_t;
@@ -120,6 +122,13 @@ int mapnet_preprocess_create(mapnet_preprocess_t** out, int Hin, int Win, int si
 int mapnet_preprocess_output_size(const mapnet_preprocess_t* h, int* Hout, int* Wout);
 int mapnet_preprocess_run(mapnet_preprocess_t* h, const void* img_nhwc_u8, int n, const float* mean3, const float* std3,
                           float* out_nchw, void* out_u8_or_null /* the resized uint8 image, tests */, void* stream);
+/* frame_index_dev: NULL, or n int32 in DEVICE memory -- output image i is cut from frame frame_index[i] of the sequence
+ * at img_nhwc_u8 (the tuple gather).  jitter_dev: NULL, or n records {int32 order[4]; float factor[4]} in DEVICE memory:
+ * the adjustments (0 brightness, 1 contrast, 2 saturation, 3 hue -- torchvision's fn_idx) in the order they are applied
+ * and their factors indexed by adjustment id, i.e. one ColorJitter.get_params() draw per image. */
+int mapnet_preprocess_run_ex(mapnet_preprocess_t* h, const void* img_nhwc_u8, int n, const int32_t* frame_index_dev,
+                             const void* jitter_dev, const float* mean3, const float* std3, float* out_nchw,
+                             void* out_u8_or_null, void* stream);
 int mapnet_preprocess_destroy(mapnet_preprocess_t* h);
 
 /* ---- measurement support (bench.py): number of kernels this library has launched so

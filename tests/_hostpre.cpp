@@ -32,3 +32,27 @@ void hp_preprocess(const uint8_t* img, int H, int W, int Ho, int Wo, const float
 }
 
 }  // extern "C"
+
+// ---- ColorJitter arithmetic (geomapnet_b200/csrc/jitter_core.h) ------------------------------------------------
+#include "../geomapnet_b200/csrc/jitter_core.h"
+
+extern "C" {
+
+// rounded mean luma of an RGB image: int(ImageStat.Stat(img.convert("L")).mean[0] + 0.5)
+int hj_gray_mean(const uint8_t* img, long long npix) {
+  unsigned long long s = 0;
+  for (long long i = 0; i < npix; ++i) s += jit_luma(img[3 * i], img[3 * i + 1], img[3 * i + 2]);
+  return (int)((double)s / (double)npix + 0.5);
+}
+
+// one adjustment of a whole image, in place
+void hj_apply(uint8_t* img, long long npix, int op, float factor) {
+  const int mean = (op == JIT_CONTRAST) ? hj_gray_mean(img, npix) : 0;
+  const uint8_t shift = jit_hue_shift(factor);
+  for (long long i = 0; i < npix; ++i) jit_apply(op, factor, mean, shift, img + 3 * i);
+}
+
+void hj_rgb2hsv(const uint8_t* in, uint8_t* out, long long npix) { for (long long i = 0; i < npix; ++i) jit_rgb2hsv(in + 3 * i, out + 3 * i); }
+void hj_hsv2rgb(const uint8_t* in, uint8_t* out, long long npix) { for (long long i = 0; i < npix; ++i) jit_hsv2rgb(in + 3 * i, out + 3 * i); }
+
+}  // extern "C"

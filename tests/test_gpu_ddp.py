@@ -57,9 +57,26 @@ def _worker(rank, world, port, q):
     sg = [torch.zeros_like(sax_local) for _ in range(world)]
     dist.all_gather(sg, sax_local)
     ok = ok and abs(float(crit.sax.grad) - float(sum(sg))) <= 1e-5 * abs(float(sum(sg))) + 1e-7
-    opt.learner.step(grad_scale=scale)
+    ok = ok and dp.overlap and net._grad_part_hook is not None      # the slices were reduced from the backward-part hook
+    g_eager = g.clone()
+    # the same step captured as CUDA graphs, slice allreduces INSIDE graph 1 (geomapnet_b200/graph.py): same weights
+    # (nothing has stepped yet, and building the graphed step restores the state) -> same reduced gradient
+    from geomapnet_b200.graph import GraphedTrainStep
+    gstep = GraphedTrainStep(model, crit, opt, xs, ts, dp=dp, warmup=2)
+    gstep.x.copy_(xs); gstep.t.copy_(ts)
+    gstep.g1.replay()
+    dp.allreduce_grads(slices_in_graph=True)
+    _, g2 = net.flat_parameters()
+    err = float((g2 - g_eager).abs().max()) / float(g_eager.abs().max())
+    ok = ok and err <= 1e-4
+    ok = ok and abs(float(crit.sax.grad) - float(sum(sg))) <= 1e-5 * abs(float(sum(sg))) + 1e-7
+    for _ in range(2):
+        loss = gstep(xs, ts)
+    ok = ok and bool(torch.isfinite(loss).all())
     after = flat.clone(); dist.broadcast(after, src=0)
     ok = ok and torch.equal(flat, after)        # replicas stay in lock-step
+    if not ok:
+        print("rank", rank, "graph-vs-eager reduced gradient rel err", err, flush=True)
     torch.cuda.synchronize()
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
