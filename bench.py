@@ -540,6 +540,12 @@ def run_b200(args, cfg, rank, local_rank, world):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # CUDA graphs that captured NCCL work must be gone before their communicator is torn down
+        step = gstep = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

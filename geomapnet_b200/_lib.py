@@ -75,6 +75,13 @@ def lib():
     for name in ("mapnet_preprocess_create", "mapnet_preprocess_output_size", "mapnet_preprocess_run",
                  "mapnet_preprocess_run_ex", "mapnet_preprocess_destroy"):
         getattr(L, name).restype = c_int
+    L.mapnet_pose_post.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    L.mapnet_pose_post.restype = c_int
+    L.mapnet_pgo_optimize.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_double, c_int, c_int, c_void_p, c_void_p]
+    L.mapnet_pgo_optimize.restype = c_int
+    L.mapnet_test_conv_epilogue.argtypes = [c_int] * 8 + [c_void_p] * 10 + [c_void_p]
+    L.mapnet_test_conv_epilogue.restype = c_int
     L.mapnet_test_plan_describe.argtypes = [c_int] * 9 + [c_char_p, c_int]
     L.mapnet_test_plan_describe.restype = c_int
     L.mapnet_launch_count.restype = ctypes.c_ulonglong
@@ -100,7 +107,7 @@ EXPORTED = ["mapnet_last_error", "mapnet_abi_version", "mapnet_trunk_create", "m
             "mapnet_adam_step_dev", "mapnet_bench_conv", "mapnet_test_stem",
             "mapnet_test_dgrad_shortcut", "mapnet_test_plan_describe", "mapnet_preprocess_create",
             "mapnet_preprocess_output_size", "mapnet_preprocess_run", "mapnet_preprocess_destroy",
-            "mapnet_backward_part", "mapnet_grad_part_range", "mapnet_preprocess_run_ex"]
+            "mapnet_backward_part", "mapnet_grad_part_range", "mapnet_preprocess_run_ex", "mapnet_test_conv_epilogue", "mapnet_pose_post", "mapnet_pgo_optimize"]
 
 
 def check(rc, what):

@@ -23,7 +23,7 @@ _SUFFIX = "" if EPI_WARPS == DEFAULT_EPI_WARPS else "_e%d" % EPI_WARPS
 OUT = os.path.join(CSRC, "libmapnet_b200%s.so" % _SUFFIX)
 OBJ = os.path.join(CSRC, "_obj" + _SUFFIX)
 SOURCES = ["api.cu", "net.cu", "bn.cu", "conv_simt.cu", "conv_tc.cu", "layout.cu", "head.cu", "loss.cu", "adam.cu",
-           "preprocess.cu"]
+           "preprocess.cu", "pgo.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v", "-DMN_EPI_WARPS=%d" % EPI_WARPS]

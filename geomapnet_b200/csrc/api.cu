@@ -1,6 +1,8 @@
 // extern "C" entry points declared in include/mapnet_b200.h.
 #include <math.h>
 
+#include <vector>
+
 #include "../../include/mapnet_b200.h"
 #include "net.h"
 
@@ -218,6 +220,55 @@ int mapnet_test_dgrad_shortcut(int B, int Hi, int Wi, int Ci, int Co, const void
   if (r == 0) r = tc_conv_run(plan, (const bf16*)dy1, (const bf16*)dy2, nullptr, dx, st);
   if (r == 0) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) { set_last_error("test_dgrad_shortcut: %s", cudaGetErrorString(e)); r = 1; } }
   tc_plan_destroy(plan);
+  return r;
+}
+
+// One tcgen05 conv launch WITH its fused epilogue, as the training step runs it (bf16 mode):
+//   kind 0 (fprop):  out = conv(in0, wmat);  sums[0..1][c] = (sum out, sum out^2) over the stored bf16 values
+//                    -- the BatchNorm batch statistics the step takes from the conv epilogue;
+//   kind 1 (dgrad):  g = conv_dgrad(in0, wmat) [+ residual], gated by the consumer BatchNorm's ReLU
+//                    (zmask > 0, or mscale * y + mshift > 0 when zmask is null), stored as bf16;
+//                    sums[0..2][c] = (sum g, sum g*y [, sum g*yd]) over the stored values -- that BatchNorm's
+//                    backward reductions.
+// host_sums: [3][C] doubles (C = output channels of the launch), replicas already summed.
+int mapnet_test_conv_epilogue(int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride, const void* in0,
+                              const void* wmat, const void* residual, const void* y, const void* zmask, const void* yd,
+                              const float* mscale, const float* mshift, void* out, double* host_sums, void* stream) {
+  MN_TRY(require_device());
+  MN_CHECK((kind == 0 || kind == 1) && in0 && wmat && out && host_sums, "test_conv_epilogue: bad argument");
+  ConvGeom g;
+  g.B = B; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Co = Co; g.KH = g.KW = k; g.stride = stride; g.pad = (k - 1) / 2;
+  g.Ho = (Hi + 2 * g.pad - k) / stride + 1; g.Wo = (Wi + 2 * g.pad - k) / stride + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = (kind == 0) ? Co : Ci;
+  const size_t acc_doubles = 32 * 3 * 512;
+  double* acc = nullptr;
+  TcConvPlan* plan = nullptr;
+  std::vector<double> h(acc_doubles);
+  auto body = [&]() -> int {
+    MN_CUDA(cudaMalloc((void**)&acc, acc_doubles * sizeof(double)));
+    MN_CUDA(cudaMemsetAsync(acc, 0, acc_doubles * sizeof(double), st));
+    MN_TRY(tc_plan_create(&plan, g, kind, (const bf16*)wmat));
+    EpiBwd E; memset(&E, 0, sizeof(E));
+    if (kind == 1) {
+      MN_CHECK(y != nullptr, "test_conv_epilogue: the dgrad epilogue needs y");
+      E.y = (const bf16*)y; E.zmask = (const bf16*)zmask; E.yd = (const bf16*)yd; E.mscale = mscale; E.mshift = mshift;
+    }
+    MN_TRY(tc_conv_run(plan, (const bf16*)in0, nullptr, (const bf16*)residual, out, st, acc, kind == 1 ? &E : nullptr));
+    MN_CUDA(cudaMemcpyAsync(h.data(), acc, acc_doubles * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  };
+  const int r = body();
+  if (r == 0)
+    for (int j = 0; j < 3; ++j)
+      for (int c = 0; c < C; ++c) {
+        double s = 0.0;
+        for (int rep = 0; rep < 32; ++rep) s += h[(size_t)rep * 3 * 512 + (size_t)j * C + c];
+        host_sums[(size_t)j * C + c] = s;
+      }
+  if (plan) tc_plan_destroy(plan);
+  cudaFree(acc);
   return r;
 }
 

@@ -79,8 +79,20 @@ class FlatDataParallel(object):
         self.overlap = bool(overlap)
         self._side = None
         self._parts_done = 0
+        self._slice_group = group
         if self.overlap:
             self.posenet._grad_part_hook = self._on_part
+            # The slice allreduces run WHILE the backward's conv kernels fill every SM (persistent CTAs, ~200 KB of
+            # shared memory each): on a normal-priority stream NCCL's CTAs only get placed when a conv kernel drains
+            # and nothing overlaps (measured at N=2: 5.678 vs 5.674 ms/step with and without the hook).  A separate
+            # NCCL communicator on HIGH-PRIORITY streams lets the block scheduler place them as soon as any CTA retires.
+            if dist.get_backend(group) == "nccl" and self.world > 1:
+                try:
+                    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                    ranks = dist.get_process_group_ranks(group) if group is not None else None
+                    self._slice_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+                except Exception:                       # older torch: keep the default communicator
+                    self._slice_group = group
 
     def close(self):
         if getattr(self.posenet, "_grad_part_hook", None) == self._on_part:
@@ -100,7 +112,7 @@ class FlatDataParallel(object):
         if device.type != "cuda":
             return None
         if self._side is None or self._side.device != device:
-            self._side = torch.cuda.Stream(device)
+            self._side = torch.cuda.Stream(device, priority=-1)
         return self._side
 
     def _on_part(self, part, grad_slice):
@@ -110,11 +122,11 @@ class FlatDataParallel(object):
             raise RuntimeError("call broadcast_parameters() once after the model is on its device")
         side = self._side_stream(grad_slice.device)
         if side is None:                         # CPU tensors (gloo tests): no streams, reduce in place now
-            dist.all_reduce(grad_slice, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(grad_slice, op=dist.ReduceOp.SUM, group=self._slice_group)
         else:
             side.wait_stream(torch.cuda.current_stream(grad_slice.device))
             with torch.cuda.stream(side):
-                dist.all_reduce(grad_slice, op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(grad_slice, op=dist.ReduceOp.SUM, group=self._slice_group)
         self._parts_done = part + 1
 
     def _criterion_grads(self):

@@ -131,6 +131,20 @@ int mapnet_preprocess_run_ex(mapnet_preprocess_t* h, const void* img_nhwc_u8, in
                              void* out_u8_or_null, void* stream);
 int mapnet_preprocess_destroy(mapnet_preprocess_t* h);
 
+/* ---- batched inference post-processing + pose-graph optimisation (csrc/pgo.cu).
+ * mapnet_pose_post: scripts/eval.py:163-181 for n poses at once -- pred6 = (t, log q) float32 -> out7 = (t * pose_s +
+ * pose_m, qexp(log q)) float64; pose_m3 / pose_s3 are HOST pointers (pose_stats.txt) or NULL (keep the translations).
+ * mapnet_pgo_optimize: common/pose_utils.py:458-804 (PoseGraph / PoseGraphFC.optimize behind optimize_poses) for
+ * n_windows windows of N <= 16 poses in one launch: poses [n_windows][N][7], vos [n_windows][E][7] (E = N-1, or N(N-1)/2
+ * pairs i<j row-major when fc_vos), quaternions (w,x,y,z), fp64, device pointers; sax..srq are the covariances
+ * eval.py passes; n_iters = 10 in the reference.  flags bit 0: 0 = the reference's linear solve taken literally
+ * (pose_utils.py:605-608 calls solve_triangular(R.T, -b) with scipy's default lower=False, which reads only the diagonal
+ * of R': x = R^-1 diag(R)^-1 (-b)), 1 = the Gauss-Newton step H^-1 (-b).  *status_dev (device int, may be NULL) is set
+ * to 1 when a window's normal matrix is not positive definite (scipy's cholesky raises there). */
+int mapnet_pose_post(const float* pred6, double* out7, int64_t n, const double* pose_m3, const double* pose_s3, void* stream);
+int mapnet_pgo_optimize(const double* poses, const double* vos, double* out, int n_windows, int N, int fc_vos,
+                        double sax, double saq, double srx, double srq, int n_iters, int flags, int* status_dev, void* stream);
+
 /* ---- measurement support (bench.py): number of kernels this library has launched so
  * far in this process, and per-class conv timing with CUDA events on the launching
  * stream (class 0 fprop, 1 dgrad, 2 wgrad; algorithmic FLOPs of each launch summed). */
@@ -152,6 +166,15 @@ int mapnet_test_plan_describe(int kind, int B, int Hi, int Wi, int Ci, int Co, i
  * (torchvision BasicBlock.forward's two uses of the block input, /root/reference/models/posenet.py:66). */
 int mapnet_test_dgrad_shortcut(int B, int Hi, int Wi, int Ci, int Co, const void* dy1, const void* dy2,
                                const void* w1_dg, const void* w2_dg, void* dx, void* stream);
+
+/* one tcgen05 conv launch with the epilogue the training step fuses into it (bf16 mode; tensors bf16 NHWC):
+ * kind 0 fprop -> out + the BatchNorm batch statistics (sum, sum of squares per output channel) of the stored values;
+ * kind 1 dgrad -> out = the gradient gated by the consumer BatchNorm's ReLU (+ residual) and that BatchNorm's backward
+ * reductions (sum g, sum g*y [, sum g*yd]).  host_sums: [3][C] doubles.  Replaces cuDNN BN forward-training statistics
+ * and the reduction half of cuDNN BN backward behind torchvision BasicBlock (/root/reference/models/posenet.py:66). */
+int mapnet_test_conv_epilogue(int kind, int B, int Hi, int Wi, int Ci, int Co, int k, int stride, const void* in0,
+                              const void* wmat, const void* residual, const void* y, const void* zmask, const void* yd,
+                              const float* mscale, const float* mshift, void* out, double* host_sums, void* stream);
 
 /* the tensor-core stem (7x7/s2/p3, 3 -> 64) alone, as the trunk runs it: space-to-depth image, packed weights,
  * fprop into y_out (bf16 NHWC [B,Hc,Wc,64]) and, when dy / dw_oihw are given, the weight gradient in the

@@ -218,6 +218,56 @@ def run_pose_math(seed=7):
     print("golden pose_math: %d arrays" % len(out), flush=True)
 
 
+def run_pgo(seed=7):
+    """Known-answer vectors of the reference's pose-graph optimisation (common/pose_utils.py:458-804), made by running
+    its own PoseGraph / PoseGraphFC classes from source (oracle.pgo_oracle.load_reference): windows of predicted poses,
+    VOs and covariances in -> optimised poses out.  Includes the covariances scripts/eval.py derives from a trained
+    criterion (exp of the learned log-variances) and a degenerate window (all poses equal)."""
+    from . import pgo_oracle as P
+    ns = P.load_reference()
+    rng = np.random.default_rng(seed)
+
+    def rand_poses(n):
+        t = rng.normal(size=(n, 3)).cumsum(0) * 0.3
+        v = rng.normal(size=(n, 3)) * 0.4
+        q = np.stack([np.concatenate(([np.cos(np.linalg.norm(a))], np.sinc(np.linalg.norm(a) / np.pi) * a)) for a in v])
+        return np.hstack((t, q))
+
+    out = {}
+    cases = [(3, False, 8, (1.0, 1.0, 1.0, 1.0)), (5, False, 6, (1.0, 0.05, 1.0, 0.05)), (7, False, 5, (2.0, 0.5, 0.5, 0.2)),
+             (4, True, 5, (1.0, 1.0, 1.0, 1.0)), (6, True, 4, (1.0, 0.05, 1.0, 0.05)), (16, False, 2, (1.0, 1.0, 1.0, 1.0))]
+    for ci, (n, fc, w, sig) in enumerate(cases):
+        P_in, V_in, ref = [], [], []
+        for k in range(w):
+            gt = rand_poses(n)
+            if ci == 0 and k == 0:
+                gt = np.tile(gt[:1], (n, 1))                    # degenerate: identical poses
+            pred = gt + rng.normal(size=gt.shape) * 0.05
+            E = P.edges(n, fc)
+            vos = np.zeros((len(E), 7))
+            for e, (i, j) in enumerate(E):
+                vos[e, :3] = P.rotate_vector(gt[j, :3] - gt[i, :3], P.qinverse(gt[i, 3:]))
+                vos[e, 3:] = P.qmult(P.qinverse(gt[i, 3:]), gt[j, 3:])
+            vos += rng.normal(size=vos.shape) * 0.01
+            r = ns["optimize_poses"](pred_poses=pred.copy(), vos=vos.copy(), fc_vos=fc, sax=sig[0], saq=sig[1], srx=sig[2], srq=sig[3])
+            P_in.append(pred); V_in.append(vos); ref.append(r)
+        out["case%d_cfg" % ci] = np.array([n, int(fc), w] + list(sig), dtype=np.float64)
+        out["case%d_poses" % ci] = np.stack(P_in); out["case%d_vos" % ci] = np.stack(V_in); out["case%d_out" % ci] = np.stack(ref)
+    # optimize_poses with target_poses instead of VOs (:793-799)
+    gt = rand_poses(5); pred = gt + rng.normal(size=gt.shape) * 0.05
+    out["targ_pred"] = pred; out["targ_gt"] = gt
+    out["targ_out"] = ns["optimize_poses"](pred_poses=pred.copy(), target_poses=gt.copy(), sax=1.0, saq=1.0, srx=0.1, srq=0.1)
+    # eval.py:163-167 qexp of predicted log-quaternions (numpy float32 arithmetic) and the angular error metric
+    lq = (rng.normal(size=(64, 3)) * 0.8).astype(np.float32); lq[0] = 0
+    out["qexp_in"] = lq
+    out["qexp_out"] = np.asarray([ns["qexp"](p) for p in lq])
+    qa, qb = rand_poses(32)[:, 3:], rand_poses(32)[:, 3:]
+    out["qerr_a"] = qa; out["qerr_b"] = qb
+    out["qerr_deg"] = np.asarray([ns["quaternion_angular_error"](a, b) for a, b in zip(qa, qb)])
+    np.savez_compressed(os.path.join(GOLD, "pgo.npz"), **out)
+    print("golden pgo: %d arrays" % len(out), flush=True)
+
+
 def run_keys():
     """The reference module's state_dict / named_parameters key order (drop-in
     contract for common/train.py:22-53,198-204)."""
@@ -249,9 +299,13 @@ def main():
         for emulate, name in EMU_CONFIGS:
             run_emulated(emulate, name)
         return
+    if a.only == "pgo":
+        run_pgo()
+        return
     if a.only is None:
         run_keys()
         run_pose_math()
+        run_pgo()
     cfgs = dict(STEP_CONFIGS)
     if a.full:
         cfgs.update(FULL_CONFIGS)

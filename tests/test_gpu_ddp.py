@@ -77,6 +77,9 @@ def _worker(rank, world, port, q):
     ok = ok and torch.equal(flat, after)        # replicas stay in lock-step
     if not ok:
         print("rank", rank, "graph-vs-eager reduced gradient rel err", err, flush=True)
+    del gstep                                   # graphs that hold captured NCCL work go before the communicator
+    import gc
+    gc.collect()
     torch.cuda.synchronize()
     q.put((rank, bool(ok)))
     dist.destroy_process_group()

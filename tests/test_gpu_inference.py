@@ -1,0 +1,116 @@
+"""GPU parity of the batched inference + pose-graph optimisation path through the C ABI:
+csrc/pgo.cu against goldens made by the reference's own PoseGraph / PoseGraphFC classes (tests/golden/pgo.npz) and the
+oracle; the post-processing and metrics of scripts/eval.py:163-199; the eval-mode batched forward against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "pgo.npz"))
+    i = 0
+    while "case%d_cfg" % i in g.files:
+        cfg = g["case%d_cfg" % i]
+        yield i, int(cfg[0]), bool(cfg[1]), tuple(cfg[3:7]), g["case%d_poses" % i], g["case%d_vos" % i], g["case%d_out" % i]
+        i += 1
+
+
+def test_batched_pgo_matches_reference_goldens(golden_dir):
+    """every window of every case in ONE launch per case; fp64; bound 1e-9 (the reference's own result, summation order
+    of H = J'J differs)"""
+    from geomapnet_b200.common.pgo import optimize_pose_windows, optimize_poses
+    for ci, N, fc, sig, poses, vos, ref in _cases(golden_dir):
+        out = optimize_pose_windows(torch.tensor(poses), torch.tensor(vos), fc_vos=fc, sax=sig[0], saq=sig[1], srx=sig[2],
+                                    srq=sig[3]).cpu().numpy()
+        err = np.abs(out - ref).max()
+        print("pgo case", ci, "N", N, "fc", fc, "windows", len(poses), "max abs err %.2e" % err)
+        assert err <= 1e-9, (ci, err)
+    g = np.load(os.path.join(golden_dir, "pgo.npz"))
+    one = optimize_poses(g["targ_pred"], target_poses=g["targ_gt"], sax=1.0, saq=1.0, srx=0.1, srq=0.1)
+    assert np.abs(one - g["targ_out"]).max() <= 1e-9
+    assert optimize_poses(g["targ_pred"]) is None                  # the reference prints and returns None
+
+
+def test_pgo_exact_solve_and_many_windows():
+    """2048 windows in one launch against the oracle on a sample; exact_solve=True is the Gauss-Newton step"""
+    from oracle import pgo_oracle as P
+    from geomapnet_b200.common.pgo import optimize_pose_windows
+    rng = np.random.default_rng(5)
+    W, N = 2048, 5
+    t = rng.normal(size=(W, N, 3)).cumsum(1) * 0.3
+    v = rng.normal(size=(W, N, 3)) * 0.4
+    n = np.linalg.norm(v, axis=-1, keepdims=True)
+    q = np.concatenate((np.cos(n), np.sinc(n / np.pi) * v), -1)
+    gt = np.concatenate((t, q), -1)
+    pred = gt + rng.normal(size=gt.shape) * 0.05
+    vos = np.zeros((W, N - 1, 7))
+    for w in range(0, W, 97):
+        for i in range(N - 1):
+            vos[w, i, :3] = P.rotate_vector(gt[w, i + 1, :3] - gt[w, i, :3], P.qinverse(gt[w, i, 3:]))
+            vos[w, i, 3:] = P.qmult(P.qinverse(gt[w, i, 3:]), gt[w, i + 1, 3:])
+    vos[:, :, 3] = np.where(vos[:, :, 3] == 0, 1.0, vos[:, :, 3])     # unsampled windows: identity VO (still a valid problem)
+    for exact in (False, True):
+        out = optimize_pose_windows(torch.tensor(pred), torch.tensor(vos), sax=1.0, saq=0.5, srx=0.3, srq=0.2,
+                                    exact_solve=exact).cpu().numpy()
+        for w in range(0, W, 97):
+            ref = P.optimize(pred[w], vos[w], 1.0, 0.5, 0.3, 0.2, exact_solve=exact)
+            assert np.abs(out[w] - ref).max() <= 1e-9, (exact, w)
+
+
+def test_post_and_metrics_match_eval_py(golden_dir):
+    from geomapnet_b200 import inference as I
+    g = np.load(os.path.join(golden_dir, "pgo.npz"))
+    lq = torch.tensor(g["qexp_in"])
+    p6 = torch.cat((torch.randn(lq.shape[0], 3), lq), 1).cuda()
+    pose_m, pose_s = np.array([0.1, -2.0, 3.5]), np.array([1.5, 0.7, 2.2])
+    out = I.post(p6, pose_m, pose_s).cpu().numpy()
+    assert np.abs(out[:, 3:] - g["qexp_out"]).max() <= 2e-7                    # numpy float32 qexp (eval.py:166)
+    assert np.abs(out[:, :3] - (p6[:, :3].cpu().numpy().astype(np.float64) * pose_s + pose_m)).max() <= 1e-12
+    a, b = torch.tensor(g["qerr_a"]).cuda(), torch.tensor(g["qerr_b"]).cuda()
+    pa = torch.cat((torch.zeros(32, 3, dtype=torch.float64, device="cuda"), a), 1)
+    pb = torch.cat((torch.ones(32, 3, dtype=torch.float64, device="cuda"), b), 1)
+    t_err, q_err = I.pose_errors(pa, pb)
+    assert np.abs(q_err.cpu().numpy() - g["qerr_deg"]).max() <= 1e-9
+    assert np.abs(t_err.cpu().numpy() - np.sqrt(3.0)).max() <= 1e-12
+
+
+def test_batched_eval_forward_and_tuple_evaluation_match_oracle():
+    """model.eval() forward in batches == the oracle's eval-mode forward (BN running statistics), then the whole
+    eval.py loop (qexp, PGO on the normalised poses, un-normalisation, middle prediction, errors) against the oracle's
+    numpy restatement of the same steps."""
+    from oracle import weights, mapnet_oracle as O, pgo_oracle as P
+    from helpers import make_product_model
+    from geomapnet_b200 import inference as I
+    st = weights.make_state(7)
+    cfg = dict(kind="mapnet", N=5, T=3, H=64, W=64)
+    x, targ = weights.make_inputs(cfg, 9)
+    model, net = make_product_model(st, "mapnet", "tc_split")
+    out6 = I.predict(model, x.cuda(), batch=2)                                 # 3 batches: 2 + 2 + 1 tuples
+    ref6 = O.mapnet_forward(st, x, training=False)
+    assert float((out6.cpu() - ref6).abs().max() / ref6.abs().max()) <= 1e-4
+    assert model.training                                                       # predict restores the mode
+    pose_m, pose_s = np.array([0.5, 1.0, -1.0]), np.array([2.0, 3.0, 1.5])
+    vos = torch.zeros(5, 2, 7, dtype=torch.float64); vos[..., 3] = 1.0
+    res = I.evaluate_tuples(model, x.cuda(), targ, vos7=vos, pose_m=pose_m, pose_s=pose_s, batch=4, sax=1.0, saq=1.0,
+                            srx=1.0, srq=1.0)
+    # numpy restatement of eval.py:163-185 on the ORACLE's predictions
+    def qexp(v):
+        n = np.linalg.norm(v)
+        return np.hstack((np.cos(n), np.sinc(n / np.pi) * v))
+    exp_pred, exp_targ = [], []
+    for k in range(5):
+        o = ref6[k].numpy().astype(np.float64); t = targ[k].numpy().astype(np.float64)
+        o7 = np.hstack((o[:, :3], np.asarray([qexp(p[3:]) for p in o])))
+        t7 = np.hstack((t[:, :3], np.asarray([qexp(p[3:]) for p in t])))
+        o7 = P.optimize_poses(o7, vos[k].numpy(), sax=1.0, saq=1.0, srx=1.0, srq=1.0)
+        o7[:, :3] = o7[:, :3] * pose_s + pose_m; t7[:, :3] = t7[:, :3] * pose_s + pose_m
+        exp_pred.append(o7[1]); exp_targ.append(t7[1])
+    exp_pred, exp_targ = np.stack(exp_pred), np.stack(exp_targ)
+    assert np.abs(res["pred7"].cpu().numpy() - exp_pred).max() <= 2e-4 * np.abs(exp_pred).max()
+    assert np.abs(res["targ7"].cpu().numpy() - exp_targ).max() <= 1e-6
+    t_ref = np.linalg.norm(exp_pred[:, :3] - exp_targ[:, :3], axis=1)
+    assert np.abs(res["t_err"].cpu().numpy() - t_ref).max() <= 1e-3 * t_ref.max()

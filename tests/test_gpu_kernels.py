@@ -217,3 +217,82 @@ def test_fused_adam_clip_matches_clip_grad_norm():
     torch.nn.utils.clip_grad_norm_([q], 5.0)
     a.step(max_grad_norm=5.0); b.step()
     assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the FUSED epilogues of the tcgen05 engines against torch (not product-vs-product): BatchNorm statistics in fprop,
+# ReLU gate + BatchNorm-backward reductions (+ residual) in dgrad
+# ---------------------------------------------------------------------------------------------------------------------
+EPI_CASES = [(2, 16, 16, 64, 64, 3, 1), (3, 9, 11, 128, 128, 3, 1), (2, 18, 22, 64, 128, 3, 2), (1, 8, 8, 256, 512, 3, 2),
+             (2, 8, 8, 512, 512, 3, 1), (4, 64, 64, 64, 64, 3, 1), (2, 16, 16, 128, 256, 1, 2)]
+
+
+def _run_epilogue(kind, geom, in0, wmat, residual, y, zmask, yd, mscale, mshift, out, C):
+    B, H, W, Ci, Co, k, stride = geom
+    sums = np.zeros((3, C), dtype=np.float64)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    _lib.check(_lib.lib().mapnet_test_conv_epilogue(
+        kind, B, H, W, Ci, Co, k, stride, ptr(in0), ptr(wmat), ptr(residual), ptr(y), ptr(zmask), ptr(yd), ptr(mscale),
+        ptr(mshift), ptr(out), sums.ctypes.data_as(ctypes.c_void_p), _lib.stream_ptr()), "mapnet_test_conv_epilogue")
+    torch.cuda.synchronize()
+    return sums
+
+
+@pytest.mark.parametrize("geom", EPI_CASES)
+def test_fprop_fused_batchnorm_statistics_vs_torch(geom):
+    """out = conv(x, w) stored as bf16; (sum, sum of squares) per channel of the STORED values, accumulated in the conv
+    epilogue -- what BatchNorm's training-mode forward then normalises with."""
+    B, H, W, Ci, Co, k, stride = geom
+    x, w, dy, y, dx, dw = _conv_case("bf16", *geom)
+    xn = x.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    w_krsc = w.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    out = torch.empty(y.permute(0, 2, 3, 1).shape, dtype=torch.bfloat16, device="cuda")
+    sums = _run_epilogue(0, geom, xn, w_krsc, None, None, None, None, None, None, out, Co)
+    ref = y.permute(0, 2, 3, 1)
+    assert float((out.float().cpu() - ref).abs().max() / ref.abs().max()) < 1.2e-2
+    stored = out.float().cpu().double().reshape(-1, Co)           # the statistics are those of the stored tensor
+    s0, s1 = stored.sum(0).numpy(), (stored * stored).sum(0).numpy()
+    assert np.abs(sums[0] - s0).max() <= 2e-5 * np.abs(stored).sum(0).max().item()
+    assert np.abs(sums[1] - s1).max() <= 2e-5 * s1.max()
+
+
+@pytest.mark.parametrize("variant", ["ymask", "zmask", "zmask_res", "zmask_res_yd"])
+@pytest.mark.parametrize("geom", EPI_CASES)
+def test_dgrad_fused_relu_gate_and_batchnorm_backward_sums_vs_torch(geom, variant):
+    """g = [gate] * (conv_dgrad(dy, w) [+ residual]) stored as bf16 and (sum g, sum g*y [, sum g*yd]) of the stored
+    values: the ReLU backward and the reduction half of BatchNorm's backward of the layer that CONSUMES this gradient,
+    fused into the dgrad epilogue.  Gate: the post-ReLU tensor's sign (zmask) or the recomputed activation
+    mscale * y + mshift > 0."""
+    B, H, W, Ci, Co, k, stride = geom
+    x, w, dy, yref, dx, dw = _conv_case("bf16", *geom)
+    gen = torch.Generator().manual_seed(1)
+    shape = (B, H, W, Ci)                                           # the dgrad output is shaped like the conv input
+    dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    w_dg = w.permute(1, 2, 3, 0).contiguous().bfloat16().cuda()
+    ybn = torch.randn(shape, generator=gen).bfloat16()              # the consumer BatchNorm's input (a forward conv output)
+    ydn = torch.randn(shape, generator=gen).bfloat16()
+    res = torch.randn(shape, generator=gen).bfloat16()
+    msc = (torch.rand(Ci, generator=gen) + 0.5)
+    msh = torch.randn(Ci, generator=gen) * 0.3
+    z = torch.relu(torch.randn(shape, generator=gen)).bfloat16()    # post-ReLU tensor: zeros where the gate is closed
+    use_z = variant != "ymask"
+    use_res = "res" in variant
+    use_yd = variant.endswith("yd")
+    out = torch.empty(shape, dtype=torch.bfloat16, device="cuda")
+    sums = _run_epilogue(1, geom, dyn, w_dg, res.cuda() if use_res else None, ybn.cuda(), z.cuda() if use_z else None,
+                         ydn.cuda() if use_yd else None, None if use_z else msc.cuda(), None if use_z else msh.cuda(), out, Ci)
+    g = dx.permute(0, 2, 3, 1).float()
+    if use_res:
+        g = g + res.float()
+    gate = (z.float() > 0) if use_z else ((ybn.float() * msc + msh) > 0)
+    g = torch.where(gate, g, torch.zeros_like(g))
+    got = out.float().cpu()
+    assert float((got - g).abs().max() / g.abs().max()) < 1.2e-2
+    assert torch.equal(got == 0, ~gate | (got == 0)) and bool((got[~gate] == 0).all())     # closed gates store exact zeros
+    st = got.double().reshape(-1, Ci)
+    yy, yd2 = ybn.double().reshape(-1, Ci), ydn.double().reshape(-1, Ci)
+    scale = st.abs().sum(0).max().item()
+    assert np.abs(sums[0] - st.sum(0).numpy()).max() <= 2e-5 * scale
+    assert np.abs(sums[1] - (st * yy).sum(0).numpy()).max() <= 2e-5 * (st.abs() * yy.abs()).sum(0).max().item()
+    if use_yd:
+        assert np.abs(sums[2] - (st * yd2).sum(0).numpy()).max() <= 2e-5 * (st.abs() * yd2.abs()).sum(0).max().item()
