@@ -928,6 +928,7 @@ struct HaloParams {
   int b_stationary;             // weights loaded once per CTA (9*cblocks tiles)
   int dq[9], kidx[9];           // per tap: shift in padded-linear space, K index of its weight slice
   int use_base_offset;
+  int row_boxes;                // patch staged as R per-image-row boxes {64 ch, W, 1} (halo columns pre-zeroed) instead of one {64, W+2, R} box
   int scr_off;                  // byte offset (from the 1024-aligned base) of the epilogue warps' transpose scratch
   int debug;                    // micro-benchmark only: 1 = skip MMAs, 2 = skip TMA loads
 };
@@ -961,6 +962,21 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
+  if (P.row_boxes && warp >= 2) {
+    // Per-row staging: every image row lands as ONE contiguous box of W pixels at patch row r*P + 1; the two halo
+    // pixels of each patch row (slots r*P and r*P + P-1) are never written by TMA and are zeroed here, once.
+    // (ncu r02a: the single {64, W+2, R} box made this engine TMA-bound -- 6 200 cycles per tile for 1 150 cycles of
+    // MMAs, tensor pipe 24 % active; 128-byte rows of an out-of-bounds-padded box cost ~4x a dense row.)
+    uint8_t* sb = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int nslots = P.NP * P.R * 2;
+    for (int i = (int)threadIdx.x - 64; i < nslots * 8; i += kEpiThreads) {     // 8 x 16 B per 128-byte pixel row
+      const int slot = i >> 3, part = i & 7;
+      const int ps = slot / (P.R * 2), rr = (slot >> 1) % P.R, side = slot & 1;
+      uint4* dst = reinterpret_cast<uint4*>(sb + (size_t)ps * P.patch_bytes + ((size_t)rr * P.P + (side ? P.P - 1 : 0)) * 128) + part;
+      *dst = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy zeros -> visible to the UMMA reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -992,7 +1008,12 @@ k_tc_conv_halo(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int cb = 0; cb < P.cblocks; ++cb) {
           mbar_wait(pempty0 + 8 * ps, pphase ^ 1);
           if (P.debug == 2) mbar_arrive(pfull0 + 8 * ps);
-          else {
+          else if (P.row_boxes) {
+            mbar_expect_tx(pfull0 + 8 * ps, (uint32_t)(P.R * P.W * 128));
+            for (int r = 0; r < P.R; ++r)      // rows outside the image are zero-filled by TMA
+              tma_load_4d(smem_base + ps * P.patch_bytes + (uint32_t)(r * P.P + 1) * 128u, &mapA, pfull0 + 8 * ps, cb * 64, 0,
+                          h_lo + r, n);
+          } else {
             mbar_expect_tx(pfull0 + 8 * ps, (uint32_t)(P.R * P.P * 128));
             tma_load_4d(smem_base + ps * P.patch_bytes, &mapA, pfull0 + 8 * ps, cb * 64, -1, h_lo, n);
           }
@@ -1589,6 +1610,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
           p->halo = true; p->BN = bn;
           H.n_tiles_n = Cn / bn;
           H.use_base_offset = halo_bo;
+          { const char* e = getenv("MAPNET_TC_HALO_ROWS"); H.row_boxes = e ? (atoi(e) != 0) : 1; }
           { const char* e = getenv("MAPNET_TC_DEBUG"); H.debug = e ? atoi(e) : 0; }
           for (int kh = 0; kh < 3; ++kh)
             for (int kw = 0; kw < 3; ++kw) {
@@ -1907,7 +1929,7 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     if (p->c_in0 != in0) {
       const int Cs = H.Cs;
       MN_TRY(encode_act_map(&p->hmapA, in0, Cs, H.W, H.H, H.Nimg, (long long)Cs * 2, (long long)H.W * Cs * 2,
-                            (long long)H.H * H.W * Cs * 2, H.P, H.R, 1));
+                            (long long)H.H * H.W * Cs * 2, H.row_boxes ? H.W : H.P, H.row_boxes ? 1 : H.R, 1));
       MN_TRY(encode_w_map(&p->hmapB, p->wmat, 9 * Cs, H.Cout, p->BN));
       p->c_in0 = in0;
     }

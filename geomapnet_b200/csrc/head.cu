@@ -9,29 +9,42 @@
 namespace mapnet {
 
 // ---- global average pool ------------------------------------------------------
+// One block per image: thread (cv, pg) sums the pixels p = pg, pg + npg, ... of channel vector cv (coalesced 16/32-byte
+// loads across cv), the npg partial sums meet in shared memory.  (The first version -- one thread per (image, 8 channels),
+// 32 blocks in all -- took 20 us for 4 MB: ncu r02a, 2.5 % of DRAM peak.)
 template <typename T>
-__global__ void k_gap(const T* __restrict__ z, float* __restrict__ feat, int B, int HW, int C) {
+__global__ void __launch_bounds__(256) k_gap(const T* __restrict__ z, float* __restrict__ feat, int B, int HW, int C) {
   pdl_prologue();
-  const int cv = C >> 3;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * cv) return;
-  const int b = i / cv, c0 = (i % cv) * 8;
+  extern __shared__ float sm[];          // [npg][C]
+  const int cv = C >> 3, npg = blockDim.x / cv;
+  const int b = blockIdx.x;
+  const int tx = threadIdx.x % cv, pg = threadIdx.x / cv;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  for (int p = 0; p < HW; ++p) {
-    Vec8<T> v; v.load(z + ((long long)b * HW + p) * C + c0);
+  if (pg < npg)
+    for (int p = pg; p < HW; p += npg) {
+      Vec8<T> v; v.load(z + ((long long)b * HW + p) * C + tx * 8);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+      for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+    }
+  if (pg < npg) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[pg * C + tx * 8 + k] = acc[k];
   }
+  __syncthreads();
   const float inv = 1.0f / (float)HW;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) feat[(long long)b * C + c0 + k] = acc[k] * inv;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < npg; ++g) s += sm[g * C + c];
+    feat[(long long)b * C + c] = s * inv;
+  }
 }
 template <typename T>
 int launch_gap(const T* z, float* feat, int B, int HW, int C, cudaStream_t st) {
-  const int n = B * (C >> 3);
-  MN_LAUNCH(k_gap<T>, cdiv(n, 128), 128, 0, st, z, feat, B, HW, C);
+  MN_CHECK(C % 8 == 0 && (C >> 3) <= 256, "gap: unsupported channel count %d", C);
+  const int npg = 256 / (C >> 3);
+  MN_LAUNCH(k_gap<T>, B, 256, (size_t)npg * C * sizeof(float), st, z, feat, B, HW, C);
   MN_LAUNCH_CHECK();
   return 0;
 }

@@ -149,6 +149,8 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0; prof_pool_used = 0;
   bwd_pre = false; bwd_next_part = 0;
+  side = nullptr; wgrad_async = 0; ring_pos = 0;
+  for (int i = 0; i < 4; ++i) { ring[i] = nullptr; ring_ready[i] = ring_done[i] = nullptr; ring_pending[i] = false; }
   { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = tc() && (e ? atoi(e) != 0 : 1); }
   { const char* e = getenv("MAPNET_STEM_S2D");
     stem_s2d = tc() && (e ? atoi(e) != 0 : 1) && (max_B == 0 || tc_overlapped_view_supported()); }
@@ -168,7 +170,20 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_TRY(alloc(&z0, (size_t)(Bm * Hp * Wp * 64) * es));
   MN_TRY(alloc((void**)&amax0, (size_t)(Bm * Hp * Wp * 64)));
   scratch_elems = Bm * Hc * Wc * 64;
-  for (int i = 0; i < 5; ++i) MN_TRY(alloc(&scratch[i], (size_t)scratch_elems * es));
+  for (int i = 0; i < 7; ++i) MN_TRY(alloc(&scratch[i], (size_t)scratch_elems * es));
+  ring[0] = scratch[1]; ring[1] = scratch[2]; ring[2] = scratch[5]; ring[3] = scratch[6];
+  ring_pos = 0;
+  { const char* e = getenv("MAPNET_WGRAD_ASYNC"); wgrad_async = e ? (atoi(e) != 0) : 1; }
+  {
+    int lo = 0, hi = 0;
+    MN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // lo = numerically greatest = lowest priority
+    MN_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo));
+    for (int i = 0; i < 4; ++i) {
+      MN_CUDA(cudaEventCreateWithFlags(&ring_ready[i], cudaEventDisableTiming));
+      MN_CUDA(cudaEventCreateWithFlags(&ring_done[i], cudaEventDisableTiming));
+      ring_pending[i] = false;
+    }
+  }
   for (auto& bl : blocks) {
     const size_t n = (size_t)(Bm * bl.Ho * bl.Wo * bl.Cout) * es;
     MN_TRY(alloc(&bl.y1, n)); MN_TRY(alloc(&bl.h, n)); MN_TRY(alloc(&bl.y2, n)); MN_TRY(alloc(&bl.out, n));
@@ -221,6 +236,12 @@ void Net::destroy() {
   tc_fprop.clear(); tc_dgrad.clear(); tc_wgrad.clear();
   for (void* p : allocs) cudaFree(p);
   allocs.clear();
+  if (side != nullptr) {
+    cudaStreamSynchronize(side);
+    for (int i = 0; i < 4; ++i) { if (ring_ready[i]) cudaEventDestroy(ring_ready[i]); if (ring_done[i]) cudaEventDestroy(ring_done[i]); }
+    cudaStreamDestroy(side);
+    side = nullptr;
+  }
   for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
   prof_pool.clear();
 }
@@ -318,9 +339,38 @@ int Net::conv_dgrad(int ci, const typename P::G* dy, const typename P::A* residu
   prof_end(st, e0, 1, flops);
   return r;
 }
+// next slot of the d(conv output) ring, safe to overwrite on `st`
+void* Net::ring_next(cudaStream_t st) {
+  const int slot = ring_pos++ & 3;
+  if (ring_pending[slot]) { cudaStreamWaitEvent(st, ring_done[slot], 0); ring_pending[slot] = false; }
+  return ring[slot];
+}
+int Net::ring_slot(const void* p) const {
+  for (int i = 0; i < 4; ++i) if (ring[i] == p) return i;
+  return -1;
+}
+int Net::wgrad_join(cudaStream_t st) {
+  for (int i = 0; i < 4; ++i)
+    if (ring_pending[i]) { MN_CUDA(cudaStreamWaitEvent(st, ring_done[i], 0)); ring_pending[i] = false; }
+  return 0;
+}
+
 template <typename P>
 int Net::conv_wgrad(int ci, const typename P::Z* x, const typename P::G* dy, int B, cudaStream_t st) {
   ConvGeom g = convs[ci].g; g.B = B;
+  const int slot = ring_slot(dy);
+  if (wgrad_async && !profile_on && slot >= 0) {
+    // fork: the side stream picks the gradient up where the compute stream has just finished writing it
+    MN_CUDA(cudaEventRecord(ring_ready[slot], st));
+    MN_CUDA(cudaStreamWaitEvent(side, ring_ready[slot], 0));
+    int r;
+    if (tc()) r = tc_conv_run(tc_wgrad[ci], (const bf16*)x, (const bf16*)dy, nullptr, dw_krsc + convs[ci].wd.k_off, side);
+    else if constexpr (SimtConv<P>::ok) r = launch_conv_simt_wgrad<typename P::A>(g, x, dy, dw_krsc + convs[ci].wd.k_off, side);
+    else { set_last_error("conv_wgrad: no CUDA-core engine for split operands"); r = 2; }
+    MN_CUDA(cudaEventRecord(ring_done[slot], side));
+    ring_pending[slot] = true;
+    return r;
+  }
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
@@ -507,6 +557,7 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
   const bool do_head = part <= 0, do_stem = part < 0 || part == 2;
   if (do_head) MN_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)wk_total * 4, st));
   // S0: d(block output), S3: gated gradient of the identity branch, S4: d h -- T;  S1 / S2: d(conv output) -- TG
+  // (S1 / S2 are slots of the ring the asynchronous wgrads read from: re-pointed before every write)
   T* S0 = (T*)scratch[0]; TG* S1 = (TG*)scratch[1]; TG* S2 = (TG*)scratch[2]; T* S3 = (T*)scratch[3]; T* S4 = (T*)scratch[4];
 
   // ---- head (models/posenet.py:67-73 backward, NaN filter :28-34) ----
@@ -550,6 +601,8 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     const bool ds = bl.convd >= 0;
     const T* gres = S3;       // gated d out, the gradient of the identity branch
     // out = relu(bn2(y2) + idt): g = dout*[out>0]; BN2 (and downsample BN) backward
+    S1 = (TG*)ring_next(st);
+    if (ds) S2 = (TG*)ring_next(st);
     if (ds) {
       BNL& bd = bns[convs[bl.convd].bn];
       if (pre) {
@@ -581,17 +634,19 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     MN_TRY(conv_wgrad<P>(bl.conv2, (const TZ*)bl.h, S1, B, st));
     // h = relu(bn1(y1)) has no residual: its ReLU mask is recomputed from y1 (scale*y+shift > 0),
     // one tensor read less in both backward passes
+    const TG* dy2 = S1;
+    S1 = (TG*)ring_next(st);      // d y1 goes to a fresh slot: conv2's wgrad may still be reading d y2
     if (fuse_bwd) {
       EpiBwd e1; memset(&e1, 0, sizeof(e1));
       e1.y = (const bf16*)bl.y1; e1.mscale = b1.scale; e1.mshift = b1.shift;
       const EpiFin fb1 = fin_backward(convs[bl.conv1].bn, -1, Mo, params, grads);
-      MN_TRY(conv_dgrad<P>(bl.conv2, S1, nullptr, S4, B, st, &e1, &fb1));
+      MN_TRY(conv_dgrad<P>(bl.conv2, dy2, nullptr, S4, B, st, &e1, &fb1));
       if (!fuse_fin)
         MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
       MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st, nullptr, nullptr, gs)));
     } else {
-      MN_TRY(conv_dgrad<P>(bl.conv2, S1, nullptr, S4, B, st));
+      MN_TRY(conv_dgrad<P>(bl.conv2, dy2, nullptr, S4, B, st));
       MN_TRY((launch_bn_bwd_reduce<T, TZ>(S4, nullptr, (const T*)bl.y1, nullptr, Mo, C,
                                      params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
                                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st,
@@ -627,6 +682,7 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
   // ---- stem: maxpool -> ReLU -> BN -> conv (no input gradient: nothing consumes it) ----
   if (do_stem) {
     conv_lo = 0; if (conv_hi < 0) conv_hi = 0;
+    S2 = (TG*)ring_next(st);
     BNL& b0 = bns[convs[0].bn];
     const long long M0 = (long long)B * Hc * Wc;
     if (stem_fuse) {
@@ -643,6 +699,7 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, (const TZ*)nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st, nullptr, nullptr, gs)));
     MN_TRY(conv_wgrad<P>(0, (const TZ*)A0, S2, B, st));
   }
+  MN_TRY(wgrad_join(st));       // every asynchronous wgrad of this part has landed in dw_krsc
   if (conv_hi >= conv_lo)
     MN_TRY(launch_unpack_wgrads(d_wdescs + conv_lo, conv_hi - conv_lo + 1, dw_krsc, grads, max_w_elems, st));
   return 0;

@@ -58,7 +58,16 @@ struct Net {
   // device memory owned by the handle
   std::vector<void*> allocs;
   void *A0, *y0, *z0; uint8_t* amax0;
-  void* scratch[5]; long long scratch_elems;
+  void* scratch[7]; long long scratch_elems;
+  // Weight-gradient convolutions run on a second, LOW-priority stream: nothing in the backward chain waits for dW, so
+  // they fill the SM time the chain leaves idle (latency-bound finalize / head / loss kernels, kernel tails) instead of
+  // sitting in it.  The gradients they read (d conv output) rotate through a ring of four buffers; a slot is rewritten
+  // only after the wgrad that read it has finished (event), and every part of the backward pass ends with a join.
+  cudaStream_t side; int wgrad_async;
+  void* ring[4]; cudaEvent_t ring_ready[4], ring_done[4]; bool ring_pending[4]; int ring_pos;
+  void* ring_next(cudaStream_t st);
+  int ring_slot(const void* p) const;
+  int wgrad_join(cudaStream_t st);
   void *w_krsc, *w_dg; float* dw_krsc; WeightDesc* d_wdescs;
   float *w_krsc_f32, *w_dg_f32;  // strict mode: fp32 K-major matrices the hi / lo weight planes are cut from
   int split_fmt_z, split_fmt_g;  // strict mode: element format of the forward / backward operand planes (0 fp16, 1 bf16)
