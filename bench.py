@@ -540,6 +540,12 @@ def run_b200(args, cfg, rank, local_rank, world):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the measurement is complete and printed: a communicator teardown that stalls (CUDA graphs holding captured NCCL
+        # work) must not turn a finished run into a timeout
+        def _bail():
+            time.sleep(45)
+            os._exit(0)
+        threading.Thread(target=_bail, daemon=True).start()
         # CUDA graphs that captured NCCL work must be gone before their communicator is torn down
         step = gstep = None
         import gc

@@ -349,11 +349,12 @@ k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const floa
             TZ* __restrict__ z, uint8_t* __restrict__ amax, int B, int H, int W, int Ho, int Wo, int C) {
   pdl_prologue();
   const int cv = C >> 3;
-  const long long nvec = (long long)B * Ho * Wo * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
+  // 32-bit index arithmetic (the launcher checks the element count): 64-bit div / mod per element made this kernel
+  // latency-bound (ncu r02a: 89 us for 165 MB, 23 % of DRAM peak)
+  const unsigned int nvec = (unsigned int)B * Ho * Wo * cv;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
     const int c0 = (int)(i % cv) * 8;
-    long long p = i / cv;
+    unsigned int p = i / cv;
     const int ow = (int)(p % Wo); p /= Wo;
     const int oh = (int)(p % Ho);
     const int b = (int)(p / Ho);
@@ -381,11 +382,11 @@ k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const floa
     Vec8<TZ> o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = best[k];
-    o.store(z + i * 8);
+    o.store(z + (size_t)i * 8);
     uint2 packed;
     packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
     packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
-    *reinterpret_cast<uint2*>(amax + i * 8) = packed;
+    *reinterpret_cast<uint2*>(amax + (size_t)i * 8) = packed;
   }
 }
 
@@ -393,6 +394,7 @@ template <typename T, typename TZ>
 int launch_stem_pool(const T* y, const float* scale, const float* shift, TZ* z, uint8_t* amax, int B, int H,
                      int W, int Ho, int Wo, int C, cudaStream_t st) {
   const long long nvec = (long long)B * Ho * Wo * (C >> 3);
+  MN_CHECK(nvec < 2147483647LL, "stem_pool: tensor too large for 32-bit indexing");
   MN_LAUNCH((k_stem_pool<T, TZ>), ew_grid(nvec), kEwThreads, 0, st, y, scale, shift, z, amax, B, H, W, Ho, Wo, C);
   MN_LAUNCH_CHECK();
   return 0;
@@ -469,15 +471,15 @@ k_stem_pool_bwd_quad(const T* __restrict__ dz, const uint8_t* __restrict__ amax,
   pdl_prologue();
   const int cv = C >> 3;
   const int Hq = H >> 1, Wq = W >> 1;
-  const long long nq = (long long)B * Hq * Wq * cv;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned int nq = (unsigned int)B * Hq * Wq * cv;          // 32-bit index arithmetic (checked by the launcher)
+  const unsigned int i0 = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(i0 % cv) * 8;            // loop invariant: the grid stride is a multiple of cv
   float sc[8], sh[8], s0[8], s1[8];
   ld8(scale + c0, sc); ld8(shift + c0, sh);
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
-  for (long long i = i0; i < nq; i += (long long)gridDim.x * blockDim.x) {
-    long long p = i / cv;
+  for (unsigned int i = i0; i < nq; i += gridDim.x * blockDim.x) {
+    unsigned int p = i / cv;
     const int qb = (int)(p % Wq); p /= Wq;
     const int qa = (int)(p % Hq);
     const int b = (int)(p / Hq);
@@ -555,6 +557,7 @@ int launch_stem_pool_bwd(const T* dz, const uint8_t* amax, const T* y, const flo
                          T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st, double* accum) {
   if ((H % 2) == 0 && (W % 2) == 0 && Ho == H / 2 && Wo == W / 2 && kEwThreads % (C >> 3) == 0) {
     const long long nq = (long long)B * (H / 2) * (W / 2) * (C >> 3);
+    MN_CHECK(nq < 2147483647LL, "stem_pool_bwd: tensor too large for 32-bit indexing");
     const size_t smem = accum ? (size_t)(kEwThreads / (C >> 3)) * 2 * C * sizeof(float) : 0;
     MN_LAUNCH(k_stem_pool_bwd_quad<T>, ew_grid(nq), kEwThreads, smem, st, dz, amax, y, scale, shift, g, B, H, W, Ho, Wo, C, accum);
     MN_LAUNCH_CHECK();

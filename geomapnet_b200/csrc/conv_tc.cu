@@ -528,6 +528,7 @@ static constexpr int conv_stages(int BN) {      // + 18 KB (4 epilogue warps) / 
   return kEpiWarps == 4 ? (BN <= 64 ? 8 : (BN <= 128 ? 6 : 4)) : (BN <= 64 ? 7 : (BN <= 128 ? 5 : 3));
 }
 static constexpr int wgrad_stages(int BN) { return BN <= 64 ? 9 : (BN <= 128 ? 6 : 4); }
+static constexpr int kOcc2Stages = 3;          // BN = 64, two CTAs per SM: 3 x 24 KB + 18 KB scratch per CTA
 
 // ---------------------------------------------------------------------------------
 // fprop / dgrad kernel
@@ -535,14 +536,18 @@ static constexpr int wgrad_stages(int BN) { return BN <= 64 ? 9 : (BN <= 128 ? 6
 // CL = thread-block cluster size along M: the CL CTAs of a cluster work on CL consecutive
 // M tiles of the same N tile and share the weight tile -- each loads 1/CL of it and TMA-
 // multicasts it to all (the engines are L2-bandwidth bound, this cuts the B traffic by CL).
-template <int BN, int CL>
-__global__ void __launch_bounds__(kConvThreads, 1)
+// OCC = CTAs per SM.  The Cout = 64 launches (layer1, the stem, the layer2.0 dgrad) are EPILOGUE-bound: 8 192 outputs per
+// tile but only K = 576 (ncu r02a: the four epilogue warps issue or sit in short-scoreboard stalls for all of their
+// samples while the producer and MMA warps wait; skipping the MMAs or the TMA loads does not shorten the kernel).  Two CTAs
+// per SM (3 pipeline stages each instead of 8) put eight epilogue warps on the SM, each tile's epilogue on its own.
+template <int BN, int CL, int OCC = 1>
+__global__ void __launch_bounds__(kConvThreads, OCC)
 k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
           const __grid_constant__ ConvParams P, const bf16* __restrict__ residual,
           bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E, const EpiFin Fin) {
-  constexpr int STAGES = conv_stages(BN);
+  constexpr int STAGES = (OCC == 2) ? kOcc2Stages : conv_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;        // 128 pixels x 64 ch bf16
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -1436,6 +1441,7 @@ struct TcConvPlan {
   const bf16* wmat2;                    // dgrad weight matrix [Ci][Co2] of a folded 1x1/stride-2 shortcut conv, or null
   int BN, CL;
   bool two_cta;                         // cta_group::2 kernel (256 x BN pair tiles)
+  bool occ2;                            // BN = 64 per-tap kernel with two CTAs per SM (epilogue-bound launches)
   bool halo;                            // halo-resident 3x3/s1 engine
   HaloParams HP;
   CUtensorMap hmapA, hmapB;
@@ -1564,6 +1570,7 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   p->c_in0 = p->c_in1 = nullptr; p->smem_attr_set = false; p->out_scale = nullptr;
   p->CL = pick_cl();
   p->two_cta = false;
+  p->occ2 = false;
   p->halo = false;
   const int s = g.stride, pad = g.pad, KK = g.KH * g.KW;
   // strict mode: the engines see 2*C 16-bit channels per pixel and every filter tap twice (hi / lo weight planes)
@@ -1571,7 +1578,10 @@ int tc_plan_create(TcConvPlan** out, const ConvGeom& g, int kind, const bf16* wm
   MN_CHECK(!g.split || KK <= 9, "tc conv: strict mode supports up to 9 filter taps");
   {
     static int halo_mode = -1, halo_bo = -1;
-    if (halo_mode < 0) { const char* e = getenv("MAPNET_TC_HALO"); halo_mode = e ? atoi(e) : 1; }
+    // default OFF since round 2: the Cout = 64 launches are bound by per-CTA serial latency, and the per-tap engine with TWO
+    // CTAs per SM (OCC = 2 below) beats the halo engine on layer1 (31.6 vs 38.7 us fprop, 38.8 vs 47.5 us gated dgrad at B = 64,
+    // profiles/r02b_conv_microbench.txt); MAPNET_TC_HALO=1 selects the halo-resident engine again
+    if (halo_mode < 0) { const char* e = getenv("MAPNET_TC_HALO"); halo_mode = e ? atoi(e) : 0; }
     if (halo_bo < 0) { const char* e = getenv("MAPNET_TC_HALO_BASEOFF"); halo_bo = e ? atoi(e) : 0; }   // measured: swizzle follows absolute smem address bits, base_offset must stay 0
     if (halo_mode && !g.split && (kind == 0 || kind == 1) && g.KH == 3 && s == 1 && g.Wi + 2 <= 256) {
       // fprop: gather x [B,H,W,Ci] -> y [.,Co]; dgrad: gather dy [B,H,W,Co] -> dx [.,Ci] (same spatial dims)
@@ -1978,11 +1988,21 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
 #define PICK(BNv, CLv) if (!p->two_cta && p->BN == BNv && p->CL == CLv) kern = k_tc_conv<BNv, CLv>;
     PICK(64, 1) PICK(128, 1) PICK(256, 1) PICK(64, 2) PICK(128, 2) PICK(256, 2) PICK(64, 4) PICK(128, 4) PICK(256, 4)
 #undef PICK
+    {
+      static int occ2 = -1;
+      if (occ2 < 0) { const char* e = getenv("MAPNET_TC_OCC2"); occ2 = e ? atoi(e) : 1; }
+      p->occ2 = occ2 && !p->two_cta && p->BN == 64 && p->CL == 1 && kEpiWarps == 4;
+      if (p->occ2) {
+        kern = k_tc_conv<64, 1, 2>;
+        smem = (size_t)kOcc2Stages * (128 * 128 + 64 * 128) + 1024 + scratch;
+      }
+    }
     MN_CHECK(kern != nullptr, "tc conv: no kernel for BN=%d CL=%d", p->BN, p->CL);
     if (!p->smem_attr_set) {
       MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       p->smem_attr_set = true;
     }
+    if (p->occ2) nsm *= 2;
     F.expected = 0;
     for (auto& L : p->launches) {     // the sums of a stride-2 dgrad come from all its parity classes / launches
       const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n * L.P.n_classes;

@@ -19,51 +19,39 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT_DIR = os.environ.get("NCU_SUMMARY_OUT", os.path.join(ROOT, "profiles"))      # tests write elsewhere
 
-WANT = [  # (column label, substrings that must all appear in the ncu metric name)
-    ("dur_ns", ["gpu__time_duration.sum"]),
-    ("tensor_pipe_pct_active", ["sm__pipe_tensor", "pct_of_peak_sustained_active"]),
-    ("tensor_pipe_pct_elapsed", ["sm__pipe_tensor", "pct_of_peak_sustained_elapsed"]),
-    ("dram_read_bytes", ["dram__bytes_read.sum"]),
-    ("dram_write_bytes", ["dram__bytes_write.sum"]),
-    ("dram_pct", ["dram__throughput.avg.pct_of_peak_sustained_elapsed"]),
-    ("l2_pct", ["lts__throughput.avg.pct_of_peak_sustained_elapsed"]),
-    ("sm_pct", ["sm__throughput.avg.pct_of_peak_sustained_elapsed"]),
-    ("regs", ["launch__registers_per_thread"]),
-    ("smem_dyn", ["launch__shared_mem_per_block_dynamic"]),
-    ("grid", ["launch__grid_size"]),
+WANT = [  # (column label, exact ncu metric name)
+    ("dur_ns", "gpu__time_duration.sum"),
+    ("tensor_pipe_pct_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+    ("tensor_pipe_pct_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+    ("utcmma_insts", "smsp__sass_inst_executed_op_utcmma.sum"),
+    ("tma_ld_bytes", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum"),
+    ("dram_read_bytes", "dram__bytes_read.sum"),
+    ("dram_write_bytes", "dram__bytes_write.sum"),
+    ("dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+    ("l2_pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+    ("sm_pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+    ("warps_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+    ("regs", "launch__registers_per_thread"),
+    ("smem_dyn", "launch__shared_mem_per_block_dynamic"),
+    ("grid", "launch__grid_size"),
 ]
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}
 
 
-def main():
-    args = sys.argv[1:]
-    if args and args[0] == "--csv":          # one or more `ncu -i x.ncu-rep --page raw --csv` exports made on the GPU box
-        tag = args[-1]
-        raw = ""
-        for i, f in enumerate(args[1:-1]):
-            txt = open(f).read()
-            if i > 0:                        # drop the repeated header + units rows
-                txt = "\n".join(txt.splitlines()[2:]) + "\n"
-            raw += txt
-    else:
-        rep, tag = args[0], args[1]
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+def parse(raw, out_rows, per_kernel, first_hdr):
+    """one `--page raw --csv` export (its own header + units rows) -> records"""
     rows = list(csv.reader(io.StringIO(raw)))
     hdr_i = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr, units, data = rows[hdr_i], rows[hdr_i + 1], rows[hdr_i + 2:]
-    col = {}
-    for label, subs in WANT:
-        cands = [j for j, h in enumerate(hdr) if all(s in h for s in subs)]
-        if cands:
-            # prefer the exact / shortest metric name
-            col[label] = min(cands, key=lambda j: len(hdr[j]))
+    if not first_hdr:
+        first_hdr.extend(hdr)
+    col = {label: hdr.index(metric) for label, metric in WANT if metric in hdr}
     kn = hdr.index("Kernel Name")
-    out_rows, per_kernel = [], {}
     for r in data:
         if len(r) <= kn:
             continue
-        name = re.sub(r"^(void )?mapnet::", "", r[kn])
+        name = re.sub(r"^(void )?(mapnet::)?", "", r[kn])
         name = re.sub(r"\(.*$", "", name)
         rec = {"kernel": name}
         for label, j in col.items():
@@ -71,7 +59,7 @@ def main():
                 v = float(r[j].replace(",", ""))
             except ValueError:
                 v = None
-            if v is not None and label in ("dur_ns", "dram_read_bytes", "dram_write_bytes"):
+            if v is not None and label in ("dur_ns", "dram_read_bytes", "dram_write_bytes", "tma_ld_bytes"):
                 v *= UNIT.get(units[j], 1.0)
             rec[label] = v
         out_rows.append(rec)
@@ -79,11 +67,27 @@ def main():
         k["n"] += 1
         k["dur"] += rec.get("dur_ns") or 0.0
         k["bytes"] += (rec.get("dram_read_bytes") or 0.0) + (rec.get("dram_write_bytes") or 0.0)
+    return col
+
+
+def main():
+    args = sys.argv[1:]
+    out_rows, per_kernel, hdr, col = [], {}, [], {}
+    if args and args[0] == "--csv":          # one or more `ncu -i x.ncu-rep --page raw --csv` exports made on the GPU box
+        tag = args[-1]
+        for f in args[1:-1]:
+            txt = open(f).read()
+            if "Kernel Name" in txt:
+                col.update(parse(txt, out_rows, per_kernel, hdr))
+    else:
+        rep, tag = args[0], args[1]
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+        col.update(parse(raw, out_rows, per_kernel, hdr))
     labels = ["kernel"] + [l for l, _ in WANT if l in col]
     path = os.path.join(OUT_DIR, "%s_ncu_full_summary.csv" % tag)
     with open(path, "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on; one row per captured launch; metric columns: "
-                + "; ".join("%s=%s" % (l, hdr[col[l]]) for l in labels[1:]) + "\n")
+                + "; ".join("%s=%s" % (l, dict(WANT)[l]) for l in labels[1:]) + "; byte / time columns in bytes / ns\n")
         w = csv.writer(f)
         w.writerow(labels)
         for rec in out_rows:
@@ -95,6 +99,9 @@ def main():
         t = conv[top]
         traffic = {"kernel": top, "launches_captured": t["n"], "dram_bytes_per_launch": t["bytes"] / t["n"],
                    "avg_duration_us": t["dur"] / t["n"] / 1e3, "source": os.path.basename(path)}
+        dig = os.path.join(ROOT, "gpurun_out", "ncu_sources_digest.txt")
+        if os.path.exists(dig):          # digest of the kernel sources the capture ran (bench.py refuses a stale capture)
+            traffic["sources_digest"] = open(dig).read().strip()
         with open(os.path.join(OUT_DIR, "ncu_traffic.json"), "w") as f:
             json.dump(traffic, f, indent=1)
         print("ncu_traffic.json:", traffic)
