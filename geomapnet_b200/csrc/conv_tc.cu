@@ -547,7 +547,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
           const __grid_constant__ ConvParams P, const bf16* __restrict__ residual,
           bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E, const EpiFin Fin) {
-  constexpr int STAGES = (OCC == 2) ? kOcc2Stages : conv_stages(BN);
+  constexpr int STAGES = (OCC == 2) ? (BN <= 64 ? kOcc2Stages : 2) : conv_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;        // 128 pixels x 64 ch bf16
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -1991,10 +1991,16 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     {
       static int occ2 = -1;
       if (occ2 < 0) { const char* e = getenv("MAPNET_TC_OCC2"); occ2 = e ? atoi(e) : 1; }
+      static int occ128 = -1;          // experiment: BN = 128 tiles, two CTAs per SM with 2 stages each
+      if (occ128 < 0) { const char* e = getenv("MAPNET_TC_OCC2_128"); occ128 = e ? atoi(e) : 0; }
       p->occ2 = occ2 && !p->two_cta && p->BN == 64 && p->CL == 1 && kEpiWarps == 4;
       if (p->occ2) {
         kern = k_tc_conv<64, 1, 2>;
         smem = (size_t)kOcc2Stages * (128 * 128 + 64 * 128) + 1024 + scratch;
+      } else if (occ128 && !p->two_cta && p->BN == 128 && p->CL == 1 && kEpiWarps == 4) {
+        p->occ2 = true;
+        kern = k_tc_conv<128, 1, 2>;
+        smem = (size_t)2 * (128 * 128 + 128 * 128) + 1024 + scratch;
       }
     }
     MN_CHECK(kern != nullptr, "tc conv: no kernel for BN=%d CL=%d", p->BN, p->CL);

@@ -63,7 +63,7 @@ def test_ncu_summary_tool_on_a_sample_report(tmp_path):
     import shutil
     if not reps or shutil.which("ncu") is None:
         pytest.skip("no Nsight Compute sample report / ncu on this machine")
-    env = dict(os.environ, NCU_SUMMARY_OUT=str(tmp_path), NCU_SUMMARY_PREFIX="void Sobel")
+    env = dict(os.environ, NCU_SUMMARY_OUT=str(tmp_path), NCU_SUMMARY_PREFIX="Sobel")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), reps[0], "t"], capture_output=True,
                        text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr[-1500:]

@@ -8,6 +8,7 @@ out-of-bounds rows read as zero, stride-2 convs read parity views -- and compare
 (the third-party arithmetic the reference calls, /root/reference/models/posenet.py:66).  Shapes are fuzzed: odd
 sizes, both strides, 1x1 and 3x3, the downsample shortcut folded into the stride-2 dgrad."""
 import ctypes
+import os
 import json
 
 import numpy as np
@@ -221,6 +222,10 @@ def test_resnet34_layer_plans_at_benchmark_size(lib):
             rows.append((name, "fprop" if kind == 0 else "dgrad", "halo" if p["halo"] else ("pair" if p["two_cta"] else "1cta"),
                          p["BN"], items))
     table = {(r[0], r[1]): r[2:] for r in rows}
-    assert table[("layer1", "fprop")][0] == "halo" and table[("layer1", "dgrad")][0] == "halo"     # weights stationary: Cin = 64
+    # round 2: layer1 runs on the per-tap engine with two CTAs per SM (BN = 64; profiles/r02b_conv_microbench.txt); the
+    # halo-resident engine (stationary weights, Cin = 64) is selected with MAPNET_TC_HALO=1
+    want = "halo" if os.environ.get("MAPNET_TC_HALO") == "1" else "1cta"
+    assert table[("layer1", "fprop")][0] == want and table[("layer1", "dgrad")][0] == want
+    assert table[("layer1", "fprop")][1] == 64
     for r in rows:
         assert r[4] >= 32, r          # enough work items to occupy a good part of the 148 SMs
