@@ -287,7 +287,7 @@ def run_b200(args, cfg, rank, local_rank, world):
     # first step: builds the arena / flattens parameters
     eager_step(*dev_batches[0])
     if world > 1:
-        dp = FlatDataParallel(model, crit, overlap=(os.environ.get("MAPNET_DDP_OVERLAP", "1") != "0"))
+        dp = FlatDataParallel(model, crit, overlap=(os.environ.get("MAPNET_DDP_OVERLAP", "0") == "1"))
         dp.broadcast_parameters()
     L = _lib.lib()
     step = eager_step

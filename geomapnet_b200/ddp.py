@@ -1,6 +1,6 @@
 """Plain data parallel over the GPUs of one box: one process per GPU, the flat
-gradient buffer sum-reduced over NCCL (NVLink 5 / NVSwitch) -- in three slices
-that overlap the rest of the backward pass.
+gradient buffer sum-reduced over NCCL (NVLink 5 / NVSwitch) -- as ONE allreduce
+after the backward pass (default), or as three slices issued from inside it.
 
 The reference is single-GPU (common/train.py:193-196); this is the multi-GPU
 row of SURVEY.md section 8e.  Tuples (the N dimension of [N,T,3,H,W]) are sharded
@@ -10,13 +10,21 @@ statistics stay per-rank (no SyncBN), as when running the reference at the
 local batch size.  Equal local batches => mean of local L1 means == global L1
 mean, so averaged gradients equal the single-process gradient.
 
-Overlap: the backward pass finishes the gradients back to front.  The library
-runs it in three parts (mapnet_backward_part: head + layer4 = 64 % of the
-89.4 MB after ~20 % of the backward FLOPs, then layer3, then the rest) and
-calls back after each one; the callback enqueues that slice's allreduce on a
-side stream behind an event, so only the last 5 MB slice (and a 16-byte reduce
-of the criterion scalars) is exposed.  Measured in round 1 with ONE blocking
-allreduce after the backward: +0.42 ms per 4.1 ms step at 8 GPUs (SCALE_r01).
+Overlap (overlap=True, MAPNET_DDP_OVERLAP=1): the backward pass finishes the
+gradients back to front.  The library runs it in three parts
+(mapnet_backward_part: head + layer4 = 64 % of the 89.4 MB after ~20 % of the
+backward FLOPs, then layer3, then the rest) and calls back after each one; the
+callback enqueues that slice's allreduce on a side stream, so that only the
+last 5 MB slice would be exposed.  MEASURED (round 2, 2 x B200, mapnet_n32t3,
+CUDA-graph step): 5.340 ms/step with the hook (high-priority NCCL communicator)
+vs 5.355 ms with one blocking allreduce, 5.132 ms on one GPU -- the 0.21 ms of
+NVLink time is NOT hidden.  The backward's kernels leave NCCL's CTAs no room: the
+conv engines hold every SM with a persistent CTA of ~200 KB shared memory, the
+element-wise kernels fill every SM's 2048 thread slots, and programmatic
+dependent launch keeps the next kernel's CTAs queued ahead.  Hiding the
+collective needs SMs reserved for it (or copy-engine collectives); until then the
+default is the single allreduce, which is also the simplest thing to capture
+around (no NCCL work inside the CUDA graph).
 
 All functions work on any device/backend (gloo on CPU in the tests).
 """
@@ -66,10 +74,11 @@ class FlatDataParallel(object):
         scale = dp.allreduce_grads()                  # joins the side stream (+ the scalars); returns 1/world
         optimizer.learner.step(grad_scale=scale)
 
-    overlap=False: one blocking allreduce of the whole buffer inside allreduce_grads() (the round-1 behaviour).
+    overlap=False (default): one allreduce of the whole buffer inside allreduce_grads(); overlap=True: three slices
+    reduced from the backward-part hook on a side stream (see the module docstring for what was measured).
     """
 
-    def __init__(self, model, criterion=None, group=None, broadcast=True, overlap=True):
+    def __init__(self, model, criterion=None, group=None, broadcast=True, overlap=False):
         self.model = model
         self.posenet = model.mapnet if hasattr(model, "mapnet") else model
         self.criterion = criterion
@@ -84,8 +93,8 @@ class FlatDataParallel(object):
             self.posenet._grad_part_hook = self._on_part
             # The slice allreduces run WHILE the backward's conv kernels fill every SM (persistent CTAs, ~200 KB of
             # shared memory each): on a normal-priority stream NCCL's CTAs only get placed when a conv kernel drains
-            # and nothing overlaps (measured at N=2: 5.678 vs 5.674 ms/step with and without the hook).  A separate
-            # NCCL communicator on HIGH-PRIORITY streams lets the block scheduler place them as soon as any CTA retires.
+            # (measured at N=2: 5.678 vs 5.674 ms/step with and without the hook).  A separate NCCL communicator on
+            # HIGH-PRIORITY streams is the documented way to get them placed first; measured: 5.340 vs 5.355 ms.
             if dist.get_backend(group) == "nccl" and self.world > 1:
                 try:
                     opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)

@@ -19,7 +19,18 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap):
+    try:
+        _worker_body(rank, world, port, q, overlap)
+    except Exception:                            # a CUDA / NCCL error in one rank: report it instead of hanging the parent
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        q.put((rank, False))
+        os._exit(1)
+
+
+def _worker_body(rank, world, port, q, overlap):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -37,7 +48,7 @@ def _worker(rank, world, port, q):
     opt = Optimizer([{"params": model.parameters()}, {"params": list(crit.parameters())}], "adam", 1e-4, 5e-4)
     model.train()
     model(xs)                                   # materialise the flat buffers on the device
-    dp = FlatDataParallel(model, crit)
+    dp = FlatDataParallel(model, crit, overlap=overlap)
     dp.broadcast_parameters()
     flat, _ = net.flat_parameters()
     ref0 = flat.clone(); dist.broadcast(ref0, src=0)
@@ -57,15 +68,15 @@ def _worker(rank, world, port, q):
     sg = [torch.zeros_like(sax_local) for _ in range(world)]
     dist.all_gather(sg, sax_local)
     ok = ok and abs(float(crit.sax.grad) - float(sum(sg))) <= 1e-5 * abs(float(sum(sg))) + 1e-7
-    ok = ok and dp.overlap and net._grad_part_hook is not None      # the slices were reduced from the backward-part hook
+    ok = ok and dp.overlap == overlap and (net._grad_part_hook is not None) == overlap   # slices reduced from the backward-part hook
     g_eager = g.clone()
-    # the same step captured as CUDA graphs, slice allreduces INSIDE graph 1 (geomapnet_b200/graph.py): same weights
+    # the same step captured as CUDA graphs (overlap: slice allreduces INSIDE graph 1, geomapnet_b200/graph.py): same weights
     # (nothing has stepped yet, and building the graphed step restores the state) -> same reduced gradient
     from geomapnet_b200.graph import GraphedTrainStep
     gstep = GraphedTrainStep(model, crit, opt, xs, ts, dp=dp, warmup=2)
     gstep.x.copy_(xs); gstep.t.copy_(ts)
     gstep.g1.replay()
-    dp.allreduce_grads(slices_in_graph=True)
+    dp.allreduce_grads(slices_in_graph=overlap)
     _, g2 = net.flat_parameters()
     err = float((g2 - g_eager).abs().max()) / float(g_eager.abs().max())
     ok = ok and err <= 1e-4
@@ -85,15 +96,30 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_flat_allreduce_nccl_world2():
+def _run_world2(overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(2)]
-    for p in procs:
-        p.join(60)
+    try:
+        res = [q.get(timeout=300) for _ in range(2)]
+    finally:
+        for p in procs:
+            p.join(60)
+            if p.is_alive():
+                p.kill()                         # exactly the processes started above
     assert sorted(res) == [(0, True), (1, True)]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_flat_allreduce_nccl_world2():
+    """The default: one allreduce of the whole flat buffer after the backward, outside the CUDA graphs."""
+    _run_world2(False)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_flat_allreduce_nccl_world2_overlap():
+    """overlap=True: three slices reduced from the backward-part hook, captured inside graph 1."""
+    _run_world2(True)
