@@ -39,6 +39,8 @@ def lib():
     L.mapnet_param_count.argtypes = [c_void_p]
     L.mapnet_param_info.argtypes = [c_void_p, c_int, c_char_p, c_int, POINTER(c_int), POINTER(c_int),
                                     POINTER(c_int64), POINTER(c_int64)]
+    L.mapnet_param_layout.argtypes = [c_void_p, c_int]
+    L.mapnet_param_layout.restype = c_int
     L.mapnet_params_numel.argtypes = [c_void_p]
     L.mapnet_params_numel.restype = c_int64
     L.mapnet_bufs_numel.argtypes = [c_void_p]
@@ -101,7 +103,7 @@ def lib():
 
 
 EXPORTED = ["mapnet_last_error", "mapnet_abi_version", "mapnet_trunk_create", "mapnet_trunk_destroy",
-            "mapnet_param_count", "mapnet_param_info", "mapnet_params_numel", "mapnet_bufs_numel",
+            "mapnet_param_count", "mapnet_param_info", "mapnet_param_layout", "mapnet_params_numel", "mapnet_bufs_numel",
             "mapnet_forward", "mapnet_backward", "mapnet_loss_fwd_bwd", "mapnet_sqnorm", "mapnet_adam_step",
             "mapnet_test_conv", "mapnet_launch_count", "mapnet_profile", "mapnet_profile_read",
             "mapnet_adam_step_dev", "mapnet_bench_conv", "mapnet_test_stem",
@@ -142,6 +144,12 @@ class Trunk(object):
                                       ctypes.byref(off)), "mapnet_param_info")
             out.append((name.value.decode(), kind.value, tuple(shape[k] for k in range(ndim.value)), off.value))
         return out, L.mapnet_params_numel(self.h), L.mapnet_bufs_numel(self.h)
+
+    def layouts(self):
+        """{entry name: 1} for the conv weights the flat buffers hold in [Co][KH][KW][Ci] order (mapnet_param_layout)."""
+        L = lib()
+        names = [e[0] for e in self.table()[0]]
+        return {nm: 1 for i, nm in enumerate(names) if L.mapnet_param_layout(self.h, i) == 1}
 
     def grad_part_ranges(self):
         """[(lo, hi)] float ranges of the flat gradient buffer completed by backward parts 0, 1, 2."""

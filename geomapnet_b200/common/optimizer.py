@@ -22,6 +22,11 @@ __all__ = ["Optimizer", "FusedAdam"]
 _PAD = 64  # alignment padding (floats) between parameters in the flat buffer
 
 
+def _dense(p):
+    """Every element of p's memory span belongs to p exactly once (elementwise kernels may sweep the span)."""
+    return p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+
+
 class FusedAdam(optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
@@ -78,7 +83,9 @@ class FusedAdam(optim.Optimizer):
             for p in r["params"]:
                 off = (p.data_ptr() - first.data_ptr()) // 4
                 st = self.state[p]
-                mv, vv = m[off:off + p.numel()].view(p.shape), v[off:off + p.numel()].view(p.shape)
+                # moments in the parameter's own element order (channels_last for the KRSC conv weights)
+                mv = torch.as_strided(m, tuple(p.shape), p.stride(), off)
+                vv = torch.as_strided(v, tuple(p.shape), p.stride(), off)
                 if "exp_avg" in st:          # resumed / re-planned: keep the moments
                     mv.copy_(st["exp_avg"].to(p.device)); vv.copy_(st["exp_avg_sq"].to(p.device))
                 st["exp_avg"], st["exp_avg_sq"] = mv, vv
@@ -111,8 +118,9 @@ class FusedAdam(optim.Optimizer):
             if not params:
                 continue
             for p in params:
-                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
-                    raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients (no CPU path)")
+                if not p.is_cuda or p.dtype != torch.float32 or not _dense(p) or p.grad.stride() != p.stride():
+                    raise RuntimeError("FusedAdam needs dense fp32 CUDA parameters with gradients in the same strides "
+                                       "(contiguous, or channels_last views of a flat buffer; no CPU path)")
             groups.append((group, self._plan(gi, params), clip_groups is None or gi in clip_groups))
         if not groups:
             return loss

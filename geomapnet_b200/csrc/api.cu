@@ -13,7 +13,7 @@ struct mapnet_trunk { Net net; };
 extern "C" {
 
 const char* mapnet_last_error(void) { return get_last_error(); }
-int mapnet_abi_version(void) { return 1; }
+int mapnet_abi_version(void) { return 2; }
 
 static int require_device() {
   int n = 0;
@@ -57,6 +57,11 @@ int mapnet_param_info(mapnet_trunk_t* h, int i, char* host_name, int name_cap, i
   if (host_shape4) for (int k = 0; k < 4; ++k) host_shape4[k] = e.shape[k];
   if (host_offset) *host_offset = e.offset;
   return 0;
+}
+
+int mapnet_param_layout(mapnet_trunk_t* h, int i) {
+  if (h == nullptr || i < 0 || i >= (int)h->net.table.size()) return -1;
+  return h->net.table[i].layout;
 }
 
 int64_t mapnet_params_numel(mapnet_trunk_t* h) { return h ? h->net.n_params : -1; }

@@ -174,6 +174,8 @@ k_bn_finalize_accum(long long M, int C, BnFin f, double* __restrict__ accum) {
 int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float* beta, float* run_mean,
                              float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift,
                              double* accum, cudaStream_t st) {
+  { static int dbg = -1, calls = 0; if (dbg < 0) { const char* e = getenv("MAPNET_DEBUG_SKIP_FIN"); dbg = e ? atoi(e) : 0; }
+    if (dbg && ++calls > 100) return 0; }   // TIMING EXPERIMENT ONLY
   MN_CHECK(C <= 512, "bn_finalize_accum: C=%d", C);
   BnFin f; memset(&f, 0, sizeof(f));
   f.gamma = gamma; f.beta = beta; f.run_mean = run_mean; f.run_var = run_var; f.mean = mean_out;
@@ -211,6 +213,8 @@ int launch_bn_bwd_finalize_accum(long long M, int C, const float* gamma, const f
                                  float* dgamma, float* dbeta, float* coef, const float* gamma2, const float* mean2,
                                  const float* invstd2, float* dgamma2, float* dbeta2, float* coef2, double* accum,
                                  cudaStream_t st) {
+  { static int dbg = -1, calls = 0; if (dbg < 0) { const char* e = getenv("MAPNET_DEBUG_SKIP_FIN"); dbg = e ? atoi(e) : 0; }
+    if (dbg && ++calls > 100) return 0; }   // TIMING EXPERIMENT ONLY
   MN_CHECK(C <= 512, "bn_bwd_finalize_accum: C=%d", C);
   BnFin f; memset(&f, 0, sizeof(f));
   f.gamma = gamma; f.mean = const_cast<float*>(mean); f.invstd = const_cast<float*>(invstd);
@@ -363,20 +367,30 @@ k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const floa
     for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
     float sc[8], sh[8];
     ld8(scale + c0, sc); ld8(shift + c0, sh);
+    // all nine window loads are issued unconditionally (border taps read a clamped, valid pixel and are masked out
+    // below): with the loads under the border branches the compiler kept them serial and the kernel ran at 23 % of the
+    // DRAM rate (ncu r02a: 89 us for 165 MB)
+    Vec8<T> v[9]; bool ok[9];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int ih = oh * 2 - 1 + kh;
-      if (ih < 0 || ih >= H) continue;
+      const bool okh = (ih >= 0) && (ih < H);
+      const int ihc = okh ? ih : oh * 2;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int iw = ow * 2 - 1 + kw;
-        if (iw < 0 || iw >= W) continue;
-        Vec8<T> v; v.load(y + (((long long)b * H + ih) * W + iw) * C + c0);
+        const bool okw = (iw >= 0) && (iw < W);
+        const int iwc = okw ? iw : ow * 2;
+        ok[kh * 3 + kw] = okh && okw;
+        v[kh * 3 + kw].load(y + ((size_t)((unsigned int)b * H + ihc) * W + iwc) * C + c0);
+      }
+    }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float a = fmaxf(v.v[k] * sc[k] + sh[k], 0.f);
-          if (a > best[k]) { best[k] = a; bi[k] = kh * 3 + kw; }
-        }
+    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float a = ok[t] ? fmaxf(v[t].v[k] * sc[k] + sh[k], 0.f) : -INFINITY;
+        if (a > best[k]) { best[k] = a; bi[k] = t; }
       }
     }
     Vec8<TZ> o;

@@ -127,6 +127,7 @@ struct ConvParams {
   int debug;     // micro-benchmark only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
   int fmt_a, fmt_b;        // UMMA operand element formats: 0 = fp16, 1 = bf16
   int out32;               // strict mode: output (and residual) are fp32 tensors
+  int epi_prefetch;        // epilogue warps pull the NEXT tile's residual / y / zmask / yd rows into L2 (env MAPNET_TC_EPI_PREFETCH)
 };
 
 // work item -> (class, N tile, first M tile of the group): classes are laid out one after the other
@@ -278,6 +279,42 @@ __device__ __forceinline__ void epi_issue_loads(EpiRegs& G, const long long (&ro
     if (F & EPI_BWD) G.y[i] = __ldg(reinterpret_cast<const uint4*>(E.y + off));
     if (F & EPI_ZMASK) G.z[i] = __ldg(reinterpret_cast<const uint4*>(E.zmask + off));
     if (F & EPI_YD) G.d[i] = __ldg(reinterpret_cast<const uint4*>(E.yd + off));
+  }
+}
+
+// The fused dgrad epilogues read up to four more tensors per output element (skip-path gradient, conv output y, ReLU
+// mask z, downsample-branch y) straight from HBM, one 32-column chunk at a time per warp: ~0.8 us of DRAM latency per
+// chunk with only 4 warps of loads in flight (layer1 / layer2 dgrads ran at half the HBM rate).  While a tile's
+// accumulator is still being produced, each epilogue warp therefore asks L2 for the rows of the tile it will process
+// NEXT: one prefetch per 128-byte line, lane p = lane & 3 takes line p of each of its 4 rows.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+template <int BN>
+__device__ __forceinline__ void epi_prefetch_next(const ConvParams& P, const int tile, const int per_class, const int cl,
+                                                  const int crank, const int q, const int lane, const bf16* residual,
+                                                  const EpiBwd& E) {
+  const int p = lane & 3;
+  if (p * 64 >= BN) return;
+  const TileCoord tc = decode_tile(tile, per_class, P.n_tiles_n);
+  const ClassDesc cd = P.cls[tc.cls];
+  int tm = tc.group * cl + crank;
+  const int tw = tm % P.tiles_w; tm /= P.tiles_w;
+  const int th = tm % P.tiles_h;
+  const int tb = tm / P.tiles_h;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = q * 32 + 8 * i + (lane >> 2);
+    const int lw = m % P.TW;
+    const int lh = (m / P.TW) % P.TH;
+    const int ln = m / (P.TW * P.TH);
+    const int jw = tw * P.TW + lw, jh = th * P.TH + lh, n = tb * P.TN + ln;
+    if (!((jw < cd.Ws) && (jh < cd.Hs) && (n < P.Nimg))) continue;
+    const long long pix = ((long long)n * P.Hout + (jh * P.os + cd.oa)) * P.Wout + (jw * P.os + cd.ob);
+    const long long off = pix * P.Cout + tc.tn * BN + p * 64;
+    if (residual != nullptr) prefetch_l2(residual + off);
+    if (E.y != nullptr) prefetch_l2(E.y + off);
+    if (E.zmask != nullptr) prefetch_l2(E.zmask + off);
+    if (E.yd != nullptr) prefetch_l2(E.yd + off);
   }
 }
 
@@ -547,7 +584,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
           const __grid_constant__ ConvParams P, const bf16* __restrict__ residual,
           bf16* __restrict__ out, double* __restrict__ stats, const EpiBwd E, const EpiFin Fin) {
-  constexpr int STAGES = (OCC == 2) ? (BN <= 64 ? kOcc2Stages : 2) : conv_stages(BN);
+  constexpr int STAGES = (OCC == 2) ? kOcc2Stages : conv_stages(BN);
   constexpr uint32_t A_BYTES = 128 * 128;        // 128 pixels x 64 ch bf16
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -704,6 +741,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const long long pix = ((long long)n * P.Hout + (jh * P.os + cd.oa)) * P.Wout + (jw * P.os + cd.ob);
         rowoff[i] = (rvalid[i] ? pix * P.Cout : 0) + tn * BN;     // outside rows: clamped, loads stay in bounds
       }
+      if (P.epi_prefetch && tile + tile_step < total_tiles)
+        epi_prefetch_next<BN>(P, tile + tile_step, per_class, CL, (int)crank, q, lane, residual, E);
       if (P.debug == 3) {           // micro-benchmark: no epilogue work at all
         mbar_wait(tfull0 + 8 * as, aphase);
         tc_fence_after();
@@ -894,6 +933,8 @@ k_tc_conv2(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const long long pix = ((long long)n * P.Hout + (jh * P.os + cd.oa)) * P.Wout + (jw * P.os + cd.ob);
         rowoff[i] = (rvalid[i] ? pix * P.Cout : 0) + tn * BN;     // outside rows: clamped, loads stay in bounds
       }
+      if (P.epi_prefetch && tile + tile_step < total_tiles)
+        epi_prefetch_next<BN>(P, tile + tile_step, per_class, 2, (int)crank, q, lane, residual, E);
       epi_tile_dispatch<BN>(epi_mode, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, kblocks > 0, tfull0 + 8 * as,
                             aphase, [&]() { mbar_arrive_cluster(mapa(tempty0 + 8 * as, 0)); }, scr, stw, rowoff, rvalid, true, tn,
                             residual, out, E, lane, half);
@@ -1991,16 +2032,10 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
     {
       static int occ2 = -1;
       if (occ2 < 0) { const char* e = getenv("MAPNET_TC_OCC2"); occ2 = e ? atoi(e) : 1; }
-      static int occ128 = -1;          // experiment: BN = 128 tiles, two CTAs per SM with 2 stages each
-      if (occ128 < 0) { const char* e = getenv("MAPNET_TC_OCC2_128"); occ128 = e ? atoi(e) : 0; }
       p->occ2 = occ2 && !p->two_cta && p->BN == 64 && p->CL == 1 && kEpiWarps == 4;
       if (p->occ2) {
         kern = k_tc_conv<64, 1, 2>;
         smem = (size_t)kOcc2Stages * (128 * 128 + 64 * 128) + 1024 + scratch;
-      } else if (occ128 && !p->two_cta && p->BN == 128 && p->CL == 1 && kEpiWarps == 4) {
-        p->occ2 = true;
-        kern = k_tc_conv<128, 1, 2>;
-        smem = (size_t)2 * (128 * 128 + 128 * 128) + 1024 + scratch;
       }
     }
     MN_CHECK(kern != nullptr, "tc conv: no kernel for BN=%d CL=%d", p->BN, p->CL);
@@ -2015,10 +2050,14 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       const int max_clusters = (p->CL == 4) ? 32 : nsm / p->CL;
       F.expected += (unsigned int)((groups < max_clusters ? groups : max_clusters) * p->CL);
     }
+    static int epi_pf = -1;
+    if (epi_pf < 0) { const char* e = getenv("MAPNET_TC_EPI_PREFETCH"); epi_pf = e ? atoi(e) : 1; }
     for (auto& L : p->launches) {
       const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n * L.P.n_classes;
       const int max_clusters = (p->CL == 4) ? 32 : nsm / p->CL;
       const int nclusters = groups < max_clusters ? groups : max_clusters;
+      // bf16 epilogues that read extra tensors (the fused dgrad variants): next-tile L2 prefetch
+      L.P.epi_prefetch = (epi_pf && !L.P.out32 && (residual != nullptr || E.y != nullptr)) ? 1 : 0;
       cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3(nclusters * p->CL); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
       cudaLaunchAttribute attr[2];

@@ -15,11 +15,12 @@ template <typename TW> __device__ __forceinline__ TW cvt_w(float v);
 template <> __device__ __forceinline__ float cvt_w<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 cvt_w<bf16>(float v) { return __float2bfloat16_rn(v); }
 
-// One block per (group of output channels, conv): a channel's [Ci][KH*KW] slab is contiguous in the torch
-// layout -> coalesced load into shared memory -> coalesced store as [KH*KW][Ci] (odd stride 9: no
-// bank conflicts).  The stem's [3][7][7] slab becomes the padded [im2col_k] row of the patch GEMM.
-// Small slabs are grouped (up to 8 channels, <= 4608 floats per block): with one 2.3 KB slab per 256-thread block the
-// 64-channel convs were latency-bound (ncu r02a: 66.8 us for 85 MB read + 42 MB written, 18 % of DRAM peak).
+// The master conv weights live in params_flat in the order the engines consume them: [Co][KH][KW][Ci] (KRSC,
+// mapnet_param_layout == 1; to PyTorch the same memory is the [Co,Ci,KH,KW] parameter in channels_last strides).  The
+// operand copy is then a plain fp32 -> TW conversion, and the weight gradients need no re-layout at all -- the two
+// transposing passes of round 1 (k_pack_weights 83 us + k_unpack_wgrads 103 us per step, cold) are gone.
+// Only the stem keeps torch's [64][3][7][7] order (layout 0): its slab becomes the padded [im2col_k] row of the patch
+// GEMM through shared memory.  One block per (group of output channels, conv).
 __host__ __device__ inline int pack_group(int n_in) { int g = 4096 / (n_in > 0 ? n_in : 1); return g < 1 ? 1 : (g > 8 ? 8 : g); }
 
 template <typename TW>
@@ -36,9 +37,9 @@ k_pack_weights(const WeightDesc* __restrict__ descs, const float* __restrict__ p
   if (co >= d.Co) return;
   const int ng = (d.Co - co < G) ? d.Co - co : G;
   const float* src = params + d.p_off + (long long)co * n_in;
-  for (int i = threadIdx.x; i < ng * n_in; i += blockDim.x) slab[i] = src[i];
-  __syncthreads();
   if (d.im2col_k > 0) {
+    for (int i = threadIdx.x; i < n_in; i += blockDim.x) slab[i] = src[i];
+    __syncthreads();
     TW* dst = w_krsc + d.k_off + (long long)co * d.im2col_k;
     for (int k = threadIdx.x; k < d.im2col_k; k += blockDim.x) {
       float v = 0.f;
@@ -54,13 +55,16 @@ k_pack_weights(const WeightDesc* __restrict__ descs, const float* __restrict__ p
       dst[k] = cvt_w<TW>(v);
     }
   } else {
-    TW* dst = w_krsc + d.k_off + (long long)co * KK * d.Ci;          // the group's rows are contiguous (n_in = KK * Ci)
-    for (int jj = threadIdx.x; jj < ng * n_in; jj += blockDim.x) {
-      const int g = jj / n_in, j = jj - g * n_in;
-      const int tap = j / d.Ci, ci = j - tap * d.Ci;
-      float v = slab[g * n_in + ci * KK + tap];
-      if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
-      dst[jj] = cvt_w<TW>(v);
+    // same element order on both sides; n_in = KK * Ci is a multiple of 64 and both offsets are 64-float aligned
+    TW* dst = w_krsc + d.k_off + (long long)co * n_in;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int jj = threadIdx.x; jj < (ng * n_in) >> 2; jj += blockDim.x) {
+      float4 v = __ldg(s4 + jj);
+      if (round_bf16) {
+        v.x = __bfloat162float(__float2bfloat16_rn(v.x)); v.y = __bfloat162float(__float2bfloat16_rn(v.y));
+        v.z = __bfloat162float(__float2bfloat16_rn(v.z)); v.w = __bfloat162float(__float2bfloat16_rn(v.w));
+      }
+      dst[4 * jj] = cvt_w<TW>(v.x); dst[4 * jj + 1] = cvt_w<TW>(v.y); dst[4 * jj + 2] = cvt_w<TW>(v.z); dst[4 * jj + 3] = cvt_w<TW>(v.w);
     }
   }
 }
@@ -100,8 +104,8 @@ k_transpose_dg(const WeightDesc* __restrict__ descs, const TW* __restrict__ w_kr
 template <typename TW>
 int launch_pack_weights(const WeightDesc* d_descs, int nconv, const float* params, TW* w_krsc, TW* w_dg,
                         int max_elems, int round_bf16, cudaStream_t st) {
-  dim3 grid(512, nconv);                 // blockIdx.x = output channel (<= 512), blocks past Co exit
-  MN_LAUNCH(k_pack_weights<TW>, grid, 256, 512 * 9 * sizeof(float), st, d_descs, params, w_krsc, w_dg, round_bf16);
+  dim3 grid(512, nconv);                 // blockIdx.x = output channel group (<= 512), blocks past Co exit
+  MN_LAUNCH(k_pack_weights<TW>, grid, 256, 3 * 49 * sizeof(float), st, d_descs, params, w_krsc, w_dg, round_bf16);
   MN_LAUNCH_CHECK();
   if (w_dg != nullptr) {
     dim3 g2(592, nconv);
@@ -256,31 +260,14 @@ k_unpack_wgrads(const WeightDesc* __restrict__ descs, const float* __restrict__ 
     }
     return;
   }
-  const int KK = d.KH * d.KW, n = KK * d.Ci, pitch = d.Ci + 1;   // +1: conflict-free column reads
-  const int G = pack_group(n);                     // channels per block (same grouping as the packer)
-  const int co = blockIdx.x * G;
-  if (co >= d.Co) return;
-  const int ng = (d.Co - co < G) ? d.Co - co : G;
-  const int gp = KK * pitch;                       // slab floats per channel
-  const float* src = dw + d.k_off + (long long)co * n;
-  for (int ii = threadIdx.x; ii < ng * n; ii += blockDim.x) {
-    const int g = ii / n, i = ii - g * n;
-    const int tap = i / d.Ci;
-    slab[g * gp + tap * pitch + (i - tap * d.Ci)] = src[ii];
-  }
-  __syncthreads();
-  float* dst = grads + d.p_off + (long long)co * n;
-  for (int ee = threadIdx.x; ee < ng * n; ee += blockDim.x) {
-    const int g = ee / n, e = ee - g * n;
-    const int tap = e % KK, ci = e / KK;           // torch layout [Ci][KH*KW]
-    dst[ee] = slab[g * gp + tap * pitch + ci];
-  }
+  // every other conv's wgrad engine accumulates straight into grads_flat (KRSC order, mapnet_param_layout == 1)
 }
 
 int launch_unpack_wgrads(const WeightDesc* d_descs, int nconv, const float* dw_krsc, float* grads,
                          int max_elems, cudaStream_t st) {
-  dim3 grid(512, nconv);
-  MN_LAUNCH(k_unpack_wgrads, grid, 256, 513 * 9 * sizeof(float), st, d_descs, dw_krsc, grads);
+  // only the stem (conv 0, patch-matrix K order) needs a re-layout; nconv is 1
+  dim3 grid(64, nconv);
+  MN_LAUNCH(k_unpack_wgrads, grid, 256, 256 * sizeof(float), st, d_descs, dw_krsc, grads);
   MN_LAUNCH_CHECK();
   return 0;
 }

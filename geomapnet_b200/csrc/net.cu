@@ -8,6 +8,7 @@
 #include "bn_fin.cuh"
 
 #include <stdarg.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -49,7 +50,7 @@ void Net::build_table() {
   n_params = n_bufs = n_nbt = 0;
   auto add = [&](const std::string& name, int kind, std::initializer_list<long long> shp) {
     ParamEntry e;
-    e.name = name; e.kind = kind; e.ndim = (int)shp.size(); e.numel = 1;
+    e.name = name; e.kind = kind; e.layout = 0; e.ndim = (int)shp.size(); e.numel = 1;
     int i = 0;
     for (long long s : shp) { e.shape[i++] = s; e.numel *= s; }
     for (; i < 4; ++i) e.shape[i] = 1;
@@ -74,6 +75,7 @@ void Net::build_table() {
   auto add_conv = [&](const std::string& name, int Ci, int Co, int k, int stride, int Hi, int Wi, bool stem) {
     ConvL c;
     const int pidx = add(name + ".weight", 0, {Co, stem ? 3 : Ci, k, k});
+    table[pidx].layout = stem ? 0 : 1;     // [Co][KH][KW][Ci] in the flat buffers (what the engines read and accumulate)
     c.wd.p_off = table[pidx].offset;
     c.wd.k_off = wk_total;
     c.wd.Co = Co; c.wd.Ci_real = stem ? 3 : Ci;
@@ -149,7 +151,7 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_CHECK(feat_dim >= 8 && feat_dim % 4 == 0, "create: feat_dim must be a multiple of 4");
   last_B = 0; last_training = 0; last_has_mask = 0; tc_B = 0; profile_on = 0; prof_pool_used = 0;
   bwd_pre = false; bwd_next_part = 0;
-  side = nullptr; wgrad_async = 0; ring_pos = 0;
+  side = nullptr; wgrad_async = 0; ring_pos = 0; cur_grads = nullptr; dw_stem_elems = 0;
   for (int i = 0; i < 4; ++i) { ring[i] = nullptr; ring_ready[i] = ring_done[i] = nullptr; ring_pending[i] = false; }
   { const char* e = getenv("MAPNET_TC_FUSE_STATS"); fuse_stats = tc() && (e ? atoi(e) != 0 : 1); }
   { const char* e = getenv("MAPNET_STEM_S2D");
@@ -197,7 +199,8 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
     MN_TRY(alloc((void**)&w_krsc_f32, (size_t)wk_total * 4));
     MN_TRY(alloc((void**)&w_dg_f32, (size_t)wk_total * 4));
   }
-  MN_TRY(alloc((void**)&dw_krsc, (size_t)wk_total * 4));
+  dw_stem_elems = align_up((long long)convs[0].wd.Co * convs[0].wd.KH * convs[0].wd.KW * convs[0].wd.Ci, 512);
+  MN_TRY(alloc((void**)&dw_krsc, (size_t)dw_stem_elems * 4));       // the stem's wgrad (conv 0, k_off == 0)
   std::vector<WeightDesc> wd;
   for (auto& c : convs) wd.push_back(c.wd);
   MN_TRY(alloc((void**)&d_wdescs, wd.size() * sizeof(WeightDesc)));
@@ -282,11 +285,17 @@ void Net::prof_end(cudaStream_t st, cudaEvent_t e0, int cls, double flops) {
 int Net::prof_read(double* ms3, double* flops3, int* launches3) {
   for (int i = 0; i < 3; ++i) { ms3[i] = 0; flops3[i] = 0; launches3[i] = 0; }
   MN_CUDA(cudaDeviceSynchronize());
+  // MAPNET_PROFILE_DUMP=<path>: one line per bracketed launch (class, algorithmic GFLOP, microseconds), in launch order
+  const char* dump = getenv("MAPNET_PROFILE_DUMP");
+  FILE* df = (dump && dump[0]) ? fopen(dump, "a") : nullptr;
   for (auto& r : prof) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
     ms3[r.cls] += ms; flops3[r.cls] += r.flops; launches3[r.cls] += 1;
+    if (df) fprintf(df, "%s %.3f GF %.2f us %.0f TF\n", r.cls == 0 ? "fprop" : (r.cls == 1 ? "dgrad" : "wgrad"), r.flops * 1e-9,
+                    ms * 1e3, ms > 0 ? r.flops / (ms * 1e-3) * 1e-12 : 0.0);
   }
+  if (df) { fprintf(df, "---\n"); fclose(df); }
   prof.clear();
   prof_pool_used = 0;
   return 0;
@@ -364,8 +373,8 @@ int Net::conv_wgrad(int ci, const typename P::Z* x, const typename P::G* dy, int
     MN_CUDA(cudaEventRecord(ring_ready[slot], st));
     MN_CUDA(cudaStreamWaitEvent(side, ring_ready[slot], 0));
     int r;
-    if (tc()) r = tc_conv_run(tc_wgrad[ci], (const bf16*)x, (const bf16*)dy, nullptr, dw_krsc + convs[ci].wd.k_off, side);
-    else if constexpr (SimtConv<P>::ok) r = launch_conv_simt_wgrad<typename P::A>(g, x, dy, dw_krsc + convs[ci].wd.k_off, side);
+    if (tc()) r = tc_conv_run(tc_wgrad[ci], (const bf16*)x, (const bf16*)dy, nullptr, wgrad_out(ci), side);
+    else if constexpr (SimtConv<P>::ok) r = launch_conv_simt_wgrad<typename P::A>(g, x, dy, wgrad_out(ci), side);
     else { set_last_error("conv_wgrad: no CUDA-core engine for split operands"); r = 2; }
     MN_CUDA(cudaEventRecord(ring_done[slot], side));
     ring_pending[slot] = true;
@@ -374,8 +383,8 @@ int Net::conv_wgrad(int ci, const typename P::Z* x, const typename P::G* dy, int
   cudaEvent_t e0 = nullptr;
   MN_TRY(prof_begin(st, &e0));
   int r;
-  if (tc()) r = tc_conv_run(tc_wgrad[ci], (const bf16*)x, (const bf16*)dy, nullptr, dw_krsc + convs[ci].wd.k_off, st);
-  else if constexpr (SimtConv<P>::ok) r = launch_conv_simt_wgrad<typename P::A>(g, x, dy, dw_krsc + convs[ci].wd.k_off, st);
+  if (tc()) r = tc_conv_run(tc_wgrad[ci], (const bf16*)x, (const bf16*)dy, nullptr, wgrad_out(ci), st);
+  else if constexpr (SimtConv<P>::ok) r = launch_conv_simt_wgrad<typename P::A>(g, x, dy, wgrad_out(ci), st);
   else { set_last_error("conv_wgrad: no CUDA-core engine for split operands"); r = 2; }
   prof_end(st, e0, 2, conv_flops(g, B, ci == 0));
   return r;
@@ -555,7 +564,13 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
   MN_CHECK(part <= 0 || bwd_next_part == part, "backward: part %d called out of order (next is %d)", part, bwd_next_part);
   bwd_next_part = (part < 0 || part == 2) ? 0 : part + 1;
   const bool do_head = part <= 0, do_stem = part < 0 || part == 2;
-  if (do_head) MN_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)wk_total * 4, st));
+  // the wgrad engines ACCUMULATE (split-K atomics) straight into grads_flat -- conv weights are stored in the engines'
+  // KRSC order there (mapnet_param_layout) -- except the stem, whose patch-matrix gradient is re-laid out from dw_krsc
+  cur_grads = grads;
+  if (do_head) {
+    MN_CUDA(cudaMemsetAsync(grads, 0, (size_t)n_params * 4, st));
+    MN_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)dw_stem_elems * 4, st));
+  }
   // S0: d(block output), S3: gated gradient of the identity branch, S4: d h -- T;  S1 / S2: d(conv output) -- TG
   // (S1 / S2 are slots of the ring the asynchronous wgrads read from: re-pointed before every write)
   T* S0 = (T*)scratch[0]; TG* S1 = (TG*)scratch[1]; TG* S2 = (TG*)scratch[2]; T* S3 = (T*)scratch[3]; T* S4 = (T*)scratch[4];
@@ -699,9 +714,9 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, (const TZ*)nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st, nullptr, nullptr, gs)));
     MN_TRY(conv_wgrad<P>(0, (const TZ*)A0, S2, B, st));
   }
-  MN_TRY(wgrad_join(st));       // every asynchronous wgrad of this part has landed in dw_krsc
-  if (conv_hi >= conv_lo)
-    MN_TRY(launch_unpack_wgrads(d_wdescs + conv_lo, conv_hi - conv_lo + 1, dw_krsc, grads, max_w_elems, st));
+  MN_TRY(wgrad_join(st));       // every asynchronous wgrad of this part has landed in grads_flat (the stem's in dw_krsc)
+  if (conv_hi >= conv_lo && conv_lo == 0)
+    MN_TRY(launch_unpack_wgrads(d_wdescs, 1, dw_krsc, grads, max_w_elems, st));
   return 0;
 }
 

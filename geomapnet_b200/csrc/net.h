@@ -16,6 +16,8 @@ enum Precision { PREC_FP32 = 0, PREC_BF16_TC = 1, PREC_BF16_SIMT = 2, PREC_TC_SP
 struct ParamEntry {
   std::string name;
   int kind;               // 0 trainable fp32 (params_flat), 1 fp32 buffer (bufs_flat), 2 int64 num_batches_tracked
+  int layout;             // 0: elements in torch's contiguous order of `shape`; 1: conv weight [Co,Ci,KH,KW] stored as
+                          //    [Co][KH][KW][Ci] (torch.channels_last strides) -- every conv except the stem
   int ndim;
   long long shape[4];
   long long numel;
@@ -69,6 +71,10 @@ struct Net {
   int ring_slot(const void* p) const;
   int wgrad_join(cudaStream_t st);
   void *w_krsc, *w_dg; float* dw_krsc; WeightDesc* d_wdescs;
+  float* cur_grads;              // grads_flat of the running backward pass
+  long long dw_stem_elems;       // floats in dw_krsc (the stem's patch-matrix weight gradient)
+  // where conv ci's wgrad engine accumulates: grads_flat at the parameter's offset (KRSC order), the stem in dw_krsc
+  float* wgrad_out(int ci) { return ci == 0 ? dw_krsc : cur_grads + convs[ci].wd.p_off; }
   float *w_krsc_f32, *w_dg_f32;  // strict mode: fp32 K-major matrices the hi / lo weight planes are cut from
   int split_fmt_z, split_fmt_g;  // strict mode: element format of the forward / backward operand planes (0 fp16, 1 bf16)
   float* gscale;                 // strict mode, device: {S, 1/S} -- this step's power-of-two gradient scale

@@ -80,6 +80,7 @@ class PoseNet(nn.Module):
 
         spec = _lib.Trunk(0, 64, 64, feat_dim, self.precision)      # spec-only handle, no device needed
         self._table, self._n_params, self._n_bufs = spec.table()
+        self._krsc = spec.layouts()       # conv weights stored [Co][KH][KW][Ci] in the flat buffers (channels_last views)
         spec.close()
         self._n_nbt = sum(1 for e in self._table if e[1] == 2)
         self._flat = torch.zeros(self._n_params, dtype=torch.float32)
@@ -113,7 +114,10 @@ class PoseNet(nn.Module):
                 init_names = [n[:-len(".weight")] for n, k, s, o in self._table
                               if k == 0 and n.endswith(".weight") and len(s) in (2, 4)]
             for nm in init_names:
-                nn.init.kaiming_normal_(self._entry_tensor(nm + ".weight"))
+                w = self._entry_tensor(nm + ".weight")
+                tmp = torch.empty(tuple(w.shape))     # contiguous: the same RNG draw -> element mapping as the reference's
+                nn.init.kaiming_normal_(tmp)          # nn.init on its contiguous parameters (channels_last views differ)
+                w.copy_(tmp)
                 if (nm + ".bias") in self._by_name:
                     nn.init.constant_(self._entry_tensor(nm + ".bias"), 0)
         self._trunks = {}
@@ -141,7 +145,7 @@ class PoseNet(nn.Module):
             for s in shape:
                 n *= s
             if kind == 0:
-                t = nn.Parameter(self._flat[off:off + n].view(shape))
+                t = nn.Parameter(self._pview(self._flat, name, off, n, shape))
                 mod.register_parameter(parts[-1], t)
                 self._param_list.append(t)
             elif kind == 1:
@@ -151,6 +155,16 @@ class PoseNet(nn.Module):
                 t = self._nbt[off:off + 1].view(())
                 mod.register_buffer(parts[-1], t)
             self._by_name[name] = (mod, parts[-1], kind, shape, off, n)
+
+    def _pview(self, flat, name, off, n, shape):
+        """The entry's tensor as a view of a flat buffer.  Conv weights (all but the stem) are stored in the order the
+        tcgen05 engines read and accumulate them, [Co][KH][KW][Ci] (mapnet_param_layout == 1): the view has the
+        reference's [Co,Ci,KH,KW] shape with torch.channels_last strides, so indexing, state_dict(), load_state_dict()
+        and optimizers see the same tensor as in the reference while no kernel ever transposes a weight or a gradient."""
+        if name in self._krsc:
+            co, ci, kh, kw = shape
+            return flat[off:off + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+        return flat[off:off + n].view(shape)
 
     def _entry_tensor(self, name):
         mod, leaf, kind, shape, off, n = self._by_name[name]
@@ -186,7 +200,7 @@ class PoseNet(nn.Module):
                 mod, leaf, _, _, _, n = self._by_name[name]
                 if kind == 0:
                     p = mod._parameters[leaf]
-                    v = flat[off:off + n].view(shape)
+                    v = self._pview(flat, name, off, n, shape)
                     v.copy_(p.data.to(device=device, dtype=torch.float32))
                     p.data = v
                     p.grad = None
@@ -294,7 +308,7 @@ class PoseNet(nn.Module):
         for name, kind, shape, off in self._table:
             if kind == 0:
                 n = self._by_name[name][5]
-                out.append(gbuf[off:off + n].view(shape))
+                out.append(self._pview(gbuf, name, off, n, shape))
         return out
 
     # ------------------------------------------------------- flat-buffer API

@@ -62,6 +62,13 @@ int mapnet_trunk_destroy(mapnet_trunk_t* h);
 int mapnet_param_count(mapnet_trunk_t* h);
 int mapnet_param_info(mapnet_trunk_t* h, int i, char* host_name, int name_cap, int* host_kind, int* host_ndim,
                       int64_t* host_shape4, int64_t* host_offset);
+/* Element order of entry i inside its flat buffer.  0: torch's contiguous order of the entry's shape.  1: a conv weight
+ * of shape [Co,Ci,KH,KW] stored as [Co][KH][KW][Ci] -- the K-major order the tcgen05 engines read (fprop operand) and
+ * accumulate (wgrad), so neither direction needs a transposing pass per step.  To PyTorch that memory is the same
+ * [Co,Ci,KH,KW] tensor in torch.channels_last strides: flat[off:off+n].view(Co,KH,KW,Ci).permute(0,3,1,2) -- logical
+ * indexing, state_dict()/load_state_dict() and the reference's optimizer code are unaffected.  Every conv except the stem
+ * (7x7, 3 input channels) has layout 1; -1 on a bad index.  (ABI version 2.) */
+int mapnet_param_layout(mapnet_trunk_t* h, int i);
 int64_t mapnet_params_numel(mapnet_trunk_t* h); /* floats in params_flat / grads_flat (padded) */
 int64_t mapnet_bufs_numel(mapnet_trunk_t* h);   /* floats in bufs_flat                          */
 

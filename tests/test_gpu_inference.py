@@ -99,20 +99,23 @@ def test_batched_eval_forward_and_tuple_evaluation_match_oracle():
     vos = torch.zeros(5, 2, 7, dtype=torch.float64); vos[..., 3] = 1.0
     res = I.evaluate_tuples(model, x.cuda(), targ, vos7=vos, pose_m=pose_m, pose_s=pose_s, batch=4, sax=1.0, saq=1.0,
                             srx=1.0, srq=1.0)
-    # numpy restatement of eval.py:163-185 on the ORACLE's predictions
+    # numpy restatement of eval.py:163-185 on the PRODUCT's network outputs (forward parity is asserted above; on this
+    # untrained net |log q| ~ 100 rad, so qexp turns the forward's 1e-4 relative error into O(0.1) quaternion differences
+    # and a comparison through the oracle's forward would test conditioning, not the post-processing / PGO path)
+    prod6 = out6.cpu()
     def qexp(v):
         n = np.linalg.norm(v)
         return np.hstack((np.cos(n), np.sinc(n / np.pi) * v))
     exp_pred, exp_targ = [], []
     for k in range(5):
-        o = ref6[k].numpy().astype(np.float64); t = targ[k].numpy().astype(np.float64)
+        o = prod6[k].numpy().astype(np.float64); t = targ[k].numpy().astype(np.float64)
         o7 = np.hstack((o[:, :3], np.asarray([qexp(p[3:]) for p in o])))
         t7 = np.hstack((t[:, :3], np.asarray([qexp(p[3:]) for p in t])))
         o7 = P.optimize_poses(o7, vos[k].numpy(), sax=1.0, saq=1.0, srx=1.0, srq=1.0)
         o7[:, :3] = o7[:, :3] * pose_s + pose_m; t7[:, :3] = t7[:, :3] * pose_s + pose_m
         exp_pred.append(o7[1]); exp_targ.append(t7[1])
     exp_pred, exp_targ = np.stack(exp_pred), np.stack(exp_targ)
-    assert np.abs(res["pred7"].cpu().numpy() - exp_pred).max() <= 5e-4 * np.abs(exp_pred).max()
+    assert np.abs(res["pred7"].cpu().numpy() - exp_pred).max() <= 2e-5 * np.abs(exp_pred).max()
     assert np.abs(res["targ7"].cpu().numpy() - exp_targ).max() <= 1e-6
     t_ref = np.linalg.norm(exp_pred[:, :3] - exp_targ[:, :3], axis=1)
     assert np.abs(res["t_err"].cpu().numpy() - t_ref).max() <= 1e-3 * t_ref.max()

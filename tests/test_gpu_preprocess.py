@@ -69,7 +69,7 @@ def test_gpu_tuple_gather_and_color_jitter_match_the_reference_transform(hw):
 
 def test_gpu_pipeline_throughput_is_reported():
     """HBM-bound byte work: algorithmic bytes = uint8 frame in + fp32 tensor out.  Not a pass/fail bar -- prints the GB/s
-    the round-2 profile quotes (tools/bench_preprocess.py) and checks the launch count."""
+    tools/bench_preprocess.py records under profiles/ and checks the launch count."""
     from geomapnet_b200 import _lib
     from geomapnet_b200.data import ImagePipeline
     frames = torch.randint(0, 256, (64, 480, 640, 3), dtype=torch.uint8, device="cuda")

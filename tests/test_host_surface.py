@@ -28,7 +28,7 @@ def test_cabi_exports_every_declared_symbol(built):
         assert hasattr(L, name), "libmapnet_b200.so does not export %s" % name
     from geomapnet_b200 import _lib
     assert sorted(_lib.EXPORTED) == declared
-    assert _lib.lib().mapnet_abi_version() == 1
+    assert _lib.lib().mapnet_abi_version() == 2
 
 
 def test_spec_table_matches_reference_module(built, golden_dir):
