@@ -174,8 +174,6 @@ k_bn_finalize_accum(long long M, int C, BnFin f, double* __restrict__ accum) {
 int launch_bn_finalize_accum(long long M, int C, const float* gamma, const float* beta, float* run_mean,
                              float* run_var, float* mean_out, float* invstd_out, float* scale, float* shift,
                              double* accum, cudaStream_t st) {
-  { static int dbg = -1, calls = 0; if (dbg < 0) { const char* e = getenv("MAPNET_DEBUG_SKIP_FIN"); dbg = e ? atoi(e) : 0; }
-    if (dbg && ++calls > 100) return 0; }   // TIMING EXPERIMENT ONLY
   MN_CHECK(C <= 512, "bn_finalize_accum: C=%d", C);
   BnFin f; memset(&f, 0, sizeof(f));
   f.gamma = gamma; f.beta = beta; f.run_mean = run_mean; f.run_var = run_var; f.mean = mean_out;
@@ -213,8 +211,6 @@ int launch_bn_bwd_finalize_accum(long long M, int C, const float* gamma, const f
                                  float* dgamma, float* dbeta, float* coef, const float* gamma2, const float* mean2,
                                  const float* invstd2, float* dgamma2, float* dbeta2, float* coef2, double* accum,
                                  cudaStream_t st) {
-  { static int dbg = -1, calls = 0; if (dbg < 0) { const char* e = getenv("MAPNET_DEBUG_SKIP_FIN"); dbg = e ? atoi(e) : 0; }
-    if (dbg && ++calls > 100) return 0; }   // TIMING EXPERIMENT ONLY
   MN_CHECK(C <= 512, "bn_bwd_finalize_accum: C=%d", C);
   BnFin f; memset(&f, 0, sizeof(f));
   f.gamma = gamma; f.mean = const_cast<float*>(mean); f.invstd = const_cast<float*>(invstd);
@@ -315,6 +311,154 @@ k_bn_apply(const T* __restrict__ y, const float* __restrict__ scale, const float
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Lazy finalize (bn_fin.cuh, BnLazy): the consuming kernel turns the accumulated sums into its per-channel parameters.
+// Blocks are laid out (x: pixel groups, y: 64-channel slices) so that a block only needs the sums of 64 channels:
+// thread t sums replicas (t >> 6), (t >> 6) + 4, ... of channel cbase + (t & 63) -- coalesced 512-byte rows of doubles --
+// the four partial sums meet in shared memory.  Thread t < 64 then owns channel cbase + t.
+// ---------------------------------------------------------------------------
+template <int NACC>
+__device__ __forceinline__ void lazy_sums(const BnLazy& L, const int C, const int cbase, double (*part)[3][64],
+                                          double (&s)[3]) {
+  const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  double t[3] = {0.0, 0.0, 0.0};
+  for (int r = rg; r < L.nrep; r += 4) {
+    const double* a = L.accum + (size_t)r * kAccStride + cbase + c;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) t[j] += __ldcg(a + (size_t)j * C);
+  }
+#pragma unroll
+  for (int j = 0; j < NACC; ++j) part[rg][j][c] = t[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 3; ++j) s[j] = (j < NACC) ? (part[0][j][c] + part[1][j][c]) + (part[2][j][c] + part[3][j][c]) : 0.0;
+  __syncthreads();                   // `part` may be reused by a second BatchNorm
+}
+
+// forward: (scale, shift) of the block's 64 channels into shared memory -- from the sums (lazy) or from memory
+__device__ __forceinline__ void lazy_forward_params(const BnLazy& L, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, const int C, const int cbase,
+                                                    double (*part)[3][64], float (*out)[64]) {
+  if (L.accum != nullptr) {
+    // gamma / beta are fetched before the sums so that the two memory latencies overlap
+    float ga = 0.f, be = 0.f;
+    if (threadIdx.x < 64) { ga = __ldg(L.f.gamma + cbase + threadIdx.x); be = __ldg(L.f.beta + cbase + threadIdx.x); }
+    double s[3];
+    lazy_sums<2>(L, C, cbase, part, s);
+    if (threadIdx.x < 64) {
+      const int c = cbase + threadIdx.x;
+      // bn_fin_forward's quantities with the fp64 division and square root taken off the critical path: 1 / M comes
+      // from the host and 1 / sqrt is the fp64 rsqrt intrinsic (a few ulp of fp64, i.e. the same fp32 value after
+      // rounding except in ~1e-8 of the cases); every block computes the same bits, block x == 0 publishes them
+      const double m = s[0] * L.invM;
+      double var = s[1] * L.invM - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)m;
+      const float invstd = (float)rsqrt(var + 1e-5);
+      const float sc = ga * invstd;
+      const float sh = be - mean * sc;
+      out[0][threadIdx.x] = sc;
+      out[1][threadIdx.x] = sh;
+      if (blockIdx.x == 0) {
+        L.f.mean[c] = mean; L.f.invstd[c] = invstd; L.f.scale[c] = sc; L.f.shift[c] = sh;
+        L.f.run_mean[c] = 0.9f * L.f.run_mean[c] + 0.1f * mean;
+        L.f.run_var[c] = 0.9f * L.f.run_var[c] + 0.1f * (float)(var * L.unbias);
+      }
+    }
+  } else if (threadIdx.x < 64) {
+    out[0][threadIdx.x] = __ldg(scale + cbase + threadIdx.x);
+    out[1][threadIdx.x] = __ldg(shift + cbase + threadIdx.x);
+  }
+}
+
+static int slice_grid_x(long long M, int C) {
+  static int per_sm = 0;
+  if (per_sm == 0) { const char* e = getenv("MAPNET_EW_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 8; if (per_sm < 1 || per_sm > 8) per_sm = 8; }
+  const long long slices = C >> 6;
+  long long gx = (M + 31) / 32;
+  long long cap = (148LL * per_sm) / slices;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  return (int)(gx < 1 ? 1 : gx);
+}
+
+// k_bn_apply with the lazy finalize: block (x, y) walks pixels x*32 + (t >> 3), ... of channel slice y; thread t owns the
+// 8 channels cbase + 8 * (t & 7) (one 128-byte line of bf16 per pixel and slice)
+template <typename T, typename TZ, int RES>
+__global__ void __launch_bounds__(kEwThreads)
+k_bn_apply_lazy(const T* __restrict__ y, const void* __restrict__ res, TZ* __restrict__ z, long long M, int C, int relu,
+                const BnLazy L1, const BnLazy L2) {
+  pdl_prologue();
+  __shared__ double part[4][3][64];
+  __shared__ float par[2][2][64];
+  const int cbase = blockIdx.y * 64;
+  const int cl = (threadIdx.x & 7) * 8;
+  // the first pixel's operands are requested BEFORE the finalize chain (sums -> fp64 math -> shared memory): their
+  // DRAM latency overlaps it
+  const long long p0 = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const long long pstep = (long long)gridDim.x * 32;
+  Raw8<T> v0raw, r0traw; Raw8<TZ> r0zraw;
+  if (p0 < M) {
+    const long long off = p0 * C + cbase + cl;
+    v0raw.load(y + off);
+    if (RES == 1) r0zraw.load(reinterpret_cast<const TZ*>(res) + off);
+    if (RES == 2) r0traw.load(reinterpret_cast<const T*>(res) + off);
+  }
+  lazy_forward_params(L1, L1.f.scale, L1.f.shift, C, cbase, part, par[0]);
+  if (RES == 2) lazy_forward_params(L2, L2.f.scale, L2.f.shift, C, cbase, part, par[1]);
+  __syncthreads();
+  float sc[8], sh[8], sc2[8], sh2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = par[0][0][cl + k]; sh[k] = par[0][1][cl + k]; }
+  if (RES == 2) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc2[k] = par[1][0][cl + k]; sh2[k] = par[1][1][cl + k]; }
+  }
+  if (p0 < M) {
+    const long long off = p0 * C + cbase + cl;
+    Vec8<T> v0, r0t; Vec8<TZ> r0z;
+    v0raw.get(v0);
+    if (RES == 1) r0zraw.get(r0z);
+    if (RES == 2) r0traw.get(r0t);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = v0.v[k] * sc[k] + sh[k];
+    if (RES == 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += r0z.v[k];
+    } else if (RES == 2) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += r0t.v[k] * sc2[k] + sh2[k];
+    }
+    Vec8<TZ> w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w.v[k] = relu ? fmaxf(o[k], 0.f) : o[k];
+    w.store(z + off);
+  }
+#pragma unroll 4
+  for (long long p = p0 + pstep; p < M; p += pstep) {
+    const long long off = p * C + cbase + cl;
+    Vec8<T> v; v.load(y + off);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = v.v[k] * sc[k] + sh[k];
+    if (RES == 1) {
+      Vec8<TZ> r; r.load(reinterpret_cast<const TZ*>(res) + off);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += r.v[k];
+    } else if (RES == 2) {
+      Vec8<T> r; r.load(reinterpret_cast<const T*>(res) + off);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += r.v[k] * sc2[k] + sh2[k];
+    }
+    Vec8<TZ> w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w.v[k] = relu ? fmaxf(o[k], 0.f) : o[k];
+    w.store(z + off);
+  }
+}
+
 static int ew_grid(long long n) {
   long long g = (n + kEwThreads - 1) / kEwThreads;
   // few fat threads: the per-thread channel-parameter prologue is amortised over several vectors and
@@ -329,7 +473,18 @@ static int ew_grid(long long n) {
 template <typename T, typename TZ>
 int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_mode, const void* res,
                     const float* scale2, const float* shift2, TZ* z, long long M, int C, int relu,
-                    cudaStream_t st) {
+                    cudaStream_t st, const BnLazy* lazy, const BnLazy* lazy2) {
+  if (lazy != nullptr) {
+    MN_CHECK(C % 64 == 0 && C <= 512, "bn_apply (lazy finalize): C=%d", C);
+    MN_CHECK(res_mode != 2 || lazy2 != nullptr, "bn_apply (lazy finalize): the downsample BN needs its descriptor too");
+    BnLazy none; memset(&none, 0, sizeof(none));
+    const dim3 grid(slice_grid_x(M, C), C >> 6);
+    if (res_mode == 0) MN_LAUNCH((k_bn_apply_lazy<T, TZ, 0>), grid, kEwThreads, 0, st, y, nullptr, z, M, C, relu, *lazy, none);
+    else if (res_mode == 1) MN_LAUNCH((k_bn_apply_lazy<T, TZ, 1>), grid, kEwThreads, 0, st, y, res, z, M, C, relu, *lazy, none);
+    else MN_LAUNCH((k_bn_apply_lazy<T, TZ, 2>), grid, kEwThreads, 0, st, y, res, z, M, C, relu, *lazy, *lazy2);
+    MN_LAUNCH_CHECK();
+    return 0;
+  }
   const long long nvec = M * (C >> 3);
   const int grid = ew_grid(nvec);
   if (res_mode == 0) MN_LAUNCH((k_bn_apply<T, TZ, 0>), grid, kEwThreads, 0, st, y, scale, shift, nullptr, nullptr, nullptr, z, nvec, C, relu);
@@ -338,7 +493,7 @@ int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_
   MN_LAUNCH_CHECK();
   return 0;
 }
-#define MN_INST_BN_APPLY(TA, TZ) template int launch_bn_apply<TA, TZ>(const TA*, const float*, const float*, int, const void*, const float*, const float*, TZ*, long long, int, int, cudaStream_t);
+#define MN_INST_BN_APPLY(TA, TZ) template int launch_bn_apply<TA, TZ>(const TA*, const float*, const float*, int, const void*, const float*, const float*, TZ*, long long, int, int, cudaStream_t, const BnLazy*, const BnLazy*);
 MN_INST_BN_APPLY(float, float)
 MN_INST_BN_APPLY(bf16, bf16)
 MN_INST_BN_APPLY(float, hsplit)
@@ -350,8 +505,15 @@ MN_INST_BN_APPLY(float, hsplit)
 template <typename T, typename TZ>
 __global__ void __launch_bounds__(kEwThreads)
 k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-            TZ* __restrict__ z, uint8_t* __restrict__ amax, int B, int H, int W, int Ho, int Wo, int C) {
+            TZ* __restrict__ z, uint8_t* __restrict__ amax, int B, int H, int W, int Ho, int Wo, int C, const BnLazy L) {
   pdl_prologue();
+  // lazy finalize of the stem BatchNorm (C == 64: one channel slice, every block derives all 64 scale / shift pairs)
+  __shared__ double part[4][3][64];
+  __shared__ float par[2][64];
+  if (L.accum != nullptr) {
+    lazy_forward_params(L, scale, shift, C, 0, part, par);
+    __syncthreads();
+  }
   const int cv = C >> 3;
   // 32-bit index arithmetic (the launcher checks the element count): 64-bit div / mod per element made this kernel
   // latency-bound (ncu r02a: 89 us for 165 MB, 23 % of DRAM peak)
@@ -366,7 +528,10 @@ k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const floa
 #pragma unroll
     for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
     float sc[8], sh[8];
-    ld8(scale + c0, sc); ld8(shift + c0, sh);
+    if (L.accum != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { sc[k] = par[0][c0 + k]; sh[k] = par[1][c0 + k]; }
+    } else { ld8(scale + c0, sc); ld8(shift + c0, sh); }
     // all nine window loads are issued unconditionally (border taps read a clamped, valid pixel and are masked out
     // below): with the loads under the border branches the compiler kept them serial and the kernel ran at 23 % of the
     // DRAM rate (ncu r02a: 89 us for 165 MB)
@@ -406,14 +571,17 @@ k_stem_pool(const T* __restrict__ y, const float* __restrict__ scale, const floa
 
 template <typename T, typename TZ>
 int launch_stem_pool(const T* y, const float* scale, const float* shift, TZ* z, uint8_t* amax, int B, int H,
-                     int W, int Ho, int Wo, int C, cudaStream_t st) {
+                     int W, int Ho, int Wo, int C, cudaStream_t st, const BnLazy* lazy) {
   const long long nvec = (long long)B * Ho * Wo * (C >> 3);
   MN_CHECK(nvec < 2147483647LL, "stem_pool: tensor too large for 32-bit indexing");
-  MN_LAUNCH((k_stem_pool<T, TZ>), ew_grid(nvec), kEwThreads, 0, st, y, scale, shift, z, amax, B, H, W, Ho, Wo, C);
+  MN_CHECK(lazy == nullptr || C == 64, "stem_pool (lazy finalize): C=%d", C);
+  BnLazy L; memset(&L, 0, sizeof(L));
+  if (lazy != nullptr) L = *lazy;
+  MN_LAUNCH((k_stem_pool<T, TZ>), ew_grid(nvec), kEwThreads, 0, st, y, scale, shift, z, amax, B, H, W, Ho, Wo, C, L);
   MN_LAUNCH_CHECK();
   return 0;
 }
-#define MN_INST_STEM_POOL(TA, TZ) template int launch_stem_pool<TA, TZ>(const TA*, const float*, const float*, TZ*, uint8_t*, int, int, int, int, int, int, cudaStream_t);
+#define MN_INST_STEM_POOL(TA, TZ) template int launch_stem_pool<TA, TZ>(const TA*, const float*, const float*, TZ*, uint8_t*, int, int, int, int, int, int, cudaStream_t, const BnLazy*);
 MN_INST_STEM_POOL(float, float)
 MN_INST_STEM_POOL(bf16, bf16)
 MN_INST_STEM_POOL(float, hsplit)
@@ -635,13 +803,145 @@ k_bn_bwd_apply(const T* __restrict__ dout, const TZ* __restrict__ zmask, const T
   }
 }
 
+// k_bn_bwd_apply with the lazy finalize (same block layout as k_bn_apply_lazy): the block derives A, B, C (and the
+// downsample BatchNorm's) for its 64 channels from the sums the producing dgrad / pool-backward kernel accumulated;
+// blockIdx.x == 0 writes d gamma / d beta (and the coefficients, for the record)
+template <typename T, typename TZ, typename TG, int DS, int GOUT>
+__global__ void __launch_bounds__(kEwThreads)
+k_bn_bwd_apply_lazy(const T* __restrict__ dout, const TZ* __restrict__ zmask, const T* __restrict__ y,
+                    TG* __restrict__ dy, const T* __restrict__ yd, TG* __restrict__ dyd, T* __restrict__ gout,
+                    long long M, int C, const float* __restrict__ mscale, const float* __restrict__ mshift,
+                    const float* __restrict__ gscale, const BnLazy L) {
+  pdl_prologue();
+  __shared__ double part[4][3][64];
+  __shared__ float par[8][64];            // A, B, C, Ad, Bd, Cd, mscale, mshift
+  const int cbase = blockIdx.y * 64;
+  const int cl = (threadIdx.x & 7) * 8;
+  // the first pixel's operands are requested before the finalize chain: their DRAM latency overlaps it
+  const long long p0 = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const long long pstep = (long long)gridDim.x * 32;
+  Raw8<T> g0raw, y0raw, yd0raw; Raw8<TZ> z0raw;
+  if (p0 < M) {
+    const long long off = p0 * C + cbase + cl;
+    g0raw.load(dout + off); y0raw.load(y + off);
+    if (zmask != nullptr) z0raw.load(zmask + off);
+    if (DS) yd0raw.load(yd + off);
+  }
+  {
+    // per-channel inputs of the finalize are fetched before the sums so that the memory latencies overlap
+    float pmu = 0.f, pis = 0.f, pga = 0.f, pmu2 = 0.f, pis2 = 0.f, pga2 = 0.f, S = 1.f;
+    if (threadIdx.x < 64) {
+      const int c = cbase + threadIdx.x;
+      pmu = __ldg(L.f.mean + c); pis = __ldg(L.f.invstd + c); pga = __ldg(L.f.gamma + c);
+      if (DS) { pmu2 = __ldg(L.f.mean2 + c); pis2 = __ldg(L.f.invstd2 + c); pga2 = __ldg(L.f.gamma2 + c); }
+      if (gscale != nullptr) S = __ldg(gscale);                      // strict mode: the step's power-of-two scale
+    }
+    double s[3];
+    lazy_sums<DS ? 3 : 2>(L, C, cbase, part, s);
+    if (threadIdx.x < 64) {
+      const int c = cbase + threadIdx.x;
+      const double invM = L.invM;
+      {   // the arithmetic of bn_fin_backward
+        const double mu = (double)pmu, is = (double)pis;
+        const double s2 = is * (s[1] - mu * s[0]);
+        const double A = (double)pga * is;
+        const double Bc = -A * is * s2 * invM;
+        const double Cc = -A * s[0] * invM - Bc * mu;
+        par[0][threadIdx.x] = (float)A * S; par[1][threadIdx.x] = (float)Bc * S; par[2][threadIdx.x] = (float)Cc * S;
+      }
+      if (DS) {
+        const double mu = (double)pmu2, is = (double)pis2;
+        const double s2 = is * (s[2] - mu * s[0]);
+        const double A = (double)pga2 * is;
+        const double Bc = -A * is * s2 * invM;
+        const double Cc = -A * s[0] * invM - Bc * mu;
+        par[3][threadIdx.x] = (float)A * S; par[4][threadIdx.x] = (float)Bc * S; par[5][threadIdx.x] = (float)Cc * S;
+      }
+      if (mscale != nullptr) { par[6][threadIdx.x] = __ldg(mscale + c); par[7][threadIdx.x] = __ldg(mshift + c); }
+      if (blockIdx.x == 0) bn_fin_backward(c, C, s[0], s[1], s[2], L.M, L.f, DS != 0);
+    }
+  }
+  __syncthreads();
+  float cA[8], cB[8], cC[8], dA[8], dB[8], dC[8], msc[8], msh[8];
+  const bool ymask = (zmask == nullptr) && (mscale != nullptr);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { cA[k] = par[0][cl + k]; cB[k] = par[1][cl + k]; cC[k] = par[2][cl + k]; }
+  if (DS) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { dA[k] = par[3][cl + k]; dB[k] = par[4][cl + k]; dC[k] = par[5][cl + k]; }
+  }
+  if (ymask) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { msc[k] = par[6][cl + k]; msh[k] = par[7][cl + k]; }
+  }
+  if (p0 < M) {
+    const long long off = p0 * C + cbase + cl;
+    Vec8<T> g, yy; g0raw.get(g); y0raw.get(yy);
+    if (zmask != nullptr) {
+      Vec8<TZ> z; z0raw.get(z);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = (z.v[k] > 0.f) ? g.v[k] : 0.f;
+    } else if (ymask) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = (yy.v[k] * msc[k] + msh[k] > 0.f) ? g.v[k] : 0.f;
+    }
+    Vec8<TG> o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = cA[k] * g.v[k] + cB[k] * yy.v[k] + cC[k];
+    o.store(dy + off);
+    if (DS) {
+      Vec8<T> y2; yd0raw.get(y2);
+      Vec8<TG> o2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o2.v[k] = dA[k] * g.v[k] + dB[k] * y2.v[k] + dC[k];
+      o2.store(dyd + off);
+    }
+    if (GOUT) g.store(gout + off);
+  }
+#pragma unroll 4
+  for (long long p = p0 + pstep; p < M; p += pstep) {
+    const long long off = p * C + cbase + cl;
+    Vec8<T> g, yy; g.load(dout + off); yy.load(y + off);
+    if (zmask != nullptr) {
+      Vec8<TZ> z; z.load(zmask + off);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = (z.v[k] > 0.f) ? g.v[k] : 0.f;
+    } else if (ymask) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = (yy.v[k] * msc[k] + msh[k] > 0.f) ? g.v[k] : 0.f;
+    }
+    Vec8<TG> o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = cA[k] * g.v[k] + cB[k] * yy.v[k] + cC[k];
+    o.store(dy + off);
+    if (DS) {
+      Vec8<T> y2; y2.load(yd + off);
+      Vec8<TG> o2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o2.v[k] = dA[k] * g.v[k] + dB[k] * y2.v[k] + dC[k];
+      o2.store(dyd + off);
+    }
+    if (GOUT) g.store(gout + off);
+  }
+}
+
 template <typename T, typename TZ, typename TG>
 int launch_bn_bwd_apply(const T* dout, const TZ* zmask, const T* y, const float* coef, TG* dy, const T* yd,
                         const float* coefd, TG* dyd, T* gout, long long M, int C, cudaStream_t st,
-                        const float* mscale, const float* mshift, const float* gscale) {
+                        const float* mscale, const float* mshift, const float* gscale, const BnLazy* lazy) {
+  const bool ds = (yd != nullptr), go = (gout != nullptr);
+  if (lazy != nullptr) {
+    MN_CHECK(C % 64 == 0 && C <= 512, "bn_bwd_apply (lazy finalize): C=%d", C);
+    const dim3 g2(slice_grid_x(M, C), C >> 6);
+    if (ds && !go) MN_LAUNCH((k_bn_bwd_apply_lazy<T, TZ, TG, 1, 0>), g2, kEwThreads, 0, st, dout, zmask, y, dy, yd, dyd, gout, M, C, mscale, mshift, gscale, *lazy);
+    else if (!ds && go) MN_LAUNCH((k_bn_bwd_apply_lazy<T, TZ, TG, 0, 1>), g2, kEwThreads, 0, st, dout, zmask, y, dy, yd, dyd, gout, M, C, mscale, mshift, gscale, *lazy);
+    else if (!ds && !go) MN_LAUNCH((k_bn_bwd_apply_lazy<T, TZ, TG, 0, 0>), g2, kEwThreads, 0, st, dout, zmask, y, dy, yd, dyd, gout, M, C, mscale, mshift, gscale, *lazy);
+    else MN_LAUNCH((k_bn_bwd_apply_lazy<T, TZ, TG, 1, 1>), g2, kEwThreads, 0, st, dout, zmask, y, dy, yd, dyd, gout, M, C, mscale, mshift, gscale, *lazy);
+    MN_LAUNCH_CHECK();
+    return 0;
+  }
   const long long nvec = M * (C >> 3);
   const int grid = ew_grid(nvec);
-  const bool ds = (yd != nullptr), go = (gout != nullptr);
   if (ds && !go) MN_LAUNCH((k_bn_bwd_apply<T, TZ, TG, 1, 0>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift, gscale);
   else if (!ds && go) MN_LAUNCH((k_bn_bwd_apply<T, TZ, TG, 0, 1>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift, gscale);
   else if (!ds && !go) MN_LAUNCH((k_bn_bwd_apply<T, TZ, TG, 0, 0>), grid, kEwThreads, 0, st, dout, zmask, y, coef, dy, yd, coefd, dyd, gout, nvec, C, mscale, mshift, gscale);
@@ -649,7 +949,7 @@ int launch_bn_bwd_apply(const T* dout, const TZ* zmask, const T* y, const float*
   MN_LAUNCH_CHECK();
   return 0;
 }
-#define MN_INST_BWD_APPLY(TA, TZ, TG) template int launch_bn_bwd_apply<TA, TZ, TG>(const TA*, const TZ*, const TA*, const float*, TG*, const TA*, const float*, TG*, TA*, long long, int, cudaStream_t, const float*, const float*, const float*);
+#define MN_INST_BWD_APPLY(TA, TZ, TG) template int launch_bn_bwd_apply<TA, TZ, TG>(const TA*, const TZ*, const TA*, const float*, TG*, const TA*, const float*, TG*, TA*, long long, int, cudaStream_t, const float*, const float*, const float*, const BnLazy*);
 MN_INST_BWD_APPLY(float, float, float)
 MN_INST_BWD_APPLY(bf16, bf16, bf16)
 MN_INST_BWD_APPLY(float, hsplit, hsplit)

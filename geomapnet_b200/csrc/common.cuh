@@ -160,6 +160,42 @@ template <> struct Vec8<hsplit> {
     *(reinterpret_cast<uint4*>(p) + 1) = b;
   }
 };
+// The same 8 elements held RAW: issue the loads early (software pipelining across a prologue or a barrier -- a warp
+// issues in order, so an early load whose conversion follows at once would stall right there), convert at first use.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(Vec8<float>& o) const {
+    o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+  }
+};
+template <> struct Raw8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(Vec8<bf16>& o) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o.v[2 * i] = f.x; o.v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Raw8<hsplit> {
+  uint4 a, b;
+  __device__ __forceinline__ void load(const hsplit* p) {
+    a = *reinterpret_cast<const uint4*>(p); b = *(reinterpret_cast<const uint4*>(p) + 1);
+  }
+  __device__ __forceinline__ void get(Vec8<hsplit>& o) const {
+    const __half2* h = reinterpret_cast<const __half2*>(&a);
+    const __half2* l = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fh = __half22float2(h[i]), fl = __half22float2(l[i]);
+      o.v[2 * i] = fh.x + fl.x; o.v[2 * i + 1] = fh.y + fl.y;
+    }
+  }
+};
 // Element types of one precision mode: A = conv outputs and everything derived by fp32 math from them
 // (what BatchNorm reads, gradients w.r.t. block outputs), Z = forward conv operands (post-BN/ReLU activations,
 // the stem operand), G = backward conv operands (gradients w.r.t. conv outputs).

@@ -1,6 +1,7 @@
 // Internal launcher declarations for the MapNet B200 kernels.
 #pragma once
 #include "common.cuh"
+#include "bn_fin.cuh"
 
 namespace mapnet {
 
@@ -34,18 +35,22 @@ int launch_bn_bwd_reduce(const T* dout, const TZ* zmask, const T* y, const T* yd
 // res: res_mode 1 -> const TZ* (identity branch), 2 -> const T* (downsample branch conv output)
 template <typename T, typename TZ>
 int launch_bn_apply(const T* y, const float* scale, const float* shift, int res_mode, const void* res,
-                    const float* scale2, const float* shift2, TZ* z, long long M, int C, int relu, cudaStream_t st);
+                    const float* scale2, const float* shift2, TZ* z, long long M, int C, int relu, cudaStream_t st,
+                    const BnLazy* lazy = nullptr, const BnLazy* lazy2 = nullptr);
+// lazy (/ lazy2 for the downsample BN): the kernel finalizes the batch statistics itself (bn_fin.cuh, BnLazy)
 template <typename T, typename TZ>
 int launch_stem_pool(const T* y, const float* scale, const float* shift, TZ* z, uint8_t* amax, int B, int H,
-                     int W, int Ho, int Wo, int C, cudaStream_t st);
+                     int W, int Ho, int Wo, int C, cudaStream_t st, const BnLazy* lazy = nullptr);
 template <typename T>
 int launch_stem_pool_bwd(const T* dz, const uint8_t* amax, const T* y, const float* scale, const float* shift,
                          T* g, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t st, double* accum = nullptr);
 template <typename T, typename TZ, typename TG>
 int launch_bn_bwd_apply(const T* dout, const TZ* zmask, const T* y, const float* coef, TG* dy, const T* yd,
                         const float* coefd, TG* dyd, T* gout, long long M, int C, cudaStream_t st,
-                        const float* mscale = nullptr, const float* mshift = nullptr, const float* gscale = nullptr);
+                        const float* mscale = nullptr, const float* mshift = nullptr, const float* gscale = nullptr,
+                        const BnLazy* lazy = nullptr);
 // gscale != nullptr (strict mode): dy / dyd are stored multiplied by the device scalar gscale[0] (a power of two)
+// lazy: coef / coefd are not read; the kernel derives them from the backward sums (3 per channel when yd != nullptr)
 
 // ---- conv_simt.cu: fp32 CUDA-core implicit GEMM (strict-parity path) -----------
 template <typename T>

@@ -162,6 +162,10 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   // and the last one a serial tail -- 4.76 ms/step against 4.57 with the separate (PDL-overlapped) finalize launches: off
   { const char* e = getenv("MAPNET_TC_FUSE_FIN"); fuse_fin = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 0); }
   { const char* e = getenv("MAPNET_TC_FUSE_BWD"); fuse_bwd = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
+  // measured on B200 (posenet_bs64, bf16): the 68 finalize launches of a step cost 0.27 ms of 3.9 (timing experiment with
+  // the launches skipped); with the lazy finalize the consuming element-wise kernels do that work in their prologue
+  { const char* e = getenv("MAPNET_BN_LAZY_FIN"); lazy_fin = (fuse_stats && !fuse_fin && (e ? atoi(e) != 0 : 1)) ? 1 : 0; }
+  stats_target = nullptr; bn_slots = nullptr; bn_slots_bytes = 0;
   { const char* e = getenv("MAPNET_TC_DS_FOLD"); ds_fold = (precision == PREC_BF16_TC) && (e ? atoi(e) != 0 : 1); }
   build_table();
   if (max_B == 0) return 0;      // spec-only handle: parameter table, no device memory
@@ -208,6 +212,10 @@ int Net::init(int max_B_, int H_, int W_, int feat_dim_, int precision_) {
   MN_TRY(alloc((void**)&bn_accum, 32 * 3 * 512 * sizeof(double) + 64));      // kReplicas x [3][512] (bn.cu)
   MN_CUDA(cudaMemset(bn_accum, 0, 32 * 3 * 512 * sizeof(double) + 64));
   bn_counter = (unsigned int*)(bn_accum + 32 * 3 * 512);
+  MN_CHECK(bns.size() <= 36, "trunk: %d BatchNorm layers (36 accumulator slots)", (int)bns.size());
+  bn_slots_bytes = (size_t)(72 * kSlotReplicas + kStemBwdReplicas) * kSlotStride * sizeof(double);
+  MN_TRY(alloc((void**)&bn_slots, bn_slots_bytes));
+  MN_CUDA(cudaMemset(bn_slots, 0, bn_slots_bytes));
   long long small = 0;
   for (auto& b : bns) small += 7LL * b.C;
   MN_TRY(alloc((void**)&bn_small, (size_t)small * sizeof(float)));
@@ -320,7 +328,7 @@ int Net::conv_fprop(int ci, const typename P::Z* x, const typename P::A* residua
   MN_TRY(prof_begin(st, &e0));
   int r;
   if (tc())
-    r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st, (with_stats && fuse_stats) ? bn_accum : nullptr,
+    r = tc_conv_run(tc_fprop[ci], (const bf16*)x, nullptr, (const bf16*)residual, y, st, (with_stats && fuse_stats) ? (stats_target ? stats_target : bn_accum) : nullptr,
                     nullptr, (with_stats && fuse_stats) ? fin : nullptr);
   else if constexpr (SimtConv<P>::ok)
     r = launch_conv_simt_fprop<typename P::A>(g, x, (const float*)w_krsc + convs[ci].wd.k_off, residual, y, st);
@@ -338,7 +346,7 @@ int Net::conv_dgrad(int ci, const typename P::G* dy, const typename P::A* residu
   double flops = conv_flops(g, B, false);
   if (tc()) {
     // dy_shortcut: the block's downsample-conv dgrad rides in the same launch (tc_plan_add_shortcut)
-    r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, (const bf16*)dy_shortcut, (const bf16*)residual, dx, st, bwd ? bn_accum : nullptr, bwd,
+    r = tc_conv_run(tc_dgrad[ci], (const bf16*)dy, (const bf16*)dy_shortcut, (const bf16*)residual, dx, st, bwd ? (stats_target ? stats_target : bn_accum) : nullptr, bwd,
                     bwd ? fin : nullptr);
     if (dy_shortcut != nullptr) { ConvGeom gs = convs[ci_shortcut].g; gs.B = B; flops += conv_flops(gs, B, false); }
   } else if constexpr (SimtConv<P>::ok) {
@@ -437,6 +445,31 @@ int Net::bn_forward(int bi, const typename P::A* y, long long M, const float* pa
                             b.mean, b.invstd, b.scale, b.shift, training, bn_accum, bn_counter, st);
 }
 
+// finalize descriptors for the consuming element-wise kernels (bn.cu, lazy finalize)
+BnLazy Net::lazy_forward(int bi, long long M, const float* params, float* bufs) {
+  BnLazy L; memset(&L, 0, sizeof(L));
+  BNL& b = bns[bi];
+  L.accum = fwd_slot(bi); L.nrep = kSlotReplicas; L.M = M;
+  L.invM = 1.0 / (double)M; L.unbias = (M > 1) ? (double)M / (double)(M - 1) : 1.0;
+  L.f.gamma = params + b.g_off; L.f.beta = params + b.b_off; L.f.run_mean = bufs + b.rm_off; L.f.run_var = bufs + b.rv_off;
+  L.f.mean = b.mean; L.f.invstd = b.invstd; L.f.scale = b.scale; L.f.shift = b.shift; L.f.training = 1;
+  return L;
+}
+BnLazy Net::lazy_backward(int bi, int bi_ds, long long M, const float* params, float* grads) {
+  BnLazy L; memset(&L, 0, sizeof(L));
+  BNL& b = bns[bi];
+  L.accum = bwd_slot(bi); L.nrep = (bi == convs[0].bn) ? kStemBwdReplicas : kSlotReplicas; L.M = M;
+  L.invM = 1.0 / (double)M; L.unbias = 1.0;
+  L.f.gamma = params + b.g_off; L.f.mean = b.mean; L.f.invstd = b.invstd;
+  L.f.dgamma = grads + b.g_off; L.f.dbeta = grads + b.b_off; L.f.coef = b.coef;
+  if (bi_ds >= 0) {
+    BNL& d = bns[bi_ds];
+    L.f.gamma2 = params + d.g_off; L.f.mean2 = d.mean; L.f.invstd2 = d.invstd;
+    L.f.dgamma2 = grads + d.g_off; L.f.dbeta2 = grads + d.b_off; L.f.coef2 = d.coef;
+  }
+  return L;
+}
+
 // finalize descriptors for the conv kernels (conv_tc.cu: the last CTA finalizes the sums it helped accumulate)
 EpiFin Net::fin_forward(int bi, long long M, const float* params, float* bufs) {
   EpiFin F; memset(&F, 0, sizeof(F));
@@ -484,14 +517,20 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
     else MN_TRY(launch_stem_s2d<TZ>(x, (TZ*)A0, B, H, W, Hc + 3, stem_s2d_wsp(Wc), st));
   }
   else MN_TRY(launch_stem_im2col<TZ>(x, (TZ*)A0, B, H, W, Hc, Wc, kStemK, st));
+  // lazy finalize: the conv epilogues accumulate into per-BatchNorm slots (zeroed here, once per step, for both passes)
+  // and the consuming element-wise kernels finalize them -- no finalize launches
+  const bool lazy = lazy_fin && training;
+  if (lazy) MN_CUDA(cudaMemsetAsync(bn_slots, 0, bn_slots_bytes, st));
   {
     const EpiFin f0 = fin_forward(convs[0].bn, (long long)B * Hc * Wc, params, bufs);
+    stats_target = lazy ? fwd_slot(convs[0].bn) : nullptr;
     MN_TRY(conv_fprop<P>(0, (const TZ*)A0, nullptr, (T*)y0, B, st, training != 0, &f0));
   }
-  MN_TRY(bn_forward<P>(convs[0].bn, (const T*)y0, (long long)B * Hc * Wc, params, bufs, training, st));
+  if (!lazy) MN_TRY(bn_forward<P>(convs[0].bn, (const T*)y0, (long long)B * Hc * Wc, params, bufs, training, st));
   {
     BNL& b = bns[convs[0].bn];
-    MN_TRY((launch_stem_pool<T, TZ>((const T*)y0, b.scale, b.shift, (TZ*)z0, amax0, B, Hc, Wc, Hp, Wp, 64, st)));
+    const BnLazy l0 = lazy_forward(convs[0].bn, (long long)B * Hc * Wc, params, bufs);
+    MN_TRY((launch_stem_pool<T, TZ>((const T*)y0, b.scale, b.shift, (TZ*)z0, amax0, B, Hc, Wc, Hp, Wp, 64, st, lazy ? &l0 : nullptr)));
   }
   const TZ* zin = (const TZ*)z0;
   for (auto& bl : blocks) {
@@ -500,22 +539,32 @@ int Net::forward_t(const float* x, const float* params, float* bufs, int B, int 
     BNL& b2 = bns[convs[bl.conv2].bn];
     const EpiFin f1 = fin_forward(convs[bl.conv1].bn, Mo, params, bufs);
     const EpiFin f2 = fin_forward(convs[bl.conv2].bn, Mo, params, bufs);
+    const BnLazy l1 = lazy_forward(convs[bl.conv1].bn, Mo, params, bufs);
+    const BnLazy l2 = lazy_forward(convs[bl.conv2].bn, Mo, params, bufs);
+    stats_target = lazy ? fwd_slot(convs[bl.conv1].bn) : nullptr;
     MN_TRY(conv_fprop<P>(bl.conv1, zin, nullptr, (T*)bl.y1, B, st, training != 0, &f1));
-    MN_TRY(bn_forward<P>(convs[bl.conv1].bn, (const T*)bl.y1, Mo, params, bufs, training, st));
-    MN_TRY((launch_bn_apply<T, TZ>((const T*)bl.y1, b1.scale, b1.shift, 0, nullptr, nullptr, nullptr, (TZ*)bl.h, Mo, bl.Cout, 1, st)));
+    if (!lazy) MN_TRY(bn_forward<P>(convs[bl.conv1].bn, (const T*)bl.y1, Mo, params, bufs, training, st));
+    MN_TRY((launch_bn_apply<T, TZ>((const T*)bl.y1, b1.scale, b1.shift, 0, nullptr, nullptr, nullptr, (TZ*)bl.h, Mo, bl.Cout, 1, st,
+                                   lazy ? &l1 : nullptr)));
+    stats_target = lazy ? fwd_slot(convs[bl.conv2].bn) : nullptr;
     MN_TRY(conv_fprop<P>(bl.conv2, (const TZ*)bl.h, nullptr, (T*)bl.y2, B, st, training != 0, &f2));
-    MN_TRY(bn_forward<P>(convs[bl.conv2].bn, (const T*)bl.y2, Mo, params, bufs, training, st));
+    if (!lazy) MN_TRY(bn_forward<P>(convs[bl.conv2].bn, (const T*)bl.y2, Mo, params, bufs, training, st));
     if (bl.convd >= 0) {
       BNL& bd = bns[convs[bl.convd].bn];
       const EpiFin fd = fin_forward(convs[bl.convd].bn, Mo, params, bufs);
+      const BnLazy ld = lazy_forward(convs[bl.convd].bn, Mo, params, bufs);
+      stats_target = lazy ? fwd_slot(convs[bl.convd].bn) : nullptr;
       MN_TRY(conv_fprop<P>(bl.convd, zin, nullptr, (T*)bl.yd, B, st, training != 0, &fd));
-      MN_TRY(bn_forward<P>(convs[bl.convd].bn, (const T*)bl.yd, Mo, params, bufs, training, st));
-      MN_TRY((launch_bn_apply<T, TZ>((const T*)bl.y2, b2.scale, b2.shift, 2, bl.yd, bd.scale, bd.shift, (TZ*)bl.out, Mo, bl.Cout, 1, st)));
+      if (!lazy) MN_TRY(bn_forward<P>(convs[bl.convd].bn, (const T*)bl.yd, Mo, params, bufs, training, st));
+      MN_TRY((launch_bn_apply<T, TZ>((const T*)bl.y2, b2.scale, b2.shift, 2, bl.yd, bd.scale, bd.shift, (TZ*)bl.out, Mo, bl.Cout, 1, st,
+                                     lazy ? &l2 : nullptr, lazy ? &ld : nullptr)));
     } else {
-      MN_TRY((launch_bn_apply<T, TZ>((const T*)bl.y2, b2.scale, b2.shift, 1, zin, nullptr, nullptr, (TZ*)bl.out, Mo, bl.Cout, 1, st)));
+      MN_TRY((launch_bn_apply<T, TZ>((const T*)bl.y2, b2.scale, b2.shift, 1, zin, nullptr, nullptr, (TZ*)bl.out, Mo, bl.Cout, 1, st,
+                                     lazy ? &l2 : nullptr)));
     }
     zin = (const TZ*)bl.out;
   }
+  stats_target = nullptr;
   // head
   MN_TRY(launch_gap<TZ>(zin, feat, B, Hf * Wf, 512, st));
   const float* mk = nullptr;
@@ -621,11 +670,13 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     if (ds) {
       BNL& bd = bns[convs[bl.convd].bn];
       if (pre) {
-        if (!fuse_fin)
+        const BnLazy lz = lazy_backward(convs[bl.conv2].bn, convs[bl.convd].bn, Mo, params, grads);
+        if (!fuse_fin && !lazy_fin)
           MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
                                               params + bd.g_off, bd.mean, bd.invstd, grads + bd.g_off, grads + bd.b_off, bd.coef,
                                               bn_accum, st));
-        MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st, nullptr, nullptr, gs)));
+        MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st, nullptr, nullptr, gs,
+                                               lazy_fin ? &lz : nullptr)));
       } else {
         MN_TRY((launch_bn_bwd_reduce<T, TZ>(S0, (const TZ*)bl.out, (const T*)bl.y2, (const T*)bl.yd, Mo, C,
                                        params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
@@ -634,10 +685,12 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
         MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S0, (const TZ*)bl.out, (const T*)bl.y2, b2.coef, S1, (const T*)bl.yd, bd.coef, S2, nullptr, Mo, C, st, nullptr, nullptr, gs)));
       }
     } else if (pre) {
-      if (!fuse_fin)
+      const BnLazy lz = lazy_backward(convs[bl.conv2].bn, -1, Mo, params, grads);
+      if (!fuse_fin && !lazy_fin)
         MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b2.g_off, b2.mean, b2.invstd, grads + b2.g_off, grads + b2.b_off, b2.coef,
                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
-      MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st, nullptr, nullptr, gs)));
+      MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S0, nullptr, (const T*)bl.y2, b2.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st, nullptr, nullptr, gs,
+                                             lazy_fin ? &lz : nullptr)));
       gres = S0;              // already gated; conv1's dgrad adds it in place
     } else {
       MN_TRY((launch_bn_bwd_reduce<T, TZ>(S0, (const TZ*)bl.out, (const T*)bl.y2, nullptr, Mo, C,
@@ -655,11 +708,15 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
       EpiBwd e1; memset(&e1, 0, sizeof(e1));
       e1.y = (const bf16*)bl.y1; e1.mscale = b1.scale; e1.mshift = b1.shift;
       const EpiFin fb1 = fin_backward(convs[bl.conv1].bn, -1, Mo, params, grads);
+      const BnLazy lz1 = lazy_backward(convs[bl.conv1].bn, -1, Mo, params, grads);
+      stats_target = lazy_fin ? bwd_slot(convs[bl.conv1].bn) : nullptr;
       MN_TRY(conv_dgrad<P>(bl.conv2, dy2, nullptr, S4, B, st, &e1, &fb1));
-      if (!fuse_fin)
+      stats_target = nullptr;
+      if (!fuse_fin && !lazy_fin)
         MN_TRY(launch_bn_bwd_finalize_accum(Mo, C, params + b1.g_off, b1.mean, b1.invstd, grads + b1.g_off, grads + b1.b_off, b1.coef,
                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
-      MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st, nullptr, nullptr, gs)));
+      MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, nullptr, (const T*)bl.y1, b1.coef, S1, nullptr, nullptr, nullptr, nullptr, Mo, C, st, nullptr, nullptr, gs,
+                                             lazy_fin ? &lz1 : nullptr)));
     } else {
       MN_TRY(conv_dgrad<P>(bl.conv2, dy2, nullptr, S4, B, st));
       MN_TRY((launch_bn_bwd_reduce<T, TZ>(S4, nullptr, (const T*)bl.y1, nullptr, Mo, C,
@@ -679,6 +736,7 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
       e2.y = (const bf16*)pb.y2; e2.zmask = (const bf16*)pb.out;
       e2.yd = (pb.convd >= 0) ? (const bf16*)pb.yd : nullptr;
       fb2 = fin_backward(convs[pb.conv2].bn, (pb.convd >= 0) ? convs[pb.convd].bn : -1, (long long)B * pb.Ho * pb.Wo, params, grads);
+      stats_target = lazy_fin ? bwd_slot(convs[pb.conv2].bn) : nullptr;      // consumed at the top of the next iteration
     }
     MN_TRY(conv_wgrad<P>(bl.conv1, zin, S1, B, st));
     if (ds && bl.ds_fold) {
@@ -691,6 +749,7 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     } else {
       MN_TRY(conv_dgrad<P>(bl.conv1, S1, gres, S0, B, st, next_pre ? &e2 : nullptr, &fb2));
     }
+    stats_target = nullptr;
     pre = next_pre;
   }
   bwd_pre = pre;
@@ -702,16 +761,20 @@ int Net::backward_t(const float* dpred, const float* params, float* grads, int f
     const long long M0 = (long long)B * Hc * Wc;
     if (stem_fuse) {
       // the pool/ReLU backward accumulates the stem BN's (sum g, sum g*y) while it has g and y in registers
-      MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S4, B, Hc, Wc, Hp, Wp, 64, st, bn_accum));
-      MN_TRY(launch_bn_bwd_finalize_accum(M0, 64, params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef,
-                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
+      MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S4, B, Hc, Wc, Hp, Wp, 64, st,
+                                     lazy_fin ? bwd_slot(convs[0].bn) : bn_accum));
+      if (!lazy_fin)
+        MN_TRY(launch_bn_bwd_finalize_accum(M0, 64, params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef,
+                                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, st));
     } else {
       MN_TRY(launch_stem_pool_bwd<T>(S0, amax0, (const T*)y0, b0.scale, b0.shift, S4, B, Hc, Wc, Hp, Wp, 64, st));
       MN_TRY((launch_bn_bwd_reduce<T, TZ>(S4, (const TZ*)nullptr, (const T*)y0, nullptr, M0, 64,
                                      params + b0.g_off, b0.mean, b0.invstd, grads + b0.g_off, grads + b0.b_off, b0.coef,
                                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, bn_accum, bn_counter, st)));
     }
-    MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, (const TZ*)nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st, nullptr, nullptr, gs)));
+    const BnLazy lz0 = lazy_backward(convs[0].bn, -1, M0, params, grads);
+    MN_TRY((launch_bn_bwd_apply<T, TZ, TG>(S4, (const TZ*)nullptr, (const T*)y0, b0.coef, S2, nullptr, nullptr, nullptr, nullptr, M0, 64, st, nullptr, nullptr, gs,
+                                           (lazy_fin && stem_fuse) ? &lz0 : nullptr)));
     MN_TRY(conv_wgrad<P>(0, (const TZ*)A0, S2, B, st));
   }
   MN_TRY(wgrad_join(st));       // every asynchronous wgrad of this part has landed in grads_flat (the stem's in dw_krsc)

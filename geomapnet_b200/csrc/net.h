@@ -79,6 +79,17 @@ struct Net {
   int split_fmt_z, split_fmt_g;  // strict mode: element format of the forward / backward operand planes (0 fp16, 1 bf16)
   float* gscale;                 // strict mode, device: {S, 1/S} -- this step's power-of-two gradient scale
   double* bn_accum; unsigned int* bn_counter;
+  // lazy BatchNorm finalize (bn_fin.cuh, BnLazy): one accumulator slot per BatchNorm and direction, zeroed once per step.
+  // Slots 0..35 forward statistics, 36..71 backward reductions (8 replicas x [3][512] doubles each, what the conv
+  // epilogues spread their flushes over), slot 72 (32 replicas) the stem's backward sums from the pool-backward kernel.
+  double* bn_slots; size_t bn_slots_bytes;
+  int lazy_fin;                  // consumers finalize the sums themselves (env MAPNET_BN_LAZY_FIN, tensor-core modes)
+  double* stats_target;          // where the next conv_fprop / conv_dgrad with fused sums accumulates (nullptr: bn_accum)
+  static constexpr int kSlotReplicas = 8, kStemBwdReplicas = 32, kSlotStride = 3 * 512;
+  double* fwd_slot(int bn) { return bn_slots + (size_t)bn * kSlotReplicas * kSlotStride; }
+  double* bwd_slot(int bn) { return bn_slots + (size_t)(bn == convs[0].bn ? 72 : 36 + bn) * kSlotReplicas * kSlotStride; }
+  BnLazy lazy_forward(int bi, long long M, const float* params, float* bufs);
+  BnLazy lazy_backward(int bi, int bi_ds, long long M, const float* params, float* grads);
   float *feat, *fcpre, *hdrop, *mask, *dh, *dfeat, *dpredf;
   float* bn_small;               // backing store of the BN small arrays
   float *sq_partials, *sq_out;
