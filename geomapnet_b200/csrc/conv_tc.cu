@@ -282,11 +282,11 @@ __device__ __forceinline__ void epi_issue_loads(EpiRegs& G, const long long (&ro
   }
 }
 
-// The fused dgrad epilogues read up to four more tensors per output element (skip-path gradient, conv output y, ReLU
-// mask z, downsample-branch y) straight from HBM, one 32-column chunk at a time per warp: ~0.8 us of DRAM latency per
-// chunk with only 4 warps of loads in flight (layer1 / layer2 dgrads ran at half the HBM rate).  While a tile's
-// accumulator is still being produced, each epilogue warp therefore asks L2 for the rows of the tile it will process
-// NEXT: one prefetch per 128-byte line, lane p = lane & 3 takes line p of each of its 4 rows.
+// EXPERIMENT (env MAPNET_TC_EPI_PREFETCH=1, default off: no gain measured).  The fused dgrad epilogues read up to four
+// more tensors per output element (skip-path gradient, conv output y, ReLU mask z, downsample-branch y), one 32-column
+// chunk at a time per warp.  Hypothesis: ~0.8 us of DRAM latency per chunk with only 4 warps of loads in flight.  While a
+// tile's accumulator is still being produced, each epilogue warp asks L2 for the rows of the tile it will process NEXT:
+// one prefetch per 128-byte line, lane p = lane & 3 takes line p of each of its 4 rows.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 template <int BN>
@@ -2051,7 +2051,9 @@ int tc_conv_run(TcConvPlan* p, const bf16* in0, const bf16* in1, const bf16* res
       F.expected += (unsigned int)((groups < max_clusters ? groups : max_clusters) * p->CL);
     }
     static int epi_pf = -1;
-    if (epi_pf < 0) { const char* e = getenv("MAPNET_TC_EPI_PREFETCH"); epi_pf = e ? atoi(e) : 1; }
+    // measured on B200 (posenet_bs64): 3.911 ms/step without, 3.917 with -- the fused dgrad epilogues are not bound by
+    // the DRAM latency of their extra operands (most are L2 hits right behind their producers): opt-in experiment
+    if (epi_pf < 0) { const char* e = getenv("MAPNET_TC_EPI_PREFETCH"); epi_pf = e ? atoi(e) : 0; }
     for (auto& L : p->launches) {
       const int groups = cdiv(L.P.n_tiles_m, p->CL) * L.P.n_tiles_n * L.P.n_classes;
       const int max_clusters = (p->CL == 4) ? 32 : nsm / p->CL;
