@@ -12,6 +12,10 @@ gain at 2 GPUs: 0.3 %, see geomapnet_b200/ddp.py).
     step = GraphedTrainStep(model, criterion, optimizer, x_example, targ_example)
     loss = step(x, targ)            # x, targ: CUDA tensors (copied into static buffers)
 
+Build it before (or without) keeping tensors of an earlier eager step alive: a live `loss` from a step that ran on the
+default stream pins the parameters' AccumulateGrad nodes to that stream and the capture then fails with
+cudaErrorStreamCaptureImplicit (torch: "delete all references to the autograd graph").
+
 Everything captured is the same product code that runs eagerly (the reference-facing
 modules and the C ABI underneath); counters that change per step (Adam bias
 correction, dropout offset) live in device memory so replays stay correct.

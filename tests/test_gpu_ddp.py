@@ -53,12 +53,23 @@ def _worker_body(rank, world, port, q, overlap):
     flat, _ = net.flat_parameters()
     ref0 = flat.clone(); dist.broadcast(ref0, src=0)
     ok = torch.equal(flat, ref0)
+    # this rank's LOCAL gradient: a backward pass with the part hook switched off (with overlap=True the hook reduces
+    # the slices in place while the pass runs, so nothing local is left to look at afterwards)
+    hook = net._grad_part_hook
+    net._grad_part_hook = None
     loss = crit(model(xs), ts)
     opt.learner.zero_grad()
     loss.backward()
     _, g = net.flat_parameters()
     g_local = g.clone()
     sax_local = crit.sax.grad.clone()
+    del loss
+    net._grad_part_hook = hook
+    # the step under test (same weights, same batch: the fp32 engine's split-K atomics move a gradient by ~1e-6)
+    loss = crit(model(xs), ts)
+    opt.learner.zero_grad()
+    loss.backward()
+    _, g = net.flat_parameters()
     scale = dp.allreduce_grads()
     gathered = [torch.zeros_like(g_local) for _ in range(world)]
     dist.all_gather(gathered, g_local)
@@ -70,6 +81,12 @@ def _worker_body(rank, world, port, q, overlap):
     ok = ok and abs(float(crit.sax.grad) - float(sum(sg))) <= 1e-5 * abs(float(sum(sg))) + 1e-7
     ok = ok and dp.overlap == overlap and (net._grad_part_hook is not None) == overlap   # slices reduced from the backward-part hook
     g_eager = g.clone()
+    # the eager pass above ran on the default stream: its autograd graph (kept alive by `loss`) pins the parameters'
+    # AccumulateGrad nodes to that stream, and a capture that reuses them fails with cudaErrorStreamCaptureImplicit
+    # ("delete all references to the autograd graph" -- torch's own advice; geomapnet_b200/graph.py says the same)
+    del loss
+    import gc
+    gc.collect()
     # the same step captured as CUDA graphs (overlap: slice allreduces INSIDE graph 1, geomapnet_b200/graph.py): same weights
     # (nothing has stepped yet, and building the graphed step restores the state) -> same reduced gradient
     from geomapnet_b200.graph import GraphedTrainStep
@@ -103,11 +120,15 @@ def _run_world2(overlap):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
+    res = []
     try:
-        res = [q.get(timeout=300) for _ in range(2)]
+        while len(res) < 2:
+            res.append(q.get(timeout=180))
+            if not res[-1][1]:                   # one rank failed: its peer would wait in a collective forever
+                break
     finally:
         for p in procs:
-            p.join(60)
+            p.join(5 if (res and not res[-1][1]) else 60)
             if p.is_alive():
                 p.kill()                         # exactly the processes started above
     assert sorted(res) == [(0, True), (1, True)]
