@@ -490,7 +490,7 @@ def run_b200(args, cfg, rank, local_rank, world):
                  other: {"images_per_s": frames(cfg) / (oms / 1000.0), "ms_per_step": oms, "steps": nsteps,
                          "parity_vs_reference": parity[other]},
                  "note": "same workload, same run, CUDA-graph step, inputs resident in HBM; fp32 CUDA-core engine "
-                         "(precision fp32, also 1e-4): 933 img/s (profiles/r02_bench_fp32.json)"}
+                         "(precision fp32, also 1e-4): 957 img/s (profiles/r02c_bench_posenet_bs64_fp32.json)"}
         del g2, model2, net2
 
     # ---------------- cpu baseline: oracle port on the host cores (rank 0, N=1 only) -------------
