@@ -538,6 +538,17 @@ def run_b200(args, cfg, rank, local_rank, world):
             "cpu_baseline": cpu,
             "precision_modes": modes,
         }
+        if world > 1 and args.workload != "posenet_bs64":
+            # the default workload differs between N = 1 (posenet_bs64, BASELINE configs[1]) and N > 1 (configs[3]): the
+            # weak-scaling baseline of THIS workload is its own one-GPU line, not the N = 1 default line
+            n1 = {"mapnet_n32t3": (19172.4, "profiles/r02c_bench_mapnet_n32t3.json"),
+                  "mapnetpp_n16t10": (20499.1, "profiles/r02c_bench_mapnetpp_n16t10.json")}.get(args.workload)
+            if n1 is not None and args.precision == "bf16":
+                line["config"]["one_gpu_same_workload"] = {
+                    "images_per_s": n1[0], "source": n1[1],
+                    "note": "bench.py --gpus 1 defaults to posenet_bs64; weak-scaling efficiency of this line = "
+                            "value / (n_gpus x images_per_s), with `python bench.py --workload %s` as the N = 1 run"
+                            % args.workload}
         print(json.dumps(line), flush=True)
     if world > 1:
         # the measurement is complete and printed: a communicator teardown that stalls (CUDA graphs holding captured NCCL
