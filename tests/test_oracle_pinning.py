@@ -132,3 +132,29 @@ def test_oracle_nan_filter_matches_live_reference_hook():
     for j in range(3):
         n_zero_rows += int(bool((grads["mapnet.fc_wpqr.weight"][j] == 0).all()))
     assert n_zero_rows >= 1, "the degenerate input was meant to wipe at least one fc_wpqr row"
+
+
+def test_baseline_config0_plumbing_single_frame():
+    """BASELINE.json configs[0] / SURVEY.md section 8d "Config 1 (plumbing)": PoseNet ResNet-34 on ONE synthetic 256x256 frame,
+    PoseNetCriterion(sax=0, saq=-3), seed 7, on the CPU: a [1,6] output and a finite loss -- through the oracle everywhere,
+    and against the reference modules executed live where the reference tree exists."""
+    st = weights.make_state(7)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 3, 256, 256, generator=g)
+    targ = torch.randn(1, 6, generator=g)
+    r = O.train_step("posenet", st, x, targ, SV, do_step=False)
+    assert tuple(r["pred"].shape) == (1, 6) and bool(torch.isfinite(r["pred"]).all())
+    assert np.isfinite(float(r["loss"]))
+    # the criterion value follows from the prediction: exp(-sax) L1(t) + sax + exp(-saq) L1(q) + saq (criterion.py:42-52)
+    want = float((r["pred"][:, :3] - targ[:, :3]).abs().mean() + 0.0
+                 + np.exp(3.0) * (r["pred"][:, 3:] - targ[:, 3:]).abs().mean() - 3.0)
+    assert abs(float(r["loss"]) - want) <= 1e-5 * abs(want)
+    if ref_loader.available():
+        ns = ref_loader.load()
+        model = ref_loader.build_reference_model(st, "posenet")
+        model.train()
+        crit = ns.PoseNetCriterion(sax=0.0, saq=-3.0, learn_beta=True)
+        loss, out, _, _ = ref_loader.reference_step(model, crit, x, targ, do_step=False)
+        assert tuple(out.shape) == (1, 6)
+        assert abs(loss - float(r["loss"])) <= 1e-6 * abs(loss)
+        assert float((out - r["pred"]).abs().max()) <= 1e-6
