@@ -1,6 +1,6 @@
 """CUDA-graph capture of the training step (common/train.py:339-361).
 
-The step is ~290 short kernel launches; replaying it as two CUDA graphs removes the
+The step is ~200 short kernel launches; replaying it as two CUDA graphs removes the
 host launch cost and most of the inter-kernel gaps (Blackwell guideline 9).  Graph 1 =
 forward + criterion + zero_grad + backward, graph 2 = [clip +] Adam.  Data parallel: the
 whole-buffer allreduce of FlatDataParallel sits between the two graphs (default).  With

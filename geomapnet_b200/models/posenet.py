@@ -64,8 +64,9 @@ class PoseNet(nn.Module):
                  precision=None, seed=None):
         """feature_extractor: a torchvision-style ResNet-34 object.  It is NEVER run:
         only ``.fc.in_features`` is read and its state_dict harvested as initial trunk
-        weights (scripts/train.py:76-78).  precision: 'bf16' (tcgen05 tensor cores,
-        default), 'fp32' (strict-parity CUDA-core path) or 'bf16_simt' (cross-check)."""
+        weights (scripts/train.py:76-78).  precision: 'bf16' (tcgen05 tensor cores, bf16 operands,
+        default), 'tc_split' (the same engines on fp16 hi/lo operand planes: 1e-4 parity on tensor cores),
+        'fp32' (strict-parity CUDA-core path) or 'bf16_simt' (cross-check)."""
         super(PoseNet, self).__init__()
         self.droprate = droprate
         self.feat_dim = feat_dim
