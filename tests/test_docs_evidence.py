@@ -90,3 +90,17 @@ def test_traffic_capture_belongs_to_these_kernel_sources():
     assert t["source"] == "r02c_ncu_full_summary.csv"
     assert t["sources_digest"] == b._digest()[:16], \
         "kernel sources changed after the ncu capture: bench.py will report roofline.traffic as stale (null)"
+
+
+def test_stage_table_accounts_for_every_conv_flop_of_the_step(capsys):
+    """tools/stage_table.py matches the 104 conv launches of the committed launch list to their layers: the algorithmic
+    FLOPs must add up to SURVEY.md 8d's per-step figure (B = 64: 1 817.6 GFLOP), and the committed table is its output."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stage_table.py"),
+                        os.path.join("profiles", "r02c_launches_raw.csv")], capture_output=True, text=True, cwd=ROOT, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "1817.6 GFLOP" in r.stdout and "all    | 36 |" in r.stdout and "all    | 32 |" in r.stdout
+    assert r.stdout == open(os.path.join(PROF, "r02c_conv_by_stage.txt")).read()
+    from oracle import mapnet_oracle as O
+    assert abs(64 * O.train_flops_per_image(256, 256) - 1817.6e9) < 0.1e9
