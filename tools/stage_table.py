@@ -71,6 +71,43 @@ def main():
                                                           tf / tu / 1e6, tf / tu / 1e6 / peak))
     print("\nall conv launches: %.1f us, %.1f GFLOP, %.0f TFLOP/s = %.2f of peak"
           % (grand_us, grand_fl / 1e9, grand_fl / grand_us / 1e6, grand_fl / grand_us / 1e6 / peak))
+    elementwise(L, split)
+
+
+def elementwise(L, split, hbm=6571.2):
+    """BatchNorm apply kernels by stage, against the HBM roofline in ALGORITHMIC bytes (bf16 tensors): forward
+    k_bn_apply_lazy<.., RES> reads y [+ the residual or the downsample conv's output] and writes z: 4 / 6 / 6 bytes per
+    element for RES = 0 / 1 / 2; backward k_bn_bwd_apply*<.., DS, ..> reads the (already ReLU-gated) gradient and y and
+    writes dy: 6 bytes per element, 10 with the downsample BN's second input / output (DS = 1), +2 with a second gradient output (GO = 1).  Two launches per
+    BasicBlock in each direction (+ the head-side one and the stem's in the backward)."""
+    per_stage = [("layer1", 3, B * 64 * 64 * 64), ("layer2", 4, B * 32 * 32 * 128), ("layer3", 6, B * 16 * 16 * 256),
+                 ("layer4", 3, B * 8 * 8 * 512)]
+    fw = [x for x in L[:split] if x[0].startswith("k_bn_apply_lazy")]
+    bw = [x for x in L[split:] if x[0].startswith("k_bn_bwd_apply")]
+    f_order = [(st, el) for st, nb, el in per_stage for _ in range(2 * nb)]
+    b_order = [(st, el) for st, nb, el in reversed(per_stage) for _ in range(2 * nb)] + [("stem", B * 128 * 128 * 64)]
+    assert len(fw) == len(f_order) == 32 and len(bw) == len(b_order) == 33, (len(fw), len(bw))
+
+    def bytes_per_elt(kernel, fwd):
+        args = kernel[kernel.index("<") + 1:kernel.rindex(">")].split(",")
+        if fwd:
+            return 4 if int(args[2]) == 0 else 6
+        return (10 if int(args[3]) == 1 else 6) + (2 if int(args[4]) == 1 else 0)      # GO = 1: a second gradient output
+
+    for name, lst, order, fwd in (("BatchNorm apply, forward", fw, f_order, True), ("BatchNorm apply, backward", bw, b_order, False)):
+        agg = {}
+        for (k, us), (st, el) in zip(lst, order):
+            a = agg.setdefault(st, [0.0, 0.0, 0])
+            a[0] += us; a[1] += el * bytes_per_elt(k, fwd); a[2] += 1
+        print("\n%s | launches | us | algorithmic MB | GB/s | of %.0f GB/s" % (name, hbm))
+        tu = tb = 0.0
+        for st in ("stem", "layer1", "layer2", "layer3", "layer4"):
+            if st in agg:
+                us, by, n = agg[st]
+                tu += us; tb += by
+                print("%-6s | %2d | %6.1f | %7.1f | %5.0f | %.2f" % (st, n, us, by / 1e6, by / us / 1e3, by / us / 1e3 / hbm))
+        print("%-6s | %2d | %6.1f | %7.1f | %5.0f | %.2f" % ("all", sum(a[2] for a in agg.values()), tu, tb / 1e6, tb / tu / 1e3,
+                                                            tb / tu / 1e3 / hbm))
 
 
 if __name__ == "__main__":
